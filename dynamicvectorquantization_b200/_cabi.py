@@ -1,0 +1,102 @@
+"""ctypes binding of the C-ABI extension (``libb200dq.so``, declared in ``include/b200dq.h``).
+
+The library is the product: there is NO fallback.  Importing this module on a machine where the
+shared object has not been built raises, and every entry point raises on a non-zero status.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200dq.so")
+
+
+class ExtensionMissing(RuntimeError):
+    pass
+
+
+class TapGemmDesc(C.Structure):
+    _fields_ = [
+        ("a_ptr", C.c_void_p), ("a_dims", C.c_longlong * 5), ("a_strides", C.c_longlong * 5),
+        ("b_ptr", C.c_void_p), ("b_rows", C.c_longlong), ("b_k", C.c_longlong),
+        ("b_batch", C.c_longlong), ("b_batch_stride", C.c_longlong),
+        ("num_taps", C.c_int), ("kchunks", C.c_int),
+        ("tap_c", C.c_int * 16), ("tap_w", C.c_int * 16), ("tap_p", C.c_int * 16),
+        ("tap_h", C.c_int * 16), ("tap_bk", C.c_int * 16),
+        ("TW", C.c_int), ("TH", C.c_int), ("TN", C.c_int),
+        ("Wout", C.c_int), ("Hout", C.c_int), ("NB", C.c_int), ("Cout", C.c_int),
+        ("out", C.c_void_p), ("oN", C.c_longlong), ("oH", C.c_longlong), ("oW", C.c_longlong),
+        ("bias", C.c_void_p),
+        ("residual", C.c_void_p), ("rN", C.c_longlong), ("rH", C.c_longlong), ("rW", C.c_longlong),
+        ("alpha", C.c_float), ("out_f32", C.c_int), ("block_n", C.c_int),
+    ]
+
+
+class MmDesc(C.Structure):
+    _fields_ = [
+        ("a_ptr", C.c_void_p), ("a_dims", C.c_longlong * 5), ("a_strides", C.c_longlong * 5),
+        ("b_ptr", C.c_void_p), ("b_dims", C.c_longlong * 5), ("b_strides", C.c_longlong * 5),
+        ("a_mn", C.c_int), ("b_mn", C.c_int), ("ntaps", C.c_int),
+        ("tap_c", C.c_int * 4), ("tap_w", C.c_int * 4), ("tap_p", C.c_int * 4), ("tap_h", C.c_int * 4),
+        ("KW", C.c_int), ("KH", C.c_int), ("KN", C.c_int),
+        ("ktiles_w", C.c_int), ("ktiles_h", C.c_int), ("kblocks", C.c_int),
+        ("splits", C.c_int), ("batches", C.c_int),
+        ("M", C.c_int), ("N", C.c_int),
+        ("out", C.c_void_p), ("oZ", C.c_longlong), ("oT", C.c_longlong), ("oM", C.c_longlong),
+        ("alpha", C.c_float), ("out_f32", C.c_int), ("block_n", C.c_int),
+    ]
+
+
+_lib = None
+
+_vp, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
+
+# name -> argtypes (restype is always int status).  Mirrors include/b200dq.h.
+SIGNATURES = {
+    "b2dq_version": [],
+    "b2dq_vq_prepare_codebook": [_vp, _vp, _vp, _i, _i, _vp],
+    "b2dq_vq_search_gather": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                              _i, _i, _i, _i, _vp],
+    "b2dq_vq_ema_finalize": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _i, _vp],
+    "b2dq_vq_bwd": [_vp, _vp, _vp, _vp, _vp, _f, _vp, _ll, _i, _vp],
+    "b2dq_tapgemm": [C.POINTER(TapGemmDesc), _vp],
+    "b2dq_mmgemm": [C.POINTER(MmDesc), _vp],
+    "b2dq_wgrad_reduce": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "b2dq_gn_stats": [_vp, _vp, _vp, _i, _i, _i, _i, _f, _vp],
+    "b2dq_gn_apply": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "b2dq_gn_bwd_stats": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "b2dq_gn_bwd_apply": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "b2dq_nchw_f32_to_nhwc_bf16": [_vp, _vp, _i, _i, _i, _vp],
+    "b2dq_nhwc_bf16_to_nchw_f32": [_vp, _vp, _i, _i, _i, _vp],
+    "b2dq_nhwc_f32_to_nchw_f32": [_vp, _vp, _i, _i, _i, _vp],
+    "b2dq_nchw_f32_to_nhwc_f32": [_vp, _vp, _i, _i, _i, _vp],
+    "b2dq_upsample2x": [_vp, _vp, _i, _i, _i, _i, _vp],
+    "b2dq_upsample2x_bwd": [_vp, _vp, _i, _i, _i, _i, _vp],
+    "b2dq_softmax_rows": [_vp, _vp, _ll, _i, _i, _vp],
+    "b2dq_softmax_bwd_rows": [_vp, _vp, _vp, _ll, _i, _f, _vp],
+    "b2dq_add_bf16": [_vp, _vp, _vp, _ll, _vp],
+    "b2dq_im2col3x3_small": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "b2dq_bias_grad": [_vp, _vp, _ll, _i, _vp],
+    "b2dq_cast_f32_to_bf16": [_vp, _vp, _ll, _vp],
+}
+
+
+def lib():
+    """Load the extension (once).  Raises ExtensionMissing if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ExtensionMissing(
+                f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  There is no CPU/PyTorch fallback for the DQ-VAE hot path.")
+        l = C.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(l, name)  # AttributeError if the symbol is not exported
+            fn.argtypes = argtypes
+            fn.restype = C.c_int
+        _lib = l
+    return _lib
+
+
+def check(status, what):
+    if status != 0:
+        raise RuntimeError(f"{what} failed with status {status}")

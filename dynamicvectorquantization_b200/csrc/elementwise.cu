@@ -1,0 +1,284 @@
+// Memory-bound helpers of the DQ-VAE hot path (all NHWC bf16 unless noted): layout changes at the
+// NCHW-fp32 module boundary, nearest-neighbour 2x up-sampling (model.py:49-50) and its gradient,
+// row softmax of the attention logits (model.py:182) and its gradient, bias gradients, the small
+// im2col used for the 3-channel edge convolutions, and their weight gradient.
+#include "common.cuh"
+
+namespace b2 {
+
+// [N][C][HW] (src) -> [N][HW][C] (dst) tiled transpose, 32x32 tiles; TI/TO = element types.
+template <typename TI, typename TO>
+__global__ void transpose_chw_hwc_kernel(const TI* __restrict__ src, TO* __restrict__ dst, int C,
+                                         int HW) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int hw0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const TI* s = src + static_cast<long long>(n) * C * HW;
+  TO* d = dst + static_cast<long long>(n) * C * HW;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, hw = hw0 + threadIdx.x;
+    if (c < C && hw < HW) tile[j][threadIdx.x] = static_cast<float>(s[static_cast<long long>(c) * HW + hw]);
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int hw = hw0 + j, c = c0 + threadIdx.x;
+    if (c < C && hw < HW) d[static_cast<long long>(hw) * C + c] = static_cast<TO>(tile[threadIdx.x][j]);
+  }
+}
+// [N][HW][C] -> [N][C][HW]
+template <typename TI, typename TO>
+__global__ void transpose_hwc_chw_kernel(const TI* __restrict__ src, TO* __restrict__ dst, int C,
+                                         int HW) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int hw0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const TI* s = src + static_cast<long long>(n) * C * HW;
+  TO* d = dst + static_cast<long long>(n) * C * HW;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int hw = hw0 + j, c = c0 + threadIdx.x;
+    if (c < C && hw < HW) tile[j][threadIdx.x] = static_cast<float>(s[static_cast<long long>(hw) * C + c]);
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, hw = hw0 + threadIdx.x;
+    if (c < C && hw < HW) d[static_cast<long long>(c) * HW + hw] = static_cast<TO>(tile[threadIdx.x][j]);
+  }
+}
+
+// nearest 2x: out[n, 2h+a, 2w+b, :] = in[n, h, w, :]
+__global__ void upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int H,
+                                  int W, int vecs, long long total_out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total_out) return;
+  const int v = static_cast<int>(i % vecs);
+  long long r = i / vecs;
+  const int ow = static_cast<int>(r % (2 * W)); r /= (2 * W);
+  const int oh = static_cast<int>(r % (2 * H));
+  const long long n = r / (2 * H);
+  out[i] = __ldg(in + ((n * H + (oh >> 1)) * W + (ow >> 1)) * vecs + v);
+}
+// gradient: in-grad[n,h,w,:] = sum of the 4 out-grads
+__global__ void upsample2x_bwd_kernel(const uint4* __restrict__ gout, uint4* __restrict__ gin,
+                                      int H, int W, int vecs, long long total_in) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total_in) return;
+  const int v = static_cast<int>(i % vecs);
+  long long r = i / vecs;
+  const int w = static_cast<int>(r % W); r /= W;
+  const int h = static_cast<int>(r % H);
+  const long long n = r / H;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const uint4 u = __ldg(gout + ((n * 2 * H + 2 * h + a) * (2 * W) + 2 * w + b) * vecs + v);
+      acc[0] += bf16_lo(u.x); acc[1] += bf16_hi(u.x); acc[2] += bf16_lo(u.y); acc[3] += bf16_hi(u.y);
+      acc[4] += bf16_lo(u.z); acc[5] += bf16_hi(u.z); acc[6] += bf16_lo(u.w); acc[7] += bf16_hi(u.w);
+    }
+  uint4 o;
+  o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
+  o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+  gin[i] = o;
+}
+
+// One warp per row; T even.  p = softmax(s) row-wise; logits fp32 (TS=float) or bf16.
+template <typename TS>
+__global__ void softmax_rows_kernel(const TS* __restrict__ s, __nv_bfloat16* __restrict__ p,
+                                    long long rows, int T) {
+  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const TS* sp = s + row * T;
+  uint32_t* pp = reinterpret_cast<uint32_t*>(p + row * T);
+  float mx = -INFINITY;
+  for (int i = lane; i < T / 2; i += 32)
+    mx = fmaxf(mx, fmaxf(static_cast<float>(sp[2 * i]), static_cast<float>(sp[2 * i + 1])));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+  for (int i = lane; i < T / 2; i += 32)
+    sum += __expf(static_cast<float>(sp[2 * i]) - mx) + __expf(static_cast<float>(sp[2 * i + 1]) - mx);
+  sum = warp_sum(sum);
+  const float inv = 1.f / sum;
+  for (int i = lane; i < T / 2; i += 32)
+    pp[i] = pack_bf16x2(__expf(static_cast<float>(sp[2 * i]) - mx) * inv,
+                        __expf(static_cast<float>(sp[2 * i + 1]) - mx) * inv);
+}
+// ds = scale * p * (dp - sum_j p_j dp_j)
+__global__ void softmax_bwd_rows_kernel(const __nv_bfloat16* __restrict__ p,
+                                        const __nv_bfloat16* __restrict__ dp,
+                                        __nv_bfloat16* __restrict__ ds, long long rows, int T,
+                                        float scale) {
+  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const uint32_t* pp = reinterpret_cast<const uint32_t*>(p + row * T);
+  const uint32_t* dpp = reinterpret_cast<const uint32_t*>(dp + row * T);
+  uint32_t* dsp = reinterpret_cast<uint32_t*>(ds + row * T);
+  float dot = 0.f;
+  for (int i = lane; i < T / 2; i += 32) {
+    const uint32_t a = pp[i], b = dpp[i];
+    dot += bf16_lo(a) * bf16_lo(b) + bf16_hi(a) * bf16_hi(b);
+  }
+  dot = warp_sum(dot);
+  for (int i = lane; i < T / 2; i += 32) {
+    const uint32_t a = pp[i], b = dpp[i];
+    dsp[i] = pack_bf16x2(scale * bf16_lo(a) * (bf16_lo(b) - dot), scale * bf16_hi(a) * (bf16_hi(b) - dot));
+  }
+}
+
+__global__ void add_bf16_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b,
+                                uint4* __restrict__ o, long long nvec) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= nvec) return;
+  const uint4 x = __ldg(a + i), y = __ldg(b + i);
+  uint4 r;
+  r.x = pack_bf16x2(bf16_lo(x.x) + bf16_lo(y.x), bf16_hi(x.x) + bf16_hi(y.x));
+  r.y = pack_bf16x2(bf16_lo(x.y) + bf16_lo(y.y), bf16_hi(x.y) + bf16_hi(y.y));
+  r.z = pack_bf16x2(bf16_lo(x.z) + bf16_lo(y.z), bf16_hi(x.z) + bf16_hi(y.z));
+  r.w = pack_bf16x2(bf16_lo(x.w) + bf16_lo(y.w), bf16_hi(x.w) + bf16_hi(y.w));
+  o[i] = r;
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ a, __nv_bfloat16* __restrict__ o,
+                                     long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) o[i] = __float2bfloat16_rn(a[i]);
+}
+
+// im2col for a 3x3 pad-1 stride-1 window over a few-channel NHWC bf16 image:
+// dst[pixel][t*Cs + c] = src[pixel + off_t][c], zero padded to 64 columns.
+// flip = 0: off_t = (r-1, s-1)   (forward / weight gradient);  flip = 1: off_t = (1-r, 1-s) (dgrad).
+__global__ void im2col3x3_small_kernel(const __nv_bfloat16* __restrict__ src,
+                                       __nv_bfloat16* __restrict__ dst, int H, int W, int Cs,
+                                       int flip, long long total) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int col = static_cast<int>(i & 63);
+  const long long pix = i >> 6;
+  const int w = static_cast<int>(pix % W);
+  const int h = static_cast<int>((pix / W) % H);
+  const long long n = pix / (static_cast<long long>(W) * H);
+  __nv_bfloat16 v = __float2bfloat16_rn(0.f);
+  if (col < 9 * Cs) {
+    const int t = col / Cs, c = col % Cs;
+    const int r = t / 3, s = t % 3;
+    const int hh = h + (flip ? 1 - r : r - 1), ww = w + (flip ? 1 - s : s - 1);
+    if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = src[((n * H + hh) * W + ww) * Cs + c];
+  }
+  dst[i] = v;
+}
+
+// out[c] = sum_rows dy[row][c]   (bias gradient), dy bf16 [rows][C]; out must be zeroed.
+__global__ void bias_grad_kernel(const __nv_bfloat16* __restrict__ dy, float* out, long long rows,
+                                 int C, int rows_per_block) {
+  const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_block;
+  const long long r1 = min(rows, r0 + rows_per_block);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (long long r = r0; r < r1; ++r) s += __bfloat162float(dy[r * C + c]);
+    atomicAdd(out + c, s);
+  }
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+template <typename K, typename... Args>
+static int launch1d(K kernel, long long total, cudaStream_t stream, Args... args) {
+  if (total <= 0) return 0;
+  kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(args...);
+  return (int)cudaGetLastError();
+}
+
+extern "C" {
+
+int b2dq_version() { return 0; }
+
+int b2dq_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int N, int C, int HW, cudaStream_t st) {
+  dim3 grid((HW + 31) / 32, (C + 31) / 32, N), block(32, 8);
+  transpose_chw_hwc_kernel<float, __nv_bfloat16><<<grid, block, 0, st>>>(
+      src, reinterpret_cast<__nv_bfloat16*>(dst), C, HW);
+  return (int)cudaGetLastError();
+}
+int b2dq_nchw_f32_to_nhwc_f32(const float* src, float* dst, int N, int C, int HW, cudaStream_t st) {
+  dim3 grid((HW + 31) / 32, (C + 31) / 32, N), block(32, 8);
+  transpose_chw_hwc_kernel<float, float><<<grid, block, 0, st>>>(src, dst, C, HW);
+  return (int)cudaGetLastError();
+}
+int b2dq_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int N, int C, int HW, cudaStream_t st) {
+  dim3 grid((HW + 31) / 32, (C + 31) / 32, N), block(32, 8);
+  transpose_hwc_chw_kernel<__nv_bfloat16, float><<<grid, block, 0, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(src), dst, C, HW);
+  return (int)cudaGetLastError();
+}
+int b2dq_nhwc_f32_to_nchw_f32(const float* src, float* dst, int N, int C, int HW, cudaStream_t st) {
+  dim3 grid((HW + 31) / 32, (C + 31) / 32, N), block(32, 8);
+  transpose_hwc_chw_kernel<float, float><<<grid, block, 0, st>>>(src, dst, C, HW);
+  return (int)cudaGetLastError();
+}
+
+int b2dq_upsample2x(const void* in, void* out, int N, int H, int W, int C, cudaStream_t st) {
+  if (C % 8) return -1;
+  const int vecs = C / 8;
+  const long long total = (long long)N * 4 * H * W * vecs;
+  return launch1d(upsample2x_kernel, total, st, reinterpret_cast<const uint4*>(in),
+                  reinterpret_cast<uint4*>(out), H, W, vecs, total);
+}
+int b2dq_upsample2x_bwd(const void* gout, void* gin, int N, int H, int W, int C, cudaStream_t st) {
+  if (C % 8) return -1;
+  const int vecs = C / 8;
+  const long long total = (long long)N * H * W * vecs;
+  return launch1d(upsample2x_bwd_kernel, total, st, reinterpret_cast<const uint4*>(gout),
+                  reinterpret_cast<uint4*>(gin), H, W, vecs, total);
+}
+
+int b2dq_softmax_rows(const void* s, void* p, long long rows, int T, int in_f32, cudaStream_t st) {
+  if (T % 2) return -1;
+  if (in_f32)
+    return launch1d(softmax_rows_kernel<float>, rows * 32, st, reinterpret_cast<const float*>(s),
+                    reinterpret_cast<__nv_bfloat16*>(p), rows, T);
+  return launch1d(softmax_rows_kernel<__nv_bfloat16>, rows * 32, st,
+                  reinterpret_cast<const __nv_bfloat16*>(s), reinterpret_cast<__nv_bfloat16*>(p),
+                  rows, T);
+}
+int b2dq_softmax_bwd_rows(const void* p, const void* dp, void* ds, long long rows, int T,
+                          float scale, cudaStream_t st) {
+  if (T % 2) return -1;
+  return launch1d(softmax_bwd_rows_kernel, rows * 32, st, reinterpret_cast<const __nv_bfloat16*>(p),
+                  reinterpret_cast<const __nv_bfloat16*>(dp), reinterpret_cast<__nv_bfloat16*>(ds),
+                  rows, T, scale);
+}
+
+int b2dq_add_bf16(const void* a, const void* b, void* o, long long n, cudaStream_t st) {
+  if (n % 8) return -1;
+  return launch1d(add_bf16_kernel, n / 8, st, reinterpret_cast<const uint4*>(a),
+                  reinterpret_cast<const uint4*>(b), reinterpret_cast<uint4*>(o), n / 8);
+}
+
+int b2dq_cast_f32_to_bf16(const float* a, void* o, long long n, cudaStream_t st) {
+  return launch1d(cast_f32_bf16_kernel, n, st, a, reinterpret_cast<__nv_bfloat16*>(o), n);
+}
+
+int b2dq_im2col3x3_small(const void* src, void* dst, int N, int H, int W, int Cs, int flip,
+                         cudaStream_t st) {
+  if (9 * Cs > 64) return -1;
+  const long long total = (long long)N * H * W * 64;
+  return launch1d(im2col3x3_small_kernel, total, st, reinterpret_cast<const __nv_bfloat16*>(src),
+                  reinterpret_cast<__nv_bfloat16*>(dst), H, W, Cs, flip, total);
+}
+
+int b2dq_bias_grad(const void* dy, float* out, long long rows, int C, cudaStream_t st) {
+  if (rows <= 0) return 0;
+  cudaMemsetAsync(out, 0, sizeof(float) * C, st);
+  int rpb = (int)((rows + 148 * 4 - 1) / (148 * 4));
+  if (rpb < 16) rpb = 16;
+  const unsigned blocks = (unsigned)((rows + rpb - 1) / rpb);
+  bias_grad_kernel<<<blocks, C < 256 ? (C < 32 ? 32 : C) : 256, 0, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dy), out, rows, C, rpb);
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -1,0 +1,299 @@
+// General batched / split-K GEMM on tcgen05 with per-operand major-ness, used for
+//   * convolution weight gradients (reference: autograd of nn.Conv2d in
+//     modules/diffusionmodules/model.py:43-47,62-66,88-115,146-165):
+//       dW[co, tap, ci] = sum_pixels dY[pixel, co] * X[pixel shifted by tap, ci]
+//     A = dY (MN-major: channels contiguous, pixels are the contraction), B = X (MN-major),
+//     up to 4 taps share one dY tile and accumulate into separate TMEM column ranges;
+//     the pixel range is split across CTAs and fp32 partials are reduced by wgrad_reduce.
+//   * the single-head attention contractions (model.py:176-188) and their gradients:
+//     any combination of K-major / MN-major A and B, batched over images.
+// Operand tiles are 128 B-swizzled TMA boxes; MN-major tiles are stacks of {64 mn, 64 k} boxes
+// (8 KB each, LBO = 8 KB between 64-wide mn groups, 2 KB per K=16 step).
+#include "common.cuh"
+#include "tmap.h"
+
+namespace b2 {
+
+struct MmParams {
+  int a_mn, b_mn;                 // 0 = K-major ([rows][K], K contiguous), 1 = MN-major ([K][rows])
+  int ntaps;                      // accumulators (B-operand shifts), 1..4
+  int tap_c[4], tap_w[4], tap_p[4], tap_h[4];
+  int KW, KH, KN;                 // MN-major k-block box extents (KW*KH*KN == 64)
+  int ktiles_w, ktiles_h;         // k-block -> (kw, kh, kn) decomposition for MN-major operands
+  int kblocks;                    // total k-blocks (of 64) in the contraction
+  int splits;                     // split-K factor; blockIdx.z = batch*splits + split
+  int M, N;                       // valid output extents
+  void* out;
+  long long oZ, oT, oM;           // element strides: per blockIdx.z, per tap, per output row
+  float alpha;
+  int out_f32;
+};
+
+template <int BN, int STAGES, int MAXTAPS>
+struct MmCfg {
+  static constexpr uint32_t A_BYTES = 128 * 128;
+  static constexpr uint32_t B_BYTES = BN * 128;
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + MAXTAPS * B_BYTES;
+  static constexpr uint32_t SMEM = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr uint32_t TMEM_COLS = (BN * MAXTAPS <= 128) ? 128 : (BN * MAXTAPS <= 256 ? 256 : 512);
+};
+
+template <int BN, int STAGES, int MAXTAPS>
+__global__ void __launch_bounds__(192, 1)
+mmgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+              const __grid_constant__ MmParams p) {
+  using Cfg = MmCfg<BN, STAGES, MAXTAPS>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sBar = base + STAGES * Cfg::STAGE_BYTES;
+  const uint32_t bar_full = sBar, bar_empty = sBar + 8 * STAGES, bar_tfull = sBar + 16 * STAGES;
+  uint32_t* tmem_slot =
+      reinterpret_cast<uint32_t*>(smem_raw + (sBar + 16 * STAGES + 16 - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * BN;
+  const int batch = blockIdx.z / p.splits, split = blockIdx.z % p.splits;
+  const int per = (p.kblocks + p.splits - 1) / p.splits;
+  const int kb0 = split * per;
+  const int kb1 = min(p.kblocks, kb0 + per);
+  const int kiters = max(kb1 - kb0, 0);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(bar_full + 8 * i, 1);
+      mbar_init(bar_empty + 8 * i, 1);
+    }
+    mbar_init(bar_tfull, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(smem_u32(tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      const uint32_t tx = Cfg::A_BYTES + p.ntaps * Cfg::B_BYTES;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        const int kw = kb % p.ktiles_w, kh = (kb / p.ktiles_w) % p.ktiles_h,
+                  kn = kb / (p.ktiles_w * p.ktiles_h);
+        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+        const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
+        const uint32_t fb = bar_full + 8 * stage;
+        mbar_arrive_expect_tx(fb, tx);
+        if (!p.a_mn) {
+          tma_load_5d(sa, &tmA, fb, kb * 64, m0, 0, 0, batch);
+        } else {
+#pragma unroll
+          for (int g = 0; g < 2; ++g)
+            tma_load_5d(sa + g * 8192, &tmA, fb, m0 + 64 * g, kw * p.KW, 0, kh * p.KH,
+                        kn * p.KN + batch);
+        }
+        for (int t = 0; t < p.ntaps; ++t) {
+          const uint32_t sb = sa + Cfg::A_BYTES + t * Cfg::B_BYTES;
+          if (!p.b_mn) {
+            tma_load_5d(sb, &tmB, fb, kb * 64, n0, 0, 0, batch);
+          } else {
+#pragma unroll
+            for (int g = 0; g < BN / 64; ++g)
+              tma_load_5d(sb + g * 8192, &tmB, fb, n0 + 64 * g + p.tap_c[t],
+                          kw * p.KW + p.tap_w[t], p.tap_p[t], kh * p.KH + p.tap_h[t],
+                          kn * p.KN + batch);
+          }
+        }
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, BN, p.a_mn, p.b_mn);
+      const uint32_t a_step = p.a_mn ? 2048u : 32u, b_step = p.b_mn ? 2048u : 32u;
+      const uint32_t a_lbo = p.a_mn ? 8192u : 0u, b_lbo = p.b_mn ? 8192u : 0u;
+      uint32_t stage = 0, phase = 0;
+      for (int it = 0; it < kiters; ++it) {
+        mbar_wait(bar_full + 8 * stage, phase);
+        tc_fence_after();
+        const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
+        for (int t = 0; t < p.ntaps; ++t) {
+          const uint32_t sb = sa + Cfg::A_BYTES + t * Cfg::B_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = make_smem_desc(sa + k * a_step, a_lbo, 1024);
+            const uint64_t db = make_smem_desc(sb + k * b_step, b_lbo, 1024);
+            umma_bf16(tmem_base + t * BN, da, db, idesc, (it | k) ? 1u : 0u);
+          }
+        }
+        umma_commit(bar_empty + 8 * stage);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(bar_tfull);
+    }
+  } else {
+    const int q = warp & 3;
+    const int m = m0 + q * 32 + lane;
+    const bool valid = m < p.M;
+    if (kiters > 0) {
+      mbar_wait(bar_tfull, 0);
+      tc_fence_after();
+    }
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    for (int t = 0; t < p.ntaps; ++t) {
+      const long long ooff = blockIdx.z * p.oZ + t * p.oT + static_cast<long long>(m) * p.oM;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        if (kiters > 0) {
+          tmem_ld_32x32(trow + t * BN + c0, r);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = 0u;
+        }
+        const int col = n0 + c0;
+        if (!valid || col >= p.N) continue;
+        if (p.out_f32) {
+          float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + ooff + col);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            op[i] = make_float4(__uint_as_float(r[4 * i]) * p.alpha,
+                                __uint_as_float(r[4 * i + 1]) * p.alpha,
+                                __uint_as_float(r[4 * i + 2]) * p.alpha,
+                                __uint_as_float(r[4 * i + 3]) * p.alpha);
+        } else {
+          uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + ooff + col);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(r[8 * i + 0]) * p.alpha, __uint_as_float(r[8 * i + 1]) * p.alpha);
+            u.y = pack_bf16x2(__uint_as_float(r[8 * i + 2]) * p.alpha, __uint_as_float(r[8 * i + 3]) * p.alpha);
+            u.z = pack_bf16x2(__uint_as_float(r[8 * i + 4]) * p.alpha, __uint_as_float(r[8 * i + 5]) * p.alpha);
+            u.w = pack_bf16x2(__uint_as_float(r[8 * i + 6]) * p.alpha, __uint_as_float(r[8 * i + 7]) * p.alpha);
+            op[i] = u;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// partial[split][tap][co][ci] (fp32)  ->  dW[co][ci][tap] (fp32, OIHW with tap = r*S+s), +=
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw,
+                                    int splits, int taps, int cout, int cin, int accumulate) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long per = static_cast<long long>(taps) * cout * cin;
+  if (i >= per) return;
+  const int ci = static_cast<int>(i % cin);
+  const int co = static_cast<int>((i / cin) % cout);
+  const int t = static_cast<int>(i / (static_cast<long long>(cin) * cout));
+  float s = 0.f;
+  for (int sp = 0; sp < splits; ++sp) s += partial[sp * per + i];
+  float* o = dw + (static_cast<long long>(co) * cin + ci) * taps + t;
+  *o = accumulate ? (*o + s) : s;
+}
+
+template <int BN, int STAGES, int MAXTAPS>
+static int launch_mm(const CUtensorMap& tmA, const CUtensorMap& tmB, const MmParams& p, dim3 grid,
+                     cudaStream_t stream) {
+  using Cfg = MmCfg<BN, STAGES, MAXTAPS>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(mmgemm_kernel<BN, STAGES, MAXTAPS>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  mmgemm_kernel<BN, STAGES, MAXTAPS><<<grid, 192, Cfg::SMEM, stream>>>(tmA, tmB, p);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+extern "C" {
+
+struct b2dq_mm_desc {
+  // 5-D bf16 views (innermost first) of the two operands; strides in elements (stride[0] ignored)
+  const void* a_ptr; long long a_dims[5]; long long a_strides[5];
+  const void* b_ptr; long long b_dims[5]; long long b_strides[5];
+  int a_mn, b_mn;
+  int ntaps;
+  int tap_c[4], tap_w[4], tap_p[4], tap_h[4];
+  int KW, KH, KN;
+  int ktiles_w, ktiles_h, kblocks;
+  int splits, batches;
+  int M, N;
+  void* out; long long oZ, oT, oM;
+  float alpha;
+  int out_f32;
+  int block_n;   // 128 or 256 (0 = auto)
+};
+
+int b2dq_mmgemm(const b2dq_mm_desc* d, cudaStream_t stream) {
+  if (!d || d->ntaps < 1 || d->ntaps > 3 || d->splits < 1 || d->batches < 1) return -1;
+  if (d->M <= 0 || d->N <= 0) return 0;
+  int bn = d->block_n ? d->block_n : ((d->N % 256 == 0 && d->ntaps == 1) ? 256 : 128);
+  if (bn * d->ntaps > 512) return -2;
+  if ((d->a_mn || d->b_mn) && d->KW * d->KH * d->KN != 64) return -3;
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[5], str[5];
+    for (int i = 0; i < 5; ++i) { dims[i] = (uint64_t)d->a_dims[i]; str[i] = (uint64_t)d->a_strides[i]; }
+    uint32_t box_k[5] = {64, 128, 1, 1, 1};
+    uint32_t box_mn[5] = {64, (uint32_t)d->KW, 1, (uint32_t)d->KH, (uint32_t)d->KN};
+    int r = make_tmap_bf16(&tmA, d->a_ptr, 5, dims, str, d->a_mn ? box_mn : box_k);
+    if (r) return r;
+  }
+  {
+    uint64_t dims[5], str[5];
+    for (int i = 0; i < 5; ++i) { dims[i] = (uint64_t)d->b_dims[i]; str[i] = (uint64_t)d->b_strides[i]; }
+    uint32_t box_k[5] = {64, (uint32_t)bn, 1, 1, 1};
+    uint32_t box_mn[5] = {64, (uint32_t)d->KW, 1, (uint32_t)d->KH, (uint32_t)d->KN};
+    int r = make_tmap_bf16(&tmB, d->b_ptr, 5, dims, str, d->b_mn ? box_mn : box_k);
+    if (r) return r - 1000;
+  }
+  MmParams p;
+  p.a_mn = d->a_mn; p.b_mn = d->b_mn; p.ntaps = d->ntaps;
+  for (int i = 0; i < 4; ++i) {
+    p.tap_c[i] = d->tap_c[i]; p.tap_w[i] = d->tap_w[i]; p.tap_p[i] = d->tap_p[i]; p.tap_h[i] = d->tap_h[i];
+  }
+  p.KW = d->KW ? d->KW : 64; p.KH = d->KH ? d->KH : 1; p.KN = d->KN ? d->KN : 1;
+  p.ktiles_w = d->ktiles_w > 0 ? d->ktiles_w : (1 << 30);
+  p.ktiles_h = d->ktiles_h > 0 ? d->ktiles_h : 1;
+  p.kblocks = d->kblocks; p.splits = d->splits;
+  p.M = d->M; p.N = d->N;
+  p.out = d->out; p.oZ = d->oZ; p.oT = d->oT; p.oM = d->oM;
+  p.alpha = d->alpha; p.out_f32 = d->out_f32;
+  dim3 grid((unsigned)((d->M + 127) / 128), (unsigned)((d->N + bn - 1) / bn),
+            (unsigned)(d->batches * d->splits));
+  if (bn == 128) {
+    if (d->ntaps == 1) return launch_mm<128, 4, 1>(tmA, tmB, p, grid, stream);
+    return launch_mm<128, 3, 3>(tmA, tmB, p, grid, stream) ;
+  } else if (bn == 256) {
+    if (d->ntaps != 1) return -4;
+    return launch_mm<256, 4, 1>(tmA, tmB, p, grid, stream);
+  }
+  return -5;
+}
+
+int b2dq_wgrad_reduce(const float* partial, float* dw, int splits, int taps, int cout, int cin,
+                      int accumulate, cudaStream_t stream) {
+  const long long per = (long long)taps * cout * cin;
+  if (per <= 0) return 0;
+  wgrad_reduce_kernel<<<(unsigned)((per + 255) / 256), 256, 0, stream>>>(partial, dw, splits, taps,
+                                                                         cout, cin, accumulate);
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -1,0 +1,298 @@
+// GroupNorm(32 groups, eps 1e-6, affine) fused with swish, NHWC bf16, forward and backward.
+// Reference: modules/diffusionmodules/model.py:29-35 (nonlinearity, Normalize) and their uses at
+// :119-127 (ResnetBlock), :170 (AttnBlock, no swish), EncoderDual.py:116-117,126-127,
+// DecoderPositional.py:142-143.  HBM-bound: forward = 2 reads + 1 write of the tensor
+// (statistics pass + apply pass), backward = 2 reads of (dy, x) + 1 write.
+// Statistics are accumulated per CTA in fp32 and across CTAs in fp64 (atomicAdd double), so the
+// E[x^2]-E[x]^2 form does not lose the variance.
+#include "common.cuh"
+
+namespace b2 {
+
+// ------------------------------------------------------------------ forward statistics
+// grid (chunks, N); block 256.  Thread t owns channel vector (8 ch) v = t % (C/8) and walks rows.
+__global__ void gn_partial_stats_kernel(const __nv_bfloat16* __restrict__ x, double* ws, int HW,
+                                        int C, int G, int rows_per_block) {
+  extern __shared__ float sh[];  // [2][C]
+  const int n = blockIdx.y;
+  const int vecs = C >> 3;
+  const int v = threadIdx.x % vecs;
+  const int rlane = threadIdx.x / vecs;
+  const int rstep = blockDim.x / vecs;
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(HW, r0 + rows_per_block);
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  float s[8], ss[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s[i] = 0.f; ss[i] = 0.f; }
+  const __nv_bfloat16* base = x + (static_cast<long long>(n) * HW) * C + v * 8;
+  if (rlane < rstep) {
+    for (int r = r0 + rlane; r < r1; r += rstep) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(r) * C));
+      const float f[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
+                          bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s[i] += f[i]; ss[i] = fmaf(f[i], f[i], ss[i]); }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomicAdd(&sh[v * 8 + i], s[i]);
+      atomicAdd(&sh[C + v * 8 + i], ss[i]);
+    }
+  }
+  __syncthreads();
+  const int cg = C / G;
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int c = 0; c < cg; ++c) { a += sh[g * cg + c]; b += sh[C + g * cg + c]; }
+    atomicAdd(&ws[(static_cast<long long>(n) * G + g) * 2 + 0], static_cast<double>(a));
+    atomicAdd(&ws[(static_cast<long long>(n) * G + g) * 2 + 1], static_cast<double>(b));
+  }
+}
+__global__ void gn_finalize_kernel(const double* __restrict__ ws, float* stats, int NG,
+                                   double inv_count, float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NG) return;
+  const double mean = ws[2 * i] * inv_count;
+  double var = ws[2 * i + 1] * inv_count - mean * mean;
+  if (var < 0) var = 0;
+  stats[2 * i] = static_cast<float>(mean);
+  stats[2 * i + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+}
+
+__device__ __forceinline__ float sigmoidf_(float z) { return 1.f / (1.f + __expf(-z)); }
+
+// ------------------------------------------------------------------ forward apply
+__global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ stats,
+                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                __nv_bfloat16* __restrict__ y, long long total_vecs, int HW, int C,
+                                int G, int swish) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total_vecs) return;
+  const int vecs = C >> 3;
+  const int v = static_cast<int>(i % vecs);
+  const long long row = i / vecs;
+  const int n = static_cast<int>(row / HW);
+  const int c0 = v * 8;
+  const int cg = C / G;
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(x) + i);
+  float f[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
+                bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = c0 + k;
+    const int g = c / cg;
+    const float mean = __ldg(&stats[(n * G + g) * 2]);
+    const float rstd = __ldg(&stats[(n * G + g) * 2 + 1]);
+    float z = (f[k] - mean) * rstd * __ldg(&gamma[c]) + __ldg(&beta[c]);
+    if (swish) z = z * sigmoidf_(z);
+    f[k] = z;
+  }
+  uint4 o;
+  o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+  o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+  reinterpret_cast<uint4*>(y)[i] = o;
+}
+
+// ------------------------------------------------------------------ backward statistics
+// ws_nc[n][c][0] = sum_hw dz,  ws_nc[n][c][1] = sum_hw dz * xhat     (dz = grad wrt GN output)
+__global__ void gn_bwd_partial_kernel(const __nv_bfloat16* __restrict__ dy,
+                                      const __nv_bfloat16* __restrict__ x,
+                                      const float* __restrict__ stats,
+                                      const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, float* ws_nc, int HW, int C,
+                                      int G, int swish, int rows_per_block) {
+  extern __shared__ float sh[];  // [2][C]
+  const int n = blockIdx.y;
+  const int vecs = C >> 3;
+  const int v = threadIdx.x % vecs;
+  const int rlane = threadIdx.x / vecs;
+  const int rstep = blockDim.x / vecs;
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(HW, r0 + rows_per_block);
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  const int cg = C / G;
+  float a[8], b[8], mean[8], rstd[8], gm[8], bt[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = v * 8 + k;
+    const int g = c / cg;
+    a[k] = 0.f; b[k] = 0.f;
+    mean[k] = stats[(n * G + g) * 2]; rstd[k] = stats[(n * G + g) * 2 + 1];
+    gm[k] = gamma[c]; bt[k] = beta[c];
+  }
+  const long long off = (static_cast<long long>(n) * HW) * C + v * 8;
+  if (rlane < rstep) {
+    for (int r = r0 + rlane; r < r1; r += rstep) {
+      const uint4 ux = __ldg(reinterpret_cast<const uint4*>(x + off + static_cast<long long>(r) * C));
+      const uint4 ud = __ldg(reinterpret_cast<const uint4*>(dy + off + static_cast<long long>(r) * C));
+      const float fx[8] = {bf16_lo(ux.x), bf16_hi(ux.x), bf16_lo(ux.y), bf16_hi(ux.y),
+                           bf16_lo(ux.z), bf16_hi(ux.z), bf16_lo(ux.w), bf16_hi(ux.w)};
+      const float fd[8] = {bf16_lo(ud.x), bf16_hi(ud.x), bf16_lo(ud.y), bf16_hi(ud.y),
+                           bf16_lo(ud.z), bf16_hi(ud.z), bf16_lo(ud.w), bf16_hi(ud.w)};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float xh = (fx[k] - mean[k]) * rstd[k];
+        float dz = fd[k];
+        if (swish) {
+          const float z = xh * gm[k] + bt[k];
+          const float sg = sigmoidf_(z);
+          dz *= sg * (1.f + z * (1.f - sg));
+        }
+        a[k] += dz;
+        b[k] = fmaf(dz, xh, b[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      atomicAdd(&sh[v * 8 + k], a[k]);
+      atomicAdd(&sh[C + v * 8 + k], b[k]);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    atomicAdd(&ws_nc[(static_cast<long long>(n) * C + c) * 2 + 0], sh[c]);
+    atomicAdd(&ws_nc[(static_cast<long long>(n) * C + c) * 2 + 1], sh[C + c]);
+  }
+}
+// dgamma[c] = sum_n ws[n][c][1], dbeta[c] = sum_n ws[n][c][0]
+__global__ void gn_bwd_param_kernel(const float* __restrict__ ws_nc, float* dgb, int N, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float a = 0.f, b = 0.f;
+  for (int n = 0; n < N; ++n) {
+    a += ws_nc[(static_cast<long long>(n) * C + c) * 2 + 0];
+    b += ws_nc[(static_cast<long long>(n) * C + c) * 2 + 1];
+  }
+  dgb[c] = b;       // dgamma
+  dgb[C + c] = a;   // dbeta
+}
+// dx = rstd * (dz*gamma - S1/cnt - xhat * S2/cnt),  S1 = sum_g dz*gamma, S2 = sum_g dz*gamma*xhat
+__global__ void gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy,
+                                    const __nv_bfloat16* __restrict__ x,
+                                    const float* __restrict__ stats,
+                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                    const float* __restrict__ ws_nc, __nv_bfloat16* __restrict__ dx,
+                                    long long total_vecs, int HW, int C, int G, int swish) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total_vecs) return;
+  const int vecs = C >> 3;
+  const int v = static_cast<int>(i % vecs);
+  const long long row = i / vecs;
+  const int n = static_cast<int>(row / HW);
+  const int c0 = v * 8;
+  const int cg = C / G;
+  const float inv_cnt = 1.f / (static_cast<float>(HW) * cg);
+  const uint4 ux = __ldg(reinterpret_cast<const uint4*>(x) + i);
+  const uint4 ud = __ldg(reinterpret_cast<const uint4*>(dy) + i);
+  const float fx[8] = {bf16_lo(ux.x), bf16_hi(ux.x), bf16_lo(ux.y), bf16_hi(ux.y),
+                       bf16_lo(ux.z), bf16_hi(ux.z), bf16_lo(ux.w), bf16_hi(ux.w)};
+  const float fd[8] = {bf16_lo(ud.x), bf16_hi(ud.x), bf16_lo(ud.y), bf16_hi(ud.y),
+                       bf16_lo(ud.z), bf16_hi(ud.z), bf16_lo(ud.w), bf16_hi(ud.w)};
+  float o[8];
+  int gprev = -1;
+  float S1 = 0.f, S2 = 0.f, mean = 0.f, rstd = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = c0 + k;
+    const int g = c / cg;
+    if (g != gprev) {
+      gprev = g;
+      mean = __ldg(&stats[(n * G + g) * 2]);
+      rstd = __ldg(&stats[(n * G + g) * 2 + 1]);
+      S1 = 0.f; S2 = 0.f;
+      for (int cc = g * cg; cc < (g + 1) * cg; ++cc) {
+        const float gmm = __ldg(&gamma[cc]);
+        S1 = fmaf(gmm, __ldg(&ws_nc[(static_cast<long long>(n) * C + cc) * 2 + 0]), S1);
+        S2 = fmaf(gmm, __ldg(&ws_nc[(static_cast<long long>(n) * C + cc) * 2 + 1]), S2);
+      }
+    }
+    const float gm = __ldg(&gamma[c]);
+    const float xh = (fx[k] - mean) * rstd;
+    float dz = fd[k];
+    if (swish) {
+      const float z = xh * gm + __ldg(&beta[c]);
+      const float sg = sigmoidf_(z);
+      dz *= sg * (1.f + z * (1.f - sg));
+    }
+    o[k] = rstd * (dz * gm - S1 * inv_cnt - xh * S2 * inv_cnt);
+  }
+  uint4 ou;
+  ou.x = pack_bf16x2(o[0], o[1]); ou.y = pack_bf16x2(o[2], o[3]);
+  ou.z = pack_bf16x2(o[4], o[5]); ou.w = pack_bf16x2(o[6], o[7]);
+  reinterpret_cast<uint4*>(dx)[i] = ou;
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+static int pick_rows_per_block(int HW, int N) {
+  // aim for >= ~4 waves of 148 SMs without making per-block work tiny
+  int chunks = (148 * 8 + N - 1) / N;
+  if (chunks < 1) chunks = 1;
+  int rpb = (HW + chunks - 1) / chunks;
+  if (rpb < 32) rpb = 32;
+  return rpb;
+}
+
+extern "C" {
+
+// stats[n][g] = (mean, rstd) fp32; ws = [N*G*2] doubles of scratch.
+int b2dq_gn_stats(const void* x, float* stats, double* ws, int N, int HW, int C, int G, float eps,
+                  cudaStream_t stream) {
+  if (N <= 0 || HW <= 0) return 0;
+  if (C % 8 || C % G || 256 % (C / 8)) return -1;
+  cudaMemsetAsync(ws, 0, sizeof(double) * 2 * N * G, stream);
+  const int rpb = pick_rows_per_block(HW, N);
+  dim3 grid((HW + rpb - 1) / rpb, N);
+  gn_partial_stats_kernel<<<grid, 256, 2 * C * sizeof(float), stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), ws, HW, C, G, rpb);
+  const int NG = N * G;
+  gn_finalize_kernel<<<(NG + 127) / 128, 128, 0, stream>>>(
+      ws, stats, NG, 1.0 / (static_cast<double>(HW) * (C / G)), eps);
+  return (int)cudaGetLastError();
+}
+
+int b2dq_gn_apply(const void* x, const float* stats, const float* gamma, const float* beta, void* y,
+                  int N, int HW, int C, int G, int swish, cudaStream_t stream) {
+  if (N <= 0 || HW <= 0) return 0;
+  if (C % 8 || C % G) return -1;
+  const long long total = static_cast<long long>(N) * HW * (C / 8);
+  gn_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), stats, gamma, beta,
+      reinterpret_cast<__nv_bfloat16*>(y), total, HW, C, G, swish);
+  return (int)cudaGetLastError();
+}
+
+// ws_nc: [N*C*2] floats of scratch (zeroed here).
+int b2dq_gn_bwd_stats(const void* dy, const void* x, const float* stats, const float* gamma,
+                      const float* beta, float* ws_nc, int N, int HW, int C, int G, int swish,
+                      cudaStream_t stream) {
+  if (N <= 0 || HW <= 0) return 0;
+  if (C % 8 || C % G || 256 % (C / 8)) return -1;
+  cudaMemsetAsync(ws_nc, 0, sizeof(float) * 2 * N * C, stream);
+  const int rpb = pick_rows_per_block(HW, N);
+  dim3 grid((HW + rpb - 1) / rpb, N);
+  gn_bwd_partial_kernel<<<grid, 256, 2 * C * sizeof(float), stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x), stats,
+      gamma, beta, ws_nc, HW, C, G, swish, rpb);
+  return (int)cudaGetLastError();
+}
+
+// dgb: [2*C] floats: dgamma then dbeta (overwritten).
+int b2dq_gn_bwd_apply(const void* dy, const void* x, const float* stats, const float* gamma,
+                      const float* beta, const float* ws_nc, void* dx, float* dgb, int N, int HW,
+                      int C, int G, int swish, cudaStream_t stream) {
+  if (N <= 0 || HW <= 0) return 0;
+  gn_bwd_param_kernel<<<(C + 127) / 128, 128, 0, stream>>>(ws_nc, dgb, N, C);
+  const long long total = static_cast<long long>(N) * HW * (C / 8);
+  gn_bwd_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x), stats,
+      gamma, beta, ws_nc, reinterpret_cast<__nv_bfloat16*>(dx), total, HW, C, G, swish);
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -1,0 +1,316 @@
+// "Tap GEMM": NHWC bf16 implicit-GEMM convolution on tcgen05 tensor cores.
+//
+//   D[pixel, co] = sum_taps sum_ci  A[pixel shifted by tap, ci] * W[co, tap, ci]  (+bias, +residual)
+//
+// One kernel covers every dense contraction of the DQ-VAE conv stacks
+// (reference: modules/diffusionmodules/model.py:43-47 Upsample conv, :62-72 Downsample conv,
+//  :88-115 ResnetBlock conv1/conv2/nin_shortcut, :146-165 AttnBlock q/k/v/proj_out):
+//   * 3x3 stride-1 pad-1: 9 taps, tap = (dh,dw) shift of the TMA box, zero fill out of bounds
+//   * 1x1 / plain row-major GEMM: 1 tap
+//   * 3x3 stride-2 (pad right/bottom): the input is viewed as [N, H/2, 2, W/2, 2*C]; a tap is
+//     a (dh, row-parity, dw, column-parity*C) offset in that 5-D view
+//   * data-gradient of all of the above (same kernel, transposed / flipped weights, strided
+//     output for the parity classes of a stride-2 transpose).
+// There is no im2col buffer: the activation tile of a tap is one 5-D TMA box
+// {64 ch, TW, 1, TH, TN} (TW*TH*TN = 128 pixels) landing as 128 rows x 128 B (SWIZZLE_128B),
+// which is exactly the K-major A operand of tcgen05.mma.  Weights are a [Cout, taps*Cin]
+// K-major matrix streamed by a 2-D/3-D TMA box {64, BN}.  fp32 accumulation in TMEM.
+//
+// CTA = 192 threads: warp 0 TMA producer, warp 1 MMA issuer (+TMEM owner), warps 2..5 epilogue
+// (one TMEM lane quadrant each).  One 128 x BN output tile per CTA; 2 CTAs/SM for BN <= 128
+// so one CTA's epilogue overlaps the other's main loop.
+#include "common.cuh"
+#include "tmap.h"
+
+namespace b2 {
+
+constexpr int TG_MAX_TAPS = 16;
+
+struct TapGemmParams {
+  int num_taps, kchunks;         // K loop = num_taps * kchunks blocks of 64 channels
+  int tap_c[TG_MAX_TAPS];        // A-map coordinate offsets per tap
+  int tap_w[TG_MAX_TAPS];
+  int tap_p[TG_MAX_TAPS];
+  int tap_h[TG_MAX_TAPS];
+  int tap_bk[TG_MAX_TAPS];       // column offset of the tap's weights in B
+  int TW, TH, TN;                // tile extents, TW*TH*TN == 128
+  int tiles_w, tiles_h;          // tiles along w / h (tiles along n = gridDim.x / (tiles_w*tiles_h))
+  int Wout, Hout, NB;            // valid output extents
+  int Cout;                      // valid output channels
+  int b_batched;                 // B map coordinate 2 = image index (batched GEMM) else 0
+  void* out;                     // bf16 (or fp32 when out_f32) [..., Cout]
+  long long oN, oH, oW;          // output element strides
+  const float* bias;             // [Cout] or null
+  const __nv_bfloat16* residual; // same indexing as out via rN/rH/rW, or null
+  long long rN, rH, rW;
+  float alpha;                   // scale applied to the accumulator before bias/residual
+  int out_f32;
+};
+
+template <int BN, int STAGES>
+struct TgCfg {
+  static constexpr uint32_t A_BYTES = 128 * 128;
+  static constexpr uint32_t B_BYTES = BN * 128;
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + ((B_BYTES + 1023) / 1024) * 1024;
+  static constexpr uint32_t SMEM = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, (BN <= 128 ? 2 : 1))
+tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ TapGemmParams p) {
+  using Cfg = TgCfg<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sBar = base + STAGES * Cfg::STAGE_BYTES;
+  const uint32_t bar_full = sBar, bar_empty = sBar + 8 * STAGES, bar_tfull = sBar + 16 * STAGES;
+  uint32_t* tmem_slot =
+      reinterpret_cast<uint32_t*>(smem_raw + (sBar + 16 * STAGES + 16 - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tw_i = blockIdx.x % p.tiles_w;
+  const int th_i = (blockIdx.x / p.tiles_w) % p.tiles_h;
+  const int tn_i = blockIdx.x / (p.tiles_w * p.tiles_h);
+  const int ow0 = tw_i * p.TW, oh0 = th_i * p.TH, n0 = tn_i * p.TN;
+  const int nt0 = blockIdx.y * BN;
+  const int kiters = p.num_taps * p.kchunks;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(bar_full + 8 * i, 1);
+      mbar_init(bar_empty + 8 * i, 1);
+    }
+    mbar_init(bar_tfull, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(smem_u32(tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int t = 0; t < p.num_taps; ++t) {
+        const int cw = ow0 + p.tap_w[t], ch = oh0 + p.tap_h[t];
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
+          mbar_arrive_expect_tx(bar_full + 8 * stage, Cfg::A_BYTES + Cfg::B_BYTES);
+          tma_load_5d(sa, &tmA, bar_full + 8 * stage, p.tap_c[t] + kc * 64, cw, p.tap_p[t], ch, n0);
+          tma_load_3d(sa + Cfg::A_BYTES, &tmB, bar_full + 8 * stage, p.tap_bk[t] + kc * 64, nt0,
+                      p.b_batched ? n0 : 0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+      uint32_t stage = 0, phase = 0;
+      for (int it = 0; it < kiters; ++it) {
+        mbar_wait(bar_full + 8 * stage, phase);
+        tc_fence_after();
+        const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t da = make_smem_desc(sa + k * 32, 0, 1024);
+          const uint64_t db = make_smem_desc(sa + Cfg::A_BYTES + k * 32, 0, 1024);
+          umma_bf16(tmem_base, da, db, idesc, (it | k) ? 1u : 0u);
+        }
+        umma_commit(bar_empty + 8 * stage);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(bar_tfull);
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue
+    const int q = warp & 3;
+    const int m = q * 32 + lane;                 // tile row == TMEM lane
+    const int iw = m % p.TW, ih = (m / p.TW) % p.TH, in_ = m / (p.TW * p.TH);
+    const int ow = ow0 + iw, oh = oh0 + ih, n = n0 + in_;
+    const bool valid = (ow < p.Wout) && (oh < p.Hout) && (n < p.NB);
+    const long long ooff = n * p.oN + oh * p.oH + ow * p.oW;
+    const long long roff = n * p.rN + oh * p.rH + ow * p.rW;
+    mbar_wait(bar_tfull, 0);
+    tc_fence_after();
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    constexpr int CW = BN < 32 ? 16 : 32;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += CW) {
+      float v[CW];
+      if constexpr (CW == 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(trow + c0, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+      } else {
+        uint32_t r[16];
+        tmem_ld_32x16(trow + c0, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+      }
+      const int col = nt0 + c0;
+      if (!valid || col >= p.Cout) continue;
+      const bool full = (col + CW <= p.Cout) && ((p.Cout & 7) == 0);
+      if (full) {
+        if (p.bias) {
+#pragma unroll
+          for (int i = 0; i < CW; i += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col + i));
+            v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+          }
+        }
+        if (p.residual) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + roff + col);
+#pragma unroll
+          for (int i = 0; i < CW / 8; ++i) {
+            const uint4 u = __ldg(rp + i);
+            v[8 * i + 0] += bf16_lo(u.x); v[8 * i + 1] += bf16_hi(u.x);
+            v[8 * i + 2] += bf16_lo(u.y); v[8 * i + 3] += bf16_hi(u.y);
+            v[8 * i + 4] += bf16_lo(u.z); v[8 * i + 5] += bf16_hi(u.z);
+            v[8 * i + 6] += bf16_lo(u.w); v[8 * i + 7] += bf16_hi(u.w);
+          }
+        }
+        if (p.out_f32) {
+          float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + ooff + col);
+#pragma unroll
+          for (int i = 0; i < CW / 4; ++i)
+            op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        } else {
+          uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + ooff + col);
+#pragma unroll
+          for (int i = 0; i < CW / 8; ++i) {
+            uint4 u;
+            u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+            u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+            u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+            u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+            op[i] = u;
+          }
+        }
+      } else {
+        // ragged channel count (e.g. Cout = 3): element-wise tail
+#pragma unroll
+        for (int i = 0; i < CW; ++i) {
+          const int c = col + i;
+          if (c < p.Cout) {
+            float o = v[i];
+            if (p.bias) o += p.bias[c];
+            if (p.residual) o += __bfloat162float(p.residual[roff + c]);
+            if (p.out_f32) static_cast<float*>(p.out)[ooff + c] = o;
+            else static_cast<__nv_bfloat16*>(p.out)[ooff + c] = __float2bfloat16_rn(o);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int BN, int STAGES>
+static int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const TapGemmParams& p,
+                          dim3 grid, cudaStream_t stream) {
+  using Cfg = TgCfg<BN, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel<BN, STAGES>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  tapgemm_kernel<BN, STAGES><<<grid, 192, Cfg::SMEM, stream>>>(tmA, tmB, p);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+extern "C" {
+
+// Geometry of one tap-GEMM launch (plain C struct shared with the Python host side).
+struct b2dq_tapgemm_desc {
+  // A operand: 5-D view (c, w, p, h, n) of a bf16 tensor, element strides for dims 1..4
+  const void* a_ptr;
+  long long a_dims[5];
+  long long a_strides[5];        // a_strides[0] ignored (contiguous)
+  // B operand: [batch][Cout_rows][Ktot] bf16, K contiguous
+  const void* b_ptr;
+  long long b_rows, b_k, b_batch;   // b_batch = 1 for shared weights
+  long long b_batch_stride;         // elements
+  int num_taps, kchunks;
+  int tap_c[16], tap_w[16], tap_p[16], tap_h[16], tap_bk[16];
+  int TW, TH, TN;
+  int Wout, Hout, NB, Cout;
+  void* out;
+  long long oN, oH, oW;
+  const float* bias;
+  const void* residual;
+  long long rN, rH, rW;
+  float alpha;
+  int out_f32;
+  int block_n;                   // 0 = auto
+};
+
+int b2dq_tapgemm(const b2dq_tapgemm_desc* d, cudaStream_t stream) {
+  if (!d || d->num_taps < 1 || d->num_taps > TG_MAX_TAPS || d->kchunks < 1) return -1;
+  if (d->TW * d->TH * d->TN != 128) return -2;
+  if (d->NB <= 0 || d->Wout <= 0 || d->Hout <= 0 || d->Cout <= 0) return 0;
+  int bn = d->block_n;
+  if (bn == 0) bn = d->Cout <= 16 ? 16 : (d->Cout <= 64 ? 64 : (d->Cout % 256 == 0 ? 256 : 128));
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[5], str[5];
+    for (int i = 0; i < 5; ++i) { dims[i] = (uint64_t)d->a_dims[i]; str[i] = (uint64_t)d->a_strides[i]; }
+    uint32_t box[5] = {64, (uint32_t)d->TW, 1, (uint32_t)d->TH, (uint32_t)d->TN};
+    int r = make_tmap_bf16(&tmA, d->a_ptr, 5, dims, str, box);
+    if (r) return r;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)d->b_k, (uint64_t)d->b_rows, (uint64_t)d->b_batch};
+    uint64_t str[3] = {1, (uint64_t)d->b_k, (uint64_t)d->b_batch_stride};
+    uint32_t box[3] = {64, (uint32_t)bn, 1};
+    int r = make_tmap_bf16(&tmB, d->b_ptr, 3, dims, str, box);
+    if (r) return r - 1000;
+  }
+  TapGemmParams p;
+  p.num_taps = d->num_taps; p.kchunks = d->kchunks;
+  for (int i = 0; i < TG_MAX_TAPS; ++i) {
+    p.tap_c[i] = d->tap_c[i]; p.tap_w[i] = d->tap_w[i]; p.tap_p[i] = d->tap_p[i];
+    p.tap_h[i] = d->tap_h[i]; p.tap_bk[i] = d->tap_bk[i];
+  }
+  p.TW = d->TW; p.TH = d->TH; p.TN = d->TN;
+  p.tiles_w = (d->Wout + d->TW - 1) / d->TW;
+  p.tiles_h = (d->Hout + d->TH - 1) / d->TH;
+  const int tiles_n = (d->NB + d->TN - 1) / d->TN;
+  p.Wout = d->Wout; p.Hout = d->Hout; p.NB = d->NB; p.Cout = d->Cout;
+  p.b_batched = d->b_batch > 1 ? 1 : 0;
+  p.out = d->out; p.oN = d->oN; p.oH = d->oH; p.oW = d->oW;
+  p.bias = d->bias;
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(d->residual);
+  p.rN = d->rN; p.rH = d->rH; p.rW = d->rW;
+  p.alpha = d->alpha; p.out_f32 = d->out_f32;
+  dim3 grid((unsigned)(p.tiles_w * p.tiles_h * tiles_n), (unsigned)((d->Cout + bn - 1) / bn));
+  switch (bn) {
+    case 16: return launch_tapgemm<16, 4>(tmA, tmB, p, grid, stream);
+    case 64: return launch_tapgemm<64, 4>(tmA, tmB, p, grid, stream);
+    case 128: return launch_tapgemm<128, 3>(tmA, tmB, p, grid, stream);
+    case 256: return launch_tapgemm<256, 4>(tmA, tmB, p, grid, stream);
+    default: return -3;
+  }
+}
+
+}  // extern "C"

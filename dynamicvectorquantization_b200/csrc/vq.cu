@@ -1,0 +1,437 @@
+// Vector-quantization bottleneck of DQ-VAE stage 1, fused for sm_100a.
+//
+// Replaces, in one pass over the latent, what the reference does with ~25 ATen launches
+// (modules/vector_quantization/quantize2_mask.py):
+//   :29-48  compute_distances   ||e||^2 - 2 x.e^T  (row constant ||x||^2 dropped: argmin-neutral)
+//   :50-55  find_nearest_embedding (argmin, lowest index on ties)
+//   :66-84  one-hot scatter + onehot@x   -> per-code counts and vector sums (red.add)
+//   :123    embed (gather of the PRE-update codebook row)
+//   :172-179 masked commitment loss       -> sum_rows m * sum_c (e - x)^2
+// The [N,K] distance matrix never leaves the SM: x.e^T tiles are produced by tcgen05.mma
+// into TMEM (two 256-column buffers) and reduced to a running (min, argmin) per row by
+// the epilogue warps while the tensor core works on the next codebook tile.
+//
+// CTA = 320 threads: warp 0 TMA producer, warp 1 MMA issuer (+TMEM owner), warps 2..9 epilogue.
+// Persistent over 128-row tiles of x; the x tile stays resident in shared memory (<= 64 KB)
+// while the codebook streams through a 4-stage 32 KB ring.
+#include "common.cuh"
+#include "tmap.h"
+
+namespace b2 {
+
+constexpr int VQ_BM = 128;        // latent rows per tile
+constexpr int VQ_BN = 256;        // codebook entries per MMA tile
+constexpr int VQ_STAGES = 4;      // codebook ring depth
+constexpr int VQ_THREADS = 320;
+constexpr uint32_t VQ_A_CHUNK = VQ_BM * 128;   // 16 KB: 128 rows x 64 bf16
+constexpr uint32_t VQ_B_CHUNK = VQ_BN * 128;   // 32 KB
+constexpr uint32_t VQ_SMEM = 4 * VQ_A_CHUNK + VQ_STAGES * VQ_B_CHUNK + 1024 /*align*/ + 8192;
+
+struct VqParams {
+  const __nv_bfloat16* x_bf16;   // [N,C] search operand (and loss/EMA operand when x_f32 == null)
+  const float* x_f32;            // [N,C] optional fp32 copy of x for loss / EMA sums
+  const float* weight_f32;       // [K(+1),C] fp32 codebook (pre-update), gather source
+  const float* cb_sqnorm;        // [round_up(K,256)] ||e||^2 of the bf16 codebook, +inf padded
+  const float* row_mask;         // [N] or null
+  long long* codes;              // [N] int64
+  __nv_bfloat16* xq_bf16;        // [N,C] or null
+  float* xq_f32;                 // [N,C] or null
+  float* loss_acc;               // [1] += sum m*(e-x)^2   (null: skip)
+  float* counts;                 // [K] += 1 per assigned row   (null: no EMA accumulation)
+  float* sums;                   // [K,C] += x row
+  int N, C, K;
+};
+
+__global__ void __launch_bounds__(VQ_THREADS, 1)
+vq_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const VqParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = base;
+  const uint32_t sB = base + 4 * VQ_A_CHUNK;
+  const uint32_t sX = sB + VQ_STAGES * VQ_B_CHUNK;  // barriers + scratch (8 KB)
+  uint8_t* gen = smem_raw + (sX - smem_u32(smem_raw));
+  // barrier slots (8 B each)
+  const uint32_t bar_full = sX;                 // [VQ_STAGES]
+  const uint32_t bar_empty = sX + 8 * VQ_STAGES;
+  const uint32_t bar_tfull = sX + 16 * VQ_STAGES;        // [2]
+  const uint32_t bar_tempty = bar_tfull + 16;            // [2]
+  const uint32_t bar_afull = bar_tempty + 16;
+  const uint32_t bar_aempty = bar_afull + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + 256);
+  float* s_best = reinterpret_cast<float*>(gen + 512);    // [2 parity][2 half][128]
+  int* s_idx = reinterpret_cast<int*>(gen + 512 + 2048);  // [2][2][128]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KC = p.C >> 6;
+  const int num_m_tiles = (p.N + VQ_BM - 1) / VQ_BM;
+  const int num_n_tiles = (p.K + VQ_BN - 1) / VQ_BN;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < VQ_STAGES; ++i) {
+      mbar_init(bar_full + 8 * i, 1);
+      mbar_init(bar_empty + 8 * i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_tfull + 8 * i, 1);
+      mbar_init(bar_tempty + 8 * i, 8);
+    }
+    mbar_init(bar_afull, 1);
+    mbar_init(bar_aempty, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) tmem_alloc<512>(smem_u32(tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------ TMA producer
+      uint32_t stage = 0, phase = 0, it = 0;
+      for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x, ++it) {
+        mbar_wait(bar_aempty, (it & 1) ^ 1);
+        mbar_arrive_expect_tx(bar_afull, KC * VQ_A_CHUNK);
+        for (int kc = 0; kc < KC; ++kc)
+          tma_load_2d(sA + kc * VQ_A_CHUNK, &tmA, bar_afull, kc * 64, tile * VQ_BM);
+        for (int j = 0; j < num_n_tiles; ++j)
+          for (int kc = 0; kc < KC; ++kc) {
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+            mbar_arrive_expect_tx(bar_full + 8 * stage, VQ_B_CHUNK);
+            tma_load_2d(sB + stage * VQ_B_CHUNK, &tmB, bar_full + 8 * stage, kc * 64, j * VQ_BN);
+            if (++stage == VQ_STAGES) { stage = 0; phase ^= 1; }
+          }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------------------------ MMA issuer
+      constexpr uint32_t idesc = make_idesc_bf16(VQ_BM, VQ_BN, 0, 0);
+      uint32_t stage = 0, phase = 0, it = 0, jj = 0;
+      for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x, ++it) {
+        mbar_wait(bar_afull, it & 1);
+        tc_fence_after();
+        for (int j = 0; j < num_n_tiles; ++j, ++jj) {
+          const uint32_t buf = jj & 1;
+          mbar_wait(bar_tempty + 8 * buf, ((jj >> 1) & 1) ^ 1);
+          tc_fence_after();
+          for (int kc = 0; kc < KC; ++kc) {
+            mbar_wait(bar_full + 8 * stage, phase);
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t da = make_smem_desc(sA + kc * VQ_A_CHUNK + k * 32, 0, 1024);
+              const uint64_t db = make_smem_desc(sB + stage * VQ_B_CHUNK + k * 32, 0, 1024);
+              umma_bf16(tmem_base + buf * VQ_BN, da, db, idesc, (kc | k) ? 1u : 0u);
+            }
+            umma_commit(bar_empty + 8 * stage);
+            if (++stage == VQ_STAGES) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(bar_tfull + 8 * buf);
+        }
+        umma_commit(bar_aempty);
+      }
+    }
+  } else {
+    // ------------------------------------------------ epilogue: running argmin, then gather
+    const int ew = warp - 2;          // 0..7
+    const int q = warp & 3;           // TMEM lane quadrant this warp may read
+    const int half = ew >> 2;         // which 128 columns of each 256-column tile
+    const int row = q * 32 + lane;    // row of the tile owned in the argmin phase
+    uint32_t jj = 0, it = 0;
+    float loss_local = 0.f;
+    for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x, ++it) {
+      float best = __int_as_float(0x7f800000);
+      int bi = 0;
+      for (int j = 0; j < num_n_tiles; ++j, ++jj) {
+        const uint32_t buf = jj & 1;
+        mbar_wait(bar_tfull + 8 * buf, (jj >> 1) & 1);
+        tc_fence_after();
+        const uint32_t tcol = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * VQ_BN +
+                              half * 128;
+        const int colbase = j * VQ_BN + half * 128;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(tcol + c0, r);
+          tmem_ld_wait();
+          const float4* sq4 = reinterpret_cast<const float4*>(p.cb_sqnorm + colbase + c0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 s = __ldg(sq4 + i);
+            const float d0 = fmaf(-2.f, __uint_as_float(r[4 * i + 0]), s.x);
+            const float d1 = fmaf(-2.f, __uint_as_float(r[4 * i + 1]), s.y);
+            const float d2 = fmaf(-2.f, __uint_as_float(r[4 * i + 2]), s.z);
+            const float d3 = fmaf(-2.f, __uint_as_float(r[4 * i + 3]), s.w);
+            const int c = colbase + c0 + 4 * i;
+            if (d0 < best) { best = d0; bi = c; }
+            if (d1 < best) { best = d1; bi = c + 1; }
+            if (d2 < best) { best = d2; bi = c + 2; }
+            if (d3 < best) { best = d3; bi = c + 3; }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+      }
+      // combine the two column halves (lower column index wins ties)
+      const int par = it & 1;
+      s_best[(par * 2 + half) * 128 + row] = best;
+      s_idx[(par * 2 + half) * 128 + row] = bi;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      // gather / loss / EMA accumulation: each warp takes 16 rows, lanes span channels
+      for (int rr = 0; rr < 16; ++rr) {
+        const int r_in = ew * 16 + rr;
+        const long long grow = static_cast<long long>(tile) * VQ_BM + r_in;
+        if (grow >= p.N) break;
+        const float b0 = s_best[(par * 2 + 0) * 128 + r_in];
+        const float b1 = s_best[(par * 2 + 1) * 128 + r_in];
+        const int i0 = s_idx[(par * 2 + 0) * 128 + r_in];
+        const int i1 = s_idx[(par * 2 + 1) * 128 + r_in];
+        int idx = (b1 < b0) ? i1 : i0;
+        if (idx >= p.K) idx = 0;
+        float lsum = 0.f;
+        for (int c = lane * 4; c < p.C; c += 128) {
+          float4 xv;
+          if (p.x_f32) {
+            xv = *reinterpret_cast<const float4*>(p.x_f32 + grow * p.C + c);
+          } else {
+            const uint2 u = *reinterpret_cast<const uint2*>(p.x_bf16 + grow * p.C + c);
+            xv = make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
+          }
+          const float4 ev = __ldg(reinterpret_cast<const float4*>(
+              p.weight_f32 + static_cast<long long>(idx) * p.C + c));
+          const float dx = ev.x - xv.x, dy = ev.y - xv.y, dz = ev.z - xv.z, dw = ev.w - xv.w;
+          lsum += dx * dx + dy * dy + dz * dz + dw * dw;
+          if (p.xq_f32) *reinterpret_cast<float4*>(p.xq_f32 + grow * p.C + c) = ev;
+          if (p.xq_bf16) {
+            uint2 o;
+            o.x = pack_bf16x2(ev.x, ev.y);
+            o.y = pack_bf16x2(ev.z, ev.w);
+            *reinterpret_cast<uint2*>(p.xq_bf16 + grow * p.C + c) = o;
+          }
+          if (p.sums) {
+            float* dst = p.sums + static_cast<long long>(idx) * p.C + c;
+            asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "f"(xv.x),
+                         "f"(xv.y), "f"(xv.z), "f"(xv.w)
+                         : "memory");
+          }
+        }
+        lsum = warp_sum(lsum);
+        if (lane == 0) {
+          p.codes[grow] = idx;
+          if (p.counts) atomicAdd(p.counts + idx, 1.0f);
+          loss_local += lsum * (p.row_mask ? p.row_mask[grow] : 1.0f);
+        }
+      }
+    }
+    if (lane == 0 && p.loss_acc) atomicAdd(p.loss_acc, loss_local);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// Codebook preparation: fp32 weight[:K] -> bf16 copy + ||bf16(e)||^2 (fp32), +inf padded
+// to a multiple of 256 so the search epilogue needs no bounds check.
+// (quantize2_mask.py:31,38: codebook = weight[:-1]; norms of the operand actually multiplied.)
+__global__ void vq_prepare_codebook_kernel(const float* __restrict__ w, __nv_bfloat16* cb,
+                                           float* sqn, int K, int C, int Kpad) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= Kpad) return;
+  if (warp >= K) {
+    if (lane == 0) sqn[warp] = __int_as_float(0x7f800000);
+    return;
+  }
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const __nv_bfloat16 b = __float2bfloat16_rn(w[static_cast<long long>(warp) * C + c]);
+    cb[static_cast<long long>(warp) * C + c] = b;
+    const float f = __bfloat162float(b);
+    s = fmaf(f, f, s);
+  }
+  s = warp_sum(s);
+  if (lane == 0) sqn[warp] = s;
+}
+
+// ---------------------------------------------------------------------------------
+// EMA finalize, step 1 (single CTA): cluster_size_ema update, restart bookkeeping, n = sum.
+// quantize2_mask.py:90 (EMA of counts), :102-105 (usage mask, dead codes reset to 1), :110.
+__global__ void vq_ema_counts_kernel(const float* __restrict__ counts, float* cluster_size_ema,
+                                     unsigned char* dead, float* n_out, int K, float decay,
+                                     int restart) {
+  __shared__ float red[32];
+  float local = 0.f;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    float cs = cluster_size_ema[k] * decay + counts[k] * (1.f - decay);
+    unsigned char d = 0;
+    if (restart && !(cs >= 1.f)) { d = 1; cs = 1.f; }
+    cluster_size_ema[k] = cs;
+    dead[k] = d;
+    local += cs;
+  }
+  local = warp_sum(local);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) *n_out = v;
+  }
+}
+// step 2: embed_ema update (+restart rows), weight = embed_ema / smoothed cluster size.
+// quantize2_mask.py:91,103 and :107-115.
+__global__ void vq_ema_embed_kernel(const float* __restrict__ sums,
+                                    const float* __restrict__ restart_rows,
+                                    const unsigned char* __restrict__ dead,
+                                    const float* __restrict__ cluster_size_ema,
+                                    const float* __restrict__ n_in, float* embed_ema,
+                                    float* weight, int K, int C, float decay, float eps) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(K) * C) return;
+  const int k = static_cast<int>(i / C);
+  float e = embed_ema[i] * decay + sums[i] * (1.f - decay);
+  if (dead[k]) e = restart_rows[i];
+  embed_ema[i] = e;
+  const float n = *n_in;
+  const float norm = n * (cluster_size_ema[k] + eps) / (n + K * eps);
+  weight[i] = e / norm;
+}
+
+// VQ backward (quantize2_mask.py:172-182): g_x = g_xq (straight-through) +
+//   g_loss * 2*beta/(N*C) * m * (x - e);   the (xq - sg(x))^2 term has no trainable input.
+__global__ void vq_bwd_kernel(const __nv_bfloat16* __restrict__ g_xq,
+                              const __nv_bfloat16* __restrict__ x,
+                              const __nv_bfloat16* __restrict__ xq,
+                              const float* __restrict__ row_mask, const float* __restrict__ g_loss,
+                              float coef, __nv_bfloat16* g_x, long long n_rows, int C) {
+  const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 2;
+  if (i >= n_rows * C) return;
+  const long long r = i / C;
+  const float s = coef * g_loss[0] * (row_mask ? row_mask[r] : 1.f);
+  const uint32_t gu = *reinterpret_cast<const uint32_t*>(g_xq + i);
+  const uint32_t xu = *reinterpret_cast<const uint32_t*>(x + i);
+  const uint32_t qu = *reinterpret_cast<const uint32_t*>(xq + i);
+  const float o0 = bf16_lo(gu) + s * (bf16_lo(xu) - bf16_lo(qu));
+  const float o1 = bf16_hi(gu) + s * (bf16_hi(xu) - bf16_hi(qu));
+  *reinterpret_cast<uint32_t*>(g_x + i) = pack_bf16x2(o0, o1);
+}
+
+}  // namespace b2
+
+// =================================================================================== C ABI
+using namespace b2;
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return g_num_sms;
+}
+
+extern "C" {
+
+int b2dq_vq_prepare_codebook(const float* weight_f32, void* cb_bf16, float* cb_sqnorm, int K, int C,
+                             cudaStream_t stream) {
+  if (K <= 0 || C <= 0) return -1;
+  const int Kpad = (K + 255) / 256 * 256;
+  const int warps_per_block = 8;
+  const int blocks = (Kpad + warps_per_block - 1) / warps_per_block;
+  vq_prepare_codebook_kernel<<<blocks, warps_per_block * 32, 0, stream>>>(
+      weight_f32, reinterpret_cast<__nv_bfloat16*>(cb_bf16), cb_sqnorm, K, C, Kpad);
+  return (int)cudaGetLastError();
+}
+
+int b2dq_vq_search_gather(const void* x_bf16, const float* x_f32, const void* cb_bf16,
+                          const float* cb_sqnorm, const float* weight_f32, const float* row_mask,
+                          long long* codes, void* xq_bf16, float* xq_f32, float* loss_acc,
+                          float* counts, float* sums, int N, int C, int K, int max_ctas,
+                          cudaStream_t stream) {
+  if (N <= 0) return 0;
+  if (C % 64 != 0 || C > 256 || C <= 0 || K <= 0) return -1;
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[2] = {(uint64_t)C, (uint64_t)N};
+    uint64_t str[2] = {1, (uint64_t)C};
+    uint32_t box[2] = {64, VQ_BM};
+    int r = make_tmap_bf16(&tmA, x_bf16, 2, dims, str, box);
+    if (r) return r;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)C, (uint64_t)K};
+    uint64_t str[2] = {1, (uint64_t)C};
+    uint32_t box[2] = {64, VQ_BN};
+    int r = make_tmap_bf16(&tmB, cb_bf16, 2, dims, str, box);
+    if (r) return r;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(vq_search_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, VQ_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  VqParams p;
+  p.x_bf16 = reinterpret_cast<const __nv_bfloat16*>(x_bf16);
+  p.x_f32 = x_f32;
+  p.weight_f32 = weight_f32;
+  p.cb_sqnorm = cb_sqnorm;
+  p.row_mask = row_mask;
+  p.codes = codes;
+  p.xq_bf16 = reinterpret_cast<__nv_bfloat16*>(xq_bf16);
+  p.xq_f32 = xq_f32;
+  p.loss_acc = loss_acc;
+  p.counts = counts;
+  p.sums = sums;
+  p.N = N; p.C = C; p.K = K;
+  const int tiles = (N + VQ_BM - 1) / VQ_BM;
+  int grid = num_sms();
+  if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
+  if (tiles < grid) grid = tiles;
+  vq_search_kernel<<<grid, VQ_THREADS, VQ_SMEM, stream>>>(tmA, tmB, p);
+  return (int)cudaGetLastError();
+}
+
+int b2dq_vq_ema_finalize(const float* counts, const float* sums, const float* restart_rows,
+                         float* cluster_size_ema, float* embed_ema, float* weight_f32,
+                         unsigned char* dead_scratch, float* n_scratch, int K, int C, float decay,
+                         float eps, int restart, cudaStream_t stream) {
+  if (K <= 0 || C <= 0) return -1;
+  if (restart && !restart_rows) return -2;
+  vq_ema_counts_kernel<<<1, 1024, 0, stream>>>(counts, cluster_size_ema, dead_scratch, n_scratch, K,
+                                               decay, restart);
+  const long long total = (long long)K * C;
+  const int blocks = (int)((total + 255) / 256);
+  vq_ema_embed_kernel<<<blocks, 256, 0, stream>>>(sums, restart_rows, dead_scratch,
+                                                  cluster_size_ema, n_scratch, embed_ema,
+                                                  weight_f32, K, C, decay, eps);
+  return (int)cudaGetLastError();
+}
+
+int b2dq_vq_bwd(const void* g_xq, const void* x, const void* xq, const float* row_mask,
+                const float* g_loss, float coef, void* g_x, long long n_rows, int C,
+                cudaStream_t stream) {
+  if (n_rows <= 0) return 0;
+  if (C % 2) return -1;
+  const long long pairs = n_rows * C / 2;
+  const int blocks = (int)((pairs + 255) / 256);
+  vq_bwd_kernel<<<blocks, 256, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(g_xq), reinterpret_cast<const __nv_bfloat16*>(x),
+      reinterpret_cast<const __nv_bfloat16*>(xq), row_mask, g_loss, coef,
+      reinterpret_cast<__nv_bfloat16*>(g_x), n_rows, C);
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -1,0 +1,364 @@
+"""Thin, autograd-free launchers for the C-ABI kernels, operating on torch CUDA tensors.
+
+Activations are NHWC bf16 ([N,H,W,C] contiguous).  Every function runs on the current CUDA
+stream and raises if the extension is missing or a launch fails - there is no fallback path.
+"""
+import ctypes as C
+
+import torch
+
+from . import _cabi
+from ._cabi import MmDesc, TapGemmDesc, check
+
+BF16 = torch.bfloat16
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _pow2ceil(v):
+    p = 1
+    while p < v:
+        p *= 2
+    return p
+
+
+def tile_shape(wout, hout, nb, pixels=128):
+    tw = min(pixels, _pow2ceil(wout))
+    th = min(pixels // tw, _pow2ceil(hout))
+    tn = pixels // (tw * th)
+    return tw, th, tn
+
+
+# ------------------------------------------------------------------------------------------ VQ
+class Codebook:
+    """bf16 copy + squared norms of the fp32 codebook (search operands)."""
+
+    def __init__(self, K, Cdim, device):
+        self.K, self.C = K, Cdim
+        kpad = (K + 255) // 256 * 256
+        self.cb = torch.empty(K, Cdim, dtype=BF16, device=device)
+        self.sqnorm = torch.empty(kpad, dtype=torch.float32, device=device)
+
+    def refresh(self, weight_f32):
+        """weight_f32: [K(+1), C] fp32 contiguous; rows [:K] are used."""
+        check(_cabi.lib().b2dq_vq_prepare_codebook(_ptr(weight_f32), _ptr(self.cb), _ptr(self.sqnorm),
+                                                   self.K, self.C, _stream()), "vq_prepare_codebook")
+
+
+def vq_search_gather(x_bf16, codebook, weight_f32, x_f32=None, row_mask=None, want_xq_bf16=True,
+                     want_xq_f32=False, counts=None, sums=None, loss_acc=None, max_ctas=0):
+    """x_bf16 [N,C].  Returns (codes int64 [N], xq_bf16 | None, xq_f32 | None)."""
+    N, Cd = x_bf16.shape
+    dev = x_bf16.device
+    codes = torch.empty(N, dtype=torch.int64, device=dev)
+    xq_b = torch.empty(N, Cd, dtype=BF16, device=dev) if want_xq_bf16 else None
+    xq_f = torch.empty(N, Cd, dtype=torch.float32, device=dev) if want_xq_f32 else None
+    check(_cabi.lib().b2dq_vq_search_gather(
+        _ptr(x_bf16), _ptr(x_f32), _ptr(codebook.cb), _ptr(codebook.sqnorm), _ptr(weight_f32),
+        _ptr(row_mask), _ptr(codes), _ptr(xq_b), _ptr(xq_f), _ptr(loss_acc), _ptr(counts), _ptr(sums),
+        N, Cd, codebook.K, max_ctas, _stream()), "vq_search_gather")
+    return codes, xq_b, xq_f
+
+
+def vq_ema_finalize(counts, sums, restart_rows, cluster_size_ema, embed_ema, weight_f32, decay, eps,
+                    restart):
+    K, Cd = embed_ema.shape
+    dead = torch.empty(K, dtype=torch.uint8, device=embed_ema.device)
+    nscr = torch.empty(1, dtype=torch.float32, device=embed_ema.device)
+    check(_cabi.lib().b2dq_vq_ema_finalize(_ptr(counts), _ptr(sums), _ptr(restart_rows),
+                                           _ptr(cluster_size_ema), _ptr(embed_ema), _ptr(weight_f32),
+                                           _ptr(dead), _ptr(nscr), K, Cd, float(decay), float(eps),
+                                           int(bool(restart)), _stream()), "vq_ema_finalize")
+    return dead
+
+
+def vq_bwd(g_xq, x, xq, row_mask, g_loss, coef):
+    g_x = torch.empty_like(x)
+    n_rows, Cd = x.shape
+    check(_cabi.lib().b2dq_vq_bwd(_ptr(g_xq), _ptr(x), _ptr(xq), _ptr(row_mask), _ptr(g_loss),
+                                  float(coef), _ptr(g_x), n_rows, Cd, _stream()), "vq_bwd")
+    return g_x
+
+
+# ------------------------------------------------------------------------------------------ conv
+def _fill(arr, vals):
+    for i, v in enumerate(vals):
+        arr[i] = v
+
+
+def tapgemm(a, a_dims, a_strides, b, b_rows, b_k, taps, kchunks, out, out_off, ostr, wout, hout, nb,
+            cout, bias=None, residual=None, res_off=0, rstr=(0, 0, 0), alpha=1.0, out_f32=False,
+            block_n=0, b_batch=1, b_batch_stride=0):
+    """taps: list of (dc, dw, dp, dh, bk)."""
+    d = TapGemmDesc()
+    d.a_ptr = a.data_ptr()
+    _fill(d.a_dims, a_dims)
+    _fill(d.a_strides, a_strides)
+    d.b_ptr = b.data_ptr()
+    d.b_rows, d.b_k, d.b_batch, d.b_batch_stride = b_rows, b_k, b_batch, b_batch_stride
+    d.num_taps, d.kchunks = len(taps), kchunks
+    for i, (tc, tw, tp, th, bk) in enumerate(taps):
+        d.tap_c[i], d.tap_w[i], d.tap_p[i], d.tap_h[i], d.tap_bk[i] = tc, tw, tp, th, bk
+    d.TW, d.TH, d.TN = tile_shape(wout, hout, nb)
+    d.Wout, d.Hout, d.NB, d.Cout = wout, hout, nb, cout
+    esz = 4 if out_f32 else 2
+    d.out = out.data_ptr() + out_off * esz
+    d.oN, d.oH, d.oW = ostr
+    d.bias = _ptr(bias)
+    d.residual = None if residual is None else residual.data_ptr() + res_off * 2
+    d.rN, d.rH, d.rW = rstr
+    d.alpha, d.out_f32, d.block_n = alpha, int(out_f32), block_n
+    check(_cabi.lib().b2dq_tapgemm(C.byref(d), _stream()), "tapgemm")
+
+
+def nhwc_view(x):
+    """5-D TMA view (c, w, p, h, n) of a contiguous NHWC tensor: dims, strides (elements)."""
+    nb, h, w, c = x.shape
+    return (c, w, 1, h, nb), (1, c, w * c, w * c, h * w * c)
+
+
+def parity_view(x):
+    """Stride-2 view [N, H/2, 2, W/2, 2C] as (c2, w2, p, h2, n)."""
+    nb, h, w, c = x.shape
+    return (2 * c, w // 2, 2, h // 2, nb), (1, 2 * c, w * c, 2 * w * c, h * w * c)
+
+
+TAPS_3x3 = [(r, s) for r in range(3) for s in range(3)]
+
+
+def pack_weight_fwd(w):
+    """OIHW fp32 -> [Cout, R*S*Cin] bf16 (tap-major, Cin contiguous)."""
+    co, ci, r, s = w.shape
+    return w.detach().permute(0, 2, 3, 1).reshape(co, r * s * ci).to(BF16).contiguous()
+
+
+def pack_weight_dgrad(w):
+    """OIHW fp32 -> [Cin, R*S*Cout] bf16 (for the data gradient: contraction over Cout)."""
+    co, ci, r, s = w.shape
+    return w.detach().permute(1, 2, 3, 0).reshape(ci, r * s * co).to(BF16).contiguous()
+
+
+def conv_fwd(x, wpack, bias, ksize, stride, cout, residual=None, out_f32=False):
+    """x NHWC bf16; wpack from pack_weight_fwd; stride-2 uses pad (0,1,0,1) like Downsample."""
+    nb, h, w, cin = x.shape
+    assert cin % 64 == 0, "Cin must be a multiple of 64 (edge layers use the im2col path)"
+    kch = cin // 64
+    if stride == 1:
+        dims, strs = nhwc_view(x)
+        if ksize == 3:
+            taps = [(0, s - 1, 0, r - 1, (r * 3 + s) * cin) for r, s in TAPS_3x3]
+        else:
+            taps = [(0, 0, 0, 0, 0)]
+        ho, wo = h, w
+    else:
+        assert ksize == 3 and h % 2 == 0 and w % 2 == 0
+        dims, strs = parity_view(x)
+        taps = [((s % 2) * cin, s // 2, r % 2, r // 2, (r * 3 + s) * cin) for r, s in TAPS_3x3]
+        ho, wo = h // 2, w // 2
+    out = torch.empty(nb, ho, wo, cout, dtype=torch.float32 if out_f32 else BF16, device=x.device)
+    ostr = (ho * wo * cout, wo * cout, cout)
+    tapgemm(x, dims, strs, wpack, wpack.shape[0], wpack.shape[1], taps, kch, out, 0, ostr, wo, ho, nb,
+            cout, bias=bias, residual=residual, rstr=ostr, out_f32=out_f32)
+    return out
+
+
+def conv_dgrad(dy, wdpack, ksize, stride, cin, in_hw):
+    """dy NHWC bf16 [N,Ho,Wo,Cout] -> dx NHWC bf16 [N,H,W,Cin]."""
+    nb, ho, wo, cout = dy.shape
+    assert cout % 64 == 0
+    kch = cout // 64
+    h, w = in_hw
+    dx = torch.empty(nb, h, w, cin, dtype=BF16, device=dy.device)
+    dims, strs = nhwc_view(dy)
+    if stride == 1:
+        if ksize == 3:
+            taps = [(0, 1 - s, 0, 1 - r, (r * 3 + s) * cout) for r, s in TAPS_3x3]
+        else:
+            taps = [(0, 0, 0, 0, 0)]
+        tapgemm(dy, dims, strs, wdpack, wdpack.shape[0], wdpack.shape[1], taps, kch, dx, 0,
+                (h * w * cin, w * cin, cin), w, h, nb, cin)
+    else:
+        # y[oh,ow] = sum W[r,s] x[2oh+r, 2ow+s]  =>  dx[2i+ph, 2j+pw] gathers the taps with
+        # r = ph (mod 2): (r, dh) in {(0,0),(2,-1)} for ph=0 and {(1,0)} for ph=1 (same for columns).
+        rsel = {0: [(0, 0), (2, -1)], 1: [(1, 0)]}
+        for ph in (0, 1):
+            for pw in (0, 1):
+                taps = [(0, dw, 0, dh, (r * 3 + s) * cout) for r, dh in rsel[ph] for s, dw in rsel[pw]]
+                tapgemm(dy, dims, strs, wdpack, wdpack.shape[0], wdpack.shape[1], taps, kch, dx,
+                        (ph * w + pw) * cin, (h * w * cin, 2 * w * cin, 2 * cin), wo, ho, nb, cin)
+    return dx
+
+
+def mmgemm(a, a_dims, a_strides, a_mn, b, b_dims, b_strides, b_mn, M, N, kblocks, out, ostr,
+           taps=((0, 0, 0, 0),), kbox=(64, 1, 1), ktiles=(0, 0), splits=1, batches=1, alpha=1.0,
+           out_f32=False, block_n=0, out_off=0):
+    d = MmDesc()
+    d.a_ptr, d.b_ptr = a.data_ptr(), b.data_ptr()
+    _fill(d.a_dims, a_dims); _fill(d.a_strides, a_strides)
+    _fill(d.b_dims, b_dims); _fill(d.b_strides, b_strides)
+    d.a_mn, d.b_mn, d.ntaps = int(a_mn), int(b_mn), len(taps)
+    for i, (tc, tw, tp, th) in enumerate(taps):
+        d.tap_c[i], d.tap_w[i], d.tap_p[i], d.tap_h[i] = tc, tw, tp, th
+    d.KW, d.KH, d.KN = kbox
+    d.ktiles_w, d.ktiles_h, d.kblocks = ktiles[0], ktiles[1], kblocks
+    d.splits, d.batches, d.M, d.N = splits, batches, M, N
+    esz = 4 if out_f32 else 2
+    d.out = out.data_ptr() + out_off * esz
+    d.oZ, d.oT, d.oM = ostr
+    d.alpha, d.out_f32, d.block_n = alpha, int(out_f32), block_n
+    check(_cabi.lib().b2dq_mmgemm(C.byref(d), _stream()), "mmgemm")
+
+
+def _wgrad_splits(kblocks, ctas_per_split):
+    target = max(1, (148 * 2) // max(1, ctas_per_split))
+    return max(1, min(target, kblocks // 4 if kblocks >= 4 else 1))
+
+
+def conv_wgrad(x, dy, ksize, stride):
+    """dW (fp32, OIHW) for y = conv(x): x NHWC bf16 [N,H,W,Cin], dy NHWC bf16 [N,Ho,Wo,Cout]."""
+    nb, h, w, cin = x.shape
+    _, ho, wo, cout = dy.shape
+    if stride == 1:
+        bdims, bstrs = nhwc_view(x)
+        if ksize == 3:
+            taps = [(0, s - 1, 0, r - 1) for r, s in TAPS_3x3]
+        else:
+            taps = [(0, 0, 0, 0)]
+    else:
+        bdims, bstrs = parity_view(x)
+        taps = [((s % 2) * cin, s // 2, r % 2, r // 2) for r, s in TAPS_3x3]
+    adims, astrs = nhwc_view(dy)
+    kw, kh, kn = tile_shape(wo, ho, nb, pixels=64)
+    ktw, kth = (wo + kw - 1) // kw, (ho + kh - 1) // kh
+    kblocks = ktw * kth * ((nb + kn - 1) // kn)
+    ntaps = len(taps)
+    mt, nt = (cout + 127) // 128, (cin + 127) // 128
+    groups = [taps[i:i + 3] for i in range(0, ntaps, 3)]
+    splits = _wgrad_splits(kblocks, mt * nt * len(groups))
+    partial = torch.empty(splits, ntaps, cout, cin, dtype=torch.float32, device=x.device)
+    for gi, grp in enumerate(groups):
+        mmgemm(dy, adims, astrs, True, x, bdims, bstrs, True, cout, cin, kblocks, partial,
+               (ntaps * cout * cin, cout * cin, cin), taps=grp, kbox=(kw, kh, kn), ktiles=(ktw, kth),
+               splits=splits, out_f32=True, block_n=128, out_off=gi * 3 * cout * cin)
+    dw = torch.empty(cout, cin, ksize, ksize, dtype=torch.float32, device=x.device)
+    check(_cabi.lib().b2dq_wgrad_reduce(_ptr(partial), _ptr(dw), splits, ntaps, cout, cin, 0, _stream()),
+          "wgrad_reduce")
+    return dw
+
+
+def bias_grad(dy):
+    cch = dy.shape[-1]
+    out = torch.empty(cch, dtype=torch.float32, device=dy.device)
+    check(_cabi.lib().b2dq_bias_grad(_ptr(dy), _ptr(out), dy.numel() // cch, cch, _stream()), "bias_grad")
+    return out
+
+
+# ------------------------------------------------------------------------------------------ GN
+def gn_stats(x, groups=32, eps=1e-6):
+    nb, h, w, c = x.shape
+    stats = torch.empty(nb, groups, 2, dtype=torch.float32, device=x.device)
+    ws = torch.empty(nb * groups * 2, dtype=torch.float64, device=x.device)
+    check(_cabi.lib().b2dq_gn_stats(_ptr(x), _ptr(stats), _ptr(ws), nb, h * w, c, groups, eps, _stream()),
+          "gn_stats")
+    return stats
+
+
+def gn_apply(x, stats, gamma, beta, swish, groups=32):
+    nb, h, w, c = x.shape
+    y = torch.empty_like(x)
+    check(_cabi.lib().b2dq_gn_apply(_ptr(x), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(y), nb, h * w, c,
+                                    groups, int(swish), _stream()), "gn_apply")
+    return y
+
+
+def gn_bwd(dy, x, stats, gamma, beta, swish, groups=32):
+    """Returns (dx bf16, dgamma f32, dbeta f32)."""
+    nb, h, w, c = x.shape
+    ws = torch.empty(nb * c * 2, dtype=torch.float32, device=x.device)
+    dx = torch.empty_like(x)
+    dgb = torch.empty(2, c, dtype=torch.float32, device=x.device)
+    l = _cabi.lib()
+    check(l.b2dq_gn_bwd_stats(_ptr(dy), _ptr(x), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(ws), nb,
+                              h * w, c, groups, int(swish), _stream()), "gn_bwd_stats")
+    check(l.b2dq_gn_bwd_apply(_ptr(dy), _ptr(x), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(ws),
+                              _ptr(dx), _ptr(dgb), nb, h * w, c, groups, int(swish), _stream()),
+          "gn_bwd_apply")
+    return dx, dgb[0], dgb[1]
+
+
+# ------------------------------------------------------------------------------------------ misc
+def nchw_f32_to_nhwc_bf16(x):
+    nb, c, h, w = x.shape
+    out = torch.empty(nb, h, w, c, dtype=BF16, device=x.device)
+    check(_cabi.lib().b2dq_nchw_f32_to_nhwc_bf16(_ptr(x), _ptr(out), nb, c, h * w, _stream()), "to_nhwc")
+    return out
+
+
+def nhwc_bf16_to_nchw_f32(x):
+    nb, h, w, c = x.shape
+    out = torch.empty(nb, c, h, w, dtype=torch.float32, device=x.device)
+    check(_cabi.lib().b2dq_nhwc_bf16_to_nchw_f32(_ptr(x), _ptr(out), nb, c, h * w, _stream()), "to_nchw")
+    return out
+
+
+def nhwc_f32_to_nchw_f32(x):
+    nb, h, w, c = x.shape
+    out = torch.empty(nb, c, h, w, dtype=torch.float32, device=x.device)
+    check(_cabi.lib().b2dq_nhwc_f32_to_nchw_f32(_ptr(x), _ptr(out), nb, c, h * w, _stream()), "to_nchw32")
+    return out
+
+
+def nchw_f32_to_nhwc_f32(x):
+    nb, c, h, w = x.shape
+    out = torch.empty(nb, h, w, c, dtype=torch.float32, device=x.device)
+    check(_cabi.lib().b2dq_nchw_f32_to_nhwc_f32(_ptr(x), _ptr(out), nb, c, h * w, _stream()), "to_nhwc32")
+    return out
+
+
+def upsample2x(x):
+    nb, h, w, c = x.shape
+    out = torch.empty(nb, 2 * h, 2 * w, c, dtype=BF16, device=x.device)
+    check(_cabi.lib().b2dq_upsample2x(_ptr(x), _ptr(out), nb, h, w, c, _stream()), "upsample2x")
+    return out
+
+
+def upsample2x_bwd(g):
+    nb, h2, w2, c = g.shape
+    out = torch.empty(nb, h2 // 2, w2 // 2, c, dtype=BF16, device=g.device)
+    check(_cabi.lib().b2dq_upsample2x_bwd(_ptr(g), _ptr(out), nb, h2 // 2, w2 // 2, c, _stream()),
+          "upsample2x_bwd")
+    return out
+
+
+def softmax_rows(s, T):
+    p = torch.empty(s.shape, dtype=BF16, device=s.device)
+    check(_cabi.lib().b2dq_softmax_rows(_ptr(s), _ptr(p), s.numel() // T, T,
+                                        int(s.dtype == torch.float32), _stream()), "softmax_rows")
+    return p
+
+
+def softmax_bwd_rows(p, dp, T, scale):
+    ds = torch.empty_like(p)
+    check(_cabi.lib().b2dq_softmax_bwd_rows(_ptr(p), _ptr(dp), _ptr(ds), p.numel() // T, T, float(scale),
+                                            _stream()), "softmax_bwd_rows")
+    return ds
+
+
+def add_bf16(a, b):
+    o = torch.empty_like(a)
+    check(_cabi.lib().b2dq_add_bf16(_ptr(a), _ptr(b), _ptr(o), a.numel(), _stream()), "add_bf16")
+    return o
+
+
+def im2col3x3_small(x, flip=False):
+    nb, h, w, cs = x.shape
+    out = torch.empty(nb, h, w, 64, dtype=BF16, device=x.device)
+    check(_cabi.lib().b2dq_im2col3x3_small(_ptr(x), _ptr(out), nb, h, w, cs, int(flip), _stream()),
+          "im2col3x3_small")
+    return out

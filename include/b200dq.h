@@ -1,0 +1,168 @@
+/*
+ * b200dq.h - C ABI of libb200dq.so: the sm_100a kernels behind the DQ-VAE stage-1 hot path.
+ *
+ * The reference (CrossmodalGroup/DynamicVectorQuantization) has no FFI: its operator interface is
+ * "a Python class at a dotted path" (utils/utils.py:41-51).  The overlay classes in
+ * dynamicvectorquantization_b200/overlay/ keep that interface and reach the GPU exclusively
+ * through the entry points below (ctypes binding: dynamicvectorquantization_b200/_cabi.py; the
+ * stub a reference maintainer would add is shown in INTEGRATION.md).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a cudaError_t (>0) or a negative argument/descriptor
+ *     error otherwise; nothing throws, allocates device memory, or synchronises;
+ *   - all pointers are device pointers owned by the caller (PyTorch); work is enqueued on `stream`;
+ *   - activations are NHWC bf16 ("[N,H,W,C]", C contiguous); parameters and statistics fp32;
+ *   - scratch buffers are passed in by the caller (sizes stated per function).
+ */
+#ifndef B200DQ_H_
+#define B200DQ_H_
+
+#include <cuda_runtime_api.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int b2dq_version(void);
+
+/* ------------------------------------------------------------------ vector quantisation
+ * Replaces modules/vector_quantization/quantize2_mask.py:
+ *   VQEmbedding.compute_distances/find_nearest_embedding (:29-55), the one-hot scatter + matmul of
+ *   _update_buffers (:77-84), embed (:123,130-132) and the masked loss of VectorQuantize2.forward
+ *   (:172-179) in one launch; _update_buffers' EMA/restart (:90-105) and _update_embedding (:107-115)
+ *   in b2dq_vq_ema_finalize; the straight-through + commitment gradient (:172-182) in b2dq_vq_bwd.
+ */
+
+/* weight_f32 [K(+1),C] -> cb_bf16 [K,C], cb_sqnorm [round_up(K,256)] (+inf padded). */
+int b2dq_vq_prepare_codebook(const float* weight_f32, void* cb_bf16, float* cb_sqnorm, int K, int C,
+                             cudaStream_t stream);
+
+/* Nearest-code search over x_bf16 [N,C] (C in {64,128,192,256}); lowest index wins ties.
+ *   x_f32      optional fp32 copy of x used for loss / EMA sums (else the bf16 values are used)
+ *   row_mask   optional [N] weights of the commitment loss (codebook_mask, EncoderDual.py:147-149)
+ *   codes      [N] int64;  xq_bf16 / xq_f32: optional gathered rows of weight_f32 (pre-update)
+ *   loss_acc   optional [1], += sum_rows mask * sum_c (e - x)^2
+ *   counts [K] / sums [K,C]: optional, += per-code row count / row sum (training mode)
+ *   max_ctas   0 = one CTA per SM */
+int b2dq_vq_search_gather(const void* x_bf16, const float* x_f32, const void* cb_bf16,
+                          const float* cb_sqnorm, const float* weight_f32, const float* row_mask,
+                          long long* codes, void* xq_bf16, float* xq_f32, float* loss_acc,
+                          float* counts, float* sums, int N, int C, int K, int max_ctas,
+                          cudaStream_t stream);
+
+/* EMA update of cluster_size_ema [K] / embed_ema [K,C], dead-code restart from restart_rows [K,C]
+ * (rows the reference draws with randperm, :97), and weight[:K] = embed_ema / smoothed size.
+ * dead_scratch [K] bytes, n_scratch [1] float. */
+int b2dq_vq_ema_finalize(const float* counts, const float* sums, const float* restart_rows,
+                         float* cluster_size_ema, float* embed_ema, float* weight_f32,
+                         unsigned char* dead_scratch, float* n_scratch, int K, int C, float decay,
+                         float eps, int restart, cudaStream_t stream);
+
+/* g_x = g_xq + g_loss[0] * coef * mask * (x - xq);  coef = 2*beta/(N*C).  All [n_rows,C] bf16. */
+int b2dq_vq_bwd(const void* g_xq, const void* x, const void* xq, const float* row_mask,
+                const float* g_loss, float coef, void* g_x, long long n_rows, int C,
+                cudaStream_t stream);
+
+/* ------------------------------------------------------------------ convolutions as tap GEMMs
+ * Replaces the cuDNN/cuBLAS calls behind nn.Conv2d at modules/diffusionmodules/model.py:43-47
+ * (Upsample), :62-72 (Downsample, pad (0,1,0,1) + stride 2), :88-115 (ResnetBlock), :146-165
+ * (AttnBlock 1x1), EncoderDual.py:41,72,83, DecoderPositional.py:62,91 and
+ * dqvae_dual_feat.py:34-35 - forward and data gradient.
+ *
+ *   D[pixel, co] = alpha * sum_t sum_ci A[pixel + tap_t, ci] * B[co, tap_bk[t] + ci] + bias + residual
+ *
+ * A is addressed through a 5-D view (c, w, p, h, n) of a bf16 tensor; a tap is a coordinate offset
+ * (tap_c, tap_w, tap_p, tap_h) in that view (out-of-range coordinates read zeros).  The output
+ * pixel (n, oh, ow) is written at out + n*oN + oh*oH + ow*oW (+ channel), so parity classes of a
+ * transposed stride-2 convolution can be written in place.
+ */
+typedef struct b2dq_tapgemm_desc {
+  const void* a_ptr;
+  long long a_dims[5];
+  long long a_strides[5]; /* elements; a_strides[0] ignored (contiguous) */
+  const void* b_ptr;      /* [b_batch][b_rows][b_k] bf16, K contiguous */
+  long long b_rows, b_k, b_batch, b_batch_stride;
+  int num_taps, kchunks;  /* kchunks = channels per tap / 64 */
+  int tap_c[16], tap_w[16], tap_p[16], tap_h[16], tap_bk[16];
+  int TW, TH, TN;         /* output tile, TW*TH*TN == 128 */
+  int Wout, Hout, NB, Cout;
+  void* out;
+  long long oN, oH, oW;
+  const float* bias;      /* [Cout] or NULL */
+  const void* residual;   /* bf16, indexed with rN/rH/rW, or NULL */
+  long long rN, rH, rW;
+  float alpha;
+  int out_f32;            /* 0: bf16 output, 1: fp32 output */
+  int block_n;            /* 0 = auto (16/64/128/256) */
+} b2dq_tapgemm_desc;
+
+int b2dq_tapgemm(const b2dq_tapgemm_desc* desc, cudaStream_t stream);
+
+/* ------------------------------------------------------------------ batched / split-K GEMM
+ * Weight gradients of the convolutions above (autograd of nn.Conv2d) and the attention
+ * contractions of AttnBlock.forward (model.py:176-188) with their gradients.
+ *   out[z][t][m][n] = alpha * sum_k A[m,k] * B_t[n,k]      z = batch*splits + split
+ * Each operand is K-major ([rows][K]) or MN-major ([K][rows]); for MN-major operands the
+ * contraction index is a 64-element box {KW,KH,KN} of a 5-D view and tap t shifts the B box.
+ */
+typedef struct b2dq_mm_desc {
+  const void* a_ptr; long long a_dims[5]; long long a_strides[5];
+  const void* b_ptr; long long b_dims[5]; long long b_strides[5];
+  int a_mn, b_mn;
+  int ntaps;              /* 1..3 accumulators */
+  int tap_c[4], tap_w[4], tap_p[4], tap_h[4];
+  int KW, KH, KN;
+  int ktiles_w, ktiles_h, kblocks;
+  int splits, batches;
+  int M, N;
+  void* out; long long oZ, oT, oM;
+  float alpha;
+  int out_f32;
+  int block_n;            /* 0 = auto, 128 or 256 */
+} b2dq_mm_desc;
+
+int b2dq_mmgemm(const b2dq_mm_desc* desc, cudaStream_t stream);
+
+/* partial [splits][taps][cout][cin] fp32 -> dw [cout][cin][taps] fp32 (OIHW); accumulate != 0: += */
+int b2dq_wgrad_reduce(const float* partial, float* dw, int splits, int taps, int cout, int cin,
+                      int accumulate, cudaStream_t stream);
+
+/* out[c] = sum_rows dy[row][c] */
+int b2dq_bias_grad(const void* dy_bf16, float* out, long long rows, int C, cudaStream_t stream);
+
+/* ------------------------------------------------------------------ GroupNorm(32, eps) + swish
+ * model.py:29-35 (Normalize, nonlinearity) as used at :119-127,170.
+ * stats [N,G,2] = (mean, rstd);  ws: [N*G*2] doubles;  ws_nc: [N*C*2] floats;  dgb: [2*C] floats. */
+int b2dq_gn_stats(const void* x, float* stats, double* ws, int N, int HW, int C, int G, float eps,
+                  cudaStream_t stream);
+int b2dq_gn_apply(const void* x, const float* stats, const float* gamma, const float* beta, void* y,
+                  int N, int HW, int C, int G, int swish, cudaStream_t stream);
+int b2dq_gn_bwd_stats(const void* dy, const void* x, const float* stats, const float* gamma,
+                      const float* beta, float* ws_nc, int N, int HW, int C, int G, int swish,
+                      cudaStream_t stream);
+int b2dq_gn_bwd_apply(const void* dy, const void* x, const float* stats, const float* gamma,
+                      const float* beta, const float* ws_nc, void* dx, float* dgb, int N, int HW,
+                      int C, int G, int swish, cudaStream_t stream);
+
+/* ------------------------------------------------------------------ layout / elementwise */
+int b2dq_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int N, int C, int HW, cudaStream_t stream);
+int b2dq_nchw_f32_to_nhwc_f32(const float* src, float* dst, int N, int C, int HW, cudaStream_t stream);
+int b2dq_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int N, int C, int HW, cudaStream_t stream);
+int b2dq_nhwc_f32_to_nchw_f32(const float* src, float* dst, int N, int C, int HW, cudaStream_t stream);
+/* nearest x2 (model.py:50) and its gradient; in [N,H,W,C] bf16 */
+int b2dq_upsample2x(const void* in, void* out, int N, int H, int W, int C, cudaStream_t stream);
+int b2dq_upsample2x_bwd(const void* gout, void* gin, int N, int H, int W, int C, cudaStream_t stream);
+/* row softmax (model.py:182): logits fp32 (in_f32) or bf16 -> probabilities bf16; and gradient */
+int b2dq_softmax_rows(const void* s, void* p, long long rows, int T, int in_f32, cudaStream_t stream);
+int b2dq_softmax_bwd_rows(const void* p, const void* dp, void* ds, long long rows, int T, float scale,
+                          cudaStream_t stream);
+int b2dq_add_bf16(const void* a, const void* b, void* out, long long n, cudaStream_t stream);
+int b2dq_cast_f32_to_bf16(const float* a, void* out, long long n, cudaStream_t stream);
+/* 3x3 window gather for the 3-channel edge convolutions: dst [N,H,W,64] */
+int b2dq_im2col3x3_small(const void* src, void* dst, int N, int H, int W, int Cs, int flip,
+                         cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200DQ_H_ */

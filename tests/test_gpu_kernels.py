@@ -1,0 +1,215 @@
+"""GPU parity tests of the individual sm_100a kernels against plain fp32 references.
+
+Floating-point kernels (convolutions, GroupNorm, attention GEMMs) are compared with a PyTorch fp32
+CPU evaluation of the same op on the same bf16-rounded operands; tolerance = bf16 output rounding
+(rel-RMS 1e-2 worst case; typically 3e-3).  The integer result of the VQ search is compared
+bit-exactly with the numpy oracle.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+BF = torch.bfloat16
+
+
+def rel_rms(a, b):
+    a = a.double().flatten().cpu()
+    b = b.double().flatten().cpu()
+    return float(((a - b).pow(2).mean() / b.pow(2).mean().clamp_min(1e-30)).sqrt())
+
+
+def _rand_bf(*shape, scale=1.0, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(BF)
+
+
+# ------------------------------------------------------------------------------------------- VQ
+@pytest.mark.parametrize("N,K,C", [(4096, 1024, 256), (1000, 1000, 256), (515, 300, 128), (8192, 2048, 64)])
+def test_vq_search_matches_oracle(N, K, C):
+    from dynamicvectorquantization_b200 import kernels as kn
+    from oracle import vq_oracle as vo
+    g = torch.Generator().manual_seed(N + K)
+    x = torch.randn(N, C, generator=g)
+    w = torch.cat([x[torch.randperm(N, generator=g)[:K]] + 0.1 * torch.randn(K, C, generator=g),
+                   torch.zeros(1, C)], 0).contiguous()
+    mask = (torch.rand(N, generator=g) > 0.5).float() * 0.75 + 0.25
+    xb = x.to(BF)
+    dev = "cuda"
+    cb = kn.Codebook(K, C, dev)
+    wd = w.to(dev)
+    cb.refresh(wd)
+    counts = torch.zeros(K, device=dev)
+    sums = torch.zeros(K, C, device=dev)
+    loss = torch.zeros(1, device=dev)
+    codes, xq_b, xq_f = kn.vq_search_gather(xb.to(dev), cb, wd, row_mask=mask.to(dev), want_xq_f32=True,
+                                            counts=counts, sums=sums, loss_acc=loss)
+    torch.cuda.synchronize()
+    # oracle on the same bf16-rounded operands
+    xr = xb.float().numpy()
+    wr = np.concatenate([vo.bf16_round(w[:-1].numpy()), np.zeros((1, C), np.float32)], 0)
+    ref = vo.find_nearest_embedding(xr, wr)
+    got = codes.cpu().numpy()
+    mism = np.nonzero(ref != got)[0]
+    if len(mism):
+        # near-tie audit in fp64: only rounding-level ties may differ
+        _, best, second = vo.nearest_fp64(xr[mism], wr)
+        d64 = (wr[:-1].astype(np.float64) ** 2).sum(1)[None, :] - 2 * xr[mism].astype(np.float64) @ wr[:-1].T.astype(np.float64)
+        gap = np.abs(d64[np.arange(len(mism)), got[mism]] - d64[np.arange(len(mism)), ref[mism]])
+        scale = (xr[mism].astype(np.float64) ** 2).sum(1) + 1.0
+        assert np.all(gap < 1e-6 * scale * 256), f"{len(mism)} real mismatches, max gap {gap.max()}"
+    assert len(mism) <= max(1, N // 2000), f"{len(mism)} near-tie mismatches of {N}"
+    # gathered rows are exactly the fp32 codebook rows
+    assert torch.equal(xq_f.cpu(), w[got])
+    assert torch.equal(xq_b.cpu(), w[got].to(BF))
+    # loss partial, counts, sums
+    d2 = ((w[got] - xb.float()) ** 2).sum(1) * mask
+    assert abs(float(loss.item()) - float(d2.sum())) <= 1e-4 * float(d2.sum())
+    assert torch.equal(counts.cpu(), torch.bincount(torch.from_numpy(got), minlength=K).float())
+    ref_sums = torch.zeros(K, C).index_add_(0, torch.from_numpy(got), xb.float())
+    assert torch.allclose(sums.cpu(), ref_sums, rtol=1e-4, atol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------- conv
+CONV_CASES = [
+    # nb, h, w, cin, cout, k, stride
+    (2, 32, 32, 128, 128, 3, 1),
+    (1, 16, 16, 256, 512, 3, 1),
+    (2, 64, 64, 64, 64, 3, 1),
+    (1, 256, 256, 128, 128, 3, 1),
+    (3, 8, 8, 512, 256, 3, 1),
+    (2, 32, 32, 256, 256, 1, 1),
+    (2, 16, 16, 128, 256, 1, 1),
+    (2, 32, 32, 128, 128, 3, 2),
+    (1, 64, 64, 256, 256, 3, 2),
+]
+
+
+def _ref_conv(x_nhwc, w, b, k, stride):
+    x = x_nhwc.float().permute(0, 3, 1, 2)
+    if stride == 2:
+        x = F.pad(x, (0, 1, 0, 1))
+        return F.conv2d(x, w, b, stride=2)
+    return F.conv2d(x, w, b, padding=k // 2)
+
+
+@pytest.mark.parametrize("nb,h,w,cin,cout,k,stride", CONV_CASES)
+def test_conv_fwd_dgrad_wgrad(nb, h, w, cin, cout, k, stride):
+    from dynamicvectorquantization_b200 import kernels as kn
+    x = _rand_bf(nb, h, w, cin, seed=1)
+    wt = _rand_bf(cout, cin, k, k, scale=(cin * k * k) ** -0.5, seed=2).float()
+    bias = torch.randn(cout, generator=torch.Generator().manual_seed(3))
+    xr = x.float().requires_grad_(True)
+    wr = wt.clone().requires_grad_(True)
+    y_ref = _ref_conv(xr, wr, bias, k, stride)
+    dy = _rand_bf(*y_ref.permute(0, 2, 3, 1).shape, seed=4)
+    y_ref.backward(dy.float().permute(0, 3, 1, 2))
+    dev = "cuda"
+    xd, dyd = x.to(dev), dy.to(dev).contiguous()
+    res = _rand_bf(*dy.shape, seed=5)
+    y = kn.conv_fwd(xd, kn.pack_weight_fwd(wt.to(dev)), bias.to(dev), k, stride, cout, residual=res.to(dev))
+    e = rel_rms(y.float().cpu(), y_ref.detach().permute(0, 2, 3, 1) + res.float())
+    assert e < 6e-3, f"fwd rel rms {e}"
+    dx = kn.conv_dgrad(dyd, kn.pack_weight_dgrad(wt.to(dev)), k, stride, cin, (h, w))
+    e = rel_rms(dx.float().cpu(), xr.grad)
+    assert e < 6e-3, f"dgrad rel rms {e}"
+    dw = kn.conv_wgrad(xd, dyd, k, stride)
+    e = rel_rms(dw.cpu(), wr.grad)
+    assert e < 2e-3, f"wgrad rel rms {e}"
+    db = kn.bias_grad(dyd)
+    assert rel_rms(db.cpu(), dy.float().sum((0, 1, 2))) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K,batch", [(1024, 1024, 256, 2), (256, 512, 256, 3), (64, 512, 64, 2)])
+def test_mmgemm_majorness(a_mn, b_mn, M, N, K, batch):
+    from dynamicvectorquantization_b200 import kernels as kn
+    A = _rand_bf(batch, M, K, seed=7)
+    B = _rand_bf(batch, N, K, seed=8)
+    ref = torch.einsum("bmk,bnk->bmn", A.float(), B.float()) * 0.5
+    dev = "cuda"
+    if a_mn:
+        a = A.transpose(1, 2).contiguous().to(dev)       # [b, K, M]
+        ad, as_ = (M, K, 1, 1, batch), (1, M, M * K, M * K, M * K)
+    else:
+        a = A.contiguous().to(dev)                        # [b, M, K]
+        ad, as_ = (K, M, 1, 1, batch), (1, K, M * K, M * K, M * K)
+    if b_mn:
+        b = B.transpose(1, 2).contiguous().to(dev)
+        bd, bs = (N, K, 1, 1, batch), (1, N, N * K, N * K, N * K)
+    else:
+        b = B.contiguous().to(dev)
+        bd, bs = (K, N, 1, 1, batch), (1, K, N * K, N * K, N * K)
+    for out_f32 in (False, True):
+        out = torch.empty(batch, M, N, dtype=torch.float32 if out_f32 else BF, device=dev)
+        kn.mmgemm(a, ad, as_, a_mn, b, bd, bs, b_mn, M, N, K // 64, out, (M * N, 0, N),
+                  kbox=(64, 1, 1), ktiles=(K // 64, 1), batches=batch, alpha=0.5, out_f32=out_f32)
+        e = rel_rms(out.float().cpu(), ref)
+        assert e < (1e-5 if out_f32 else 4e-3), f"a_mn={a_mn} b_mn={b_mn} f32={out_f32}: {e}"
+
+
+# ------------------------------------------------------------------------------------------- GN
+@pytest.mark.parametrize("nb,h,w,c,swish", [(2, 32, 32, 128, True), (3, 16, 16, 512, True),
+                                            (2, 64, 64, 256, False), (1, 256, 256, 128, True)])
+def test_groupnorm_swish_fwd_bwd(nb, h, w, c, swish):
+    from dynamicvectorquantization_b200 import kernels as kn
+    x = (_rand_bf(nb, h, w, c, seed=11).float() * 1.5 + 0.3).to(BF)
+    gamma = 1 + 0.2 * torch.randn(c, generator=torch.Generator().manual_seed(12))
+    beta = 0.1 * torch.randn(c, generator=torch.Generator().manual_seed(13))
+    dy = _rand_bf(nb, h, w, c, seed=14)
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    yr = F.group_norm(xr, 32, gr, br, eps=1e-6)
+    if swish:
+        yr = yr * torch.sigmoid(yr)
+    yr.backward(dy.float().permute(0, 3, 1, 2))
+    dev = "cuda"
+    xd = x.to(dev)
+    st = kn.gn_stats(xd)
+    y = kn.gn_apply(xd, st, gamma.to(dev), beta.to(dev), swish)
+    assert rel_rms(y.float().cpu(), yr.detach().permute(0, 2, 3, 1)) < 5e-3
+    dx, dg, db = kn.gn_bwd(dy.to(dev), xd, st, gamma.to(dev), beta.to(dev), swish)
+    assert rel_rms(dx.float().cpu(), xr.grad.permute(0, 2, 3, 1)) < 6e-3
+    assert rel_rms(dg.cpu(), gr.grad) < 2e-3
+    assert rel_rms(db.cpu(), br.grad) < 2e-3
+
+
+# ------------------------------------------------------------------------------------------- misc
+def test_layout_upsample_softmax():
+    from dynamicvectorquantization_b200 import kernels as kn
+    dev = "cuda"
+    x = torch.randn(2, 3, 40, 24, generator=torch.Generator().manual_seed(1))
+    xn = kn.nchw_f32_to_nhwc_bf16(x.to(dev))
+    assert torch.equal(xn.cpu(), x.permute(0, 2, 3, 1).to(BF))
+    back = kn.nhwc_bf16_to_nchw_f32(xn)
+    assert torch.equal(back.cpu(), x.to(BF).float())
+    x32 = kn.nchw_f32_to_nhwc_f32(x.to(dev))
+    assert torch.equal(x32.cpu(), x.permute(0, 2, 3, 1).contiguous())
+    assert torch.equal(kn.nhwc_f32_to_nchw_f32(x32).cpu(), x)
+    a = _rand_bf(2, 8, 12, 64, seed=3)
+    up = kn.upsample2x(a.to(dev))
+    ref = a.float().permute(0, 3, 1, 2).repeat_interleave(2, 2).repeat_interleave(2, 3).permute(0, 2, 3, 1)
+    assert torch.equal(up.float().cpu(), ref)
+    g = _rand_bf(2, 16, 24, 64, seed=4)
+    gi = kn.upsample2x_bwd(g.to(dev))
+    refg = F.avg_pool2d(g.float().permute(0, 3, 1, 2), 2) * 4
+    assert rel_rms(gi.float().cpu(), refg.permute(0, 2, 3, 1)) < 4e-3
+    s = torch.randn(6, 256, generator=torch.Generator().manual_seed(5)) * 3
+    p = kn.softmax_rows(s.to(dev), 256)
+    assert rel_rms(p.float().cpu(), torch.softmax(s, -1)) < 4e-3
+    dp = _rand_bf(6, 256, seed=6)
+    ds = kn.softmax_bwd_rows(p, dp.to(dev), 256, 0.25)
+    pr = p.float().cpu()
+    ref_ds = 0.25 * pr * (dp.float() - (pr * dp.float()).sum(-1, keepdim=True))
+    assert rel_rms(ds.float().cpu(), ref_ds) < 6e-3
+    u, v = _rand_bf(1024, seed=7), _rand_bf(1024, seed=8)
+    assert torch.equal(kn.add_bf16(u.to(dev), v.to(dev)).cpu(), (u.float() + v.float()).to(BF))
+    img = _rand_bf(2, 6, 5, 3, seed=9)
+    col = kn.im2col3x3_small(img.to(dev)).cpu().float()
+    pad = F.pad(img.float().permute(0, 3, 1, 2), (1, 1, 1, 1))
+    for t, (r, s_) in enumerate([(r, s_) for r in range(3) for s_ in range(3)]):
+        assert torch.equal(col[..., t * 3:(t + 1) * 3], pad[:, :, r:r + 6, s_:s_ + 5].permute(0, 2, 3, 1))
+    assert float(col[..., 27:].abs().sum()) == 0.0

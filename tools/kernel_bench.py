@@ -1,0 +1,79 @@
+"""Per-kernel timing on one GPU (CUDA events, L2 flushed between iterations)."""
+import sys, os, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from dynamicvectorquantization_b200 import kernels as kn
+
+dev = "cuda"
+BF = torch.bfloat16
+flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+
+def timeit(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(iters):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); fn(); e.record(); torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def vq(N=65536, C=256):
+    for K in (256, 1024, 8192, 16384):
+        g = torch.Generator(device=dev).manual_seed(0)
+        x = torch.randn(N, C, device=dev, generator=g)
+        w = torch.cat([x[torch.randperm(N, device=dev)[:K]] + 0.1 * torch.randn(K, C, device=dev), torch.zeros(1, C, device=dev)])
+        cb = kn.Codebook(K, C, dev); cb.refresh(w)
+        xb = x.to(BF)
+        ms = timeit(lambda: kn.vq_search_gather(xb, cb, w))
+        fl = 2.0 * N * K * C
+        by = 2 * N * C + 2 * K * C + 8 * N + 2 * N * C
+        print(json.dumps(dict(k="vq_search_gather", N=N, K=K, ms=round(ms, 4), tflops=round(fl / ms / 1e9, 1), alg_GBs=round(by / ms / 1e6, 1))))
+        counts = torch.zeros(K, device=dev); sums = torch.zeros(K, C, device=dev); loss = torch.zeros(1, device=dev)
+        ms = timeit(lambda: kn.vq_search_gather(xb, cb, w, counts=counts, sums=sums, loss_acc=loss))
+        print(json.dumps(dict(k="vq_search_gather+ema", N=N, K=K, ms=round(ms, 4), tflops=round(fl / ms / 1e9, 1))))
+
+
+def conv(nb, h, w, cin, cout, k, stride):
+    x = torch.randn(nb, h, w, cin, device=dev).to(BF)
+    wt = torch.randn(cout, cin, k, k, device=dev) * (cin * k * k) ** -0.5
+    b = torch.zeros(cout, device=dev)
+    wp, wd = kn.pack_weight_fwd(wt), kn.pack_weight_dgrad(wt)
+    ho, wo = h // stride, w // stride
+    dy = torch.randn(nb, ho, wo, cout, device=dev).to(BF)
+    fl = 2.0 * nb * ho * wo * cin * cout * k * k
+    r = dict(k=f"conv{k}x{k}s{stride}", nb=nb, hw=h, cin=cin, cout=cout)
+    for name, fn in (("fwd", lambda: kn.conv_fwd(x, wp, b, k, stride, cout)),
+                     ("dgrad", lambda: kn.conv_dgrad(dy, wd, k, stride, cin, (h, w))),
+                     ("wgrad", lambda: kn.conv_wgrad(x, dy, k, stride))):
+        ms = timeit(fn, iters=5, warm=2)
+        r[name + "_ms"] = round(ms, 3); r[name + "_tflops"] = round(fl / ms / 1e9, 1)
+    print(json.dumps(r))
+
+
+def gn(nb, h, w, c):
+    x = torch.randn(nb, h, w, c, device=dev).to(BF)
+    g, b = torch.ones(c, device=dev), torch.zeros(c, device=dev)
+    dy = torch.randn(nb, h, w, c, device=dev).to(BF)
+    by = x.numel() * 2
+    ms1 = timeit(lambda: kn.gn_stats(x)); st = kn.gn_stats(x)
+    ms2 = timeit(lambda: kn.gn_apply(x, st, g, b, True))
+    ms3 = timeit(lambda: kn.gn_bwd(dy, x, st, g, b, True))
+    print(json.dumps(dict(k="gn", nb=nb, hw=h, c=c, stats_ms=round(ms1, 3), stats_GBs=round(by / ms1 / 1e6), apply_ms=round(ms2, 3),
+                          apply_GBs=round(2 * by / ms2 / 1e6), bwd_ms=round(ms3, 3), bwd_GBs=round(5 * by / ms3 / 1e6))))
+
+
+if __name__ == "__main__":
+    what = sys.argv[1:] or ["vq", "conv", "gn"]
+    if "vq" in what:
+        vq()
+    if "conv" in what:
+        for c in [(32, 256, 256, 128, 128, 3, 1), (32, 128, 128, 128, 128, 3, 1), (32, 64, 64, 256, 256, 3, 1), (32, 32, 32, 256, 256, 3, 1),
+                  (32, 16, 16, 512, 512, 3, 1), (32, 32, 32, 256, 256, 1, 1), (32, 256, 256, 128, 128, 3, 2), (32, 128, 128, 256, 256, 3, 1)]:
+            conv(*c)
+    if "gn" in what:
+        gn(32, 256, 256, 128); gn(32, 64, 64, 256); gn(32, 16, 16, 512)
