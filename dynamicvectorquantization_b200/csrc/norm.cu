@@ -9,6 +9,18 @@
 
 namespace b2 {
 
+__device__ __forceinline__ float sigmoidf_(float z) { return __fdividef(1.f, 1.f + __expf(-z)); }
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 o;
+  o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+  o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+  return o;
+}
+
 // ------------------------------------------------------------------ forward statistics
 // grid (chunks, N); block 256.  Thread t owns channel vector (8 ch) v = t % (C/8) and walks rows.
 __global__ void gn_partial_stats_kernel(const __nv_bfloat16* __restrict__ x, double* ws, int HW,
@@ -27,11 +39,25 @@ __global__ void gn_partial_stats_kernel(const __nv_bfloat16* __restrict__ x, dou
 #pragma unroll
   for (int i = 0; i < 8; ++i) { s[i] = 0.f; ss[i] = 0.f; }
   const __nv_bfloat16* base = x + (static_cast<long long>(n) * HW) * C + v * 8;
-  if (rlane < rstep) {
-    for (int r = r0 + rlane; r < r1; r += rstep) {
+  {
+    int r = r0 + rlane;
+    for (; r + 3 * rstep < r1; r += 4 * rstep) {
+      uint4 u[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        u[j] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(r + j * rstep) * C));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float f[8];
+        unpack8(u[j], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s[i] += f[i]; ss[i] = fmaf(f[i], f[i], ss[i]); }
+      }
+    }
+    for (; r < r1; r += rstep) {
       const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(r) * C));
-      const float f[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
-                          bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+      float f[8];
+      unpack8(u, f);
 #pragma unroll
       for (int i = 0; i < 8; ++i) { s[i] += f[i]; ss[i] = fmaf(f[i], f[i], ss[i]); }
     }
@@ -61,38 +87,62 @@ __global__ void gn_finalize_kernel(const double* __restrict__ ws, float* stats, 
   stats[2 * i + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
 }
 
-__device__ __forceinline__ float sigmoidf_(float z) { return 1.f / (1.f + __expf(-z)); }
-
 // ------------------------------------------------------------------ forward apply
+// grid (chunks, N); thread = (channel vector v, row lane): y = swish(x * a + b) with the per-channel
+// a = rstd*gamma, b = beta - mean*rstd*gamma held in registers.
 __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ stats,
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
-                                __nv_bfloat16* __restrict__ y, long long total_vecs, int HW, int C,
-                                int G, int swish) {
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= total_vecs) return;
+                                __nv_bfloat16* __restrict__ y, int HW, int C, int G, int swish,
+                                int rows_per_block) {
+  const int n = blockIdx.y;
   const int vecs = C >> 3;
-  const int v = static_cast<int>(i % vecs);
-  const long long row = i / vecs;
-  const int n = static_cast<int>(row / HW);
-  const int c0 = v * 8;
+  const int v = threadIdx.x % vecs;
+  const int rlane = threadIdx.x / vecs;
+  const int rstep = blockDim.x / vecs;
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(HW, r0 + rows_per_block);
   const int cg = C / G;
-  const uint4 u = __ldg(reinterpret_cast<const uint4*>(x) + i);
-  float f[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
-                bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+  float a[8], b[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    const int c = c0 + k;
+    const int c = v * 8 + k;
     const int g = c / cg;
-    const float mean = __ldg(&stats[(n * G + g) * 2]);
-    const float rstd = __ldg(&stats[(n * G + g) * 2 + 1]);
-    float z = (f[k] - mean) * rstd * __ldg(&gamma[c]) + __ldg(&beta[c]);
-    if (swish) z = z * sigmoidf_(z);
-    f[k] = z;
+    const float mean = stats[(n * G + g) * 2], rstd = stats[(n * G + g) * 2 + 1];
+    a[k] = rstd * gamma[c];
+    b[k] = beta[c] - mean * a[k];
   }
-  uint4 o;
-  o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
-  o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
-  reinterpret_cast<uint4*>(y)[i] = o;
+  const long long off = (static_cast<long long>(n) * HW) * C + v * 8;
+  int r = r0 + rlane;
+  for (; r + 3 * rstep < r1; r += 4 * rstep) {
+    uint4 u[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      u[j] = __ldg(reinterpret_cast<const uint4*>(x + off + static_cast<long long>(r + j * rstep) * C));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float f[8];
+      unpack8(u[j], f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float z = fmaf(f[k], a[k], b[k]);
+        if (swish) z *= sigmoidf_(z);
+        f[k] = z;
+      }
+      *reinterpret_cast<uint4*>(y + off + static_cast<long long>(r + j * rstep) * C) = pack8(f);
+    }
+  }
+  for (; r < r1; r += rstep) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + off + static_cast<long long>(r) * C));
+    float f[8];
+    unpack8(u, f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float z = fmaf(f[k], a[k], b[k]);
+      if (swish) z *= sigmoidf_(z);
+      f[k] = z;
+    }
+    *reinterpret_cast<uint4*>(y + off + static_cast<long long>(r) * C) = pack8(f);
+  }
 }
 
 // ------------------------------------------------------------------ backward statistics
@@ -124,26 +174,36 @@ __global__ void gn_bwd_partial_kernel(const __nv_bfloat16* __restrict__ dy,
     gm[k] = gamma[c]; bt[k] = beta[c];
   }
   const long long off = (static_cast<long long>(n) * HW) * C + v * 8;
-  if (rlane < rstep) {
-    for (int r = r0 + rlane; r < r1; r += rstep) {
-      const uint4 ux = __ldg(reinterpret_cast<const uint4*>(x + off + static_cast<long long>(r) * C));
-      const uint4 ud = __ldg(reinterpret_cast<const uint4*>(dy + off + static_cast<long long>(r) * C));
-      const float fx[8] = {bf16_lo(ux.x), bf16_hi(ux.x), bf16_lo(ux.y), bf16_hi(ux.y),
-                           bf16_lo(ux.z), bf16_hi(ux.z), bf16_lo(ux.w), bf16_hi(ux.w)};
-      const float fd[8] = {bf16_lo(ud.x), bf16_hi(ud.x), bf16_lo(ud.y), bf16_hi(ud.y),
-                           bf16_lo(ud.z), bf16_hi(ud.z), bf16_lo(ud.w), bf16_hi(ud.w)};
+  {
+    auto accum = [&](const uint4& ux, const uint4& ud) {
+      float fx[8], fd[8];
+      unpack8(ux, fx); unpack8(ud, fd);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const float xh = (fx[k] - mean[k]) * rstd[k];
         float dz = fd[k];
         if (swish) {
-          const float z = xh * gm[k] + bt[k];
+          const float z = fmaf(xh, gm[k], bt[k]);
           const float sg = sigmoidf_(z);
           dz *= sg * (1.f + z * (1.f - sg));
         }
         a[k] += dz;
         b[k] = fmaf(dz, xh, b[k]);
       }
+    };
+    int r = r0 + rlane;
+    for (; r + rstep < r1; r += 2 * rstep) {
+      const uint4 ux0 = __ldg(reinterpret_cast<const uint4*>(x + off + static_cast<long long>(r) * C));
+      const uint4 ud0 = __ldg(reinterpret_cast<const uint4*>(dy + off + static_cast<long long>(r) * C));
+      const uint4 ux1 = __ldg(reinterpret_cast<const uint4*>(x + off + static_cast<long long>(r + rstep) * C));
+      const uint4 ud1 = __ldg(reinterpret_cast<const uint4*>(dy + off + static_cast<long long>(r + rstep) * C));
+      accum(ux0, ud0);
+      accum(ux1, ud1);
+    }
+    for (; r < r1; r += rstep) {
+      const uint4 ux = __ldg(reinterpret_cast<const uint4*>(x + off + static_cast<long long>(r) * C));
+      const uint4 ud = __ldg(reinterpret_cast<const uint4*>(dy + off + static_cast<long long>(r) * C));
+      accum(ux, ud);
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -170,59 +230,82 @@ __global__ void gn_bwd_param_kernel(const float* __restrict__ ws_nc, float* dgb,
   dgb[C + c] = a;   // dbeta
 }
 // dx = rstd * (dz*gamma - S1/cnt - xhat * S2/cnt),  S1 = sum_g dz*gamma, S2 = sum_g dz*gamma*xhat
+// Same thread mapping as the forward apply; per-channel constants live in registers.
 __global__ void gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy,
                                     const __nv_bfloat16* __restrict__ x,
                                     const float* __restrict__ stats,
                                     const float* __restrict__ gamma, const float* __restrict__ beta,
                                     const float* __restrict__ ws_nc, __nv_bfloat16* __restrict__ dx,
-                                    long long total_vecs, int HW, int C, int G, int swish) {
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= total_vecs) return;
+                                    int HW, int C, int G, int swish, int rows_per_block) {
+  const int n = blockIdx.y;
   const int vecs = C >> 3;
-  const int v = static_cast<int>(i % vecs);
-  const long long row = i / vecs;
-  const int n = static_cast<int>(row / HW);
-  const int c0 = v * 8;
+  const int v = threadIdx.x % vecs;
+  const int rlane = threadIdx.x / vecs;
+  const int rstep = blockDim.x / vecs;
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(HW, r0 + rows_per_block);
   const int cg = C / G;
   const float inv_cnt = 1.f / (static_cast<float>(HW) * cg);
-  const uint4 ux = __ldg(reinterpret_cast<const uint4*>(x) + i);
-  const uint4 ud = __ldg(reinterpret_cast<const uint4*>(dy) + i);
-  const float fx[8] = {bf16_lo(ux.x), bf16_hi(ux.x), bf16_lo(ux.y), bf16_hi(ux.y),
-                       bf16_lo(ux.z), bf16_hi(ux.z), bf16_lo(ux.w), bf16_hi(ux.w)};
-  const float fd[8] = {bf16_lo(ud.x), bf16_hi(ud.x), bf16_lo(ud.y), bf16_hi(ud.y),
-                       bf16_lo(ud.z), bf16_hi(ud.z), bf16_lo(ud.w), bf16_hi(ud.w)};
-  float o[8];
-  int gprev = -1;
-  float S1 = 0.f, S2 = 0.f, mean = 0.f, rstd = 0.f;
+  float mean[8], rstd[8], gm[8], bt[8], k1[8], k2[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    const int c = c0 + k;
+    const int c = v * 8 + k;
     const int g = c / cg;
-    if (g != gprev) {
-      gprev = g;
-      mean = __ldg(&stats[(n * G + g) * 2]);
-      rstd = __ldg(&stats[(n * G + g) * 2 + 1]);
-      S1 = 0.f; S2 = 0.f;
-      for (int cc = g * cg; cc < (g + 1) * cg; ++cc) {
-        const float gmm = __ldg(&gamma[cc]);
-        S1 = fmaf(gmm, __ldg(&ws_nc[(static_cast<long long>(n) * C + cc) * 2 + 0]), S1);
-        S2 = fmaf(gmm, __ldg(&ws_nc[(static_cast<long long>(n) * C + cc) * 2 + 1]), S2);
-      }
+    mean[k] = stats[(n * G + g) * 2]; rstd[k] = stats[(n * G + g) * 2 + 1];
+    gm[k] = gamma[c]; bt[k] = beta[c];
+    float S1 = 0.f, S2 = 0.f;
+    for (int cc = g * cg; cc < (g + 1) * cg; ++cc) {
+      const float gmm = gamma[cc];
+      S1 = fmaf(gmm, ws_nc[(static_cast<long long>(n) * C + cc) * 2 + 0], S1);
+      S2 = fmaf(gmm, ws_nc[(static_cast<long long>(n) * C + cc) * 2 + 1], S2);
     }
-    const float gm = __ldg(&gamma[c]);
-    const float xh = (fx[k] - mean) * rstd;
-    float dz = fd[k];
-    if (swish) {
-      const float z = xh * gm + __ldg(&beta[c]);
-      const float sg = sigmoidf_(z);
-      dz *= sg * (1.f + z * (1.f - sg));
-    }
-    o[k] = rstd * (dz * gm - S1 * inv_cnt - xh * S2 * inv_cnt);
+    k1[k] = S1 * inv_cnt; k2[k] = S2 * inv_cnt;
   }
-  uint4 ou;
-  ou.x = pack_bf16x2(o[0], o[1]); ou.y = pack_bf16x2(o[2], o[3]);
-  ou.z = pack_bf16x2(o[4], o[5]); ou.w = pack_bf16x2(o[6], o[7]);
-  reinterpret_cast<uint4*>(dx)[i] = ou;
+  const long long off = (static_cast<long long>(n) * HW) * C + v * 8;
+  int r = r0 + rlane;
+  for (; r + rstep < r1; r += 2 * rstep) {
+    uint4 ux[2], ud[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      ux[j] = __ldg(reinterpret_cast<const uint4*>(x + off + static_cast<long long>(r + j * rstep) * C));
+      ud[j] = __ldg(reinterpret_cast<const uint4*>(dy + off + static_cast<long long>(r + j * rstep) * C));
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      float fx[8], fd[8], o[8];
+      unpack8(ux[j], fx); unpack8(ud[j], fd);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float xh = (fx[k] - mean[k]) * rstd[k];
+        float dz = fd[k];
+        if (swish) {
+          const float z = fmaf(xh, gm[k], bt[k]);
+          const float sg = sigmoidf_(z);
+          dz *= sg * (1.f + z * (1.f - sg));
+        }
+        o[k] = rstd[k] * (dz * gm[k] - k1[k] - xh * k2[k]);
+      }
+      *reinterpret_cast<uint4*>(dx + off + static_cast<long long>(r + j * rstep) * C) = pack8(o);
+    }
+  }
+  for (; r < r1; r += rstep) {
+    const uint4 ux = __ldg(reinterpret_cast<const uint4*>(x + off + static_cast<long long>(r) * C));
+    const uint4 ud = __ldg(reinterpret_cast<const uint4*>(dy + off + static_cast<long long>(r) * C));
+    float fx[8], fd[8], o[8];
+    unpack8(ux, fx); unpack8(ud, fd);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float xh = (fx[k] - mean[k]) * rstd[k];
+      float dz = fd[k];
+      if (swish) {
+        const float z = fmaf(xh, gm[k], bt[k]);
+        const float sg = sigmoidf_(z);
+        dz *= sg * (1.f + z * (1.f - sg));
+      }
+      o[k] = rstd[k] * (dz * gm[k] - k1[k] - xh * k2[k]);
+    }
+    *reinterpret_cast<uint4*>(dx + off + static_cast<long long>(r) * C) = pack8(o);
+  }
 }
 
 }  // namespace b2
@@ -260,10 +343,12 @@ int b2dq_gn_apply(const void* x, const float* stats, const float* gamma, const f
                   int N, int HW, int C, int G, int swish, cudaStream_t stream) {
   if (N <= 0 || HW <= 0) return 0;
   if (C % 8 || C % G) return -1;
-  const long long total = static_cast<long long>(N) * HW * (C / 8);
-  gn_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+  if (256 % (C / 8)) return -1;
+  const int rpb = pick_rows_per_block(HW, N);
+  dim3 grid((HW + rpb - 1) / rpb, N);
+  gn_apply_kernel<<<grid, 256, 0, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), stats, gamma, beta,
-      reinterpret_cast<__nv_bfloat16*>(y), total, HW, C, G, swish);
+      reinterpret_cast<__nv_bfloat16*>(y), HW, C, G, swish, rpb);
   return (int)cudaGetLastError();
 }
 
@@ -288,10 +373,11 @@ int b2dq_gn_bwd_apply(const void* dy, const void* x, const float* stats, const f
                       int C, int G, int swish, cudaStream_t stream) {
   if (N <= 0 || HW <= 0) return 0;
   gn_bwd_param_kernel<<<(C + 127) / 128, 128, 0, stream>>>(ws_nc, dgb, N, C);
-  const long long total = static_cast<long long>(N) * HW * (C / 8);
-  gn_bwd_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+  const int rpb = pick_rows_per_block(HW, N);
+  dim3 grid((HW + rpb - 1) / rpb, N);
+  gn_bwd_apply_kernel<<<grid, 256, 0, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x), stats,
-      gamma, beta, ws_nc, reinterpret_cast<__nv_bfloat16*>(dx), total, HW, C, G, swish);
+      gamma, beta, ws_nc, reinterpret_cast<__nv_bfloat16*>(dx), HW, C, G, swish, rpb);
   return (int)cudaGetLastError();
 }
 

@@ -8,9 +8,25 @@ import ctypes as C
 import torch
 
 from . import _cabi
-from ._cabi import MmDesc, TapGemmDesc, check
+from ._cabi import MmDesc, TapGemmDesc
+from ._cabi import check as _check
 
 BF16 = torch.bfloat16
+
+# kernels launched per C-ABI call (for bench.py's gpu_launches); everything else launches one
+_MULTI = {"vq_ema_finalize": 2, "gn_stats": 2, "gn_bwd_apply": 2}
+_launches = 0
+
+
+def check(status, what):
+    global _launches
+    _check(status, what)
+    _launches += _MULTI.get(what, 1)
+
+
+def launch_count():
+    """Number of kernels of libb200dq.so launched by this process so far."""
+    return _launches
 
 
 def _stream():

@@ -1,0 +1,332 @@
+"""torch.autograd.Function wrappers around the C-ABI kernels.
+
+Internal activation format: NHWC bf16 ([N,H,W,C] contiguous CUDA tensors).  Parameters stay the
+reference's fp32 OIHW ``nn.Parameter``s (master copy, optimizer-visible); their bf16 GEMM packings
+are derived caches keyed on the parameter's version counter.  All Functions are re-entrant (saved
+tensors are never modified), because the reference loss calls ``torch.autograd.grad(...,
+retain_graph=True)`` on ``decoder.conv_out.weight`` before ``backward``
+(modules/losses/vqperceptual_multidisc.py:102-113).
+"""
+import torch
+
+from . import kernels as kn
+
+BF16 = torch.bfloat16
+
+_pack_cache = {}
+
+
+def _packed(weight, kind):
+    key = (weight.data_ptr(), kind)
+    ent = _pack_cache.get(key)
+    ver = weight._version
+    if ent is not None and ent[0] == ver and ent[1].device == weight.device:
+        return ent[1]
+    w = weight.detach()
+    co, ci, r, s = w.shape
+    if kind == "fwd":
+        p = kn.pack_weight_fwd(w)
+    elif kind == "dgrad":
+        p = kn.pack_weight_dgrad(w)
+    elif kind == "fwd_pad16":                       # Cout < 16 (conv_out): pad rows to 16
+        p = torch.zeros(16, r * s * ci, dtype=BF16, device=w.device)
+        p[:co] = kn.pack_weight_fwd(w)
+    elif kind == "col_fwd":                         # Cin*9 <= 64 (conv_in): [Cout, 64], col = t*Cin + c
+        p = torch.zeros(co, 64, dtype=BF16, device=w.device)
+        p[:, :r * s * ci] = w.permute(0, 2, 3, 1).reshape(co, -1).to(BF16)
+    elif kind == "col_dgrad":                       # Cout*9 <= 64 (conv_out): [Cin, 64], col = t*Cout + co
+        p = torch.zeros(ci, 64, dtype=BF16, device=w.device)
+        p[:, :r * s * co] = w.permute(1, 2, 3, 0).reshape(ci, -1).to(BF16)
+    else:
+        raise ValueError(kind)
+    _pack_cache[key] = (ver, p)
+    return p
+
+
+def clear_weight_cache():
+    _pack_cache.clear()
+
+
+def _f32(t):
+    return None if t is None else t.detach().float().contiguous()
+
+
+class Conv2dFn(torch.autograd.Function):
+    """NHWC bf16 convolution (3x3 s1 p1 | 1x1 | 3x3 s2 with the Downsample padding) + bias
+    (+ residual, which may be broadcast over the batch)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, ksize, stride):
+        cout, cin = weight.shape[0], weight.shape[1]
+        y = kn.conv_fwd(x, _packed(weight, "fwd"), _f32(bias), ksize, stride, cout,
+                        residual=None if residual is None else _bcast_res(residual, x.shape[0]))
+        ctx.save_for_backward(x, weight)
+        ctx.meta = (ksize, stride, cin, cout, bias is not None,
+                    None if residual is None else tuple(residual.shape))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        ksize, stride, cin, cout, has_bias, res_shape = ctx.meta
+        dy = dy.contiguous()
+        dx = dw = db = dres = None
+        if ctx.needs_input_grad[0]:
+            dx = kn.conv_dgrad(dy, _packed(weight, "dgrad"), ksize, stride, cin, x.shape[1:3])
+        if ctx.needs_input_grad[1]:
+            dw = kn.conv_wgrad(x, dy, ksize, stride)
+        if has_bias and ctx.needs_input_grad[2]:
+            db = kn.bias_grad(dy)
+        if res_shape is not None and ctx.needs_input_grad[3]:
+            dres = dy if res_shape[0] == dy.shape[0] else dy.float().sum(0, keepdim=True).to(BF16)
+        return dx, dw, db, dres, None, None
+
+
+def _bcast_res(res, nb):
+    if res.shape[0] == nb:
+        return res.contiguous()
+    return res.expand(nb, *res.shape[1:]).contiguous()
+
+
+class ConvInFn(torch.autograd.Function):
+    """3x3 s1 p1 convolution of a few-channel image (Cin*9 <= 64, e.g. RGB -> 128): the 3x3 window
+    is gathered to 64 columns and contracted as one GEMM tap (EncoderDual.py:41)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        nb, h, w, cin = x.shape
+        cout = weight.shape[0]
+        col = kn.im2col3x3_small(x)
+        dims, strs = kn.nhwc_view(col)
+        y = torch.empty(nb, h, w, cout, dtype=BF16, device=x.device)
+        wp = _packed(weight, "col_fwd")
+        kn.tapgemm(col, dims, strs, wp, cout, 64, [(0, 0, 0, 0, 0)], 1, y, 0,
+                   (h * w * cout, w * cout, cout), w, h, nb, cout, bias=_f32(bias))
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy = dy.contiguous()
+        nb, h, w, cin = x.shape
+        cout = weight.shape[0]
+        dw = db = None
+        if ctx.needs_input_grad[1]:
+            col = kn.im2col3x3_small(x)
+            dwc = _col_wgrad(dy, col, cout)                        # [cout, 64]
+            dw = dwc[:, :9 * cin].reshape(cout, 3, 3, cin).permute(0, 3, 1, 2).contiguous()
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = kn.bias_grad(dy)
+        return None, dw, db                                        # no gradient to the image
+
+
+def _col_wgrad(a_nhwc, col, m_channels):
+    """out[m, j] = sum_pixels a[pixel, m] * col[pixel, j]  (fp32 [m_channels, 64])."""
+    nb, h, w, _ = a_nhwc.shape
+    adims, astrs = kn.nhwc_view(a_nhwc)
+    bdims, bstrs = kn.nhwc_view(col)
+    kw, kh, kq = kn.tile_shape(w, h, nb, pixels=64)
+    ktw, kth = (w + kw - 1) // kw, (h + kh - 1) // kh
+    kblocks = ktw * kth * ((nb + kq - 1) // kq)
+    splits = max(1, min(148, kblocks // 4))
+    partial = torch.empty(splits, 1, m_channels, 64, dtype=torch.float32, device=col.device)
+    kn.mmgemm(a_nhwc, adims, astrs, True, col, bdims, bstrs, True, m_channels, 64, kblocks, partial,
+              (m_channels * 64, m_channels * 64, 64), kbox=(kw, kh, kq), ktiles=(ktw, kth), splits=splits,
+              out_f32=True, block_n=128)
+    return partial.sum(0)[0]
+
+
+class ConvOutFn(torch.autograd.Function):
+    """3x3 s1 p1 convolution to a few channels (128 -> RGB, DecoderPositional.py:91), fp32 NHWC
+    output.  Backward gathers the 3x3 window of dy once and reuses it for dX and dW."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        nb, h, w, cin = x.shape
+        cout = weight.shape[0]
+        dims, strs = kn.nhwc_view(x)
+        taps = [(0, s - 1, 0, r - 1, (r * 3 + s) * cin) for r, s in kn.TAPS_3x3]
+        y = torch.empty(nb, h, w, cout, dtype=torch.float32, device=x.device)
+        wp = _packed(weight, "fwd_pad16")
+        kn.tapgemm(x, dims, strs, wp, 16, wp.shape[1], taps, cin // 64, y, 0,
+                   (h * w * cout, w * cout, cout), w, h, nb, cout, bias=_f32(bias), out_f32=True, block_n=16)
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        nb, h, w, cin = x.shape
+        cout = weight.shape[0]
+        dyb = dy.to(BF16).contiguous()
+        colf = kn.im2col3x3_small(dyb, flip=True)                  # [N,H,W,64], col = t*cout + co
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(nb, h, w, cin, dtype=BF16, device=x.device)
+            dims, strs = kn.nhwc_view(colf)
+            kn.tapgemm(colf, dims, strs, _packed(weight, "col_dgrad"), cin, 64, [(0, 0, 0, 0, 0)], 1, dx, 0,
+                       (h * w * cin, w * cin, cin), w, h, nb, cin)
+        if ctx.needs_input_grad[1]:
+            dwc = _col_wgrad(x, colf, cin)                          # [cin, 64]: [ci, t*cout + co]
+            dw = dwc[:, :9 * cout].reshape(cin, 3, 3, cout).permute(3, 0, 1, 2).contiguous()
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy.float().sum((0, 1, 2))
+        return dx, dw, db
+
+
+class GroupNormSwishFn(torch.autograd.Function):
+    """GroupNorm(32, eps=1e-6, affine) optionally followed by swish (model.py:29-35)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, swish):
+        g, b = _f32(gamma), _f32(beta)
+        stats = kn.gn_stats(x)
+        y = kn.gn_apply(x, stats, g, b, swish)
+        ctx.save_for_backward(x, stats, g, b)
+        ctx.swish = swish
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, stats, g, b = ctx.saved_tensors
+        dx, dg, db = kn.gn_bwd(dy.contiguous(), x, stats, g, b, ctx.swish)
+        return dx, dg, db, None
+
+
+class AttentionFn(torch.autograd.Function):
+    """softmax(q k^T / sqrt(C)) v over the T = h*w positions of each image, single head of width C
+    (model.py:176-188).  q, k, v: [B, T, C] bf16 (any row stride that is a multiple of 8)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v):
+        bsz, t, c = q.shape
+        scale = float(int(c) ** -0.5)
+        s = torch.empty(bsz, t, t, dtype=torch.float32, device=q.device)
+        _mm(q, False, k, False, t, t, c, s, alpha=scale, out_f32=True)
+        p = kn.softmax_rows(s, t)
+        o = torch.empty(bsz, t, c, dtype=BF16, device=q.device)
+        _mm(p, False, v, True, t, c, t, o)
+        ctx.save_for_backward(q, k, v, p)
+        ctx.scale = scale
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        q, k, v, p = ctx.saved_tensors
+        do = do.contiguous()
+        bsz, t, c = q.shape
+        dv = torch.empty(bsz, t, c, dtype=BF16, device=q.device)
+        _mm(p, True, do, True, t, c, t, dv)                       # P^T dO
+        dp = torch.empty(bsz, t, t, dtype=BF16, device=q.device)
+        _mm(do, False, v, False, t, t, c, dp)                     # dO V^T
+        ds = kn.softmax_bwd_rows(p, dp, t, ctx.scale)
+        dq = torch.empty(bsz, t, c, dtype=BF16, device=q.device)
+        _mm(ds, False, k, True, t, c, t, dq)                      # dS K
+        dk = torch.empty(bsz, t, c, dtype=BF16, device=q.device)
+        _mm(ds, True, q, True, t, c, t, dk)                       # dS^T Q
+        return dq, dk, dv
+
+
+def _mm(a, a_mn, b, b_mn, M, N, K, out, alpha=1.0, out_f32=False):
+    """Batched out[z] = alpha * A B^T with A:[M,K] (K-major) or stored [K,M] (a_mn), same for B."""
+    bsz = a.shape[0]
+    assert a.stride(2) == 1 and b.stride(2) == 1 and out.is_contiguous()
+
+    def view(t, mn, rows):
+        sb, sr = t.stride(0), t.stride(1)
+        if mn:   # stored [K][rows]
+            return (rows, K, 1, 1, bsz), (1, sr, sb, sb, sb)
+        return (K, rows, 1, 1, bsz), (1, sr, sb, sb, sb)
+
+    ad, as_ = view(a, a_mn, M)
+    bd, bs = view(b, b_mn, N)
+    kn.mmgemm(a, ad, as_, a_mn, b, bd, bs, b_mn, M, N, K // 64, out, (M * N, 0, N),
+              kbox=(64, 1, 1), ktiles=(K // 64, 1), batches=bsz, alpha=alpha, out_f32=out_f32)
+
+
+class Upsample2xFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return kn.upsample2x(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return kn.upsample2x_bwd(g.contiguous())
+
+
+class ToNHWCFn(torch.autograd.Function):
+    """NCHW fp32 -> NHWC bf16 (module boundary)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return kn.nchw_f32_to_nhwc_bf16(x.float().contiguous())
+
+    @staticmethod
+    def backward(ctx, g):
+        return kn.nhwc_bf16_to_nchw_f32(g.contiguous())
+
+
+class ToNCHWFn(torch.autograd.Function):
+    """NHWC (bf16 or fp32) -> NCHW fp32 (module boundary)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.was_bf16 = x.dtype == BF16
+        if ctx.was_bf16:
+            return kn.nhwc_bf16_to_nchw_f32(x.contiguous())
+        return kn.nhwc_f32_to_nchw_f32(x.contiguous())
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.float().contiguous()
+        if ctx.was_bf16:
+            return kn.nchw_f32_to_nhwc_bf16(g)
+        return kn.nchw_f32_to_nhwc_f32(g)
+
+
+class ToNHWC32Fn(torch.autograd.Function):
+    """NCHW fp32 -> NHWC fp32 (kept in fp32: the reference-facing VQ entry point)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return kn.nchw_f32_to_nhwc_f32(x.float().contiguous())
+
+    @staticmethod
+    def backward(ctx, g):
+        return kn.nhwc_f32_to_nchw_f32(g.float().contiguous())
+
+
+ToNCHWInvFn = ToNHWC32Fn
+
+
+class AddFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        return kn.add_bf16(a.contiguous(), b.contiguous())
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, g
+
+
+# convenience wrappers -------------------------------------------------------------------------
+def conv2d(x, conv, residual=None, stride=None):
+    """x NHWC bf16; conv: an nn.Conv2d used as a parameter container."""
+    k = conv.kernel_size[0]
+    st = conv.stride[0] if stride is None else stride
+    return Conv2dFn.apply(x, conv.weight, conv.bias, residual, k, st)
+
+
+def gn_swish(x, norm, swish=True):
+    return GroupNormSwishFn.apply(x, norm.weight, norm.bias, swish)
+
+
+def to_nhwc(x):
+    return ToNHWCFn.apply(x)
+
+
+def to_nchw(x):
+    return ToNCHWFn.apply(x)

@@ -33,6 +33,17 @@ TINY_CFG = dict(
 )
 
 
+# 64-channel-granular variant (every conv input is a multiple of 64 channels, as the CUDA kernels
+# require) used by the GPU parity tests: same topology, half width, 64x64 images
+SMALL_CFG = dict(
+    ch=64, ch_mult=(1, 1, 2, 2, 4), num_res_blocks=2, attn_resolutions=(4, 8), in_channels=3,
+    resolution=64, z_channels=64,
+    dec_ch=64, dec_ch_mult=(1, 1, 2, 2), dec_attn_resolutions=(8,), out_ch=3, latent_size=8,
+    codebook_size=128, codebook_dim=64, beta=0.25, decay=0.99,
+    router="feature",
+)
+
+
 # --------------------------------------------------------------------------- parameter inventory
 def _conv(shapes, p, cin, cout, k):
     shapes[p + ".weight"] = (cout, cin, k, k)
@@ -320,7 +331,7 @@ def decoder(sd, cfg, z, p="decoder"):
 
 
 # --------------------------------------------------------------------------- VQ (torch version, differentiable)
-def vq_forward(sd, cfg, h, mask, search_bf16=False, p="quantize.codebook"):
+def vq_forward(sd, cfg, h, mask, search_bf16=False, p="quantize.codebook", forced_codes=None):
     """quantize2_mask.py:157-191 in eval mode.  search_bf16 evaluates the nearest-code search on
     bf16-rounded operands (what the CUDA kernel multiplies); everything else stays fp32."""
     b, c, hh, ww = h.shape
@@ -332,6 +343,8 @@ def vq_forward(sd, cfg, h, mask, search_bf16=False, p="quantize.codebook"):
     flat = xs.reshape(-1, c)
     d = (flat.pow(2).sum(1, keepdim=True) + cb.t().pow(2).sum(0, keepdim=True)) - 2.0 * flat @ cb.t()
     codes = d.argmin(-1).reshape(b, hh * ww)
+    if forced_codes is not None:          # teacher forcing: replay the codes of another run
+        codes = forced_codes.reshape(b, hh * ww)
     xq = w[codes]
     m = mask.permute(0, 2, 3, 1).reshape(b, hh * ww, 1)
     loss = cfg["beta"] * torch.mean((xq.detach() - x) ** 2 * m) + torch.mean((xq - x.detach()) ** 2 * m)
@@ -347,13 +360,15 @@ def budget_loss_dual(gate, target_ratio=0.5, gamma=10.0, min_grain=16, max_grain
     return last + last
 
 
-def model_forward(sd, cfg, x, search_bf16=False, forced_gate=None, x_entropy=None, entropy_threshold=None):
+def model_forward(sd, cfg, x, search_bf16=False, forced_gate=None, x_entropy=None, entropy_threshold=None,
+                  forced_codes=None):
     """models/stage1_dynamic/dqvae_dual_feat.py:59-78: encode -> quant_conv -> VQ -> post_quant_conv
     -> decode.  Returns dict(xrec, qloss, codes, indices, gate, h_dual)."""
     enc = dual_encoder(sd, cfg, x, x_entropy=x_entropy, forced_gate=forced_gate,
                        entropy_threshold=entropy_threshold)
     h = conv2d(sd, "quant_conv", enc["h_dual"])
-    quant, qloss, codes = vq_forward(sd, cfg, h, enc["codebook_mask"], search_bf16=search_bf16)
+    quant, qloss, codes = vq_forward(sd, cfg, h, enc["codebook_mask"], search_bf16=search_bf16,
+                                     forced_codes=forced_codes)
     xrec = decoder(sd, cfg, conv2d(sd, "post_quant_conv", quant))
     return dict(xrec=xrec, qloss=qloss, codes=codes, indices=enc["indices"], gate=enc["gate"],
                 h_dual=enc["h_dual"], h_pre_vq=h)

@@ -77,7 +77,8 @@ def update_embedding(cluster_size_ema, embed_ema, eps=1e-5):
 def vq_forward(x, weight, mask=None, beta=0.25):
     """quantize2_mask.py:117-132 + :157-191 on a flattened [N,C] latent (eval mode).
 
-    Returns (x_q [N,C] = weight[idx], loss scalar, idx [N]).
+    Returns (x_q [N,C], loss scalar, idx [N]).  x_q is the straight-through value
+    x + (weight[idx] - x) exactly as :182 evaluates it in fp32 (equal to weight[idx] up to 1 ulp).
     loss = beta*mean((xq-x)^2 m) + mean((xq-x)^2 m), mean over N*C (:172-179).
     """
     idx = find_nearest_embedding(x, weight)
@@ -86,4 +87,5 @@ def vq_forward(x, weight, mask=None, beta=0.25):
     if mask is not None:
         d2 = d2 * mask.reshape(-1, 1)
     m = d2.mean(dtype=np.float64)
-    return xq, np.float32(beta * m + m), idx
+    x = x.astype(np.float32)
+    return x + (xq - x), np.float32(beta * m + m), idx

@@ -1,0 +1,148 @@
+"""Mint golden vectors from the UNMODIFIED reference (run in the build container only).
+
+    python tests/golden/make_golden.py            # needs /root/reference
+
+Imports the reference's own classes from /root/reference (with a 3-line pytorch_lightning shim,
+SURVEY.md 8c), loads deterministic weights from oracle.dqvae_oracle.make_weights into them, runs
+them on seeded inputs (CPU, fp32) and stores the results as small .npz fixtures next to this
+file.  /root/reference does not exist on the GPU box: tests only read the .npz files.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+import torch.nn as nn
+import yaml
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+sys.path.insert(0, ROOT)
+sys.path.insert(1, REF)
+os.chdir(REF)  # the reference resolves relative paths (thresholds json) from its root
+
+pl = types.ModuleType("pytorch_lightning")
+pl.LightningModule = nn.Module
+sys.modules["pytorch_lightning"] = pl
+
+from oracle import dqvae_oracle as orc  # noqa: E402
+
+from modules.vector_quantization.quantize2_mask import VectorQuantize2  # noqa: E402
+from utils.utils import instantiate_from_config  # noqa: E402
+
+
+def save(name, **arrs):
+    out = {k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in arrs.items()}
+    np.savez_compressed(os.path.join(HERE, name), **out)
+    print("wrote", name, {k: v.shape for k, v in out.items()})
+
+
+# ----------------------------------------------------------------------------------- VQ goldens
+def vq_goldens():
+    torch.manual_seed(1234)
+    K, C, B, H = 64, 64, 2, 8
+    vq = VectorQuantize2(codebook_size=K, codebook_dim=C)
+    g = torch.Generator().manual_seed(5)
+    w = torch.randn(K + 1, C, generator=g)
+    with torch.no_grad():
+        vq.codebook.weight.copy_(w)
+        vq.codebook.embed_ema.copy_(w[:-1])
+        vq.codebook.cluster_size_ema.fill_(1.0)
+    x = torch.randn(B, C, H, H, generator=g)
+    mask = torch.where(torch.rand(B, 1, H, H, generator=g) > 0.5, 1.0, 0.25)
+    # eval forward + backward
+    vq.eval()
+    xin = x.clone().requires_grad_(True)
+    xq, loss, (_, _, codes) = vq(xin, codebook_mask=mask)
+    gq = torch.randn(xq.shape, generator=g)
+    (xq * gq).sum().backward(retain_graph=True)
+    gx_ste = xin.grad.clone()
+    xin.grad = None
+    loss.backward()
+    # three train steps with the restart rows replayed: make randperm deterministic by seeding
+    vq.train()
+    states = []
+    xs = []
+    for step in range(3):
+        xt = torch.randn(B, C, H, H, generator=g) * (1 + step)
+        torch.manual_seed(100 + step)
+        perm = torch.randperm(B * H * H)  # what _update_buffers will draw after manual_seed
+        torch.manual_seed(100 + step)
+        xq_t, loss_t, (_, _, codes_t) = vq(xt, codebook_mask=mask)
+        flat = xt.permute(0, 2, 3, 1).reshape(-1, C)
+        states.append(dict(codes=codes_t.clone(), xq=xq_t.detach().clone(), loss=loss_t.detach().clone(),
+                           cs=vq.codebook.cluster_size_ema.clone(), em=vq.codebook.embed_ema.clone(),
+                           w=vq.codebook.weight.detach().clone(), restart=flat[perm][:K].clone()))
+        xs.append(xt)
+    save("vq_small.npz", weight=w, x=x, mask=mask, xq=xq, loss=loss, codes=codes, gq=gq, gx_ste=gx_ste,
+         gx_loss=xin.grad,
+         **{f"t{i}_{k}": v for i, s in enumerate(states) for k, v in s.items()},
+         **{f"t{i}_x": v for i, v in enumerate(xs)})
+
+
+# ----------------------------------------------------------------------------------- model goldens
+def build_reference_modules(cfg, yaml_name="dqvae-dual-r-05_imagenet.yml"):
+    conf = yaml.safe_load(open(os.path.join(REF, "configs/stage1", yaml_name)))["model"]["params"]
+    enc_p, dec_p = dict(conf["encoderconfig"]["params"]), dict(conf["decoderconfig"]["params"])
+    enc_p.update(ch=cfg["ch"], resolution=cfg["resolution"], z_channels=cfg["z_channels"],
+                 attn_resolutions=list(cfg["attn_resolutions"]))
+    enc_p["router_config"] = dict(enc_p["router_config"])
+    enc_p["router_config"]["params"] = dict(enc_p["router_config"]["params"], num_channels=cfg["z_channels"])
+    dec_p.update(ch=cfg["dec_ch"], in_ch=cfg["z_channels"], resolution=cfg["resolution"],
+                 attn_resolutions=list(cfg["dec_attn_resolutions"]), latent_size=cfg["latent_size"])
+    enc = instantiate_from_config(dict(target=conf["encoderconfig"]["target"], params=enc_p))
+    dec = instantiate_from_config(dict(target=conf["decoderconfig"]["target"], params=dec_p))
+    vq_p = dict(conf["vqconfig"]["params"], codebook_size=cfg["codebook_size"], codebook_dim=cfg["codebook_dim"])
+    vq = instantiate_from_config(dict(target=conf["vqconfig"]["target"], params=vq_p))
+    m = nn.Module()
+    m.encoder, m.decoder, m.quantize = enc, dec, vq
+    m.quant_conv = nn.Conv2d(cfg["z_channels"], cfg["codebook_dim"], 1)
+    m.post_quant_conv = nn.Conv2d(cfg["codebook_dim"], cfg["z_channels"], 1)
+    return m
+
+
+def model_goldens(cfg, tag, batch, seed):
+    m = build_reference_modules(cfg)
+    shapes = orc.model_shapes(cfg)
+    ref_sd = m.state_dict()
+    assert set(ref_sd) == set(shapes), (sorted(set(ref_sd) ^ set(shapes)))
+    for k in shapes:
+        assert tuple(ref_sd[k].shape) == tuple(shapes[k]), (k, ref_sd[k].shape, shapes[k])
+    sd = orc.make_weights(shapes, seed=seed)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    g = torch.Generator().manual_seed(seed + 77)
+    x = torch.rand(batch, 3, cfg["resolution"], cfg["resolution"], generator=g) * 2 - 1
+    h_dict = m.encoder(x, None)
+    h = m.quant_conv(h_dict["h_dual"])
+    quant, qloss, (_, _, codes) = m.quantize(x=h, temp=0.0, codebook_mask=h_dict["codebook_mask"])
+    xrec = m.decoder(m.post_quant_conv(quant), h_dict["indices"])
+    loss = (xrec - x).abs().mean() + qloss
+    loss.backward()
+    grads = {n: p.grad for n, p in m.named_parameters() if p.grad is not None}
+    pick = ["encoder.conv_in.weight", "encoder.down.0.block.0.conv1.weight", "encoder.down.0.block.0.norm1.weight",
+            "encoder.down.3.attn.0.q.weight", "encoder.down.2.block.0.nin_shortcut.weight",
+            "encoder.down.1.downsample.conv.weight", "encoder.conv_out_fine.bias",
+            "quant_conv.weight", "post_quant_conv.weight", "decoder.conv_in.weight",
+            "decoder.up.3.attn.1.proj_out.weight", "decoder.up.1.upsample.conv.weight",
+            "decoder.up.0.block.2.conv2.weight", "decoder.norm_out.weight", "decoder.conv_out.weight",
+            "decoder.conv_out.bias", "decoder.position_bias_learned.row_embed.weight",
+            "decoder.position_bias_fourier.lff.ffm.conv.weight"]
+    gsel = {"grad__" + k.replace(".", "__"): grads[k] for k in pick}
+    gnorm = {k: float(v.double().pow(2).sum().sqrt()) for k, v in grads.items()}
+    names = sorted(gnorm)
+    save(f"model_{tag}.npz", x=x, xrec=xrec, qloss=qloss, codes=codes.to(torch.int16), indices=h_dict["indices"].to(torch.int8),
+         gate=h_dict["gate"], h_dual=h_dict["h_dual"].to(torch.float16) if tag != "tiny" else h_dict["h_dual"],
+         loss=loss, grad_norm_names=np.array(names), grad_norms=np.array([gnorm[n] for n in names]), **gsel)
+
+
+if __name__ == "__main__":
+    what = sys.argv[1:] or ["vq", "tiny", "dual"]
+    if "vq" in what:
+        vq_goldens()
+    if "tiny" in what:
+        model_goldens(orc.TINY_CFG, "tiny", batch=2, seed=3)
+    if "dual" in what:
+        model_goldens(orc.DUAL_CFG, "dual", batch=1, seed=7)
