@@ -150,29 +150,74 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ a, __nv_bfloat16*
 // im2col for a 3x3 pad-1 stride-1 window over a few-channel NHWC bf16 image:
 // dst[pixel][t*Cs + c] = src[pixel + off_t][c], zero padded to 64 columns.
 // flip = 0: off_t = (r-1, s-1)   (forward / weight gradient);  flip = 1: off_t = (1-r, 1-s) (dgrad).
+// One thread produces 8 columns (one 16 B store).
 __global__ void im2col3x3_small_kernel(const __nv_bfloat16* __restrict__ src,
                                        __nv_bfloat16* __restrict__ dst, int H, int W, int Cs,
-                                       int flip, long long total) {
+                                       int flip, long long total_vecs) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int col = static_cast<int>(i & 63);
-  const long long pix = i >> 6;
+  if (i >= total_vecs) return;
+  const int cv = static_cast<int>(i & 7);
+  const long long pix = i >> 3;
   const int w = static_cast<int>(pix % W);
   const int h = static_cast<int>((pix / W) % H);
   const long long n = pix / (static_cast<long long>(W) * H);
-  __nv_bfloat16 v = __float2bfloat16_rn(0.f);
-  if (col < 9 * Cs) {
-    const int t = col / Cs, c = col % Cs;
-    const int r = t / 3, s = t % 3;
-    const int hh = h + (flip ? 1 - r : r - 1), ww = w + (flip ? 1 - s : s - 1);
-    if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = src[((n * H + hh) * W + ww) * Cs + c];
+  __align__(16) __nv_bfloat16 vals[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int col = cv * 8 + k;
+    __nv_bfloat16 v = __float2bfloat16_rn(0.f);
+    if (col < 9 * Cs) {
+      const int t = col / Cs, c = col - t * Cs;
+      const int r = t / 3, s = t - 3 * r;
+      const int hh = h + (flip ? 1 - r : r - 1), ww = w + (flip ? 1 - s : s - 1);
+      if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = src[((n * H + hh) * W + ww) * Cs + c];
+    }
+    vals[k] = v;
   }
-  dst[i] = v;
+  reinterpret_cast<uint4*>(dst)[i] = *reinterpret_cast<const uint4*>(vals);
 }
 
-// out[c] = sum_rows dy[row][c]   (bias gradient), dy bf16 [rows][C]; out must be zeroed.
+// out[c] = sum_rows dy[row][c]   (bias gradient), dy bf16 [rows][C], C % 8 == 0; out must be zeroed.
+// Thread = (8-channel vector, row lane); 16 B loads, 4 rows in flight; smem then global atomics.
 __global__ void bias_grad_kernel(const __nv_bfloat16* __restrict__ dy, float* out, long long rows,
                                  int C, int rows_per_block) {
+  extern __shared__ float sh[];  // [C]
+  const int vecs = C >> 3;
+  const int v = threadIdx.x % vecs;
+  const int rlane = threadIdx.x / vecs;
+  const int rstep = blockDim.x / vecs;
+  const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_block;
+  const long long r1 = min(rows, r0 + rows_per_block);
+  for (int i = threadIdx.x; i < C; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const __nv_bfloat16* base = dy + v * 8;
+  if (rlane < rstep) {
+    long long r = r0 + rlane;
+    for (; r + 3 * rstep < r1; r += 4 * rstep) {
+      uint4 u[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) u[j] = __ldg(reinterpret_cast<const uint4*>(base + (r + j * rstep) * C));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        s[0] += bf16_lo(u[j].x); s[1] += bf16_hi(u[j].x); s[2] += bf16_lo(u[j].y); s[3] += bf16_hi(u[j].y);
+        s[4] += bf16_lo(u[j].z); s[5] += bf16_hi(u[j].z); s[6] += bf16_lo(u[j].w); s[7] += bf16_hi(u[j].w);
+      }
+    }
+    for (; r < r1; r += rstep) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + r * C));
+      s[0] += bf16_lo(u.x); s[1] += bf16_hi(u.x); s[2] += bf16_lo(u.y); s[3] += bf16_hi(u.y);
+      s[4] += bf16_lo(u.z); s[5] += bf16_hi(u.z); s[6] += bf16_lo(u.w); s[7] += bf16_hi(u.w);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) atomicAdd(&sh[v * 8 + k], s[k]);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(out + c, sh[c]);
+}
+// generic fallback for channel counts that are not a multiple of 8
+__global__ void bias_grad_generic_kernel(const __nv_bfloat16* __restrict__ dy, float* out,
+                                         long long rows, int C, int rows_per_block) {
   const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_block;
   const long long r1 = min(rows, r0 + rows_per_block);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -265,7 +310,7 @@ int b2dq_cast_f32_to_bf16(const float* a, void* o, long long n, cudaStream_t st)
 int b2dq_im2col3x3_small(const void* src, void* dst, int N, int H, int W, int Cs, int flip,
                          cudaStream_t st) {
   if (9 * Cs > 64) return -1;
-  const long long total = (long long)N * H * W * 64;
+  const long long total = (long long)N * H * W * 8;
   return launch1d(im2col3x3_small_kernel, total, st, reinterpret_cast<const __nv_bfloat16*>(src),
                   reinterpret_cast<__nv_bfloat16*>(dst), H, W, Cs, flip, total);
 }
@@ -273,11 +318,16 @@ int b2dq_im2col3x3_small(const void* src, void* dst, int N, int H, int W, int Cs
 int b2dq_bias_grad(const void* dy, float* out, long long rows, int C, cudaStream_t st) {
   if (rows <= 0) return 0;
   cudaMemsetAsync(out, 0, sizeof(float) * C, st);
-  int rpb = (int)((rows + 148 * 4 - 1) / (148 * 4));
-  if (rpb < 16) rpb = 16;
+  long long rpb = (rows + 148 * 8 - 1) / (148 * 8);
+  if (rpb < 64) rpb = 64;
   const unsigned blocks = (unsigned)((rows + rpb - 1) / rpb);
-  bias_grad_kernel<<<blocks, C < 256 ? (C < 32 ? 32 : C) : 256, 0, st>>>(
-      reinterpret_cast<const __nv_bfloat16*>(dy), out, rows, C, rpb);
+  if (C % 8 == 0 && 256 % (C / 8) == 0) {
+    bias_grad_kernel<<<blocks, 256, C * sizeof(float), st>>>(reinterpret_cast<const __nv_bfloat16*>(dy),
+                                                            out, rows, C, (int)rpb);
+  } else {
+    bias_grad_generic_kernel<<<blocks, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dy), out,
+                                                     rows, C, (int)rpb);
+  }
   return (int)cudaGetLastError();
 }
 

@@ -62,6 +62,21 @@ class _VQFn(torch.autograd.Function):
         return None, g, None, None, None, None
 
 
+def reduce_ema_stats(acc):
+    """Data-parallel exchange of the per-code statistics: ONE all-reduce of the packed
+    [K*C sums | K counts] buffer instead of the reference's two (quantize2_mask.py:86-88)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+    return acc
+
+
+def share_restart_rows(rows):
+    """Every rank restarts dead codes from rank 0's candidate rows (quantize2_mask.py:99-100)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.broadcast(rows, 0)
+    return rows
+
+
 class VQEmbedding(nn.Embedding):
     """VQ embedding module with EMA update (quantize2_mask.py:10-132)."""
 
@@ -139,8 +154,7 @@ class VQEmbedding(nn.Embedding):
     def _ema_step(self, rows_f32_fn, n_vectors):
         """EMA + restart + re-normalisation after the search kernel has filled self._acc
         (:86-105 and :107-115).  rows_f32_fn(idx) returns fp32 input rows for the restart."""
-        if dist.is_available() and dist.is_initialized():
-            dist.all_reduce(self._acc, op=dist.ReduceOp.SUM)       # sums and counts in one buffer
+        reduce_ema_stats(self._acc)
         sums, counts = self._acc_views()
         restart_rows = None
         if self.restart_unused_codes:
@@ -151,9 +165,7 @@ class VQEmbedding(nn.Embedding):
             else:
                 perm = torch.randperm(n_vectors, device=self.weight.device)   # same RNG draw as :97
                 restart_rows = rows_f32_fn(perm[:k])
-            restart_rows = restart_rows.float().contiguous()
-            if dist.is_available() and dist.is_initialized():
-                dist.broadcast(restart_rows, 0)
+            restart_rows = share_restart_rows(restart_rows.float().contiguous())
         kn.vq_ema_finalize(counts, sums, restart_rows, self.cluster_size_ema, self.embed_ema,
                            self.weight.data, self.decay, self.eps, self.restart_unused_codes)
         self._mark_dirty()

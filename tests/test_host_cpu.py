@@ -1,0 +1,205 @@
+"""CPU-only tests: host-side logic, C-ABI surface, drop-in conformance with the reference tree,
+and the data-parallel exchange of the VQ statistics (gloo, world_size 2)."""
+import ctypes
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+
+
+# ------------------------------------------------------------------------------- C ABI surface
+def test_cabi_exports_every_declared_symbol():
+    from dynamicvectorquantization_b200 import _cabi, build
+    build.build()
+    lib = _cabi.lib()
+    header = open(os.path.join(ROOT, "include", "b200dq.h")).read()
+    declared = set(re.findall(r"\bint\s+(b2dq_\w+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(_cabi.SIGNATURES), declared ^ set(_cabi.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.b2dq_version() == 0
+
+
+def test_struct_layouts_match_header_field_order():
+    from dynamicvectorquantization_b200 import _cabi
+    header = open(os.path.join(ROOT, "include", "b200dq.h")).read()
+    for cname, cls in (("b2dq_tapgemm_desc", _cabi.TapGemmDesc), ("b2dq_mm_desc", _cabi.MmDesc)):
+        body = header[header.index("typedef struct " + cname):]
+        body = body[body.index("{") + 1:body.index("} " + cname)]
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        names = []
+        for stmt in body.split(";"):
+            stmt = stmt.strip()
+            if not stmt:
+                continue
+            stmt = re.sub(r"^(const\s+)?(void\*|float\*|long long|int|float)\s*", "", stmt)
+            for piece in stmt.split(","):
+                names.append(re.sub(r"[\*\s]|\[.*?\]", "", piece))
+        assert names == [f[0] for f in cls._fields_], (cname, names)
+
+
+def test_extension_missing_is_loud(monkeypatch, tmp_path):
+    from dynamicvectorquantization_b200 import _cabi
+    monkeypatch.setattr(_cabi, "_lib", None)
+    monkeypatch.setattr(_cabi, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_cabi.ExtensionMissing):
+        _cabi.lib()
+
+
+def test_cpu_tensors_are_rejected_not_silently_computed():
+    from dynamicvectorquantization_b200 import configs
+    configs.activate_overlay()
+    from modules.vector_quantization.quantize2_mask import VectorQuantize2
+    vq = VectorQuantize2(codebook_size=64, codebook_dim=64)
+    with pytest.raises(RuntimeError):
+        vq(torch.zeros(1, 64, 4, 4))
+
+
+# ------------------------------------------------------------------------------- host geometry
+def test_tile_shapes_and_tap_tables():
+    from dynamicvectorquantization_b200 import kernels as kn
+    for w, h, nb in [(256, 256, 32), (64, 64, 2), (32, 32, 1), (16, 16, 32), (8, 8, 3), (4, 4, 5)]:
+        tw, th, tn = kn.tile_shape(w, h, nb)
+        assert tw * th * tn == 128 and tw <= max(w, 1) * 2
+        kw, kh, kq = kn.tile_shape(w, h, nb, pixels=64)
+        assert kw * kh * kq == 64
+    # stride-2 taps address x[2*oh + r, 2*ow + s] through the [N, H/2, 2, W/2, 2C] view
+    cin = 64
+    for r, s in kn.TAPS_3x3:
+        dc, dw, dp, dh = (s % 2) * cin, s // 2, r % 2, r // 2
+        for oh, ow in [(0, 0), (3, 5)]:
+            assert 2 * (oh + dh) + dp == 2 * oh + r and 2 * (ow + dw) + dc // cin == 2 * ow + s
+
+
+def test_weight_packings_are_consistent():
+    from dynamicvectorquantization_b200 import kernels as kn
+    w = torch.randn(8, 4, 3, 3)
+    f, d = kn.pack_weight_fwd(w).float(), kn.pack_weight_dgrad(w).float()
+    wb = w.bfloat16().float()
+    for r, s in kn.TAPS_3x3:
+        t = r * 3 + s
+        assert torch.equal(f[:, t * 4:(t + 1) * 4], wb[:, :, r, s])
+        assert torch.equal(d[:, t * 8:(t + 1) * 8], wb[:, :, r, s].t())
+
+
+# ------------------------------------------------------------------------------- drop-in conformance
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not mounted")
+@pytest.mark.parametrize("name,yml", [("dqvae-dual-r-05", "dqvae-dual-r-05_imagenet.yml"),
+                                      ("dqvae-entropy-dual-r05", "dqvae-entropy-dual-r05_imagenet.yml"),
+                                      ("dqvae-triple-r-03-03", "dqvae-triple-r-03-03_imagenet.yml")])
+def test_configs_match_reference_yaml(name, yml):
+    import yaml
+    from dynamicvectorquantization_b200 import configs
+    ref = yaml.safe_load(open(os.path.join(REF, "configs/stage1", yml)))["model"]
+    mine = configs.stage1_config(name)
+    assert mine["target"] == ref["target"]
+    for key in ("encoderconfig", "decoderconfig", "vqconfig"):
+        assert mine["params"][key] == ref["params"][key], key
+    for key in ("quant_before_dim", "quant_after_dim", "quant_sample_temperature", "image_key", "monitor",
+                "warmup_epochs", "scheduler_type"):
+        assert mine["params"][key] == ref["params"][key], key
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not mounted")
+def test_overlay_loads_reference_yaml_and_state_dict_keys_match():
+    """The reference's own YAML (unchanged apart from the loss, which needs downloaded VGG weights)
+    instantiates through the overlay, and the resulting state_dict has the reference's keys/shapes."""
+    import subprocess
+    code = r'''
+import sys, types, yaml, torch, torch.nn as nn
+sys.path.insert(0, %r); sys.path.insert(0, %r + "/dynamicvectorquantization_b200/overlay"); sys.path.append(%r)
+import os; os.chdir(%r)
+from utils.utils import instantiate_from_config          # the REFERENCE's plugin loader
+conf = yaml.safe_load(open("configs/stage1/dqvae-dual-r-05_imagenet.yml"))["model"]
+conf["params"]["lossconfig"] = {"target": "dynamicvectorquantization_b200.nn.model.SurrogateAELoss"}
+m = instantiate_from_config(conf)
+assert type(m).__module__.startswith("dynamicvectorquantization_b200"), type(m)
+mine = {k: tuple(v.shape) for k, v in m.state_dict().items() if not k.startswith("loss.")}
+# now the reference classes themselves (overlay removed from the path)
+sys.path = [p for p in sys.path if "overlay" not in p]
+for k in [k for k in sys.modules if k.split(".")[0] in ("modules", "models")]:
+    del sys.modules[k]
+pl = types.ModuleType("pytorch_lightning"); pl.LightningModule = nn.Module; sys.modules["pytorch_lightning"] = pl
+from modules.dynamic_modules.EncoderDual import DualGrainEncoder
+from modules.dynamic_modules.DecoderPositional import Decoder
+from modules.vector_quantization.quantize2_mask import VectorQuantize2
+assert DualGrainEncoder.__module__ == "modules.dynamic_modules.EncoderDual"
+p = conf["params"]
+ref = {}
+for pref, mod in (("encoder.", DualGrainEncoder(**p["encoderconfig"]["params"])), ("decoder.", Decoder(**p["decoderconfig"]["params"])),
+                  ("quantize.", VectorQuantize2(**p["vqconfig"]["params"]))):
+    ref.update({pref + k: tuple(v.shape) for k, v in mod.state_dict().items()})
+for k in ("quant_conv", "post_quant_conv"):
+    ref[k + ".weight"] = (256, 256, 1, 1); ref[k + ".bias"] = (256,)
+assert mine == ref, sorted(set(mine.items()) ^ set(ref.items()))[:10]
+# seeded default init is identical (same construction order and init calls)
+torch.manual_seed(5); a = DualGrainEncoder(**p["encoderconfig"]["params"]).state_dict()
+sys.path.insert(0, %r + "/dynamicvectorquantization_b200/overlay")
+for k in [k for k in sys.modules if k.split(".")[0] in ("modules", "models")]:
+    del sys.modules[k]
+from modules.dynamic_modules.EncoderDual import DualGrainEncoder as Mine
+torch.manual_seed(5); b = Mine(**p["encoderconfig"]["params"]).state_dict()
+assert all(torch.equal(a[k], b[k]) for k in a), "seeded init differs"
+print("CONFORMANCE_OK")
+''' % (ROOT, ROOT, REF, REF, ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert "CONFORMANCE_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+# ------------------------------------------------------------------------------- data parallel (gloo)
+def _ddp_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from dynamicvectorquantization_b200.nn import quantize as Q
+    from oracle import vq_oracle as vo
+    K, C, N = 16, 8, 40
+    g = np.random.RandomState(0)
+    w = np.concatenate([g.randn(K, C).astype(np.float32), np.zeros((1, C), np.float32)])
+    x_all = g.randn(world * N, C).astype(np.float32)
+    x = x_all[rank * N:(rank + 1) * N]
+    idx = vo.find_nearest_embedding(x, w)
+    acc = torch.zeros(K * C + K)
+    acc[:K * C].view(K, C).index_add_(0, torch.from_numpy(idx), torch.from_numpy(x))
+    acc[K * C:] += torch.bincount(torch.from_numpy(idx), minlength=K).float()
+    Q.reduce_ema_stats(acc)
+    rows = torch.from_numpy(x[:K].copy())
+    Q.share_restart_rows(rows)
+    # single-process statistics over the concatenated batch must equal the reduced ones
+    idx_all = vo.find_nearest_embedding(x_all, w)
+    sums = np.zeros((K, C), np.float32); np.add.at(sums, idx_all, x_all)
+    ok = np.allclose(acc[:K * C].view(K, C).numpy(), sums, atol=1e-5) and \
+        np.array_equal(acc[K * C:].numpy(), np.bincount(idx_all, minlength=K).astype(np.float32)) and \
+        np.array_equal(rows.numpy(), x_all[:K])
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_vq_statistics_exchange_world_size_2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    [p.join(30) for p in procs]
+    assert res == [(0, True), (1, True)]
+
+
+def test_bench_reference_arm_json_contract():
+    """--impl reference prints one JSON line with the contract keys (rank != 0 prints nothing)."""
+    import json
+    import subprocess
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "1"], capture_output=True, text=True, env=env, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == ""
