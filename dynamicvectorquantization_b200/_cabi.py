@@ -27,7 +27,7 @@ class TapGemmDesc(C.Structure):
         ("out", C.c_void_p), ("oN", C.c_longlong), ("oH", C.c_longlong), ("oW", C.c_longlong),
         ("bias", C.c_void_p),
         ("residual", C.c_void_p), ("rN", C.c_longlong), ("rH", C.c_longlong), ("rW", C.c_longlong),
-        ("alpha", C.c_float), ("out_f32", C.c_int), ("block_n", C.c_int),
+        ("alpha", C.c_float), ("out_f32", C.c_int), ("block_n", C.c_int), ("m_tiles_per_cta", C.c_int),
     ]
 
 

@@ -47,20 +47,23 @@ struct TapGemmParams {
   int out_f32;
 };
 
-template <int BN, int STAGES>
+// MT = number of 128-pixel output tiles per CTA that share one weight tile per pipeline stage
+// (MT = 2 halves the weight traffic from L2 per FLOP: the 128-channel layers are L2-bound).
+template <int BN, int STAGES, int MT>
 struct TgCfg {
   static constexpr uint32_t A_BYTES = 128 * 128;
   static constexpr uint32_t B_BYTES = BN * 128;
-  static constexpr uint32_t STAGE_BYTES = A_BYTES + ((B_BYTES + 1023) / 1024) * 1024;
+  static constexpr uint32_t STAGE_BYTES = MT * A_BYTES + ((B_BYTES + 1023) / 1024) * 1024;
   static constexpr uint32_t SMEM = STAGES * STAGE_BYTES + 1024 + 256;
-  static constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  static constexpr uint32_t TMEM_COLS = (MT * BN) < 32 ? 32 : (MT * BN);
+  static constexpr int CTAS_PER_SM = (SMEM <= 110 * 1024 && TMEM_COLS <= 256) ? 2 : 1;
 };
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(192, (BN <= 128 ? 2 : 1))
+template <int BN, int STAGES, int MT>
+__global__ void __launch_bounds__(192, (TgCfg<BN, STAGES, MT>::CTAS_PER_SM))
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ TapGemmParams p) {
-  using Cfg = TgCfg<BN, STAGES>;
+  using Cfg = TgCfg<BN, STAGES, MT>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sBar = base + STAGES * Cfg::STAGE_BYTES;
@@ -69,10 +72,14 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       reinterpret_cast<uint32_t*>(smem_raw + (sBar + 16 * STAGES + 16 - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tw_i = blockIdx.x % p.tiles_w;
-  const int th_i = (blockIdx.x / p.tiles_w) % p.tiles_h;
-  const int tn_i = blockIdx.x / (p.tiles_w * p.tiles_h);
-  const int ow0 = tw_i * p.TW, oh0 = th_i * p.TH, n0 = tn_i * p.TN;
+  int ow0[MT], oh0[MT], n0[MT];
+#pragma unroll
+  for (int j = 0; j < MT; ++j) {
+    const int t = blockIdx.x * MT + j;          // tiles past the end address image >= NB: all masked
+    ow0[j] = (t % p.tiles_w) * p.TW;
+    oh0[j] = ((t / p.tiles_w) % p.tiles_h) * p.TH;
+    n0[j] = (t / (p.tiles_w * p.tiles_h)) * p.TN;
+  }
   const int nt0 = blockIdx.y * BN;
   const int kiters = p.num_taps * p.kchunks;
 
@@ -96,14 +103,16 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (int t = 0; t < p.num_taps; ++t) {
-        const int cw = ow0 + p.tap_w[t], ch = oh0 + p.tap_h[t];
         for (int kc = 0; kc < p.kchunks; ++kc) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
-          mbar_arrive_expect_tx(bar_full + 8 * stage, Cfg::A_BYTES + Cfg::B_BYTES);
-          tma_load_5d(sa, &tmA, bar_full + 8 * stage, p.tap_c[t] + kc * 64, cw, p.tap_p[t], ch, n0);
-          tma_load_3d(sa + Cfg::A_BYTES, &tmB, bar_full + 8 * stage, p.tap_bk[t] + kc * 64, nt0,
-                      p.b_batched ? n0 : 0);
+          mbar_arrive_expect_tx(bar_full + 8 * stage, MT * Cfg::A_BYTES + Cfg::B_BYTES);
+#pragma unroll
+          for (int j = 0; j < MT; ++j)
+            tma_load_5d(sa + j * Cfg::A_BYTES, &tmA, bar_full + 8 * stage, p.tap_c[t] + kc * 64,
+                        ow0[j] + p.tap_w[t], p.tap_p[t], oh0[j] + p.tap_h[t], n0[j]);
+          tma_load_3d(sa + MT * Cfg::A_BYTES, &tmB, bar_full + 8 * stage, p.tap_bk[t] + kc * 64, nt0,
+                      p.b_batched ? n0[0] : 0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -117,10 +126,13 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_after();
         const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t da = make_smem_desc(sa + k * 32, 0, 1024);
-          const uint64_t db = make_smem_desc(sa + Cfg::A_BYTES + k * 32, 0, 1024);
-          umma_bf16(tmem_base, da, db, idesc, (it | k) ? 1u : 0u);
+        for (int j = 0; j < MT; ++j) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = make_smem_desc(sa + j * Cfg::A_BYTES + k * 32, 0, 1024);
+            const uint64_t db = make_smem_desc(sa + MT * Cfg::A_BYTES + k * 32, 0, 1024);
+            umma_bf16(tmem_base + j * BN, da, db, idesc, (it | k) ? 1u : 0u);
+          }
         }
         umma_commit(bar_empty + 8 * stage);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -132,14 +144,16 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int q = warp & 3;
     const int m = q * 32 + lane;                 // tile row == TMEM lane
     const int iw = m % p.TW, ih = (m / p.TW) % p.TH, in_ = m / (p.TW * p.TH);
-    const int ow = ow0 + iw, oh = oh0 + ih, n = n0 + in_;
+    mbar_wait(bar_tfull, 0);
+    tc_fence_after();
+    constexpr int CW = BN < 32 ? 16 : 32;
+#pragma unroll
+    for (int j = 0; j < MT; ++j) {
+    const int ow = ow0[j] + iw, oh = oh0[j] + ih, n = n0[j] + in_;
     const bool valid = (ow < p.Wout) && (oh < p.Hout) && (n < p.NB);
     const long long ooff = n * p.oN + oh * p.oH + ow * p.oW;
     const long long roff = n * p.rN + oh * p.rH + ow * p.rW;
-    mbar_wait(bar_tfull, 0);
-    tc_fence_after();
-    const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    constexpr int CW = BN < 32 ? 16 : 32;
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + j * BN;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += CW) {
       float v[CW];
@@ -210,6 +224,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
+    }
   }
 
   tc_fence_before();
@@ -220,18 +235,19 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int MT>
 static int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const TapGemmParams& p,
                           dim3 grid, cudaStream_t stream) {
-  using Cfg = TgCfg<BN, STAGES>;
+  using Cfg = TgCfg<BN, STAGES, MT>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel<BN, STAGES>,
+    cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel<BN, STAGES, MT>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  tapgemm_kernel<BN, STAGES><<<grid, 192, Cfg::SMEM, stream>>>(tmA, tmB, p);
+  grid.x = (grid.x + MT - 1) / MT;
+  tapgemm_kernel<BN, STAGES, MT><<<grid, 192, Cfg::SMEM, stream>>>(tmA, tmB, p);
   return (int)cudaGetLastError();
 }
 
@@ -263,6 +279,7 @@ struct b2dq_tapgemm_desc {
   float alpha;
   int out_f32;
   int block_n;                   // 0 = auto
+  int m_tiles_per_cta;           // 0 = auto, 1 or 2
 };
 
 int b2dq_tapgemm(const b2dq_tapgemm_desc* d, cudaStream_t stream) {
@@ -304,11 +321,15 @@ int b2dq_tapgemm(const b2dq_tapgemm_desc* d, cudaStream_t stream) {
   p.rN = d->rN; p.rH = d->rH; p.rW = d->rW;
   p.alpha = d->alpha; p.out_f32 = d->out_f32;
   dim3 grid((unsigned)(p.tiles_w * p.tiles_h * tiles_n), (unsigned)((d->Cout + bn - 1) / bn));
+  // two 128-pixel tiles per CTA once there are enough tiles for >= 2 waves of 2 CTAs/SM
+  const bool mt2 = d->m_tiles_per_cta == 2 || (d->m_tiles_per_cta == 0 && grid.x * grid.y >= 8 * 148);
   switch (bn) {
-    case 16: return launch_tapgemm<16, 4>(tmA, tmB, p, grid, stream);
-    case 64: return launch_tapgemm<64, 4>(tmA, tmB, p, grid, stream);
-    case 128: return launch_tapgemm<128, 3>(tmA, tmB, p, grid, stream);
-    case 256: return launch_tapgemm<256, 4>(tmA, tmB, p, grid, stream);
+    case 16: return launch_tapgemm<16, 4, 1>(tmA, tmB, p, grid, stream);
+    case 64: return launch_tapgemm<64, 4, 1>(tmA, tmB, p, grid, stream);
+    case 128:
+      if (mt2) return launch_tapgemm<128, 2, 2>(tmA, tmB, p, grid, stream);
+      return launch_tapgemm<128, 3, 1>(tmA, tmB, p, grid, stream);
+    case 256: return launch_tapgemm<256, 4, 1>(tmA, tmB, p, grid, stream);
     default: return -3;
   }
 }

@@ -110,7 +110,7 @@ def _fill(arr, vals):
 
 def tapgemm(a, a_dims, a_strides, b, b_rows, b_k, taps, kchunks, out, out_off, ostr, wout, hout, nb,
             cout, bias=None, residual=None, res_off=0, rstr=(0, 0, 0), alpha=1.0, out_f32=False,
-            block_n=0, b_batch=1, b_batch_stride=0):
+            block_n=0, b_batch=1, b_batch_stride=0, m_tiles_per_cta=0):
     """taps: list of (dc, dw, dp, dh, bk)."""
     d = TapGemmDesc()
     d.a_ptr = a.data_ptr()
@@ -129,7 +129,10 @@ def tapgemm(a, a_dims, a_strides, b, b_rows, b_k, taps, kchunks, out, out_off, o
     d.bias = _ptr(bias)
     d.residual = None if residual is None else residual.data_ptr() + res_off * 2
     d.rN, d.rH, d.rW = rstr
-    d.alpha, d.out_f32, d.block_n = alpha, int(out_f32), block_n
+    if block_n == 0:
+        m_tiles = -(-wout // d.TW) * -(-hout // d.TH) * -(-nb // d.TN)
+        block_n = _pick_block_n(m_tiles, cout)
+    d.alpha, d.out_f32, d.block_n, d.m_tiles_per_cta = alpha, int(out_f32), block_n, (m_tiles_per_cta or FORCE_MT)
     check(_cabi.lib().b2dq_tapgemm(C.byref(d), _stream()), "tapgemm")
 
 
@@ -231,9 +234,29 @@ def mmgemm(a, a_dims, a_strides, a_mn, b, b_dims, b_strides, b_mn, M, N, kblocks
     check(_cabi.lib().b2dq_mmgemm(C.byref(d), _stream()), "mmgemm")
 
 
+NUM_SMS = 148
+FORCE_MT = 0          # tests / tuning: force m_tiles_per_cta of the tap GEMM (0 = library heuristic)
+
+
 def _wgrad_splits(kblocks, ctas_per_split):
-    target = max(1, (148 * 2) // max(1, ctas_per_split))
+    """Split-K factor so that one launch (ctas_per_split output tiles x splits CTAs, 1 CTA/SM)
+    fills the 148 SMs in whole waves, with at least 4 k-blocks per CTA."""
+    target = max(1, NUM_SMS // max(1, ctas_per_split))
+    if kblocks >= 16 * target * 2:          # plenty of work: two full waves balance better than one
+        target *= 2
     return max(1, min(target, kblocks // 4 if kblocks >= 4 else 1))
+
+
+def _pick_block_n(m_tiles, cout):
+    """128 x BN output tiles: prefer BN=256 (A tile read once) unless that leaves the grid under
+    two waves of 148 SMs, where BN=128 (2 CTAs/SM, epilogue overlap) balances better."""
+    if cout % 256 == 0 and m_tiles * (cout // 256) >= 4 * NUM_SMS:
+        return 256
+    if cout <= 16:
+        return 16
+    if cout <= 64:
+        return 64
+    return 128
 
 
 def conv_wgrad(x, dy, ksize, stride):
@@ -256,7 +279,7 @@ def conv_wgrad(x, dy, ksize, stride):
     ntaps = len(taps)
     mt, nt = (cout + 127) // 128, (cin + 127) // 128
     groups = [taps[i:i + 3] for i in range(0, ntaps, 3)]
-    splits = _wgrad_splits(kblocks, mt * nt * len(groups))
+    splits = _wgrad_splits(kblocks, mt * nt)
     partial = torch.empty(splits, ntaps, cout, cin, dtype=torch.float32, device=x.device)
     for gi, grp in enumerate(groups):
         mmgemm(dy, adims, astrs, True, x, bdims, bstrs, True, cout, cin, kblocks, partial,

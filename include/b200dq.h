@@ -94,6 +94,7 @@ typedef struct b2dq_tapgemm_desc {
   float alpha;
   int out_f32;            /* 0: bf16 output, 1: fp32 output */
   int block_n;            /* 0 = auto (16/64/128/256) */
+  int m_tiles_per_cta;    /* 0 = auto, 1 or 2 (two 128-pixel tiles share each weight tile) */
 } b2dq_tapgemm_desc;
 
 int b2dq_tapgemm(const b2dq_tapgemm_desc* desc, cudaStream_t stream);

@@ -95,9 +95,11 @@ def _ref_conv(x_nhwc, w, b, k, stride):
     return F.conv2d(x, w, b, padding=k // 2)
 
 
+@pytest.mark.parametrize("mt", [1, 2])
 @pytest.mark.parametrize("nb,h,w,cin,cout,k,stride", CONV_CASES)
-def test_conv_fwd_dgrad_wgrad(nb, h, w, cin, cout, k, stride):
+def test_conv_fwd_dgrad_wgrad(nb, h, w, cin, cout, k, stride, mt, monkeypatch):
     from dynamicvectorquantization_b200 import kernels as kn
+    monkeypatch.setattr(kn, "FORCE_MT", mt)       # 1 or 2 output tiles per CTA (both code paths)
     x = _rand_bf(nb, h, w, cin, seed=1)
     wt = _rand_bf(cout, cin, k, k, scale=(cin * k * k) ** -0.5, seed=2).float()
     bias = torch.randn(cout, generator=torch.Generator().manual_seed(3))

@@ -47,7 +47,14 @@ def conv(nb, h, w, cin, cout, k, stride):
     dy = torch.randn(nb, ho, wo, cout, device=dev).to(BF)
     fl = 2.0 * nb * ho * wo * cin * cout * k * k
     r = dict(k=f"conv{k}x{k}s{stride}", nb=nb, hw=h, cin=cin, cout=cout)
+    def fwd_mt(mt):
+        def f():
+            kn.FORCE_MT = mt
+            kn.conv_fwd(x, wp, b, k, stride, cout)
+            kn.FORCE_MT = 0
+        return f
     for name, fn in (("fwd", lambda: kn.conv_fwd(x, wp, b, k, stride, cout)),
+                     ("fwd_mt1", fwd_mt(1)), ("fwd_mt2", fwd_mt(2)),
                      ("dgrad", lambda: kn.conv_dgrad(dy, wd, k, stride, cin, (h, w))),
                      ("wgrad", lambda: kn.conv_wgrad(x, dy, k, stride))):
         ms = timeit(fn, iters=5, warm=2)
