@@ -36,6 +36,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=32, help="images per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--config", default="dqvae-dual-r-05")
+    ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph (N=1)")
     return ap.parse_args()
 
 
@@ -157,7 +158,8 @@ def run_b200(args):
         p.requires_grad_(False)
     model.learning_rate = 4.5e-6 * world * args.batch
     ae_params = [p for n, p in model.named_parameters() if not n.startswith("loss.") and p.requires_grad]
-    opt = torch.optim.Adam(ae_params, lr=model.learning_rate, betas=(0.5, 0.9))
+    use_graph = (world == 1) and not args.no_graph
+    opt = torch.optim.Adam(ae_params, lr=model.learning_rate, betas=(0.5, 0.9), capturable=use_graph)
     net = model
     if world > 1:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
@@ -183,6 +185,33 @@ def run_b200(args):
     for _ in range(max(args.warmup, 3)):         # also runs the 3 EMA warm-up passes of SURVEY 8d
         step(x_dev)
     barrier()
+    # Single-GPU: capture the whole step (forward, backward, EMA update, Adam) in ONE CUDA graph so
+    # the ~1900 launches of a step are replayed without host involvement.
+    graph = None
+    launches_per_step = None
+    if use_graph:
+        try:
+            static_x = x_dev.clone()
+            l0 = kn.launch_count()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_loss = step(static_x)
+            launches_per_step = kn.launch_count() - l0
+            eager_step = step
+
+            def step(x):                          # noqa: F811  (graph replay with the eager signature)
+                if x is not static_x:
+                    static_x.copy_(x, non_blocking=True)
+                graph.replay()
+                return static_loss
+            for _ in range(2):
+                step(static_x)
+            x_dev = static_x
+        except Exception as e:                    # capture is an optimisation, not a requirement
+            sys.stderr.write(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); running eagerly\n")
+            graph = None
+            torch.cuda.synchronize()
+    barrier()
     sampler = ClockSampler(local); sampler.start()
     launches0 = kn.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -194,6 +223,8 @@ def run_b200(args):
     barrier()
     ms = ev0.elapsed_time(ev1)
     launches = kn.launch_count() - launches0
+    if graph is not None:
+        launches = launches_per_step * args.steps   # replayed from the graph, counted at capture
     # end-to-end: host buffers in, loss out, every step
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -227,6 +258,7 @@ def run_b200(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": world * B, "parallelism": f"dp{world}",
                        "step": "fwd + bwd (surrogate L1 + qloss + budget loss) + DDP all-reduce + Adam",
+                       "cuda_graph": graph is not None,
                        "l2": "per-step working set (~40 GB of activations) >> 126 MB L2, no flush needed",
                        "model_tflops_per_step": 3 * FLOP_PER_IMAGE_FWD * B / 1e12},
             "clocks": clocks, "gpu_launches": launches,

@@ -35,8 +35,8 @@ class MmDesc(C.Structure):
     _fields_ = [
         ("a_ptr", C.c_void_p), ("a_dims", C.c_longlong * 5), ("a_strides", C.c_longlong * 5),
         ("b_ptr", C.c_void_p), ("b_dims", C.c_longlong * 5), ("b_strides", C.c_longlong * 5),
-        ("a_mn", C.c_int), ("b_mn", C.c_int), ("ntaps", C.c_int),
-        ("tap_c", C.c_int * 4), ("tap_w", C.c_int * 4), ("tap_p", C.c_int * 4), ("tap_h", C.c_int * 4),
+        ("a_mn", C.c_int), ("b_mn", C.c_int), ("ntaps", C.c_int), ("taps_per_cta", C.c_int),
+        ("tap_c", C.c_int * 12), ("tap_w", C.c_int * 12), ("tap_p", C.c_int * 12), ("tap_h", C.c_int * 12),
         ("KW", C.c_int), ("KH", C.c_int), ("KN", C.c_int),
         ("ktiles_w", C.c_int), ("ktiles_h", C.c_int), ("kblocks", C.c_int),
         ("splits", C.c_int), ("batches", C.c_int),

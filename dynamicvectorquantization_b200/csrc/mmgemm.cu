@@ -16,8 +16,9 @@ namespace b2 {
 
 struct MmParams {
   int a_mn, b_mn;                 // 0 = K-major ([rows][K], K contiguous), 1 = MN-major ([K][rows])
-  int ntaps;                      // accumulators (B-operand shifts), 1..4
-  int tap_c[4], tap_w[4], tap_p[4], tap_h[4];
+  int ntaps;                      // total B-operand shifts (filter taps), 1..12
+  int taps_per_cta;               // accumulators per CTA (1..3); tap groups are folded into grid.x
+  int tap_c[12], tap_w[12], tap_p[12], tap_h[12];
   int KW, KH, KN;                 // MN-major k-block box extents (KW*KH*KN == 64)
   int ktiles_w, ktiles_h;         // k-block -> (kw, kh, kn) decomposition for MN-major operands
   int kblocks;                    // total k-blocks (of 64) in the contraction
@@ -51,7 +52,13 @@ mmgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       reinterpret_cast<uint32_t*>(smem_raw + (sBar + 16 * STAGES + 16 - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * BN;
+  // tap group = fastest grid index: the CTAs working on the same pixel range with different
+  // filter rows run at the same time, so dY / X are fetched from HBM once and hit in L2 after.
+  const int ngroups = (p.ntaps + p.taps_per_cta - 1) / p.taps_per_cta;
+  const int group = blockIdx.x % ngroups;
+  const int tap0 = group * p.taps_per_cta;
+  const int ntl = min(p.taps_per_cta, p.ntaps - tap0);          // taps handled by this CTA
+  const int m0 = (blockIdx.x / ngroups) * 128, n0 = blockIdx.y * BN;
   const int batch = blockIdx.z / p.splits, split = blockIdx.z % p.splits;
   const int per = (p.kblocks + p.splits - 1) / p.splits;
   const int kb0 = split * per;
@@ -77,7 +84,7 @@ mmgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   if (warp == 0) {
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      const uint32_t tx = Cfg::A_BYTES + p.ntaps * Cfg::B_BYTES;
+      const uint32_t tx = Cfg::A_BYTES + ntl * Cfg::B_BYTES;
       for (int kb = kb0; kb < kb1; ++kb) {
         const int kw = kb % p.ktiles_w, kh = (kb / p.ktiles_w) % p.ktiles_h,
                   kn = kb / (p.ktiles_w * p.ktiles_h);
@@ -93,15 +100,16 @@ mmgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             tma_load_5d(sa + g * 8192, &tmA, fb, m0 + 64 * g, kw * p.KW, 0, kh * p.KH,
                         kn * p.KN + batch);
         }
-        for (int t = 0; t < p.ntaps; ++t) {
+        for (int t = 0; t < ntl; ++t) {
           const uint32_t sb = sa + Cfg::A_BYTES + t * Cfg::B_BYTES;
+          const int tg = tap0 + t;
           if (!p.b_mn) {
             tma_load_5d(sb, &tmB, fb, kb * 64, n0, 0, 0, batch);
           } else {
 #pragma unroll
             for (int g = 0; g < BN / 64; ++g)
-              tma_load_5d(sb + g * 8192, &tmB, fb, n0 + 64 * g + p.tap_c[t],
-                          kw * p.KW + p.tap_w[t], p.tap_p[t], kh * p.KH + p.tap_h[t],
+              tma_load_5d(sb + g * 8192, &tmB, fb, n0 + 64 * g + p.tap_c[tg],
+                          kw * p.KW + p.tap_w[tg], p.tap_p[tg], kh * p.KH + p.tap_h[tg],
                           kn * p.KN + batch);
           }
         }
@@ -118,7 +126,7 @@ mmgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         mbar_wait(bar_full + 8 * stage, phase);
         tc_fence_after();
         const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
-        for (int t = 0; t < p.ntaps; ++t) {
+        for (int t = 0; t < ntl; ++t) {
           const uint32_t sb = sa + Cfg::A_BYTES + t * Cfg::B_BYTES;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -141,8 +149,8 @@ mmgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       tc_fence_after();
     }
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    for (int t = 0; t < p.ntaps; ++t) {
-      const long long ooff = blockIdx.z * p.oZ + t * p.oT + static_cast<long long>(m) * p.oM;
+    for (int t = 0; t < ntl; ++t) {
+      const long long ooff = blockIdx.z * p.oZ + (tap0 + t) * p.oT + static_cast<long long>(m) * p.oM;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t r[32];
@@ -155,6 +163,14 @@ mmgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         }
         const int col = n0 + c0;
         if (!valid || col >= p.N) continue;
+        if (col + 32 > p.N) {                       // ragged last columns: element-wise
+          for (int i = 0; i < 32 && col + i < p.N; ++i) {
+            const float o = __uint_as_float(r[i]) * p.alpha;
+            if (p.out_f32) static_cast<float*>(p.out)[ooff + col + i] = o;
+            else static_cast<__nv_bfloat16*>(p.out)[ooff + col + i] = __float2bfloat16_rn(o);
+          }
+          continue;
+        }
         if (p.out_f32) {
           float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + ooff + col);
 #pragma unroll
@@ -228,8 +244,9 @@ struct b2dq_mm_desc {
   const void* a_ptr; long long a_dims[5]; long long a_strides[5];
   const void* b_ptr; long long b_dims[5]; long long b_strides[5];
   int a_mn, b_mn;
-  int ntaps;
-  int tap_c[4], tap_w[4], tap_p[4], tap_h[4];
+  int ntaps;          // total taps (1..12)
+  int taps_per_cta;   // accumulators per CTA (1..3)
+  int tap_c[12], tap_w[12], tap_p[12], tap_h[12];
   int KW, KH, KN;
   int ktiles_w, ktiles_h, kblocks;
   int splits, batches;
@@ -241,10 +258,12 @@ struct b2dq_mm_desc {
 };
 
 int b2dq_mmgemm(const b2dq_mm_desc* d, cudaStream_t stream) {
-  if (!d || d->ntaps < 1 || d->ntaps > 3 || d->splits < 1 || d->batches < 1) return -1;
+  if (!d || d->ntaps < 1 || d->ntaps > 12 || d->splits < 1 || d->batches < 1) return -1;
+  const int tpc = d->taps_per_cta > 0 ? d->taps_per_cta : (d->ntaps < 3 ? d->ntaps : 3);
+  if (tpc > 3) return -1;
   if (d->M <= 0 || d->N <= 0) return 0;
-  int bn = d->block_n ? d->block_n : ((d->N % 256 == 0 && d->ntaps == 1) ? 256 : 128);
-  if (bn * d->ntaps > 512) return -2;
+  int bn = d->block_n ? d->block_n : ((d->N % 256 == 0 && tpc == 1) ? 256 : 128);
+  if (bn * tpc > 512) return -2;
   if ((d->a_mn || d->b_mn) && d->KW * d->KH * d->KN != 64) return -3;
   CUtensorMap tmA, tmB;
   {
@@ -264,8 +283,9 @@ int b2dq_mmgemm(const b2dq_mm_desc* d, cudaStream_t stream) {
     if (r) return r - 1000;
   }
   MmParams p;
-  p.a_mn = d->a_mn; p.b_mn = d->b_mn; p.ntaps = d->ntaps;
-  for (int i = 0; i < 4; ++i) {
+  p.a_mn = d->a_mn; p.b_mn = d->b_mn; p.ntaps = d->ntaps; p.taps_per_cta = tpc;
+  const int ngroups = (d->ntaps + tpc - 1) / tpc;
+  for (int i = 0; i < 12; ++i) {
     p.tap_c[i] = d->tap_c[i]; p.tap_w[i] = d->tap_w[i]; p.tap_p[i] = d->tap_p[i]; p.tap_h[i] = d->tap_h[i];
   }
   p.KW = d->KW ? d->KW : 64; p.KH = d->KH ? d->KH : 1; p.KN = d->KN ? d->KN : 1;
@@ -275,13 +295,13 @@ int b2dq_mmgemm(const b2dq_mm_desc* d, cudaStream_t stream) {
   p.M = d->M; p.N = d->N;
   p.out = d->out; p.oZ = d->oZ; p.oT = d->oT; p.oM = d->oM;
   p.alpha = d->alpha; p.out_f32 = d->out_f32;
-  dim3 grid((unsigned)((d->M + 127) / 128), (unsigned)((d->N + bn - 1) / bn),
+  dim3 grid((unsigned)(((d->M + 127) / 128) * ngroups), (unsigned)((d->N + bn - 1) / bn),
             (unsigned)(d->batches * d->splits));
   if (bn == 128) {
-    if (d->ntaps == 1) return launch_mm<128, 4, 1>(tmA, tmB, p, grid, stream);
+    if (tpc == 1) return launch_mm<128, 4, 1>(tmA, tmB, p, grid, stream);
     return launch_mm<128, 3, 3>(tmA, tmB, p, grid, stream) ;
   } else if (bn == 256) {
-    if (d->ntaps != 1) return -4;
+    if (tpc != 1) return -4;
     return launch_mm<256, 4, 1>(tmA, tmB, p, grid, stream);
   }
   return -5;

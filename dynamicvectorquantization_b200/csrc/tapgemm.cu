@@ -54,7 +54,7 @@ struct TgCfg {
   static constexpr uint32_t A_BYTES = 128 * 128;
   static constexpr uint32_t B_BYTES = BN * 128;
   static constexpr uint32_t STAGE_BYTES = MT * A_BYTES + ((B_BYTES + 1023) / 1024) * 1024;
-  static constexpr uint32_t SMEM = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr uint32_t SMEM = STAGES * STAGE_BYTES + 1024 + 256 + 1024;   // + bias slice
   static constexpr uint32_t TMEM_COLS = (MT * BN) < 32 ? 32 : (MT * BN);
   static constexpr int CTAS_PER_SM = (SMEM <= 110 * 1024 && TMEM_COLS <= 256) ? 2 : 1;
 };
@@ -144,86 +144,110 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int q = warp & 3;
     const int m = q * 32 + lane;                 // tile row == TMEM lane
     const int iw = m % p.TW, ih = (m / p.TW) % p.TH, in_ = m / (p.TW * p.TH);
-    mbar_wait(bar_tfull, 0);
-    tc_fence_after();
     constexpr int CW = BN < 32 ? 16 : 32;
+    constexpr int RV = BN / 8;                     // uint4 (8 bf16) per residual row slice
+    // While the main loop runs, the epilogue warps fetch everything that does not depend on the
+    // accumulator: the bias slice (to shared memory) and this thread's residual row (to registers),
+    // so that after the accumulator barrier only TMEM loads, FMAs and stores remain.
+    float* bias_s = reinterpret_cast<float*>(smem_raw + (sBar + 256 - smem_u32(smem_raw)));
+    const bool vec_ok = ((p.Cout & 7) == 0) && (nt0 + BN <= p.Cout);
+    {
+      const int t = threadIdx.x - 64;              // 0..127
+      for (int c = t; c < BN; c += 128)
+        bias_s[c] = (p.bias && nt0 + c < p.Cout) ? p.bias[nt0 + c] : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+    bool valid[MT];
+    long long ooff[MT], roff[MT];
 #pragma unroll
     for (int j = 0; j < MT; ++j) {
-    const int ow = ow0[j] + iw, oh = oh0[j] + ih, n = n0[j] + in_;
-    const bool valid = (ow < p.Wout) && (oh < p.Hout) && (n < p.NB);
-    const long long ooff = n * p.oN + oh * p.oH + ow * p.oW;
-    const long long roff = n * p.rN + oh * p.rH + ow * p.rW;
-    const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + j * BN;
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += CW) {
-      float v[CW];
-      if constexpr (CW == 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(trow + c0, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
-      } else {
-        uint32_t r[16];
-        tmem_ld_32x16(trow + c0, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
-      }
-      const int col = nt0 + c0;
-      if (!valid || col >= p.Cout) continue;
-      const bool full = (col + CW <= p.Cout) && ((p.Cout & 7) == 0);
-      if (full) {
-        if (p.bias) {
-#pragma unroll
-          for (int i = 0; i < CW; i += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col + i));
-            v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
-          }
-        }
-        if (p.residual) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + roff + col);
-#pragma unroll
-          for (int i = 0; i < CW / 8; ++i) {
-            const uint4 u = __ldg(rp + i);
-            v[8 * i + 0] += bf16_lo(u.x); v[8 * i + 1] += bf16_hi(u.x);
-            v[8 * i + 2] += bf16_lo(u.y); v[8 * i + 3] += bf16_hi(u.y);
-            v[8 * i + 4] += bf16_lo(u.z); v[8 * i + 5] += bf16_hi(u.z);
-            v[8 * i + 6] += bf16_lo(u.w); v[8 * i + 7] += bf16_hi(u.w);
-          }
-        }
-        if (p.out_f32) {
-          float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + ooff + col);
-#pragma unroll
-          for (int i = 0; i < CW / 4; ++i)
-            op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        } else {
-          uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + ooff + col);
-#pragma unroll
-          for (int i = 0; i < CW / 8; ++i) {
-            uint4 u;
-            u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
-            u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-            u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-            u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-            op[i] = u;
-          }
-        }
-      } else {
-        // ragged channel count (e.g. Cout = 3): element-wise tail
-#pragma unroll
-        for (int i = 0; i < CW; ++i) {
-          const int c = col + i;
-          if (c < p.Cout) {
-            float o = v[i];
-            if (p.bias) o += p.bias[c];
-            if (p.residual) o += __bfloat162float(p.residual[roff + c]);
-            if (p.out_f32) static_cast<float*>(p.out)[ooff + c] = o;
-            else static_cast<__nv_bfloat16*>(p.out)[ooff + c] = __float2bfloat16_rn(o);
-          }
-        }
-      }
+      const int ow = ow0[j] + iw, oh = oh0[j] + ih, n = n0[j] + in_;
+      valid[j] = (ow < p.Wout) && (oh < p.Hout) && (n < p.NB);
+      ooff[j] = n * p.oN + oh * p.oH + ow * p.oW;
+      roff[j] = n * p.rN + oh * p.rH + ow * p.rW;
     }
+    uint4 res[RV > 0 ? RV : 1];
+    const bool pre_res = (BN >= 64) && p.residual && vec_ok;
+    if (pre_res && valid[0]) {
+      const uint4* rp = reinterpret_cast<const uint4*>(p.residual + roff[0] + nt0);
+#pragma unroll
+      for (int i = 0; i < RV; ++i) res[i] = __ldg(rp + i);
+    }
+    mbar_wait(bar_tfull, 0);
+    tc_fence_after();
+#pragma unroll
+    for (int j = 0; j < MT; ++j) {
+      if (j > 0 && pre_res && valid[j]) {          // next tile's residual row (registers are free again)
+        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + roff[j] + nt0);
+#pragma unroll
+        for (int i = 0; i < RV; ++i) res[i] = __ldg(rp + i);
+      }
+      const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + j * BN;
+#pragma unroll
+      for (int c0 = 0; c0 < BN; c0 += CW) {
+        float v[CW];
+        if constexpr (CW == 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(trow + c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaf(__uint_as_float(r[i]), p.alpha, bias_s[c0 + i]);
+        } else {
+          uint32_t r[16];
+          tmem_ld_32x16(trow + c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = fmaf(__uint_as_float(r[i]), p.alpha, bias_s[c0 + i]);
+        }
+        const int col = nt0 + c0;
+        if (!valid[j] || col >= p.Cout) continue;
+        if (vec_ok) {
+          if (p.residual) {
+            if constexpr (BN >= 64) {
+#pragma unroll
+              for (int i = 0; i < CW / 8; ++i) {
+                const uint4 u = res[c0 / 8 + i];
+                v[8 * i + 0] += bf16_lo(u.x); v[8 * i + 1] += bf16_hi(u.x);
+                v[8 * i + 2] += bf16_lo(u.y); v[8 * i + 3] += bf16_hi(u.y);
+                v[8 * i + 4] += bf16_lo(u.z); v[8 * i + 5] += bf16_hi(u.z);
+                v[8 * i + 6] += bf16_lo(u.w); v[8 * i + 7] += bf16_hi(u.w);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < CW; ++i) v[i] += __bfloat162float(p.residual[roff[j] + col + i]);
+            }
+          }
+          if (p.out_f32) {
+            float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + ooff[j] + col);
+#pragma unroll
+            for (int i = 0; i < CW / 4; ++i)
+              op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          } else {
+            uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + ooff[j] + col);
+#pragma unroll
+            for (int i = 0; i < CW / 8; ++i) {
+              uint4 u;
+              u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+              u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+              u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+              u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+              op[i] = u;
+            }
+          }
+        } else {
+          // ragged channel count (e.g. Cout = 3): element-wise tail
+#pragma unroll
+          for (int i = 0; i < CW; ++i) {
+            const int c = col + i;
+            if (c < p.Cout) {
+              float o = v[i];
+              if (p.residual) o += __bfloat162float(p.residual[roff[j] + c]);
+              if (p.out_f32) static_cast<float*>(p.out)[ooff[j] + c] = o;
+              else static_cast<__nv_bfloat16*>(p.out)[ooff[j] + c] = __float2bfloat16_rn(o);
+            }
+          }
+        }
+      }
     }
   }
 

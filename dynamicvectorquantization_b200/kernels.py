@@ -216,12 +216,12 @@ def conv_dgrad(dy, wdpack, ksize, stride, cin, in_hw):
 
 def mmgemm(a, a_dims, a_strides, a_mn, b, b_dims, b_strides, b_mn, M, N, kblocks, out, ostr,
            taps=((0, 0, 0, 0),), kbox=(64, 1, 1), ktiles=(0, 0), splits=1, batches=1, alpha=1.0,
-           out_f32=False, block_n=0, out_off=0):
+           out_f32=False, block_n=0, out_off=0, taps_per_cta=0):
     d = MmDesc()
     d.a_ptr, d.b_ptr = a.data_ptr(), b.data_ptr()
     _fill(d.a_dims, a_dims); _fill(d.a_strides, a_strides)
     _fill(d.b_dims, b_dims); _fill(d.b_strides, b_strides)
-    d.a_mn, d.b_mn, d.ntaps = int(a_mn), int(b_mn), len(taps)
+    d.a_mn, d.b_mn, d.ntaps, d.taps_per_cta = int(a_mn), int(b_mn), len(taps), taps_per_cta
     for i, (tc, tw, tp, th) in enumerate(taps):
         d.tap_c[i], d.tap_w[i], d.tap_p[i], d.tap_h[i] = tc, tw, tp, th
     d.KW, d.KH, d.KN = kbox
@@ -278,13 +278,12 @@ def conv_wgrad(x, dy, ksize, stride):
     kblocks = ktw * kth * ((nb + kn - 1) // kn)
     ntaps = len(taps)
     mt, nt = (cout + 127) // 128, (cin + 127) // 128
-    groups = [taps[i:i + 3] for i in range(0, ntaps, 3)]
-    splits = _wgrad_splits(kblocks, mt * nt)
+    ngroups = (ntaps + 2) // 3                 # <= 3 taps (TMEM accumulators) per CTA, folded into the grid
+    splits = _wgrad_splits(kblocks, mt * nt * ngroups)
     partial = torch.empty(splits, ntaps, cout, cin, dtype=torch.float32, device=x.device)
-    for gi, grp in enumerate(groups):
-        mmgemm(dy, adims, astrs, True, x, bdims, bstrs, True, cout, cin, kblocks, partial,
-               (ntaps * cout * cin, cout * cin, cin), taps=grp, kbox=(kw, kh, kn), ktiles=(ktw, kth),
-               splits=splits, out_f32=True, block_n=128, out_off=gi * 3 * cout * cin)
+    mmgemm(dy, adims, astrs, True, x, bdims, bstrs, True, cout, cin, kblocks, partial,
+           (ntaps * cout * cin, cout * cin, cin), taps=taps, kbox=(kw, kh, kn), ktiles=(ktw, kth),
+           splits=splits, out_f32=True, block_n=128, taps_per_cta=min(3, ntaps))
     dw = torch.empty(cout, cin, ksize, ksize, dtype=torch.float32, device=x.device)
     check(_cabi.lib().b2dq_wgrad_reduce(_ptr(partial), _ptr(dw), splits, ntaps, cout, cin, 0, _stream()),
           "wgrad_reduce")

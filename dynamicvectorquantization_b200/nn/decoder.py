@@ -67,7 +67,12 @@ class FourierPositionEmbedding(nn.Module):
         self.lff = LFF(hidden_size)
 
     def bias(self, device):
-        return self.lff(self.coord.to(device))                 # [1, C, h, w]
+        dev = torch.device(device)
+        cached = getattr(self, "_coord_dev", None)
+        if cached is None or cached.device != dev:             # one H2D copy per device, not per step
+            cached = self.coord.to(dev)
+            self._coord_dev = cached
+        return self.lff(cached)                                # [1, C, h, w]
 
     def forward(self, x):
         return x + self.bias(x.device)

@@ -243,8 +243,9 @@ def _mm(a, a_mn, b, b_mn, M, N, K, out, alpha=1.0, out_f32=False):
 
     ad, as_ = view(a, a_mn, M)
     bd, bs = view(b, b_mn, N)
-    kn.mmgemm(a, ad, as_, a_mn, b, bd, bs, b_mn, M, N, K // 64, out, (M * N, 0, N),
-              kbox=(64, 1, 1), ktiles=(K // 64, 1), batches=bsz, alpha=alpha, out_f32=out_f32)
+    kb = (K + 63) // 64                       # a ragged last block reads zeros (TMA out-of-bounds fill)
+    kn.mmgemm(a, ad, as_, a_mn, b, bd, bs, b_mn, M, N, kb, out, (M * N, 0, N),
+              kbox=(64, 1, 1), ktiles=(kb, 1), batches=bsz, alpha=alpha, out_f32=out_f32)
 
 
 class Upsample2xFn(torch.autograd.Function):

@@ -110,8 +110,9 @@ typedef struct b2dq_mm_desc {
   const void* a_ptr; long long a_dims[5]; long long a_strides[5];
   const void* b_ptr; long long b_dims[5]; long long b_strides[5];
   int a_mn, b_mn;
-  int ntaps;              /* 1..3 accumulators */
-  int tap_c[4], tap_w[4], tap_p[4], tap_h[4];
+  int ntaps;              /* total B shifts (filter taps), 1..12 */
+  int taps_per_cta;       /* accumulators per CTA, 1..3 (0 = auto); tap groups are spread over grid.x */
+  int tap_c[12], tap_w[12], tap_p[12], tap_h[12];
   int KW, KH, KN;
   int ktiles_w, ktiles_h, kblocks;
   int splits, batches;
