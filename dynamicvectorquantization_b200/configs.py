@@ -97,6 +97,37 @@ def scaled_dual_config(ch=64, resolution=64, z_channels=64, codebook_size=128, a
     return cfg
 
 
+def scaled_triple_config(ch=64, resolution=128, z_channels=64, codebook_size=128):
+    """dqvae-triple-r-03-03 topology at reduced width / resolution (parity tests)."""
+    cfg = stage1_config("dqvae-triple-r-03-03")
+    p = cfg["params"]
+    lat = resolution // 8
+    p["encoderconfig"]["params"].update(ch=ch, resolution=resolution, z_channels=z_channels,
+                                        attn_resolutions=[lat // 4, lat // 2, lat])
+    p["encoderconfig"]["params"]["router_config"]["params"]["num_channels"] = z_channels
+    p["decoderconfig"]["params"].update(ch=ch, in_ch=z_channels, resolution=resolution,
+                                        attn_resolutions=[lat], latent_size=lat)
+    p["vqconfig"]["params"].update(codebook_size=codebook_size, codebook_dim=z_channels)
+    p["lossconfig"]["params"]["budget_loss_config"]["params"].update(
+        min_grain_size=lat // 4, median_grain_size=lat // 2, max_grain_size=lat)
+    p.update(quant_before_dim=z_channels, quant_after_dim=z_channels)
+    return cfg
+
+
+def scaled_entropy_config(json_path, ch=64, resolution=64, z_channels=64, codebook_size=128):
+    """dqvae-entropy-dual-r05 topology at reduced width; `json_path` holds the entropy thresholds."""
+    cfg = stage1_config("dqvae-entropy-dual-r05")
+    small = scaled_dual_config(ch=ch, resolution=resolution, z_channels=z_channels, codebook_size=codebook_size)
+    p, sp = cfg["params"], small["params"]
+    router = p["encoderconfig"]["params"]["router_config"]
+    router["params"]["json_path"] = json_path
+    p["encoderconfig"]["params"] = dict(sp["encoderconfig"]["params"], router_config=router, update_router=False)
+    p["decoderconfig"], p["vqconfig"] = sp["decoderconfig"], sp["vqconfig"]
+    p.update(quant_before_dim=z_channels, quant_after_dim=z_channels,
+             entropy_patch_size=resolution // (resolution // 8 // 2), image_size=resolution)
+    return cfg
+
+
 def build_model(cfg):
     activate_overlay()
     from dynamicvectorquantization_b200.config import instantiate_from_config

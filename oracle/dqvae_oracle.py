@@ -44,6 +44,32 @@ SMALL_CFG = dict(
 )
 
 
+TRIPLE_CFG = dict(
+    ch=128, ch_mult=(1, 1, 2, 2, 4, 4), num_res_blocks=2, attn_resolutions=(8, 16, 32), in_channels=3,
+    resolution=256, z_channels=256,                        # dqvae-triple-r-03-03_imagenet.yml:6-16
+    dec_ch=128, dec_ch_mult=(1, 1, 2, 2), dec_attn_resolutions=(32,), out_ch=3, latent_size=32,
+    codebook_size=1024, codebook_dim=256, beta=0.25, decay=0.99,
+    router="feature", grains=3,
+)
+TINY_TRIPLE_CFG = dict(
+    ch=32, ch_mult=(1, 1, 2, 2, 4, 4), num_res_blocks=2, attn_resolutions=(2, 4, 8), in_channels=3,
+    resolution=64, z_channels=64,
+    dec_ch=32, dec_ch_mult=(1, 1, 2, 2), dec_attn_resolutions=(8,), out_ch=3, latent_size=8,
+    codebook_size=128, codebook_dim=64, beta=0.25, decay=0.99,
+    router="feature", grains=3,
+)
+SMALL_TRIPLE_CFG = dict(
+    ch=64, ch_mult=(1, 1, 2, 2, 4, 4), num_res_blocks=2, attn_resolutions=(4, 8, 16), in_channels=3,
+    resolution=128, z_channels=64,
+    dec_ch=64, dec_ch_mult=(1, 1, 2, 2), dec_attn_resolutions=(16,), out_ch=3, latent_size=16,
+    codebook_size=128, codebook_dim=64, beta=0.25, decay=0.99,
+    router="feature", grains=3,
+)
+# entropy-routed dual model (dqvae-entropy-dual-r05_imagenet.yml): no router parameters
+SMALL_ENTROPY_CFG = dict(SMALL_CFG, router="entropy")
+TINY_ENTROPY_CFG = dict(TINY_CFG, router="entropy")
+
+
 # --------------------------------------------------------------------------- parameter inventory
 def _conv(shapes, p, cin, cout, k):
     shapes[p + ".weight"] = (cout, cin, k, k)
@@ -88,20 +114,25 @@ def encoder_shapes(cfg, prefix="encoder"):
         if lvl != len(mult) - 1:
             _conv(s, f"{prefix}.down.{lvl}.downsample.conv", block_in, block_in, 3)
             res //= 2
-    for grain, c in (("coarse", block_in), ("fine", block_in // (mult[-1] // mult[-2]))):
+    if cfg.get("grains", 2) == 3:                         # EncoderTriple.py:63-93
+        c_med = block_in // (mult[-1] // mult[-2])
+        heads = (("coarse", block_in), ("median", c_med), ("fine", c_med // (mult[-2] // mult[-3])))
+    else:
+        heads = (("coarse", block_in), ("fine", block_in // (mult[-1] // mult[-2])))
+    for grain, c in heads:
         _resblock(s, f"{prefix}.mid_{grain}.block_1", c, c)
         _attn(s, f"{prefix}.mid_{grain}.attn_1", c)
         _resblock(s, f"{prefix}.mid_{grain}.block_2", c, c)
         _norm(s, f"{prefix}.norm_out_{grain}", c)
         _conv(s, f"{prefix}.conv_out_{grain}", c, cfg["z_channels"], 3)
-    if cfg["router"] == "feature":                       # RouterDual.py:7-32 (2layer-fc-SiLu, group-32)
-        z = cfg["z_channels"]
-        s[f"{prefix}.router.gate.0.weight"] = (2 * z, 2 * z)
-        s[f"{prefix}.router.gate.0.bias"] = (2 * z,)
-        s[f"{prefix}.router.gate.2.weight"] = (2, 2 * z)
-        s[f"{prefix}.router.gate.2.bias"] = (2,)
-        _norm(s, f"{prefix}.router.feature_norm_fine", z)
-        _norm(s, f"{prefix}.router.feature_norm_coarse", z)
+    if cfg["router"] == "feature":                       # RouterDual.py:7-32 / RouterTriple.py:6-44
+        z, ng = cfg["z_channels"], len(heads)
+        s[f"{prefix}.router.gate.0.weight"] = (ng * z, ng * z)
+        s[f"{prefix}.router.gate.0.bias"] = (ng * z,)
+        s[f"{prefix}.router.gate.2.weight"] = (ng, ng * z)
+        s[f"{prefix}.router.gate.2.bias"] = (ng,)
+        for grain, _ in heads:
+            _norm(s, f"{prefix}.router.feature_norm_{grain}", z)
     return s
 
 
@@ -299,6 +330,62 @@ def dual_encoder(sd, cfg, x, x_entropy=None, forced_gate=None, entropy_threshold
                 h_fine=h_fine, h_coarse=h_coarse)
 
 
+def triple_router(sd, p, h_fine, h_median, h_coarse):
+    """RouterTriple.py:46-55."""
+    def gn(t, n):
+        return F.group_norm(t, 32, sd[f"{p}.feature_norm_{n}.weight"], sd[f"{p}.feature_norm_{n}.bias"], eps=1e-6)
+    z = torch.cat([gn(h_coarse, "coarse"), F.avg_pool2d(gn(h_median, "median"), 2, 2),
+                   F.avg_pool2d(gn(h_fine, "fine"), 4, 4)], dim=1).permute(0, 2, 3, 1)
+    z = F.silu(F.linear(z, sd[p + ".gate.0.weight"], sd[p + ".gate.0.bias"]))
+    return F.linear(z, sd[p + ".gate.2.weight"], sd[p + ".gate.2.bias"])
+
+
+def triple_encoder(sd, cfg, x, forced_gate=None, p="encoder"):
+    """EncoderTriple.py:95-183 in eval mode (0 coarse / 1 median / 2 fine; masks 1/16, 1/4, 1)."""
+    nlev = len(cfg["ch_mult"])
+    res = cfg["resolution"]
+    h = conv2d(sd, p + ".conv_in", x)
+    taps = {}
+    for lvl in range(nlev):
+        for b in range(cfg["num_res_blocks"]):
+            h = resnet_block(sd, f"{p}.down.{lvl}.block.{b}", h)
+            if res in cfg["attn_resolutions"]:
+                h = attn_block(sd, f"{p}.down.{lvl}.attn.{b}", h)
+        taps[lvl] = h
+        if lvl != nlev - 1:
+            h = downsample(sd, f"{p}.down.{lvl}.downsample", h)
+            res //= 2
+    heads = {}
+    for grain, t in (("coarse", taps[nlev - 1]), ("median", taps[nlev - 2]), ("fine", taps[nlev - 3])):
+        t = resnet_block(sd, f"{p}.mid_{grain}.block_1", t)
+        t = attn_block(sd, f"{p}.mid_{grain}.attn_1", t)
+        t = resnet_block(sd, f"{p}.mid_{grain}.block_2", t)
+        heads[grain] = conv2d(sd, f"{p}.conv_out_{grain}", swish(group_norm(sd, f"{p}.norm_out_{grain}", t)))
+    gate = forced_gate if forced_gate is not None else triple_router(
+        sd, p + ".router", heads["fine"], heads["median"], heads["coarse"])
+    gate = gate.permute(0, 3, 1, 2)
+    indices = gate.argmax(dim=1)
+    up_c = heads["coarse"].repeat_interleave(4, dim=-1).repeat_interleave(4, dim=-2)
+    up_m = heads["median"].repeat_interleave(2, dim=-1).repeat_interleave(2, dim=-2)
+    idx = indices.repeat_interleave(4, dim=-1).repeat_interleave(4, dim=-2).unsqueeze(1)
+    h_triple = torch.where(idx == 0, up_c, torch.where(idx == 1, up_m, heads["fine"]))
+    one = torch.ones((), dtype=torch.float32)
+    mask = torch.where(idx == 0, 0.0625 * one, torch.where(idx == 1, 0.25 * one, one))
+    return dict(h_dual=h_triple, indices=indices, codebook_mask=mask, gate=gate)
+
+
+def budget_loss_triple(gate, target_fine=0.3, target_median=0.3, gamma=1.0, min_grain=8, median_grain=16,
+                       max_grain=32):
+    """modules/dynamic_modules/budget.py:43-59."""
+    n = gate.size(0)
+    med = (gate[:, 0] + 4.0 * gate[:, 1] + gate[:, 2]).sum() / n - min_grain ** 2
+    r_med = med / (median_grain ** 2 - min_grain ** 2)
+    fine = (gate[:, 0] + 16.0 * gate[:, 2] + gate[:, 1]).sum() / n - min_grain ** 2
+    r_fine = fine / (max_grain ** 2 - min_grain ** 2)
+    return gamma * F.mse_loss(r_fine, torch.full_like(r_fine, target_fine)) + \
+        F.mse_loss(r_med, torch.full_like(r_med, target_median))
+
+
 def position_bias(sd, cfg, p="decoder"):
     """fourier_embedding.py:5-55 (linspace coords, sin(conv1x1)) + DecoderPositional.py:27-39."""
     n = cfg["latent_size"]
@@ -364,8 +451,13 @@ def model_forward(sd, cfg, x, search_bf16=False, forced_gate=None, x_entropy=Non
                   forced_codes=None):
     """models/stage1_dynamic/dqvae_dual_feat.py:59-78: encode -> quant_conv -> VQ -> post_quant_conv
     -> decode.  Returns dict(xrec, qloss, codes, indices, gate, h_dual)."""
-    enc = dual_encoder(sd, cfg, x, x_entropy=x_entropy, forced_gate=forced_gate,
-                       entropy_threshold=entropy_threshold)
+    if cfg.get("grains", 2) == 3:
+        enc = triple_encoder(sd, cfg, x, forced_gate=forced_gate)
+    else:
+        if cfg["router"] == "entropy" and x_entropy is None and forced_gate is None:
+            x_entropy = patch_entropy(x, patch=cfg["resolution"] // (cfg["latent_size"] // 2))
+        enc = dual_encoder(sd, cfg, x, x_entropy=x_entropy, forced_gate=forced_gate,
+                           entropy_threshold=entropy_threshold)
     h = conv2d(sd, "quant_conv", enc["h_dual"])
     quant, qloss, codes = vq_forward(sd, cfg, h, enc["codebook_mask"], search_bf16=search_bf16,
                                      forced_codes=forced_codes)

@@ -138,8 +138,66 @@ def model_goldens(cfg, tag, batch, seed):
          loss=loss, grad_norm_names=np.array(names), grad_norms=np.array([gnorm[n] for n in names]), **gsel)
 
 
+def triple_entropy_goldens():
+    """Tiny triple-grain model (EncoderTriple + RouterTriple + triple budget loss) and the entropy
+    branch (Entropy module + fixed-threshold router) of the reference, eval mode."""
+    import json
+    import tempfile
+    from modules.dynamic_modules.budget import (BudgetConstraint_NormedSeperateRatioMSE_TripleGrain,
+                                                BudgetConstraint_RatioMSE_DualGrain)
+    conf = yaml.safe_load(open(os.path.join(REF, "configs/stage1/dqvae-triple-r-03-03_imagenet.yml")))["model"]["params"]
+    cfg = orc.TINY_TRIPLE_CFG
+    enc_p = dict(conf["encoderconfig"]["params"], ch=cfg["ch"], resolution=cfg["resolution"],
+                 z_channels=cfg["z_channels"], attn_resolutions=list(cfg["attn_resolutions"]))
+    enc_p["router_config"] = dict(enc_p["router_config"], params=dict(enc_p["router_config"]["params"],
+                                                                      num_channels=cfg["z_channels"]))
+    dec_p = dict(conf["decoderconfig"]["params"], ch=cfg["dec_ch"], in_ch=cfg["z_channels"],
+                 resolution=cfg["resolution"], attn_resolutions=list(cfg["dec_attn_resolutions"]),
+                 latent_size=cfg["latent_size"])
+    m = nn.Module()
+    m.encoder = instantiate_from_config(dict(target=conf["encoderconfig"]["target"], params=enc_p))
+    m.decoder = instantiate_from_config(dict(target=conf["decoderconfig"]["target"], params=dec_p))
+    m.quantize = instantiate_from_config(dict(target=conf["vqconfig"]["target"], params=dict(
+        conf["vqconfig"]["params"], codebook_size=cfg["codebook_size"], codebook_dim=cfg["codebook_dim"])))
+    m.quant_conv = nn.Conv2d(cfg["z_channels"], cfg["codebook_dim"], 1)
+    m.post_quant_conv = nn.Conv2d(cfg["codebook_dim"], cfg["z_channels"], 1)
+    shapes = orc.model_shapes(cfg)
+    ref_sd = m.state_dict()
+    assert set(ref_sd) == set(shapes), sorted(set(ref_sd) ^ set(shapes))
+    assert all(tuple(ref_sd[k].shape) == tuple(shapes[k]) for k in shapes)
+    m.load_state_dict(orc.make_weights(shapes, seed=5), strict=True)
+    m.eval()
+    g = torch.Generator().manual_seed(55)
+    x = torch.rand(2, 3, cfg["resolution"], cfg["resolution"], generator=g) * 2 - 1
+    hd = m.encoder(x, None)
+    h = m.quant_conv(hd["h_triple"])
+    quant, qloss, (_, _, codes) = m.quantize(x=h, temp=0.0, codebook_mask=hd["codebook_mask"])
+    xrec = m.decoder(m.post_quant_conv(quant), None)
+    budget = BudgetConstraint_NormedSeperateRatioMSE_TripleGrain(
+        target_fine_ratio=0.3, target_median_ratio=0.3, gamma=1.0, min_grain_size=2, median_grain_size=4,
+        max_grain_size=8)(hd["gate"])
+    save("model_tiny_triple.npz", x=x, xrec=xrec, qloss=qloss, codes=codes.to(torch.int16),
+         indices=hd["indices"].to(torch.int8), gate=hd["gate"], mask=hd["codebook_mask"], budget=budget)
+
+    # entropy branch: Entropy module + fixed-threshold router + dual budget loss
+    from models.stage1_dynamic.dqvae_dual_entropy import Entropy
+    from modules.dynamic_modules.RouterDual import DualGrainFixedEntropyRouter
+    xe = torch.rand(2, 3, 64, 64, generator=g) * 2 - 1
+    xe[:, :, :32] = xe[:, :, :32].mean(dim=(2, 3), keepdim=True) + 0.02 * xe[:, :, :32]   # flat top half
+    ent = Entropy(16, 64, 64)(xe)
+    with tempfile.NamedTemporaryFile("w", suffix=".json", delete=False) as f:
+        json.dump({"50": 1.5}, f)
+    router = DualGrainFixedEntropyRouter(json_path=f.name, fine_grain_ratito=0.5)
+    gate_e = router(entropy=ent)
+    bud = BudgetConstraint_RatioMSE_DualGrain(target_ratio=0.5, gamma=10.0, min_grain_size=4, max_grain_size=8,
+                                              calculate_all=True)(gate_e.permute(0, 3, 1, 2).float())
+    save("entropy_small.npz", x=xe, entropy=ent, gate=gate_e, threshold=1.5, budget=bud)
+
+
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["vq", "tiny", "dual"]
+    what = sys.argv[1:] or ["vq", "tiny", "dual", "variants"]
+    if "variants" in what:
+        triple_entropy_goldens()
     if "vq" in what:
         vq_goldens()
     if "tiny" in what:

@@ -39,7 +39,10 @@ def test_small_model_forward_backward_parity(batch):
     g = torch.Generator().manual_seed(5)
     x = torch.rand(batch, 3, ocfg["resolution"], ocfg["resolution"], generator=g) * 2 - 1
     xrec, qloss, indices, gate = model(x.cuda())
-    loss = (xrec - x.cuda()).abs().mean() + qloss
+    # smooth reconstruction loss for the gradient comparison: with L1, |xrec - x| sign flips caused by
+    # the ~1e-2 bf16 forward noise alone change the gradient by O(10 %), which says nothing about
+    # the backward kernels
+    loss = (xrec - x.cuda()).pow(2).mean() + qloss
     loss.backward()
     torch.cuda.synchronize()
     # oracle with the product's routing decisions and codes replayed
@@ -63,7 +66,7 @@ def test_small_model_forward_backward_parity(batch):
     e = rel_mse(xrec.detach(), out["xrec"].detach())
     assert e < 1e-3, f"reconstruction rel-MSE {e}"
     assert abs(float(qloss.detach()) - float(out["qloss"].detach())) < 3e-2 * abs(float(out["qloss"])) + 1e-6
-    oloss = (out["xrec"] - x).abs().mean() + out["qloss"]
+    oloss = (out["xrec"] - x).pow(2).mean() + out["qloss"]
     oloss.backward()
     # gradient comparison, scaled by each tensor's own norm; tensors whose true gradient is ~0
     # (e.g. the attention k-bias: softmax is invariant to it) are compared on an absolute scale
@@ -88,6 +91,54 @@ def test_small_model_forward_backward_parity(batch):
     med = worst[len(worst) // 2][0]
     assert med < 0.04, f"median gradient rel-RMS {med}; worst {worst[:5]}"
     print("gradient rel-RMS: worst", worst[:3], "median", med, "min cosine", cosines[:2])
+
+
+def test_small_triple_model_forward_parity():
+    """TripleGrainVQModel (three heads, 3-way router, masks 1/16, 1/4, 1) vs the oracle, eval mode."""
+    from dynamicvectorquantization_b200 import configs
+    from oracle import dqvae_oracle as orc
+    ocfg = orc.SMALL_TRIPLE_CFG
+    model, sd = _build(lambda: configs.scaled_triple_config(), ocfg, seed=21)
+    model.eval()
+    x = torch.rand(2, 3, ocfg["resolution"], ocfg["resolution"], generator=torch.Generator().manual_seed(6)) * 2 - 1
+    xrec, qloss, indices, gate = model(x.cuda())
+    with torch.no_grad():
+        _, _, info, _, _ = model.encode(x.cuda())
+    free = orc.model_forward(sd, ocfg, x)
+    assert float((free["indices"] == indices.cpu()).float().mean()) > 0.85
+    assert set(indices.unique().tolist()) <= {0, 1, 2}
+    out = orc.model_forward(sd, ocfg, x, forced_gate=gate.detach().cpu().permute(0, 2, 3, 1), forced_codes=info[2].cpu())
+    e = rel_mse(xrec.detach(), out["xrec"])
+    assert e < 1e-3, f"triple reconstruction rel-MSE {e}"
+    assert abs(float(qloss.detach()) - float(out["qloss"])) < 3e-2 * abs(float(out["qloss"])) + 1e-6
+    (xrec.pow(2).mean() + qloss).backward()                    # backward runs through all three heads
+    assert model.encoder.conv_out_median.weight.grad is not None
+
+
+def test_small_entropy_model_forward_parity(tmp_path):
+    """Entropy-routed dual model: Entropy module + fixed-threshold router (deterministic in the image)."""
+    import json
+    from dynamicvectorquantization_b200 import configs
+    from oracle import dqvae_oracle as orc
+    ocfg = orc.SMALL_ENTROPY_CFG
+    thr = tmp_path / "thr.json"
+    thr.write_text(json.dumps({"50": 1.5}))
+    model, sd = _build(lambda: configs.scaled_entropy_config(str(thr)), ocfg, seed=31)
+    model.train()                                               # update_router=False: no gumbel even in train mode
+    g = torch.Generator().manual_seed(9)
+    x = torch.rand(2, 3, 64, 64, generator=g) * 2 - 1
+    x[:, :, :32] = x[:, :, :32].mean(dim=(2, 3), keepdim=True) + 0.02 * x[:, :, :32]      # flat top half -> coarse
+    model.eval()
+    xrec, qloss, indices, gate, x_entropy = model(x.cuda())
+    ent = orc.patch_entropy(x, patch=16)
+    assert torch.allclose(x_entropy.cpu(), ent, rtol=1e-4, atol=1e-5)
+    oi = orc.entropy_router(ent, 1.5).argmax(-1)
+    assert torch.equal(indices.cpu(), oi) and 0 < int(oi.sum()) < oi.numel()
+    with torch.no_grad():
+        info = model.encode(x.cuda())[2]
+    out = orc.model_forward(sd, ocfg, x, entropy_threshold=1.5, forced_codes=info[2].cpu())
+    e = rel_mse(xrec.detach(), out["xrec"])
+    assert e < 1e-3, f"entropy-model reconstruction rel-MSE {e}"
 
 
 def test_vq_module_matches_oracle_and_golden():

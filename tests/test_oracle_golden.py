@@ -85,3 +85,28 @@ def test_model_oracle_matches_reference(tag, cfg, seed):
         if n in params and params[n].grad is not None:
             got = float(params[n].grad.double().pow(2).sum().sqrt())
             assert abs(got - ref) <= 2e-3 * ref + 1e-7, (n, got, ref)
+
+
+def test_triple_oracle_matches_reference():
+    g = _load("model_tiny_triple.npz")
+    cfg = orc.TINY_TRIPLE_CFG
+    sd = orc.make_weights(orc.model_shapes(cfg), seed=5)
+    out = orc.model_forward(sd, cfg, torch.from_numpy(g["x"]))
+    assert np.array_equal(out["indices"].numpy(), g["indices"].astype(np.int64))
+    assert np.array_equal(out["codes"].numpy(), g["codes"].astype(np.int64))
+    assert torch.allclose(out["xrec"], torch.from_numpy(g["xrec"]), rtol=1e-4, atol=1e-5)
+    assert abs(float(out["qloss"]) - float(g["qloss"])) < 1e-5 * abs(float(g["qloss"]))
+    b = orc.budget_loss_triple(out["gate"], min_grain=2, median_grain=4, max_grain=8)
+    assert abs(float(b) - float(g["budget"])) < 1e-5 * abs(float(g["budget"])) + 1e-8
+
+
+def test_entropy_oracle_matches_reference():
+    g = _load("entropy_small.npz")
+    x = torch.from_numpy(g["x"])
+    ent = orc.patch_entropy(x, patch=16)
+    assert torch.allclose(ent, torch.from_numpy(g["entropy"]), rtol=1e-5, atol=1e-6)
+    gate = orc.entropy_router(ent, float(g["threshold"]))
+    assert np.array_equal(gate.numpy(), g["gate"])
+    assert 0 < int(gate[..., 1].sum()) < gate[..., 1].numel()          # both grains present
+    b = orc.budget_loss_dual(gate.permute(0, 3, 1, 2).float(), min_grain=4, max_grain=8)
+    assert abs(float(b) - float(g["budget"])) < 1e-6 * abs(float(g["budget"])) + 1e-9
