@@ -151,7 +151,7 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
 // Shared-memory matrix descriptor (tcgen05, 64 bit):
 //   [0,14)  start address >> 4        [16,30) leading-dim byte offset >> 4
 //   [32,46) stride-dim byte offset>>4 [46,48) version = 1
-//   [49,52) base offset               [61,64) layout: 0 none, 2 = 128B swizzle
+//   [49,52) base offset (kept 0)      [61,64) layout: 0 none, 2 = 128B swizzle
 // K-major SW128 tile (rows of 128 B = 64 bf16 along K, 8-row 1024 B atoms):
 //   SBO = 1024 (next 8 rows), LBO unused.
 // MN-major SW128 tile (rows of 128 B = 64 bf16 along M/N, one row per K index):
@@ -163,7 +163,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= static_cast<uint64_t>(1) << 46;                     // descriptor version (sm_100)
-  d |= static_cast<uint64_t>((saddr >> 7) & 0x7) << 49;    // base offset (0 when 1024 B aligned)
+  // base offset (bits 49..51) stays 0: measured on B200, the 128 B swizzle of both TMA and
+  // tcgen05.mma is a function of the ABSOLUTE shared-memory address bits [7,10), so a tile written
+  // by TMA can be read from any 128 B-row offset (start + s*128 B) with base offset 0
+  // (tools/debug_pconv.py: base offset = (addr>>7)&7 reads garbage, 0 is exact).
   d |= static_cast<uint64_t>(2) << 61;                     // SWIZZLE_128B
   return d;
 }

@@ -30,20 +30,25 @@ struct MmParams {
   int out_f32;
 };
 
-template <int BN, int STAGES, int MAXTAPS>
+// STRIP: the (up to 3) taps of a CTA are horizontal 1-pixel shifts of each other (one 3x3 filter row):
+// the B operand is loaded ONCE per k-block as a strip of KW+2 = 66 pixels and tap t is read from pixel
+// row t of the strip (descriptor start + t*128 B; the 128 B swizzle is an absolute-address function).
+template <int BN, int STAGES, int MAXTAPS, bool STRIP = false>
 struct MmCfg {
   static constexpr uint32_t A_BYTES = 128 * 128;
   static constexpr uint32_t B_BYTES = BN * 128;
-  static constexpr uint32_t STAGE_BYTES = A_BYTES + MAXTAPS * B_BYTES;
+  static constexpr uint32_t STRIP_ROWS = 66;
+  static constexpr uint32_t STRIP_SLOT = 9 * 1024;                   // 66 x 128 B padded to 1 KB multiple
+  static constexpr uint32_t STAGE_BYTES = STRIP ? (A_BYTES + (BN / 64) * STRIP_SLOT) : (A_BYTES + MAXTAPS * B_BYTES);
   static constexpr uint32_t SMEM = STAGES * STAGE_BYTES + 1024 + 256;
   static constexpr uint32_t TMEM_COLS = (BN * MAXTAPS <= 128) ? 128 : (BN * MAXTAPS <= 256 ? 256 : 512);
 };
 
-template <int BN, int STAGES, int MAXTAPS>
+template <int BN, int STAGES, int MAXTAPS, bool STRIP = false>
 __global__ void __launch_bounds__(192, 1)
 mmgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
               const __grid_constant__ MmParams p) {
-  using Cfg = MmCfg<BN, STAGES, MAXTAPS>;
+  using Cfg = MmCfg<BN, STAGES, MAXTAPS, STRIP>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sBar = base + STAGES * Cfg::STAGE_BYTES;
@@ -84,7 +89,8 @@ mmgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   if (warp == 0) {
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      const uint32_t tx = Cfg::A_BYTES + ntl * Cfg::B_BYTES;
+      const uint32_t tx = STRIP ? (Cfg::A_BYTES + (BN / 64) * Cfg::STRIP_ROWS * 128)
+                                : (Cfg::A_BYTES + ntl * Cfg::B_BYTES);
       for (int kb = kb0; kb < kb1; ++kb) {
         const int kw = kb % p.ktiles_w, kh = (kb / p.ktiles_w) % p.ktiles_h,
                   kn = kb / (p.ktiles_w * p.ktiles_h);
@@ -100,6 +106,13 @@ mmgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             tma_load_5d(sa + g * 8192, &tmA, fb, m0 + 64 * g, kw * p.KW, 0, kh * p.KH,
                         kn * p.KN + batch);
         }
+        if constexpr (STRIP) {
+#pragma unroll
+          for (int g = 0; g < BN / 64; ++g)
+            tma_load_5d(sa + Cfg::A_BYTES + g * Cfg::STRIP_SLOT, &tmB, fb, n0 + 64 * g + p.tap_c[tap0],
+                        kw * p.KW + p.tap_w[tap0], p.tap_p[tap0], kh * p.KH + p.tap_h[tap0],
+                        kn * p.KN + batch);
+        } else
         for (int t = 0; t < ntl; ++t) {
           const uint32_t sb = sa + Cfg::A_BYTES + t * Cfg::B_BYTES;
           const int tg = tap0 + t;
@@ -127,11 +140,11 @@ mmgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         tc_fence_after();
         const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
         for (int t = 0; t < ntl; ++t) {
-          const uint32_t sb = sa + Cfg::A_BYTES + t * Cfg::B_BYTES;
+          const uint32_t sb = sa + Cfg::A_BYTES + (STRIP ? t * 128u : t * Cfg::B_BYTES);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint64_t da = make_smem_desc(sa + k * a_step, a_lbo, 1024);
-            const uint64_t db = make_smem_desc(sb + k * b_step, b_lbo, 1024);
+            const uint64_t db = make_smem_desc(sb + k * b_step, STRIP ? Cfg::STRIP_SLOT : b_lbo, 1024);
             umma_bf16(tmem_base + t * BN, da, db, idesc, (it | k) ? 1u : 0u);
           }
         }
@@ -218,18 +231,18 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
   *o = accumulate ? (*o + s) : s;
 }
 
-template <int BN, int STAGES, int MAXTAPS>
+template <int BN, int STAGES, int MAXTAPS, bool STRIP = false>
 static int launch_mm(const CUtensorMap& tmA, const CUtensorMap& tmB, const MmParams& p, dim3 grid,
                      cudaStream_t stream) {
-  using Cfg = MmCfg<BN, STAGES, MAXTAPS>;
+  using Cfg = MmCfg<BN, STAGES, MAXTAPS, STRIP>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(mmgemm_kernel<BN, STAGES, MAXTAPS>,
+    cudaError_t e = cudaFuncSetAttribute(mmgemm_kernel<BN, STAGES, MAXTAPS, STRIP>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  mmgemm_kernel<BN, STAGES, MAXTAPS><<<grid, 192, Cfg::SMEM, stream>>>(tmA, tmB, p);
+  mmgemm_kernel<BN, STAGES, MAXTAPS, STRIP><<<grid, 192, Cfg::SMEM, stream>>>(tmA, tmB, p);
   return (int)cudaGetLastError();
 }
 
@@ -255,6 +268,7 @@ struct b2dq_mm_desc {
   float alpha;
   int out_f32;
   int block_n;   // 128 or 256 (0 = auto)
+  int b_strip;   // 1: the taps of a CTA are 1-pixel horizontal shifts -> one 66-pixel strip load per k-block
 };
 
 int b2dq_mmgemm(const b2dq_mm_desc* d, cudaStream_t stream) {
@@ -278,7 +292,7 @@ int b2dq_mmgemm(const b2dq_mm_desc* d, cudaStream_t stream) {
     uint64_t dims[5], str[5];
     for (int i = 0; i < 5; ++i) { dims[i] = (uint64_t)d->b_dims[i]; str[i] = (uint64_t)d->b_strides[i]; }
     uint32_t box_k[5] = {64, (uint32_t)bn, 1, 1, 1};
-    uint32_t box_mn[5] = {64, (uint32_t)d->KW, 1, (uint32_t)d->KH, (uint32_t)d->KN};
+    uint32_t box_mn[5] = {64, (uint32_t)d->KW + (d->b_strip ? 2u : 0u), 1, (uint32_t)d->KH, (uint32_t)d->KN};
     int r = make_tmap_bf16(&tmB, d->b_ptr, 5, dims, str, d->b_mn ? box_mn : box_k);
     if (r) return r - 1000;
   }
@@ -297,6 +311,12 @@ int b2dq_mmgemm(const b2dq_mm_desc* d, cudaStream_t stream) {
   p.alpha = d->alpha; p.out_f32 = d->out_f32;
   dim3 grid((unsigned)(((d->M + 127) / 128) * ngroups), (unsigned)((d->N + bn - 1) / bn),
             (unsigned)(d->batches * d->splits));
+  if (d->b_strip) {
+    if (!(d->a_mn && d->b_mn) || d->KW != 64 || d->KH != 1 || d->KN != 1 || bn != 128 || tpc != 3 ||
+        d->ntaps % 3 != 0)
+      return -6;
+    return launch_mm<128, 5, 3, true>(tmA, tmB, p, grid, stream);
+  }
   if (bn == 128) {
     if (tpc == 1) return launch_mm<128, 4, 1>(tmA, tmB, p, grid, stream);
     return launch_mm<128, 3, 3>(tmA, tmB, p, grid, stream) ;

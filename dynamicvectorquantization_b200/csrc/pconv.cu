@@ -1,0 +1,283 @@
+// Persistent 3x3 (stride 1, pad 1) convolution for the wide, 128-output-channel layers of the
+// DQ-VAE stacks (the 128->128 convolutions at 256x256 / 128x128 that carry 54 % of the model FLOPs;
+// reference: modules/diffusionmodules/model.py:88-102 ResnetBlock conv1/conv2, :43-47 Upsample conv)
+// - forward and data gradient.
+//
+// Why a second kernel next to tapgemm_kernel: at Cout = 128 the one-tile-per-CTA tap GEMM needs
+// 128 B of L2->SM operand traffic per tensor-core cycle and saturates the L2 fabric at ~43 % tensor
+// utilisation (profiles/r01_ncu_full_summary.md).  This kernel cuts the traffic per FLOP 2.4x:
+//   * the three horizontal taps (s = 0,1,2) of a filter row read ONE activation strip of 130
+//     pixels x 64 channels (TMA box {64,130}); tap s is the same shared-memory strip addressed from
+//     row s (UMMA descriptor start + s*128 B; the 128 B swizzle is a function of absolute smem
+//     address bits, so the shifted view needs no descriptor base offset);
+//   * two 128-pixel output tiles share every weight tile (6 MMA groups per 3 weight tiles);
+//   * the CTA is persistent (one per SM) with two TMEM accumulator sets, so the epilogue of one
+//     tile pair overlaps the main loop of the next and the TMA ring never drains.
+// Per pipeline stage: 2 strips (2 x 16.6 KB) + 3 weight tiles (3 x 16 KB) feed 24 MMAs
+// (128x128x16) = 1536 tensor cycles -> 53 B/cycle/SM instead of 128.
+#include "common.cuh"
+#include "tmap.h"
+
+namespace b2 {
+
+constexpr int PC_BN = 128;
+constexpr int PC_MT = 2;
+constexpr int PC_STAGES = 2;
+constexpr uint32_t PC_STRIP_ROWS = 130;
+constexpr uint32_t PC_STRIP_BYTES = PC_STRIP_ROWS * 128;           // 16,640
+constexpr uint32_t PC_STRIP_SLOT = 17 * 1024;                      // padded, keeps 1024 B alignment
+constexpr uint32_t PC_B_BYTES = PC_BN * 128;                       // 16 KB
+constexpr uint32_t PC_STAGE_BYTES = PC_MT * PC_STRIP_SLOT + 3 * PC_B_BYTES;   // 83,968
+constexpr uint32_t PC_SMEM = PC_STAGES * PC_STAGE_BYTES + 1024 + 256 + 1024;
+
+struct PconvParams {
+  int kchunks;                 // Cin / 64
+  int cin;                     // weight column stride between taps
+  int row_dh[3];               // input row offset of filter row r
+  int col_off[3];              // strip row (pixel) offset of filter column s: 0..2
+  int tiles_w, H, NB, W;       // tiles per image row, image height, images, width
+  int num_tiles;               // NB * H * tiles_w
+  int Cout;
+  __nv_bfloat16* out;
+  long long oN, oH, oW;
+  const float* bias;
+  const __nv_bfloat16* residual;
+  long long rN, rH, rW;
+};
+
+__global__ void __launch_bounds__(192, 1)
+pconv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ PconvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sBar = base + PC_STAGES * PC_STAGE_BYTES;
+  const uint32_t bar_full = sBar, bar_empty = sBar + 16, bar_tfull = sBar + 32, bar_tempty = sBar + 48;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + (sBar + 64 - smem_u32(smem_raw)));
+  float* bias_s = reinterpret_cast<float*>(smem_raw + (sBar + 256 - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_items = (p.num_tiles + PC_MT - 1) / PC_MT;
+  const int kiters = 3 * p.kchunks;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < PC_STAGES; ++i) {
+      mbar_init(bar_full + 8 * i, 1);
+      mbar_init(bar_empty + 8 * i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_tfull + 8 * i, 1);
+      mbar_init(bar_tempty + 8 * i, 4);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) tmem_alloc<512>(smem_u32(tmem_slot));
+  if (threadIdx.x >= 64) {
+    const int t = threadIdx.x - 64;
+    bias_s[t] = (p.bias && t < p.Cout) ? p.bias[t] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto tile_coords = [&](int t, int& ow0, int& oh, int& n) {
+    ow0 = (t % p.tiles_w) * 128;
+    oh = (t / p.tiles_w) % p.H;
+    n = t / (p.tiles_w * p.H);          // tiles past the end give n >= NB: loads read zeros, stores masked
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        int ow0[PC_MT], oh[PC_MT], n[PC_MT];
+#pragma unroll
+        for (int j = 0; j < PC_MT; ++j) tile_coords(item * PC_MT + j, ow0[j], oh[j], n[j]);
+        for (int r = 0; r < 3; ++r)
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+            const uint32_t sa = base + stage * PC_STAGE_BYTES;
+            const uint32_t fb = bar_full + 8 * stage;
+            mbar_arrive_expect_tx(fb, PC_MT * PC_STRIP_BYTES + 3 * PC_B_BYTES);
+#pragma unroll
+            for (int j = 0; j < PC_MT; ++j)
+              tma_load_5d(sa + j * PC_STRIP_SLOT, &tmA, fb, kc * 64, ow0[j] - 1, 0, oh[j] + p.row_dh[r], n[j]);
+#pragma unroll
+            for (int s = 0; s < 3; ++s)
+              tma_load_2d(sa + PC_MT * PC_STRIP_SLOT + s * PC_B_BYTES, &tmB, fb,
+                          (r * 3 + s) * p.cin + kc * 64, 0);
+            if (++stage == PC_STAGES) { stage = 0; phase ^= 1; }
+          }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, PC_BN, 0, 0);
+      uint32_t stage = 0, phase = 0, it_item = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it_item) {
+        const uint32_t buf = it_item & 1;
+        mbar_wait(bar_tempty + 8 * buf, ((it_item >> 1) & 1) ^ 1);
+        tc_fence_after();
+        for (int it = 0; it < kiters; ++it) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = base + stage * PC_STAGE_BYTES;
+#pragma unroll
+          for (int j = 0; j < PC_MT; ++j) {
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+              const uint32_t a0 = sa + j * PC_STRIP_SLOT + p.col_off[s] * 128;
+              const uint32_t b0 = sa + PC_MT * PC_STRIP_SLOT + s * PC_B_BYTES;
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(tmem_base + buf * (PC_MT * PC_BN) + j * PC_BN, make_smem_desc(a0 + k * 32, 0, 1024),
+                          make_smem_desc(b0 + k * 32, 0, 1024), idesc, (it | s | k) ? 1u : 0u);
+            }
+          }
+          umma_commit(bar_empty + 8 * stage);
+          if (++stage == PC_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(bar_tfull + 8 * buf);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    uint32_t it_item = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it_item) {
+      const uint32_t buf = it_item & 1;
+      bool valid[PC_MT];
+      long long ooff[PC_MT], roff[PC_MT];
+#pragma unroll
+      for (int j = 0; j < PC_MT; ++j) {
+        int ow0, oh, n;
+        tile_coords(item * PC_MT + j, ow0, oh, n);
+        const int ow = ow0 + m;
+        valid[j] = (ow < p.W) && (n < p.NB);
+        ooff[j] = n * p.oN + oh * p.oH + ow * p.oW;
+        roff[j] = n * p.rN + oh * p.rH + ow * p.rW;
+      }
+      uint4 res[PC_BN / 8];
+      if (p.residual && valid[0]) {
+        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + roff[0]);
+#pragma unroll
+        for (int i = 0; i < PC_BN / 8; ++i) res[i] = __ldg(rp + i);
+      }
+      mbar_wait(bar_tfull + 8 * buf, (it_item >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int j = 0; j < PC_MT; ++j) {
+        if (j > 0 && p.residual && valid[j]) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + roff[j]);
+#pragma unroll
+          for (int i = 0; i < PC_BN / 8; ++i) res[i] = __ldg(rp + i);
+        }
+        const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * (PC_MT * PC_BN) + j * PC_BN;
+#pragma unroll
+        for (int c0 = 0; c0 < PC_BN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(trow + c0, r);
+          tmem_ld_wait();
+          if (!valid[j]) continue;
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + bias_s[c0 + i];
+          if (p.residual) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint4 u = res[c0 / 8 + i];
+              v[8 * i + 0] += bf16_lo(u.x); v[8 * i + 1] += bf16_hi(u.x);
+              v[8 * i + 2] += bf16_lo(u.y); v[8 * i + 3] += bf16_hi(u.y);
+              v[8 * i + 4] += bf16_lo(u.z); v[8 * i + 5] += bf16_hi(u.z);
+              v[8 * i + 6] += bf16_lo(u.w); v[8 * i + 7] += bf16_hi(u.w);
+            }
+          }
+          uint4* op = reinterpret_cast<uint4*>(p.out + ooff[j] + c0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 u;
+            u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+            u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+            u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+            u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+            op[i] = u;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+extern "C" {
+
+// 3x3 stride-1 pad-1 convolution (or its data gradient) of an NHWC bf16 tensor with Cout == 128,
+// W % 128 == 0, Cin % 64 == 0.  b_ptr: [128, 9*Cin] bf16, column = (r*3+s)*Cin + ci.
+// dgrad != 0: tap (r,s) reads the pixel at (+1-r, +1-s) instead of (r-1, s-1).
+int b2dq_pconv3x3(const void* a_ptr, const void* b_ptr, void* out, const float* bias,
+                  const void* residual, int NB, int H, int W, int Cin, int dgrad, int max_ctas,
+                  cudaStream_t stream) {
+  if (NB <= 0 || H <= 0 || W <= 0) return 0;
+  if (W % 128 != 0 || Cin % 64 != 0 || Cin <= 0) return -1;
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[5] = {(uint64_t)Cin, (uint64_t)W, 1, (uint64_t)H, (uint64_t)NB};
+    uint64_t str[5] = {1, (uint64_t)Cin, (uint64_t)W * Cin, (uint64_t)W * Cin, (uint64_t)H * W * Cin};
+    uint32_t box[5] = {64, PC_STRIP_ROWS, 1, 1, 1};
+    int r = make_tmap_bf16(&tmA, a_ptr, 5, dims, str, box);
+    if (r) return r;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)9 * Cin, (uint64_t)PC_BN};
+    uint64_t str[2] = {1, (uint64_t)9 * Cin};
+    uint32_t box[2] = {64, PC_BN};
+    int r = make_tmap_bf16(&tmB, b_ptr, 2, dims, str, box);
+    if (r) return r - 1000;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(pconv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  PconvParams p;
+  p.kchunks = Cin / 64; p.cin = Cin;
+  for (int i = 0; i < 3; ++i) {
+    p.row_dh[i] = dgrad ? 1 - i : i - 1;
+    p.col_off[i] = dgrad ? 2 - i : i;
+  }
+  p.tiles_w = W / 128; p.H = H; p.NB = NB; p.W = W;
+  p.num_tiles = NB * H * p.tiles_w;
+  p.Cout = PC_BN;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.oN = (long long)H * W * PC_BN; p.oH = (long long)W * PC_BN; p.oW = PC_BN;
+  p.bias = bias;
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
+  p.rN = p.oN; p.rH = p.oH; p.rW = p.oW;
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int grid = sms;
+  if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
+  const int items = (p.num_tiles + PC_MT - 1) / PC_MT;
+  if (items < grid) grid = items;
+  pconv3x3_kernel<<<grid, 192, PC_SMEM, stream>>>(tmA, tmB, p);
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -167,6 +167,8 @@ def conv_fwd(x, wpack, bias, ksize, stride, cout, residual=None, out_f32=False):
     """x NHWC bf16; wpack from pack_weight_fwd; stride-2 uses pad (0,1,0,1) like Downsample."""
     nb, h, w, cin = x.shape
     assert cin % 64 == 0, "Cin must be a multiple of 64 (edge layers use the im2col path)"
+    if not out_f32 and _pconv_ok(ksize, stride, w, cin, cout, nb, h):
+        return pconv3x3(x, wpack, bias, residual, dgrad=False)
     kch = cin // 64
     if stride == 1:
         dims, strs = nhwc_view(x)
@@ -191,6 +193,8 @@ def conv_dgrad(dy, wdpack, ksize, stride, cin, in_hw):
     """dy NHWC bf16 [N,Ho,Wo,Cout] -> dx NHWC bf16 [N,H,W,Cin]."""
     nb, ho, wo, cout = dy.shape
     assert cout % 64 == 0
+    if _pconv_ok(ksize, stride, wo, cout, cin, nb, ho):
+        return pconv3x3(dy, wdpack, None, None, dgrad=True)
     kch = cout // 64
     h, w = in_hw
     dx = torch.empty(nb, h, w, cin, dtype=BF16, device=dy.device)
@@ -216,7 +220,7 @@ def conv_dgrad(dy, wdpack, ksize, stride, cin, in_hw):
 
 def mmgemm(a, a_dims, a_strides, a_mn, b, b_dims, b_strides, b_mn, M, N, kblocks, out, ostr,
            taps=((0, 0, 0, 0),), kbox=(64, 1, 1), ktiles=(0, 0), splits=1, batches=1, alpha=1.0,
-           out_f32=False, block_n=0, out_off=0, taps_per_cta=0):
+           out_f32=False, block_n=0, out_off=0, taps_per_cta=0, b_strip=False):
     d = MmDesc()
     d.a_ptr, d.b_ptr = a.data_ptr(), b.data_ptr()
     _fill(d.a_dims, a_dims); _fill(d.a_strides, a_strides)
@@ -230,12 +234,27 @@ def mmgemm(a, a_dims, a_strides, a_mn, b, b_dims, b_strides, b_mn, M, N, kblocks
     esz = 4 if out_f32 else 2
     d.out = out.data_ptr() + out_off * esz
     d.oZ, d.oT, d.oM = ostr
-    d.alpha, d.out_f32, d.block_n = alpha, int(out_f32), block_n
+    d.alpha, d.out_f32, d.block_n, d.b_strip = alpha, int(out_f32), block_n, int(b_strip)
     check(_cabi.lib().b2dq_mmgemm(C.byref(d), _stream()), "mmgemm")
 
 
 NUM_SMS = 148
 FORCE_MT = 0          # tests / tuning: force m_tiles_per_cta of the tap GEMM (0 = library heuristic)
+USE_WGRAD_STRIP = True   # 3x3 s1 weight gradient: one 66-pixel activation strip per k-block for a filter row
+USE_PCONV = True      # persistent strip kernel for 3x3 s1 layers with 128 output channels and W % 128 == 0
+
+
+def _pconv_ok(ksize, stride, w, cin, cout, nb, h):
+    return (USE_PCONV and ksize == 3 and stride == 1 and cout == 128 and w % 128 == 0 and cin % 64 == 0
+            and nb * h * (w // 128) >= 2 * NUM_SMS)
+
+
+def pconv3x3(x, wpack, bias, residual, dgrad):
+    nb, h, w, cin = x.shape
+    out = torch.empty(nb, h, w, 128, dtype=BF16, device=x.device)
+    check(_cabi.lib().b2dq_pconv3x3(_ptr(x), _ptr(wpack), _ptr(out), _ptr(bias), _ptr(residual), nb, h, w, cin,
+                                    int(dgrad), 0, _stream()), "pconv3x3")
+    return out
 
 
 def _wgrad_splits(kblocks, ctas_per_split):
@@ -283,7 +302,8 @@ def conv_wgrad(x, dy, ksize, stride):
     partial = torch.empty(splits, ntaps, cout, cin, dtype=torch.float32, device=x.device)
     mmgemm(dy, adims, astrs, True, x, bdims, bstrs, True, cout, cin, kblocks, partial,
            (ntaps * cout * cin, cout * cin, cin), taps=taps, kbox=(kw, kh, kn), ktiles=(ktw, kth),
-           splits=splits, out_f32=True, block_n=128, taps_per_cta=min(3, ntaps))
+           splits=splits, out_f32=True, block_n=128, taps_per_cta=min(3, ntaps),
+           b_strip=USE_WGRAD_STRIP and ksize == 3 and stride == 1 and (kw, kh, kn) == (64, 1, 1))
     dw = torch.empty(cout, cin, ksize, ksize, dtype=torch.float32, device=x.device)
     check(_cabi.lib().b2dq_wgrad_reduce(_ptr(partial), _ptr(dw), splits, ntaps, cout, cin, 0, _stream()),
           "wgrad_reduce")

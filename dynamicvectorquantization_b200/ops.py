@@ -13,14 +13,13 @@ from . import kernels as kn
 
 BF16 = torch.bfloat16
 
-_pack_cache = {}
-
-
 def _packed(weight, kind):
-    key = (weight.data_ptr(), kind)
-    ent = _pack_cache.get(key)
-    ver = weight._version
-    if ent is not None and ent[0] == ver and ent[1].device == weight.device:
+    """bf16 GEMM packing of an OIHW fp32 parameter, cached ON the parameter object (so the cache
+    dies with it) and validated against the storage pointer and the in-place version counter."""
+    cache = weight.__dict__.setdefault("_b2_packs", {})
+    ent = cache.get(kind)
+    stamp = (weight.data_ptr(), weight._version, weight.device)
+    if ent is not None and ent[0] == stamp:
         return ent[1]
     w = weight.detach()
     co, ci, r, s = w.shape
@@ -39,12 +38,8 @@ def _packed(weight, kind):
         p[:, :r * s * co] = w.permute(1, 2, 3, 0).reshape(ci, -1).to(BF16)
     else:
         raise ValueError(kind)
-    _pack_cache[key] = (ver, p)
+    cache[kind] = (stamp, p)
     return p
-
-
-def clear_weight_cache():
-    _pack_cache.clear()
 
 
 def _f32(t):

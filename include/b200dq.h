@@ -99,6 +99,14 @@ typedef struct b2dq_tapgemm_desc {
 
 int b2dq_tapgemm(const b2dq_tapgemm_desc* desc, cudaStream_t stream);
 
+/* Persistent variant for the wide 128-output-channel 3x3 stride-1 layers (W % 128 == 0, Cout == 128,
+ * Cin % 64 == 0): one activation strip serves the three horizontal taps, two output tiles share
+ * each weight tile, epilogue overlapped through double-buffered TMEM.  Same maths as b2dq_tapgemm
+ * with the 3x3 tap table; dgrad != 0 mirrors the taps (data gradient).  b: [128, 9*Cin] bf16. */
+int b2dq_pconv3x3(const void* a_bf16, const void* b_bf16, void* out_bf16, const float* bias,
+                  const void* residual_bf16, int NB, int H, int W, int Cin, int dgrad, int max_ctas,
+                  cudaStream_t stream);
+
 /* ------------------------------------------------------------------ batched / split-K GEMM
  * Weight gradients of the convolutions above (autograd of nn.Conv2d) and the attention
  * contractions of AttnBlock.forward (model.py:176-188) with their gradients.
@@ -121,6 +129,8 @@ typedef struct b2dq_mm_desc {
   float alpha;
   int out_f32;
   int block_n;            /* 0 = auto, 128 or 256 */
+  int b_strip;            /* 1: the 3 taps of a CTA are 1-pixel shifts (3x3 filter row): B is loaded once
+                             per k-block as a 66-pixel strip (needs a_mn = b_mn = 1, KW = 64, KH = KN = 1) */
 } b2dq_mm_desc;
 
 int b2dq_mmgemm(const b2dq_mm_desc* desc, cudaStream_t stream);

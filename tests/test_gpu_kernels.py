@@ -80,6 +80,8 @@ CONV_CASES = [
     (2, 64, 64, 64, 64, 3, 1),
     (1, 256, 256, 128, 128, 3, 1),
     (3, 8, 8, 512, 256, 3, 1),
+    (3, 128, 128, 128, 128, 3, 1),
+    (2, 128, 256, 256, 128, 3, 1),
     (2, 32, 32, 256, 256, 1, 1),
     (2, 16, 16, 128, 256, 1, 1),
     (2, 32, 32, 128, 128, 3, 2),
@@ -95,11 +97,19 @@ def _ref_conv(x_nhwc, w, b, k, stride):
     return F.conv2d(x, w, b, padding=k // 2)
 
 
-@pytest.mark.parametrize("mt", [1, 2])
+@pytest.mark.parametrize("mt", [1, 2, "pconv"])
 @pytest.mark.parametrize("nb,h,w,cin,cout,k,stride", CONV_CASES)
 def test_conv_fwd_dgrad_wgrad(nb, h, w, cin, cout, k, stride, mt, monkeypatch):
     from dynamicvectorquantization_b200 import kernels as kn
-    monkeypatch.setattr(kn, "FORCE_MT", mt)       # 1 or 2 output tiles per CTA (both code paths)
+    if mt == "pconv":                             # persistent strip kernel (where it applies)
+        if not (k == 3 and stride == 1 and w % 128 == 0 and (cout == 128 or cin == 128)):
+            pytest.skip("pconv handles 3x3 s1, W % 128 == 0, 128 output channels")
+        monkeypatch.setattr(kn, "USE_PCONV", True)
+        monkeypatch.setattr(kn, "NUM_SMS", 1)     # lift the "enough tiles" heuristic for the small test shapes
+    else:
+        monkeypatch.setattr(kn, "USE_PCONV", False)
+        monkeypatch.setattr(kn, "USE_WGRAD_STRIP", mt == 2)   # strip and per-tap weight-gradient loads
+        monkeypatch.setattr(kn, "FORCE_MT", mt)   # 1 or 2 output tiles per CTA (both code paths)
     x = _rand_bf(nb, h, w, cin, seed=1)
     wt = _rand_bf(cout, cin, k, k, scale=(cin * k * k) ** -0.5, seed=2).float()
     bias = torch.randn(cout, generator=torch.Generator().manual_seed(3))
@@ -151,6 +161,25 @@ def test_mmgemm_majorness(a_mn, b_mn, M, N, K, batch):
                   kbox=(64, 1, 1), ktiles=(K // 64, 1), batches=batch, alpha=0.5, out_f32=out_f32)
         e = rel_rms(out.float().cpu(), ref)
         assert e < (1e-5 if out_f32 else 4e-3), f"a_mn={a_mn} b_mn={b_mn} f32={out_f32}: {e}"
+
+
+@pytest.mark.parametrize("T,C,B", [(16, 256, 2), (64, 64, 3), (256, 512, 2), (1024, 256, 1)])
+def test_attention_fwd_bwd(T, C, B):
+    """Single-head attention of AttnBlock (model.py:176-188) incl. the ragged T < 64 cases."""
+    from dynamicvectorquantization_b200 import ops
+    q, k, v = (_rand_bf(B, T, C, seed=20 + i) for i in range(3))
+    do = _rand_bf(B, T, C, seed=30)
+    qr, kr, vr = (t.float().requires_grad_(True) for t in (q, k, v))
+    w = torch.softmax(torch.bmm(qr, kr.transpose(1, 2)) * C ** -0.5, dim=2)
+    o_ref = torch.bmm(w, vr)
+    o_ref.backward(do.float())
+    qd, kd, vd = (t.cuda().requires_grad_(True) for t in (q, k, v))
+    o = ops.AttentionFn.apply(qd, kd, vd)
+    o.backward(do.cuda())
+    assert rel_rms(o.float(), o_ref.detach()) < 1e-2
+    assert rel_rms(qd.grad.float(), qr.grad) < 2e-2
+    assert rel_rms(kd.grad.float(), kr.grad) < 2e-2
+    assert rel_rms(vd.grad.float(), vr.grad) < 1e-2
 
 
 # ------------------------------------------------------------------------------------------- GN

@@ -89,6 +89,28 @@ def test_weight_packings_are_consistent():
         assert torch.equal(d[:, t * 8:(t + 1) * 8], wb[:, :, r, s].t())
 
 
+def test_weight_pack_cache_follows_the_parameter():
+    """The bf16 packings are cached on the parameter and refreshed on in-place updates; a new
+    parameter that happens to reuse a freed storage address must not see the old packing."""
+    from dynamicvectorquantization_b200 import ops
+    w = torch.nn.Parameter(torch.randn(8, 4, 3, 3))
+    p1 = ops._packed(w, "fwd")
+    assert ops._packed(w, "fwd") is p1
+    with torch.no_grad():
+        w.mul_(2.0)
+    p2 = ops._packed(w, "fwd")
+    assert p2 is not p1 and torch.equal(p2.float(), (p1.float() * 2).bfloat16().float())
+    ptr = w.data_ptr()
+    del w, p1, p2
+    seen = False
+    for _ in range(8):
+        w2 = torch.nn.Parameter(torch.randn(8, 4, 3, 3))
+        seen |= w2.data_ptr() == ptr
+        assert torch.equal(ops._packed(w2, "fwd").float(),
+                           w2.detach().permute(0, 2, 3, 1).reshape(8, -1).bfloat16().float())
+        del w2
+
+
 # ------------------------------------------------------------------------------- drop-in conformance
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not mounted")
 @pytest.mark.parametrize("name,yml", [("dqvae-dual-r-05", "dqvae-dual-r-05_imagenet.yml"),

@@ -53,8 +53,12 @@ def conv(nb, h, w, cin, cout, k, stride):
             kn.conv_fwd(x, wp, b, k, stride, cout)
             kn.FORCE_MT = 0
         return f
+    def fwd_nopconv():
+        kn.USE_PCONV = False
+        kn.conv_fwd(x, wp, b, k, stride, cout)
+        kn.USE_PCONV = True
     for name, fn in (("fwd", lambda: kn.conv_fwd(x, wp, b, k, stride, cout)),
-                     ("fwd_mt1", fwd_mt(1)), ("fwd_mt2", fwd_mt(2)),
+                     ("fwd_tap", fwd_nopconv),
                      ("dgrad", lambda: kn.conv_dgrad(dy, wd, k, stride, cin, (h, w))),
                      ("wgrad", lambda: kn.conv_wgrad(x, dy, k, stride))):
         ms = timeit(fn, iters=5, warm=2)
