@@ -62,9 +62,10 @@ SIGNATURES = {
     "b2dq_mmgemm": [C.POINTER(MmDesc), _vp],
     "b2dq_pconv3x3": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "b2dq_wgrad_reduce": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "b2dq_gn_chunks": [_i, _i],
     "b2dq_gn_stats": [_vp, _vp, _vp, _i, _i, _i, _i, _f, _vp],
     "b2dq_gn_apply": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
-    "b2dq_gn_bwd_stats": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "b2dq_gn_bwd_stats": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "b2dq_gn_bwd_apply": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "b2dq_nchw_f32_to_nhwc_bf16": [_vp, _vp, _i, _i, _i, _vp],
     "b2dq_nhwc_bf16_to_nchw_f32": [_vp, _vp, _i, _i, _i, _vp],
@@ -76,7 +77,8 @@ SIGNATURES = {
     "b2dq_softmax_bwd_rows": [_vp, _vp, _vp, _ll, _i, _f, _vp],
     "b2dq_add_bf16": [_vp, _vp, _vp, _ll, _vp],
     "b2dq_im2col3x3_small": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
-    "b2dq_bias_grad": [_vp, _vp, _ll, _i, _vp],
+    "b2dq_bias_grad_blocks": [_ll],
+    "b2dq_bias_grad": [_vp, _vp, _vp, _ll, _i, _vp],
     "b2dq_cast_f32_to_bf16": [_vp, _vp, _ll, _vp],
 }
 

@@ -177,54 +177,62 @@ __global__ void im2col3x3_small_kernel(const __nv_bfloat16* __restrict__ src,
   reinterpret_cast<uint4*>(dst)[i] = *reinterpret_cast<const uint4*>(vals);
 }
 
-// out[c] = sum_rows dy[row][c]   (bias gradient), dy bf16 [rows][C], C % 8 == 0; out must be zeroed.
-// Thread = (8-channel vector, row lane); 16 B loads, 4 rows in flight; smem then global atomics.
-__global__ void bias_grad_kernel(const __nv_bfloat16* __restrict__ dy, float* out, long long rows,
+// part[block][c] = sum over the block's rows of dy[row][c] (bias gradient), dy bf16 [rows][C],
+// C % 8 == 0.  Thread = (8-channel vector, row lane); 16 B loads, 4 rows in flight; the per-thread
+// sums are combined in a fixed order (deterministic), bias_grad_reduce adds the blocks in order.
+__global__ void bias_grad_kernel(const __nv_bfloat16* __restrict__ dy, float* part, long long rows,
                                  int C, int rows_per_block) {
-  extern __shared__ float sh[];  // [C]
+  extern __shared__ float sh[];  // [rstep][C]
   const int vecs = C >> 3;
   const int v = threadIdx.x % vecs;
   const int rlane = threadIdx.x / vecs;
   const int rstep = blockDim.x / vecs;
   const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_block;
   const long long r1 = min(rows, r0 + rows_per_block);
-  for (int i = threadIdx.x; i < C; i += blockDim.x) sh[i] = 0.f;
-  __syncthreads();
   float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const __nv_bfloat16* base = dy + v * 8;
-  if (rlane < rstep) {
-    long long r = r0 + rlane;
-    for (; r + 3 * rstep < r1; r += 4 * rstep) {
-      uint4 u[4];
+  long long r = r0 + rlane;
+  for (; r + 3 * rstep < r1; r += 4 * rstep) {
+    uint4 u[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) u[j] = __ldg(reinterpret_cast<const uint4*>(base + (r + j * rstep) * C));
+    for (int j = 0; j < 4; ++j) u[j] = __ldg(reinterpret_cast<const uint4*>(base + (r + j * rstep) * C));
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        s[0] += bf16_lo(u[j].x); s[1] += bf16_hi(u[j].x); s[2] += bf16_lo(u[j].y); s[3] += bf16_hi(u[j].y);
-        s[4] += bf16_lo(u[j].z); s[5] += bf16_hi(u[j].z); s[6] += bf16_lo(u[j].w); s[7] += bf16_hi(u[j].w);
-      }
+    for (int j = 0; j < 4; ++j) {
+      s[0] += bf16_lo(u[j].x); s[1] += bf16_hi(u[j].x); s[2] += bf16_lo(u[j].y); s[3] += bf16_hi(u[j].y);
+      s[4] += bf16_lo(u[j].z); s[5] += bf16_hi(u[j].z); s[6] += bf16_lo(u[j].w); s[7] += bf16_hi(u[j].w);
     }
-    for (; r < r1; r += rstep) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + r * C));
-      s[0] += bf16_lo(u.x); s[1] += bf16_hi(u.x); s[2] += bf16_lo(u.y); s[3] += bf16_hi(u.y);
-      s[4] += bf16_lo(u.z); s[5] += bf16_hi(u.z); s[6] += bf16_lo(u.w); s[7] += bf16_hi(u.w);
-    }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) atomicAdd(&sh[v * 8 + k], s[k]);
   }
+  for (; r < r1; r += rstep) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + r * C));
+    s[0] += bf16_lo(u.x); s[1] += bf16_hi(u.x); s[2] += bf16_lo(u.y); s[3] += bf16_hi(u.y);
+    s[4] += bf16_lo(u.z); s[5] += bf16_hi(u.z); s[6] += bf16_lo(u.w); s[7] += bf16_hi(u.w);
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) sh[rlane * C + v * 8 + k] = s[k];
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(out + c, sh[c]);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f;
+    for (int rl = 0; rl < rstep; ++rl) a += sh[rl * C + c];
+    part[static_cast<long long>(blockIdx.x) * C + c] = a;
+  }
 }
-// generic fallback for channel counts that are not a multiple of 8
-__global__ void bias_grad_generic_kernel(const __nv_bfloat16* __restrict__ dy, float* out,
+// generic variant for channel counts that are not a multiple of 8
+__global__ void bias_grad_generic_kernel(const __nv_bfloat16* __restrict__ dy, float* part,
                                          long long rows, int C, int rows_per_block) {
   const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_block;
   const long long r1 = min(rows, r0 + rows_per_block);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float s = 0.f;
     for (long long r = r0; r < r1; ++r) s += __bfloat162float(dy[r * C + c]);
-    atomicAdd(out + c, s);
+    part[static_cast<long long>(blockIdx.x) * C + c] = s;
   }
+}
+__global__ void bias_grad_reduce_kernel(const float* __restrict__ part, float* out, int blocks, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float a = 0.f;
+  for (int b = 0; b < blocks; ++b) a += part[static_cast<long long>(b) * C + c];
+  out[c] = a;
 }
 
 }  // namespace b2
@@ -315,19 +323,27 @@ int b2dq_im2col3x3_small(const void* src, void* dst, int N, int H, int W, int Cs
                   reinterpret_cast<__nv_bfloat16*>(dst), H, W, Cs, flip, total);
 }
 
-int b2dq_bias_grad(const void* dy, float* out, long long rows, int C, cudaStream_t st) {
+// Number of row blocks b2dq_bias_grad uses (scratch = blocks * C floats).
+int b2dq_bias_grad_blocks(long long rows) {
   if (rows <= 0) return 0;
-  cudaMemsetAsync(out, 0, sizeof(float) * C, st);
+  long long rpb = (rows + 148 * 8 - 1) / (148 * 8);
+  if (rpb < 64) rpb = 64;
+  return (int)((rows + rpb - 1) / rpb);
+}
+
+int b2dq_bias_grad(const void* dy, float* out, float* part, long long rows, int C, cudaStream_t st) {
+  if (rows <= 0) return 0;
   long long rpb = (rows + 148 * 8 - 1) / (148 * 8);
   if (rpb < 64) rpb = 64;
   const unsigned blocks = (unsigned)((rows + rpb - 1) / rpb);
   if (C % 8 == 0 && 256 % (C / 8) == 0) {
-    bias_grad_kernel<<<blocks, 256, C * sizeof(float), st>>>(reinterpret_cast<const __nv_bfloat16*>(dy),
-                                                            out, rows, C, (int)rpb);
+    bias_grad_kernel<<<blocks, 256, 256 * 8 * sizeof(float), st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(dy), part, rows, C, (int)rpb);
   } else {
-    bias_grad_generic_kernel<<<blocks, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dy), out,
+    bias_grad_generic_kernel<<<blocks, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dy), part,
                                                      rows, C, (int)rpb);
   }
+  bias_grad_reduce_kernel<<<(C + 127) / 128, 128, 0, st>>>(part, out, (int)blocks, C);
   return (int)cudaGetLastError();
 }
 

@@ -23,9 +23,11 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 
 // ------------------------------------------------------------------ forward statistics
 // grid (chunks, N); block 256.  Thread t owns channel vector (8 ch) v = t % (C/8) and walks rows.
-__global__ void gn_partial_stats_kernel(const __nv_bfloat16* __restrict__ x, double* ws, int HW,
+// Deterministic: per-thread sums are combined in a fixed order in shared memory, every CTA writes its
+// (sum, sum of squares) per group to part[n][chunk][g], and gn_finalize adds the chunks in order.
+__global__ void gn_partial_stats_kernel(const __nv_bfloat16* __restrict__ x, float* part, int HW,
                                         int C, int G, int rows_per_block) {
-  extern __shared__ float sh[];  // [2][C]
+  extern __shared__ float sh[];  // [2][rstep][C]
   const int n = blockIdx.y;
   const int vecs = C >> 3;
   const int v = threadIdx.x % vecs;
@@ -33,55 +35,65 @@ __global__ void gn_partial_stats_kernel(const __nv_bfloat16* __restrict__ x, dou
   const int rstep = blockDim.x / vecs;
   const int r0 = blockIdx.x * rows_per_block;
   const int r1 = min(HW, r0 + rows_per_block);
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
-  __syncthreads();
   float s[8], ss[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { s[i] = 0.f; ss[i] = 0.f; }
   const __nv_bfloat16* base = x + (static_cast<long long>(n) * HW) * C + v * 8;
-  {
-    int r = r0 + rlane;
-    for (; r + 3 * rstep < r1; r += 4 * rstep) {
-      uint4 u[4];
+  int r = r0 + rlane;
+  for (; r + 3 * rstep < r1; r += 4 * rstep) {
+    uint4 u[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        u[j] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(r + j * rstep) * C));
+    for (int j = 0; j < 4; ++j)
+      u[j] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(r + j * rstep) * C));
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float f[8];
-        unpack8(u[j], f);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { s[i] += f[i]; ss[i] = fmaf(f[i], f[i], ss[i]); }
-      }
-    }
-    for (; r < r1; r += rstep) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(r) * C));
+    for (int j = 0; j < 4; ++j) {
       float f[8];
-      unpack8(u, f);
+      unpack8(u[j], f);
 #pragma unroll
       for (int i = 0; i < 8; ++i) { s[i] += f[i]; ss[i] = fmaf(f[i], f[i], ss[i]); }
     }
+  }
+  for (; r < r1; r += rstep) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(r) * C));
+    float f[8];
+    unpack8(u, f);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      atomicAdd(&sh[v * 8 + i], s[i]);
-      atomicAdd(&sh[C + v * 8 + i], ss[i]);
-    }
+    for (int i = 0; i < 8; ++i) { s[i] += f[i]; ss[i] = fmaf(f[i], f[i], ss[i]); }
+  }
+  float* sh_s = sh;
+  float* sh_q = sh + rstep * C;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    sh_s[rlane * C + v * 8 + i] = s[i];
+    sh_q[rlane * C + v * 8 + i] = ss[i];
   }
   __syncthreads();
   const int cg = C / G;
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
     float a = 0.f, b = 0.f;
-    for (int c = 0; c < cg; ++c) { a += sh[g * cg + c]; b += sh[C + g * cg + c]; }
-    atomicAdd(&ws[(static_cast<long long>(n) * G + g) * 2 + 0], static_cast<double>(a));
-    atomicAdd(&ws[(static_cast<long long>(n) * G + g) * 2 + 1], static_cast<double>(b));
+    for (int rl = 0; rl < rstep; ++rl)
+      for (int c = 0; c < cg; ++c) {
+        a += sh_s[rl * C + g * cg + c];
+        b += sh_q[rl * C + g * cg + c];
+      }
+    float* o = part + ((static_cast<long long>(n) * gridDim.x + blockIdx.x) * G + g) * 2;
+    o[0] = a;
+    o[1] = b;
   }
 }
-__global__ void gn_finalize_kernel(const double* __restrict__ ws, float* stats, int NG,
-                                   double inv_count, float eps) {
+__global__ void gn_finalize_kernel(const float* __restrict__ part, float* stats, int N, int G,
+                                   int chunks, double inv_count, float eps) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= NG) return;
-  const double mean = ws[2 * i] * inv_count;
-  double var = ws[2 * i + 1] * inv_count - mean * mean;
+  if (i >= N * G) return;
+  const int n = i / G, g = i % G;
+  double a = 0.0, b = 0.0;
+  for (int c = 0; c < chunks; ++c) {
+    const float* p = part + ((static_cast<long long>(n) * chunks + c) * G + g) * 2;
+    a += p[0];
+    b += p[1];
+  }
+  const double mean = a * inv_count;
+  double var = b * inv_count - mean * mean;
   if (var < 0) var = 0;
   stats[2 * i] = static_cast<float>(mean);
   stats[2 * i + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
@@ -146,14 +158,15 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float
 }
 
 // ------------------------------------------------------------------ backward statistics
-// ws_nc[n][c][0] = sum_hw dz,  ws_nc[n][c][1] = sum_hw dz * xhat     (dz = grad wrt GN output)
+// part[n][chunk][c] = (sum_rows dz, sum_rows dz * xhat) over the chunk's rows (dz = grad wrt GN output),
+// combined in a fixed order; gn_bwd_reduce adds the chunks in order into ws_nc[n][c].
 __global__ void gn_bwd_partial_kernel(const __nv_bfloat16* __restrict__ dy,
                                       const __nv_bfloat16* __restrict__ x,
                                       const float* __restrict__ stats,
                                       const float* __restrict__ gamma,
-                                      const float* __restrict__ beta, float* ws_nc, int HW, int C,
+                                      const float* __restrict__ beta, float* part, int HW, int C,
                                       int G, int swish, int rows_per_block) {
-  extern __shared__ float sh[];  // [2][C]
+  extern __shared__ float sh[];  // [2][rstep][C]
   const int n = blockIdx.y;
   const int vecs = C >> 3;
   const int v = threadIdx.x % vecs;
@@ -161,8 +174,6 @@ __global__ void gn_bwd_partial_kernel(const __nv_bfloat16* __restrict__ dy,
   const int rstep = blockDim.x / vecs;
   const int r0 = blockIdx.x * rows_per_block;
   const int r1 = min(HW, r0 + rows_per_block);
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
-  __syncthreads();
   const int cg = C / G;
   float a[8], b[8], mean[8], rstd[8], gm[8], bt[8];
 #pragma unroll
@@ -174,48 +185,65 @@ __global__ void gn_bwd_partial_kernel(const __nv_bfloat16* __restrict__ dy,
     gm[k] = gamma[c]; bt[k] = beta[c];
   }
   const long long off = (static_cast<long long>(n) * HW) * C + v * 8;
-  {
-    auto accum = [&](const uint4& ux, const uint4& ud) {
-      float fx[8], fd[8];
-      unpack8(ux, fx); unpack8(ud, fd);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float xh = (fx[k] - mean[k]) * rstd[k];
-        float dz = fd[k];
-        if (swish) {
-          const float z = fmaf(xh, gm[k], bt[k]);
-          const float sg = sigmoidf_(z);
-          dz *= sg * (1.f + z * (1.f - sg));
-        }
-        a[k] += dz;
-        b[k] = fmaf(dz, xh, b[k]);
-      }
-    };
-    int r = r0 + rlane;
-    for (; r + rstep < r1; r += 2 * rstep) {
-      const uint4 ux0 = __ldg(reinterpret_cast<const uint4*>(x + off + static_cast<long long>(r) * C));
-      const uint4 ud0 = __ldg(reinterpret_cast<const uint4*>(dy + off + static_cast<long long>(r) * C));
-      const uint4 ux1 = __ldg(reinterpret_cast<const uint4*>(x + off + static_cast<long long>(r + rstep) * C));
-      const uint4 ud1 = __ldg(reinterpret_cast<const uint4*>(dy + off + static_cast<long long>(r + rstep) * C));
-      accum(ux0, ud0);
-      accum(ux1, ud1);
-    }
-    for (; r < r1; r += rstep) {
-      const uint4 ux = __ldg(reinterpret_cast<const uint4*>(x + off + static_cast<long long>(r) * C));
-      const uint4 ud = __ldg(reinterpret_cast<const uint4*>(dy + off + static_cast<long long>(r) * C));
-      accum(ux, ud);
-    }
+  auto accum = [&](const uint4& ux, const uint4& ud) {
+    float fx[8], fd[8];
+    unpack8(ux, fx); unpack8(ud, fd);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      atomicAdd(&sh[v * 8 + k], a[k]);
-      atomicAdd(&sh[C + v * 8 + k], b[k]);
+      const float xh = (fx[k] - mean[k]) * rstd[k];
+      float dz = fd[k];
+      if (swish) {
+        const float z = fmaf(xh, gm[k], bt[k]);
+        const float sg = sigmoidf_(z);
+        dz *= sg * (1.f + z * (1.f - sg));
+      }
+      a[k] += dz;
+      b[k] = fmaf(dz, xh, b[k]);
     }
+  };
+  int r = r0 + rlane;
+  for (; r + rstep < r1; r += 2 * rstep) {
+    const uint4 ux0 = __ldg(reinterpret_cast<const uint4*>(x + off + static_cast<long long>(r) * C));
+    const uint4 ud0 = __ldg(reinterpret_cast<const uint4*>(dy + off + static_cast<long long>(r) * C));
+    const uint4 ux1 = __ldg(reinterpret_cast<const uint4*>(x + off + static_cast<long long>(r + rstep) * C));
+    const uint4 ud1 = __ldg(reinterpret_cast<const uint4*>(dy + off + static_cast<long long>(r + rstep) * C));
+    accum(ux0, ud0);
+    accum(ux1, ud1);
+  }
+  for (; r < r1; r += rstep) {
+    const uint4 ux = __ldg(reinterpret_cast<const uint4*>(x + off + static_cast<long long>(r) * C));
+    const uint4 ud = __ldg(reinterpret_cast<const uint4*>(dy + off + static_cast<long long>(r) * C));
+    accum(ux, ud);
+  }
+  float* sh_a = sh;
+  float* sh_b = sh + rstep * C;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    sh_a[rlane * C + v * 8 + k] = a[k];
+    sh_b[rlane * C + v * 8 + k] = b[k];
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    atomicAdd(&ws_nc[(static_cast<long long>(n) * C + c) * 2 + 0], sh[c]);
-    atomicAdd(&ws_nc[(static_cast<long long>(n) * C + c) * 2 + 1], sh[C + c]);
+    float sa = 0.f, sb = 0.f;
+    for (int rl = 0; rl < rstep; ++rl) { sa += sh_a[rl * C + c]; sb += sh_b[rl * C + c]; }
+    float* o = part + ((static_cast<long long>(n) * gridDim.x + blockIdx.x) * C + c) * 2;
+    o[0] = sa;
+    o[1] = sb;
   }
+}
+__global__ void gn_bwd_reduce_kernel(const float* __restrict__ part, float* ws_nc, int N, int C,
+                                     int chunks) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * C) return;
+  const int n = i / C, c = i % C;
+  float a = 0.f, b = 0.f;
+  for (int k = 0; k < chunks; ++k) {
+    const float* p = part + ((static_cast<long long>(n) * chunks + k) * C + c) * 2;
+    a += p[0];
+    b += p[1];
+  }
+  ws_nc[2 * i] = a;
+  ws_nc[2 * i + 1] = b;
 }
 // dgamma[c] = sum_n ws[n][c][1], dbeta[c] = sum_n ws[n][c][0]
 __global__ void gn_bwd_param_kernel(const float* __restrict__ ws_nc, float* dgb, int N, int C) {
@@ -323,19 +351,27 @@ static int pick_rows_per_block(int HW, int N) {
 
 extern "C" {
 
-// stats[n][g] = (mean, rstd) fp32; ws = [N*G*2] doubles of scratch.
-int b2dq_gn_stats(const void* x, float* stats, double* ws, int N, int HW, int C, int G, float eps,
+// Number of row chunks (CTAs per image) the statistics kernels use for an [N, HW, C] tensor; callers
+// size their scratch with it: gn_stats ws = N*chunks*G*2 floats, gn_bwd_stats part = N*chunks*C*2 floats.
+int b2dq_gn_chunks(int N, int HW) {
+  if (N <= 0 || HW <= 0) return 0;
+  const int rpb = pick_rows_per_block(HW, N);
+  return (HW + rpb - 1) / rpb;
+}
+
+// stats[n][g] = (mean, rstd) fp32; ws = [N * chunks * G * 2] floats of scratch (b2dq_gn_chunks).
+int b2dq_gn_stats(const void* x, float* stats, float* ws, int N, int HW, int C, int G, float eps,
                   cudaStream_t stream) {
   if (N <= 0 || HW <= 0) return 0;
   if (C % 8 || C % G || 256 % (C / 8)) return -1;
-  cudaMemsetAsync(ws, 0, sizeof(double) * 2 * N * G, stream);
   const int rpb = pick_rows_per_block(HW, N);
-  dim3 grid((HW + rpb - 1) / rpb, N);
-  gn_partial_stats_kernel<<<grid, 256, 2 * C * sizeof(float), stream>>>(
+  const int chunks = (HW + rpb - 1) / rpb;
+  dim3 grid(chunks, N);
+  gn_partial_stats_kernel<<<grid, 256, 2 * 256 * 8 * sizeof(float), stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), ws, HW, C, G, rpb);
   const int NG = N * G;
   gn_finalize_kernel<<<(NG + 127) / 128, 128, 0, stream>>>(
-      ws, stats, NG, 1.0 / (static_cast<double>(HW) * (C / G)), eps);
+      ws, stats, N, G, chunks, 1.0 / (static_cast<double>(HW) * (C / G)), eps);
   return (int)cudaGetLastError();
 }
 
@@ -352,18 +388,19 @@ int b2dq_gn_apply(const void* x, const float* stats, const float* gamma, const f
   return (int)cudaGetLastError();
 }
 
-// ws_nc: [N*C*2] floats of scratch (zeroed here).
+// part: [N*chunks*C*2] floats of scratch (b2dq_gn_chunks); ws_nc: [N*C*2] floats (output of the pass).
 int b2dq_gn_bwd_stats(const void* dy, const void* x, const float* stats, const float* gamma,
-                      const float* beta, float* ws_nc, int N, int HW, int C, int G, int swish,
-                      cudaStream_t stream) {
+                      const float* beta, float* part, float* ws_nc, int N, int HW, int C, int G,
+                      int swish, cudaStream_t stream) {
   if (N <= 0 || HW <= 0) return 0;
   if (C % 8 || C % G || 256 % (C / 8)) return -1;
-  cudaMemsetAsync(ws_nc, 0, sizeof(float) * 2 * N * C, stream);
   const int rpb = pick_rows_per_block(HW, N);
-  dim3 grid((HW + rpb - 1) / rpb, N);
-  gn_bwd_partial_kernel<<<grid, 256, 2 * C * sizeof(float), stream>>>(
+  const int chunks = (HW + rpb - 1) / rpb;
+  dim3 grid(chunks, N);
+  gn_bwd_partial_kernel<<<grid, 256, 2 * 256 * 8 * sizeof(float), stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x), stats,
-      gamma, beta, ws_nc, HW, C, G, swish, rpb);
+      gamma, beta, part, HW, C, G, swish, rpb);
+  gn_bwd_reduce_kernel<<<(N * C + 255) / 256, 256, 0, stream>>>(part, ws_nc, N, C, chunks);
   return (int)cudaGetLastError();
 }
 

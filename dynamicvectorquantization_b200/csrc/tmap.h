@@ -33,6 +33,13 @@ inline int make_tmap_bf16(CUtensorMap* tm, const void* base, int rank, const uin
                           const uint64_t* strides_elems, const uint32_t* box) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return -100;
+  // cuTensorMapEncodeTiled is a driver call and needs a current context; a thread that has not made
+  // a runtime call yet (e.g. PyTorch's autograd worker entering our backward first) has none bound.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    cudaFree(0);
+    ctx_bound = true;
+  }
   cuuint64_t gdims[5];
   cuuint64_t gstr[4];
   cuuint32_t gbox[5];

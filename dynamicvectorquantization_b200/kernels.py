@@ -14,7 +14,7 @@ from ._cabi import check as _check
 BF16 = torch.bfloat16
 
 # kernels launched per C-ABI call (for bench.py's gpu_launches); everything else launches one
-_MULTI = {"vq_ema_finalize": 2, "gn_stats": 2, "gn_bwd_apply": 2}
+_MULTI = {"vq_ema_finalize": 2, "gn_stats": 2, "gn_bwd_stats": 2, "gn_bwd_apply": 2, "bias_grad": 2}
 _launches = 0
 
 
@@ -312,8 +312,11 @@ def conv_wgrad(x, dy, ksize, stride):
 
 def bias_grad(dy):
     cch = dy.shape[-1]
+    rows = dy.numel() // cch
+    lib = _cabi.lib()
     out = torch.empty(cch, dtype=torch.float32, device=dy.device)
-    check(_cabi.lib().b2dq_bias_grad(_ptr(dy), _ptr(out), dy.numel() // cch, cch, _stream()), "bias_grad")
+    part = torch.empty(lib.b2dq_bias_grad_blocks(rows) * cch, dtype=torch.float32, device=dy.device)
+    check(lib.b2dq_bias_grad(_ptr(dy), _ptr(out), _ptr(part), rows, cch, _stream()), "bias_grad")
     return out
 
 
@@ -321,7 +324,8 @@ def bias_grad(dy):
 def gn_stats(x, groups=32, eps=1e-6):
     nb, h, w, c = x.shape
     stats = torch.empty(nb, groups, 2, dtype=torch.float32, device=x.device)
-    ws = torch.empty(nb * groups * 2, dtype=torch.float64, device=x.device)
+    chunks = _cabi.lib().b2dq_gn_chunks(nb, h * w)
+    ws = torch.empty(nb * chunks * groups * 2, dtype=torch.float32, device=x.device)
     check(_cabi.lib().b2dq_gn_stats(_ptr(x), _ptr(stats), _ptr(ws), nb, h * w, c, groups, eps, _stream()),
           "gn_stats")
     return stats
@@ -338,12 +342,13 @@ def gn_apply(x, stats, gamma, beta, swish, groups=32):
 def gn_bwd(dy, x, stats, gamma, beta, swish, groups=32):
     """Returns (dx bf16, dgamma f32, dbeta f32)."""
     nb, h, w, c = x.shape
+    l = _cabi.lib()
     ws = torch.empty(nb * c * 2, dtype=torch.float32, device=x.device)
+    part = torch.empty(nb * l.b2dq_gn_chunks(nb, h * w) * c * 2, dtype=torch.float32, device=x.device)
     dx = torch.empty_like(x)
     dgb = torch.empty(2, c, dtype=torch.float32, device=x.device)
-    l = _cabi.lib()
-    check(l.b2dq_gn_bwd_stats(_ptr(dy), _ptr(x), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(ws), nb,
-                              h * w, c, groups, int(swish), _stream()), "gn_bwd_stats")
+    check(l.b2dq_gn_bwd_stats(_ptr(dy), _ptr(x), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(part), _ptr(ws),
+                              nb, h * w, c, groups, int(swish), _stream()), "gn_bwd_stats")
     check(l.b2dq_gn_bwd_apply(_ptr(dy), _ptr(x), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(ws),
                               _ptr(dx), _ptr(dgb), nb, h * w, c, groups, int(swish), _stream()),
           "gn_bwd_apply")

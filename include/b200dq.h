@@ -139,19 +139,23 @@ int b2dq_mmgemm(const b2dq_mm_desc* desc, cudaStream_t stream);
 int b2dq_wgrad_reduce(const float* partial, float* dw, int splits, int taps, int cout, int cin,
                       int accumulate, cudaStream_t stream);
 
-/* out[c] = sum_rows dy[row][c] */
-int b2dq_bias_grad(const void* dy_bf16, float* out, long long rows, int C, cudaStream_t stream);
+/* out[c] = sum_rows dy[row][c]; deterministic two-stage sum, part = b2dq_bias_grad_blocks(rows)*C floats */
+int b2dq_bias_grad_blocks(long long rows);
+int b2dq_bias_grad(const void* dy_bf16, float* out, float* part, long long rows, int C, cudaStream_t stream);
 
 /* ------------------------------------------------------------------ GroupNorm(32, eps) + swish
  * model.py:29-35 (Normalize, nonlinearity) as used at :119-127,170.
- * stats [N,G,2] = (mean, rstd);  ws: [N*G*2] doubles;  ws_nc: [N*C*2] floats;  dgb: [2*C] floats. */
-int b2dq_gn_stats(const void* x, float* stats, double* ws, int N, int HW, int C, int G, float eps,
+ * stats [N,G,2] = (mean, rstd);  chunks = b2dq_gn_chunks(N, HW);  ws: [N*chunks*G*2] floats;
+ * part: [N*chunks*C*2] floats;  ws_nc: [N*C*2] floats;  dgb: [2*C] floats.  All sums are combined in a
+ * fixed order (no atomics): results are bit-reproducible run to run. */
+int b2dq_gn_chunks(int N, int HW);
+int b2dq_gn_stats(const void* x, float* stats, float* ws, int N, int HW, int C, int G, float eps,
                   cudaStream_t stream);
 int b2dq_gn_apply(const void* x, const float* stats, const float* gamma, const float* beta, void* y,
                   int N, int HW, int C, int G, int swish, cudaStream_t stream);
 int b2dq_gn_bwd_stats(const void* dy, const void* x, const float* stats, const float* gamma,
-                      const float* beta, float* ws_nc, int N, int HW, int C, int G, int swish,
-                      cudaStream_t stream);
+                      const float* beta, float* part, float* ws_nc, int N, int HW, int C, int G,
+                      int swish, cudaStream_t stream);
 int b2dq_gn_bwd_apply(const void* dy, const void* x, const float* stats, const float* gamma,
                       const float* beta, const float* ws_nc, void* dx, float* dgb, int N, int HW,
                       int C, int G, int swish, cudaStream_t stream);
