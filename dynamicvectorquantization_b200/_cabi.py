@@ -67,6 +67,7 @@ SIGNATURES = {
     "b2dq_gn_apply": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "b2dq_gn_bwd_stats": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "b2dq_gn_bwd_apply": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "b2dq_gn_bwd_param": [_vp, _vp, _i, _i, _vp],
     "b2dq_nchw_f32_to_nhwc_bf16": [_vp, _vp, _i, _i, _i, _vp],
     "b2dq_nhwc_bf16_to_nchw_f32": [_vp, _vp, _i, _i, _i, _vp],
     "b2dq_nhwc_f32_to_nchw_f32": [_vp, _vp, _i, _i, _i, _vp],

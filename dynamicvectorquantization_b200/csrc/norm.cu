@@ -409,12 +409,20 @@ int b2dq_gn_bwd_apply(const void* dy, const void* x, const float* stats, const f
                       const float* beta, const float* ws_nc, void* dx, float* dgb, int N, int HW,
                       int C, int G, int swish, cudaStream_t stream) {
   if (N <= 0 || HW <= 0) return 0;
-  gn_bwd_param_kernel<<<(C + 127) / 128, 128, 0, stream>>>(ws_nc, dgb, N, C);
+  if (dgb) gn_bwd_param_kernel<<<(C + 127) / 128, 128, 0, stream>>>(ws_nc, dgb, N, C);
   const int rpb = pick_rows_per_block(HW, N);
   dim3 grid((HW + rpb - 1) / rpb, N);
   gn_bwd_apply_kernel<<<grid, 256, 0, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x), stats,
       gamma, beta, ws_nc, reinterpret_cast<__nv_bfloat16*>(dx), HW, C, G, swish, rpb);
+  return (int)cudaGetLastError();
+}
+
+// dgb [2*C] = (dgamma, dbeta) from ws_nc [N*C*2] (for callers that run the backward in image groups and
+// pass dgb = NULL to b2dq_gn_bwd_apply).
+int b2dq_gn_bwd_param(const float* ws_nc, float* dgb, int N, int C, cudaStream_t stream) {
+  if (N <= 0 || C <= 0) return 0;
+  gn_bwd_param_kernel<<<(C + 127) / 128, 128, 0, stream>>>(ws_nc, dgb, N, C);
   return (int)cudaGetLastError();
 }
 

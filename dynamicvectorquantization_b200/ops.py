@@ -178,8 +178,7 @@ class GroupNormSwishFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, gamma, beta, swish):
         g, b = _f32(gamma), _f32(beta)
-        stats = kn.gn_stats(x)
-        y = kn.gn_apply(x, stats, g, b, swish)
+        y, stats = kn.gn_forward(x, g, b, swish)
         ctx.save_for_backward(x, stats, g, b)
         ctx.swish = swish
         return y

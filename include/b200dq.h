@@ -160,6 +160,10 @@ int b2dq_gn_bwd_apply(const void* dy, const void* x, const float* stats, const f
                       const float* beta, const float* ws_nc, void* dx, float* dgb, int N, int HW,
                       int C, int G, int swish, cudaStream_t stream);
 
+/* dgb = NULL in b2dq_gn_bwd_apply skips the (dgamma, dbeta) reduction; b2dq_gn_bwd_param does it alone
+ * (used when the backward is run in L2-sized image groups). */
+int b2dq_gn_bwd_param(const float* ws_nc, float* dgb, int N, int C, cudaStream_t stream);
+
 /* ------------------------------------------------------------------ layout / elementwise */
 int b2dq_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int N, int C, int HW, cudaStream_t stream);
 int b2dq_nchw_f32_to_nhwc_f32(const float* src, float* dst, int N, int C, int HW, cudaStream_t stream);
