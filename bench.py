@@ -86,6 +86,45 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- reference / CPU arm
+def usable_cores():
+    """CPU cores this process may really use: affinity mask and cgroup quota, not the host total."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
+def pick_threads(torch):
+    """All usable host threads is not the fastest setting for batch-1 convolutions on a many-core
+    host (oneDNN oversubscribes): time a proxy layer (3x3 128->128 at 256x256, fwd+bwd) at a few
+    thread counts and keep the best."""
+    import torch.nn.functional as F
+    cores = usable_cores()
+    cands = sorted({c for c in (cores, cores // 2, cores // 4, 64, 32, 16, 8) if 1 <= c <= cores}, reverse=True)
+    x = torch.randn(1, 128, 256, 256)
+    w = torch.randn(128, 128, 3, 3, requires_grad=True)
+    best = (None, 1e30)
+    for t in cands:
+        torch.set_num_threads(t)
+        F.conv2d(x, w, padding=1).sum().backward()          # warm the pool at this size
+        t0 = time.perf_counter()
+        for _ in range(2):
+            F.conv2d(x, w, padding=1).sum().backward()
+        dt = time.perf_counter() - t0
+        if dt < best[1]:
+            best = (t, dt)
+    torch.set_num_threads(best[0])
+    return best[0], cores
+
+
 def oracle_step_fn(cfg_name, batch, seed=0):
     """One fwd+bwd of the fp32 oracle port (reference algorithm) on the host cores."""
     import torch
@@ -112,12 +151,11 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    threads, cores = pick_threads(torch)
     sample_b = 1
     step = oracle_step_fn(args.config, sample_b)
     t0 = time.perf_counter(); step(); first = time.perf_counter() - t0
-    budget_s = 240.0
+    budget_s = 150.0
     warm = max(0, min(args.warmup - 1, int(budget_s * 0.2 / max(first, 1e-3))))
     for _ in range(warm):
         step()
@@ -131,10 +169,11 @@ def run_reference(args):
             "steps": steps, "warmup": warm + 1, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "sample": f"{sample_b} image per step (bounded CPU sample)"},
-            "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
+            "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
                              "sample": f"{steps} x fwd+bwd of {sample_b} image, dual config, fp32 oracle port "
                                        f"of the reference modules (reference is pure PyTorch; not installable "
-                                       f"offline as a package)"},
+                                       f"offline as a package); {threads} threads = fastest of the thread counts "
+                                       f"tried on the {cores} usable cores"},
             "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -306,12 +345,14 @@ def kernel_rooflines(torch, kn, dev, peaks):
     except Exception:
         pass
     peak_t = peaks.get("bf16_tflops_sustained")
-    roof = {"kernel": "tapgemm_kernel<128,3> (conv3x3 128->128 @256x256, batch 32)", "bound": "tensor",
+    roof = {"kernel": "pconv3x3_kernel (conv3x3 128->128 @256x256, batch 32, forward)", "bound": "tensor",
             "achieved": flops / ms / 1e9, "peak": peak_t, "unit": "TFLOP/s",
             "frac": (flops / ms / 1e9 / peak_t) if peak_t else None,
             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed back-to-back inside a long run)"
             if peak_t else "unavailable",
-            "ms_per_launch": ms, "traffic": prof.get("tapgemm_dram_bytes_per_launch")}
+            "ms_per_launch": ms, "traffic": prof.get("pconv_dram_bytes_per_launch"),
+            "burst_peak": peaks.get("bf16_tflops"),
+            "frac_of_burst_peak": (flops / ms / 1e9 / peaks["bf16_tflops"]) if peaks.get("bf16_tflops") else None}
     # VQ search (+gather) at N=65536, C=256, K=1024: algorithmic bytes = 2NC + 2KC + 8N + 2NC
     N, C, K = 65536, 256, 1024
     xv = torch.randn(N, C, device=dev)
@@ -333,18 +374,20 @@ def kernel_rooflines(torch, kn, dev, peaks):
 
 def cpu_baseline(args):
     import torch
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    threads, cores = pick_threads(torch)
     step = oracle_step_fn(args.config, 1)
-    step()                                        # warm-up (thread pools, allocator)
-    t0 = time.perf_counter()
-    n = 0
-    while n < 2 or (time.perf_counter() - t0 < 10 and n < 8):
-        step(); n += 1
-    dt = time.perf_counter() - t0
-    return {"value": n / dt, "unit": "images/s", "cores": cores, "kind": "port",
-            "sample": f"{n} x fwd+bwd of 1 image (dual config, fp32 oracle port of the reference modules, "
-                      f"torch CPU with {cores} threads)"}
+    t0 = time.perf_counter(); step(); first = time.perf_counter() - t0   # also warms pools / allocator
+    if first > 20.0:                              # slow host: the first step is the bounded sample
+        n, dt = 1, first
+    else:
+        t0 = time.perf_counter()
+        n = 0
+        while n < 1 or (time.perf_counter() - t0 < 15 and n < 6):
+            step(); n += 1
+        dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "images/s", "cores": threads, "kind": "port",
+            "sample": f"{n} x fwd+bwd of 1 image (dual config, fp32 oracle port of the reference modules, torch CPU, "
+                      f"{threads} threads = fastest of the thread counts tried on the {cores} usable cores)"}
 
 
 if __name__ == "__main__":

@@ -43,6 +43,7 @@ class MmDesc(C.Structure):
         ("M", C.c_int), ("N", C.c_int),
         ("out", C.c_void_p), ("oZ", C.c_longlong), ("oT", C.c_longlong), ("oM", C.c_longlong),
         ("alpha", C.c_float), ("out_f32", C.c_int), ("block_n", C.c_int), ("b_strip", C.c_int),
+        ("colsum", C.c_void_p),
     ]
 
 
@@ -60,7 +61,9 @@ SIGNATURES = {
     "b2dq_vq_bwd": [_vp, _vp, _vp, _vp, _vp, _f, _vp, _ll, _i, _vp],
     "b2dq_tapgemm": [C.POINTER(TapGemmDesc), _vp],
     "b2dq_mmgemm": [C.POINTER(MmDesc), _vp],
-    "b2dq_pconv3x3": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    "b2dq_pconv3x3": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    "b2dq_gn_finalize_tiles": [_vp, _vp, _i, _i, _i, _f, _vp],
+    "b2dq_colsum_reduce": [_vp, _vp, _i, _i, _vp],
     "b2dq_wgrad_reduce": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
     "b2dq_gn_chunks": [_i, _i],
     "b2dq_gn_stats": [_vp, _vp, _vp, _i, _i, _i, _i, _f, _vp],

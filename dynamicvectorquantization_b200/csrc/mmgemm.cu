@@ -28,6 +28,9 @@ struct MmParams {
   long long oZ, oT, oM;           // element strides: per blockIdx.z, per tap, per output row
   float alpha;
   int out_f32;
+  float* colsum;                  // optional [splits][M] fp32: sum over the contraction index of A[m,k]
+                                  // (bias gradient = column sums of dY), computed by the tensor core as
+                                  // A x ones; written by the tap-group-0 CTAs (MAXTAPS == 3 kernels only)
 };
 
 // STRIP: the (up to 3) taps of a CTA are horizontal 1-pixel shifts of each other (one 3x3 filter row):
@@ -40,7 +43,8 @@ struct MmCfg {
   static constexpr uint32_t STRIP_ROWS = 66;
   static constexpr uint32_t STRIP_SLOT = 9 * 1024;                   // 66 x 128 B padded to 1 KB multiple
   static constexpr uint32_t STAGE_BYTES = STRIP ? (A_BYTES + (BN / 64) * STRIP_SLOT) : (A_BYTES + MAXTAPS * B_BYTES);
-  static constexpr uint32_t SMEM = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr uint32_t ONES_BYTES = 16 * 128;                   // K-major [16 n][64 k] tile of bf16 1.0
+  static constexpr uint32_t SMEM = STAGES * STAGE_BYTES + 1024 + 256 + ONES_BYTES + 1024;
   static constexpr uint32_t TMEM_COLS = (BN * MAXTAPS <= 128) ? 128 : (BN * MAXTAPS <= 256 ? 256 : 512);
 };
 
@@ -69,6 +73,14 @@ mmgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   const int kb0 = split * per;
   const int kb1 = min(p.kblocks, kb0 + per);
   const int kiters = max(kb1 - kb0, 0);
+  // tile of ones (B operand of the column-sum MMA), after the barrier block, 1 KB aligned
+  const uint32_t sOnes = (sBar + 256 + 1023u) & ~1023u;
+  const bool do_colsum = (MAXTAPS == 3) && p.colsum != nullptr && group == 0 && p.a_mn;
+  if (do_colsum) {
+    uint32_t* o = reinterpret_cast<uint32_t*>(smem_raw + (sOnes - smem_u32(smem_raw)));
+    for (int i = threadIdx.x; i < (int)(Cfg::ONES_BYTES / 4); i += blockDim.x) o[i] = 0x3F803F80u;
+    fence_proxy_async_smem();
+  }
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -148,6 +160,13 @@ mmgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             umma_bf16(tmem_base + t * BN, da, db, idesc, (it | k) ? 1u : 0u);
           }
         }
+        if (do_colsum) {
+          const uint32_t idesc1 = make_idesc_bf16(128, 16, 1, 0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + MAXTAPS * BN, make_smem_desc(sa + k * a_step, a_lbo, 1024),
+                      make_smem_desc(sOnes + k * 32, 0, 1024), idesc1, (it | k) ? 1u : 0u);
+        }
         umma_commit(bar_empty + 8 * stage);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
@@ -162,6 +181,16 @@ mmgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       tc_fence_after();
     }
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    if (do_colsum && blockIdx.y == 0) {
+      uint32_t r[16];
+      if (kiters > 0) {
+        tmem_ld_32x16(trow + MAXTAPS * BN, r);
+        tmem_ld_wait();
+      } else {
+        r[0] = 0u;
+      }
+      if (valid) p.colsum[static_cast<long long>(blockIdx.z) * p.M + m] = __uint_as_float(r[0]);
+    }
     for (int t = 0; t < ntl; ++t) {
       const long long ooff = blockIdx.z * p.oZ + (tap0 + t) * p.oT + static_cast<long long>(m) * p.oM;
 #pragma unroll 1
@@ -231,6 +260,15 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
   *o = accumulate ? (*o + s) : s;
 }
 
+// out[m] = sum_splits colsum[split][m]  (ordered: deterministic)
+__global__ void colsum_reduce_kernel(const float* __restrict__ part, float* out, int splits, int M) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  float a = 0.f;
+  for (int s = 0; s < splits; ++s) a += part[static_cast<long long>(s) * M + m];
+  out[m] = a;
+}
+
 template <int BN, int STAGES, int MAXTAPS, bool STRIP = false>
 static int launch_mm(const CUtensorMap& tmA, const CUtensorMap& tmB, const MmParams& p, dim3 grid,
                      cudaStream_t stream) {
@@ -269,6 +307,7 @@ struct b2dq_mm_desc {
   int out_f32;
   int block_n;   // 128 or 256 (0 = auto)
   int b_strip;   // 1: the taps of a CTA are 1-pixel horizontal shifts -> one 66-pixel strip load per k-block
+  float* colsum; // optional [splits][M] scratch: per-split sums of A over the contraction (bias gradient)
 };
 
 int b2dq_mmgemm(const b2dq_mm_desc* d, cudaStream_t stream) {
@@ -309,6 +348,8 @@ int b2dq_mmgemm(const b2dq_mm_desc* d, cudaStream_t stream) {
   p.M = d->M; p.N = d->N;
   p.out = d->out; p.oZ = d->oZ; p.oT = d->oT; p.oM = d->oM;
   p.alpha = d->alpha; p.out_f32 = d->out_f32;
+  p.colsum = (tpc == 3 && d->a_mn) ? d->colsum : nullptr;
+  if (d->colsum && !p.colsum) return -7;
   dim3 grid((unsigned)(((d->M + 127) / 128) * ngroups), (unsigned)((d->N + bn - 1) / bn),
             (unsigned)(d->batches * d->splits));
   if (d->b_strip) {
@@ -325,6 +366,12 @@ int b2dq_mmgemm(const b2dq_mm_desc* d, cudaStream_t stream) {
     return launch_mm<256, 4, 1>(tmA, tmB, p, grid, stream);
   }
   return -5;
+}
+
+int b2dq_colsum_reduce(const float* part, float* out, int splits, int M, cudaStream_t stream) {
+  if (M <= 0) return 0;
+  colsum_reduce_kernel<<<(M + 127) / 128, 128, 0, stream>>>(part, out, splits, M);
+  return (int)cudaGetLastError();
 }
 
 int b2dq_wgrad_reduce(const float* partial, float* dw, int splits, int taps, int cout, int cin,

@@ -28,7 +28,7 @@ constexpr uint32_t PC_STRIP_BYTES = PC_STRIP_ROWS * 128;           // 16,640
 constexpr uint32_t PC_STRIP_SLOT = 17 * 1024;                      // padded, keeps 1024 B alignment
 constexpr uint32_t PC_B_BYTES = PC_BN * 128;                       // 16 KB
 constexpr uint32_t PC_STAGE_BYTES = PC_MT * PC_STRIP_SLOT + 3 * PC_B_BYTES;   // 83,968
-constexpr uint32_t PC_SMEM = PC_STAGES * PC_STAGE_BYTES + 1024 + 256 + 1024;
+constexpr uint32_t PC_SMEM = PC_STAGES * PC_STAGE_BYTES + 1024 + 256 + 1024 + 2048;   // + GN partials
 
 struct PconvParams {
   int kchunks;                 // Cin / 64
@@ -43,6 +43,8 @@ struct PconvParams {
   const float* bias;
   const __nv_bfloat16* residual;
   long long rN, rH, rW;
+  float* gn_part;              // optional [num_tiles][32 groups][2]: per-tile (sum, sum of squares) of the
+                               // OUTPUT per GroupNorm group of 4 channels (statistics for the next GroupNorm)
 };
 
 __global__ void __launch_bounds__(192, 1)
@@ -54,6 +56,7 @@ pconv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t bar_full = sBar, bar_empty = sBar + 16, bar_tfull = sBar + 32, bar_tempty = sBar + 48;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + (sBar + 64 - smem_u32(smem_raw)));
   float* bias_s = reinterpret_cast<float*>(smem_raw + (sBar + 256 - smem_u32(smem_raw)));
+  float* gn_red = bias_s + 128;                  // [4 warps][64]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_items = (p.num_tiles + PC_MT - 1) / PC_MT;
@@ -180,7 +183,7 @@ pconv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           uint32_t r[32];
           tmem_ld_32x32(trow + c0, r);
           tmem_ld_wait();
-          if (!valid[j]) continue;
+          if (!valid[j] && !p.gn_part) continue;
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + bias_s[c0 + i];
@@ -194,16 +197,71 @@ pconv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               v[8 * i + 6] += bf16_lo(u.w); v[8 * i + 7] += bf16_hi(u.w);
             }
           }
-          uint4* op = reinterpret_cast<uint4*>(p.out + ooff[j] + c0);
+          if (valid[j]) {
+            uint4* op = reinterpret_cast<uint4*>(p.out + ooff[j] + c0);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint4 u;
-            u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
-            u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-            u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-            u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-            op[i] = u;
+            for (int i = 0; i < 4; ++i) {
+              uint4 u;
+              u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+              u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+              u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+              u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+              op[i] = u;
+            }
           }
+          if (p.gn_part) {
+            // per-group (4 channels) sum / sum of squares of this row, then a fixed-order transposed
+            // butterfly over the warp's 32 rows: 16 values -> lane pair (2i, 2i+1) holds total i
+            float a8[8], a4[4], a2[2], a1;
+            {
+              float vals[16];
+#pragma unroll
+              for (int g8 = 0; g8 < 8; ++g8) {
+                const float x0 = valid[j] ? v[4 * g8] : 0.f, x1 = valid[j] ? v[4 * g8 + 1] : 0.f;
+                const float x2 = valid[j] ? v[4 * g8 + 2] : 0.f, x3 = valid[j] ? v[4 * g8 + 3] : 0.f;
+                vals[g8] = (x0 + x1) + (x2 + x3);
+                vals[8 + g8] = fmaf(x0, x0, x1 * x1) + fmaf(x2, x2, x3 * x3);
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float send = (lane & 16) ? vals[i] : vals[i + 8];
+                const float keep = (lane & 16) ? vals[i + 8] : vals[i];
+                a8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float send = (lane & 8) ? a8[i] : a8[i + 4];
+              const float keep = (lane & 8) ? a8[i + 4] : a8[i];
+              a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const float send = (lane & 4) ? a4[i] : a4[i + 2];
+              const float keep = (lane & 4) ? a4[i + 2] : a4[i];
+              a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+            {
+              const float send = (lane & 2) ? a2[0] : a2[1];
+              const float keep = (lane & 2) ? a2[1] : a2[0];
+              a1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+            }
+            a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+            if ((lane & 1) == 0) {
+              const int idx = lane >> 1;                     // 0..7: group sums, 8..15: group sums of squares
+              const int group = (c0 >> 2) + (idx & 7);
+              gn_red[q * 64 + group * 2 + (idx >> 3)] = a1;
+            }
+          }
+        }
+        if (p.gn_part) {
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+          const int te = threadIdx.x - 64;
+          const int tile = item * PC_MT + j;
+          if (te < 64 && tile < p.num_tiles)
+            p.gn_part[static_cast<long long>(tile) * 64 + te] =
+                (gn_red[te] + gn_red[64 + te]) + (gn_red[128 + te] + gn_red[192 + te]);
+          asm volatile("bar.sync 2, 128;" ::: "memory");
         }
       }
       tc_fence_before();
@@ -230,8 +288,8 @@ extern "C" {
 // W % 128 == 0, Cin % 64 == 0.  b_ptr: [128, 9*Cin] bf16, column = (r*3+s)*Cin + ci.
 // dgrad != 0: tap (r,s) reads the pixel at (+1-r, +1-s) instead of (r-1, s-1).
 int b2dq_pconv3x3(const void* a_ptr, const void* b_ptr, void* out, const float* bias,
-                  const void* residual, int NB, int H, int W, int Cin, int dgrad, int max_ctas,
-                  cudaStream_t stream) {
+                  const void* residual, float* gn_part, int NB, int H, int W, int Cin, int dgrad,
+                  int max_ctas, cudaStream_t stream) {
   if (NB <= 0 || H <= 0 || W <= 0) return 0;
   if (W % 128 != 0 || Cin % 64 != 0 || Cin <= 0) return -1;
   CUtensorMap tmA, tmB;
@@ -269,6 +327,7 @@ int b2dq_pconv3x3(const void* a_ptr, const void* b_ptr, void* out, const float* 
   p.bias = bias;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
   p.rN = p.oN; p.rH = p.oH; p.rW = p.oW;
+  p.gn_part = gn_part;
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -277,6 +336,36 @@ int b2dq_pconv3x3(const void* a_ptr, const void* b_ptr, void* out, const float* 
   const int items = (p.num_tiles + PC_MT - 1) / PC_MT;
   if (items < grid) grid = items;
   pconv3x3_kernel<<<grid, 192, PC_SMEM, stream>>>(tmA, tmB, p);
+  return (int)cudaGetLastError();
+}
+
+// stats[n][g] = (mean, rstd) from the per-tile partials written by b2dq_pconv3x3 (tiles of an image are
+// contiguous; added in tile order: deterministic).  count = H*W*4 elements per group.
+__global__ void gn_finalize_tiles_kernel(const float* __restrict__ part, float* stats, int N,
+                                         int tiles_per_image, double inv_count, float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * 32) return;
+  const int n = i / 32, g = i % 32;
+  double a = 0.0, b = 0.0;
+  const float* pp = part + (static_cast<long long>(n) * tiles_per_image) * 64 + g * 2;
+  for (int t = 0; t < tiles_per_image; ++t) {
+    a += pp[static_cast<long long>(t) * 64];
+    b += pp[static_cast<long long>(t) * 64 + 1];
+  }
+  const double mean = a * inv_count;
+  double var = b * inv_count - mean * mean;
+  if (var < 0) var = 0;
+  stats[2 * i] = static_cast<float>(mean);
+  stats[2 * i + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+}
+
+int b2dq_gn_finalize_tiles(const float* gn_part, float* stats, int N, int H, int W, float eps,
+                           cudaStream_t stream) {
+  if (N <= 0) return 0;
+  if (W % 128) return -1;
+  const int tpi = H * (W / 128);
+  gn_finalize_tiles_kernel<<<(N * 32 + 127) / 128, 128, 0, stream>>>(
+      gn_part, stats, N, tpi, 1.0 / (static_cast<double>(H) * W * 4), eps);
   return (int)cudaGetLastError();
 }
 

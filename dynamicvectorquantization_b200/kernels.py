@@ -165,10 +165,12 @@ def pack_weight_dgrad(w):
 
 def conv_fwd(x, wpack, bias, ksize, stride, cout, residual=None, out_f32=False):
     """x NHWC bf16; wpack from pack_weight_fwd; stride-2 uses pad (0,1,0,1) like Downsample."""
+    global last_conv_stats
+    last_conv_stats = None
     nb, h, w, cin = x.shape
     assert cin % 64 == 0, "Cin must be a multiple of 64 (edge layers use the im2col path)"
     if not out_f32 and _pconv_ok(ksize, stride, w, cin, cout, nb, h):
-        return pconv3x3(x, wpack, bias, residual, dgrad=False)
+        return pconv3x3(x, wpack, bias, residual, dgrad=False, want_stats=FUSE_GN_STATS)
     kch = cin // 64
     if stride == 1:
         dims, strs = nhwc_view(x)
@@ -220,7 +222,7 @@ def conv_dgrad(dy, wdpack, ksize, stride, cin, in_hw):
 
 def mmgemm(a, a_dims, a_strides, a_mn, b, b_dims, b_strides, b_mn, M, N, kblocks, out, ostr,
            taps=((0, 0, 0, 0),), kbox=(64, 1, 1), ktiles=(0, 0), splits=1, batches=1, alpha=1.0,
-           out_f32=False, block_n=0, out_off=0, taps_per_cta=0, b_strip=False):
+           out_f32=False, block_n=0, out_off=0, taps_per_cta=0, b_strip=False, colsum=None):
     d = MmDesc()
     d.a_ptr, d.b_ptr = a.data_ptr(), b.data_ptr()
     _fill(d.a_dims, a_dims); _fill(d.a_strides, a_strides)
@@ -235,11 +237,13 @@ def mmgemm(a, a_dims, a_strides, a_mn, b, b_dims, b_strides, b_mn, M, N, kblocks
     d.out = out.data_ptr() + out_off * esz
     d.oZ, d.oT, d.oM = ostr
     d.alpha, d.out_f32, d.block_n, d.b_strip = alpha, int(out_f32), block_n, int(b_strip)
+    d.colsum = _ptr(colsum)
     check(_cabi.lib().b2dq_mmgemm(C.byref(d), _stream()), "mmgemm")
 
 
 NUM_SMS = 148
 FORCE_MT = 0          # tests / tuning: force m_tiles_per_cta of the tap GEMM (0 = library heuristic)
+FUSE_BIAS_GRAD = True    # 3x3 convs: bias gradient from the weight-gradient GEMM (dY x ones on the tensor core)
 USE_WGRAD_STRIP = True   # 3x3 s1 weight gradient: one 66-pixel activation strip per k-block for a filter row
 USE_PCONV = True      # persistent strip kernel for 3x3 s1 layers with 128 output channels and W % 128 == 0
 
@@ -249,11 +253,22 @@ def _pconv_ok(ksize, stride, w, cin, cout, nb, h):
             and nb * h * (w // 128) >= 2 * NUM_SMS)
 
 
-def pconv3x3(x, wpack, bias, residual, dgrad):
+FUSE_GN_STATS = True     # pconv forward also emits the GroupNorm statistics of its output
+last_conv_stats = None   # (mean, rstd) [N,32,2] of the most recent conv_fwd output, or None
+
+
+def pconv3x3(x, wpack, bias, residual, dgrad, want_stats=False):
+    global last_conv_stats
     nb, h, w, cin = x.shape
+    lib = _cabi.lib()
     out = torch.empty(nb, h, w, 128, dtype=BF16, device=x.device)
-    check(_cabi.lib().b2dq_pconv3x3(_ptr(x), _ptr(wpack), _ptr(out), _ptr(bias), _ptr(residual), nb, h, w, cin,
-                                    int(dgrad), 0, _stream()), "pconv3x3")
+    part = torch.empty(nb * h * (w // 128), 64, dtype=torch.float32, device=x.device) if want_stats else None
+    check(lib.b2dq_pconv3x3(_ptr(x), _ptr(wpack), _ptr(out), _ptr(bias), _ptr(residual), _ptr(part), nb, h, w, cin,
+                            int(dgrad), 0, _stream()), "pconv3x3")
+    if want_stats:
+        stats = torch.empty(nb, 32, 2, dtype=torch.float32, device=x.device)
+        check(lib.b2dq_gn_finalize_tiles(_ptr(part), _ptr(stats), nb, h, w, 1e-6, _stream()), "gn_finalize_tiles")
+        last_conv_stats = stats
     return out
 
 
@@ -278,8 +293,9 @@ def _pick_block_n(m_tiles, cout):
     return 128
 
 
-def conv_wgrad(x, dy, ksize, stride):
-    """dW (fp32, OIHW) for y = conv(x): x NHWC bf16 [N,H,W,Cin], dy NHWC bf16 [N,Ho,Wo,Cout]."""
+def conv_wgrad(x, dy, ksize, stride, want_bias=False):
+    """dW (fp32, OIHW) for y = conv(x): x NHWC bf16 [N,H,W,Cin], dy NHWC bf16 [N,Ho,Wo,Cout].
+    want_bias: also return db = sum_pixels dy (3x3 convs get it from the same GEMM as dY x ones)."""
     nb, h, w, cin = x.shape
     _, ho, wo, cout = dy.shape
     if stride == 1:
@@ -300,14 +316,24 @@ def conv_wgrad(x, dy, ksize, stride):
     ngroups = (ntaps + 2) // 3                 # <= 3 taps (TMEM accumulators) per CTA, folded into the grid
     splits = _wgrad_splits(kblocks, mt * nt * ngroups)
     partial = torch.empty(splits, ntaps, cout, cin, dtype=torch.float32, device=x.device)
+    fuse_bias = want_bias and ntaps >= 3 and FUSE_BIAS_GRAD
+    colsum = torch.empty(splits, cout, dtype=torch.float32, device=x.device) if fuse_bias else None
     mmgemm(dy, adims, astrs, True, x, bdims, bstrs, True, cout, cin, kblocks, partial,
            (ntaps * cout * cin, cout * cin, cin), taps=taps, kbox=(kw, kh, kn), ktiles=(ktw, kth),
            splits=splits, out_f32=True, block_n=128, taps_per_cta=min(3, ntaps),
-           b_strip=USE_WGRAD_STRIP and ksize == 3 and stride == 1 and (kw, kh, kn) == (64, 1, 1))
+           b_strip=USE_WGRAD_STRIP and ksize == 3 and stride == 1 and (kw, kh, kn) == (64, 1, 1),
+           colsum=colsum)
     dw = torch.empty(cout, cin, ksize, ksize, dtype=torch.float32, device=x.device)
     check(_cabi.lib().b2dq_wgrad_reduce(_ptr(partial), _ptr(dw), splits, ntaps, cout, cin, 0, _stream()),
           "wgrad_reduce")
-    return dw
+    if not want_bias:
+        return dw
+    if fuse_bias:
+        db = torch.empty(cout, dtype=torch.float32, device=x.device)
+        check(_cabi.lib().b2dq_colsum_reduce(_ptr(colsum), _ptr(db), splits, cout, _stream()), "colsum_reduce")
+    else:
+        db = bias_grad(dy)
+    return dw, db
 
 
 def bias_grad(dy):

@@ -7,11 +7,17 @@ tensors are never modified), because the reference loss calls ``torch.autograd.g
 retain_graph=True)`` on ``decoder.conv_out.weight`` before ``backward``
 (modules/losses/vqperceptual_multidisc.py:102-113).
 """
+import weakref
+
 import torch
 
 from . import kernels as kn
 
 BF16 = torch.bfloat16
+
+# GroupNorm statistics produced by the epilogue of the conv that made a tensor: (weakref(tensor), stats).
+# Consumed by the very next gn_swish on THAT tensor object; anything else recomputes them.
+_pending_stats = None
 
 def _packed(weight, kind):
     """bf16 GEMM packing of an OIHW fp32 parameter, cached ON the parameter object (so the cache
@@ -68,9 +74,13 @@ class Conv2dFn(torch.autograd.Function):
         dx = dw = db = dres = None
         if ctx.needs_input_grad[0]:
             dx = kn.conv_dgrad(dy, _packed(weight, "dgrad"), ksize, stride, cin, x.shape[1:3])
+        want_db = has_bias and ctx.needs_input_grad[2]
         if ctx.needs_input_grad[1]:
-            dw = kn.conv_wgrad(x, dy, ksize, stride)
-        if has_bias and ctx.needs_input_grad[2]:
+            if want_db:
+                dw, db = kn.conv_wgrad(x, dy, ksize, stride, want_bias=True)
+            else:
+                dw = kn.conv_wgrad(x, dy, ksize, stride)
+        elif want_db:
             db = kn.bias_grad(dy)
         if res_shape is not None and ctx.needs_input_grad[3]:
             dres = dy if res_shape[0] == dy.shape[0] else dy.float().sum(0, keepdim=True).to(BF16)
@@ -176,9 +186,12 @@ class GroupNormSwishFn(torch.autograd.Function):
     """GroupNorm(32, eps=1e-6, affine) optionally followed by swish (model.py:29-35)."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, swish):
+    def forward(ctx, x, gamma, beta, swish, stats=None):
         g, b = _f32(gamma), _f32(beta)
-        y, stats = kn.gn_forward(x, g, b, swish)
+        if stats is not None:
+            y = kn.gn_apply(x, stats, g, b, swish)
+        else:
+            y, stats = kn.gn_forward(x, g, b, swish)
         ctx.save_for_backward(x, stats, g, b)
         ctx.swish = swish
         return y
@@ -187,7 +200,7 @@ class GroupNormSwishFn(torch.autograd.Function):
     def backward(ctx, dy):
         x, stats, g, b = ctx.saved_tensors
         dx, dg, db = kn.gn_bwd(dy.contiguous(), x, stats, g, b, ctx.swish)
-        return dx, dg, db, None
+        return dx, dg, db, None, None
 
 
 class AttentionFn(torch.autograd.Function):
@@ -310,13 +323,23 @@ class AddFn(torch.autograd.Function):
 # convenience wrappers -------------------------------------------------------------------------
 def conv2d(x, conv, residual=None, stride=None):
     """x NHWC bf16; conv: an nn.Conv2d used as a parameter container."""
+    global _pending_stats
     k = conv.kernel_size[0]
     st = conv.stride[0] if stride is None else stride
-    return Conv2dFn.apply(x, conv.weight, conv.bias, residual, k, st)
+    y = Conv2dFn.apply(x, conv.weight, conv.bias, residual, k, st)
+    stats = kn.last_conv_stats                      # set by the forward that just ran (or None)
+    kn.last_conv_stats = None
+    _pending_stats = (weakref.ref(y), stats) if stats is not None else None
+    return y
 
 
 def gn_swish(x, norm, swish=True):
-    return GroupNormSwishFn.apply(x, norm.weight, norm.bias, swish)
+    global _pending_stats
+    stats = None
+    if _pending_stats is not None and _pending_stats[0]() is x and norm.num_groups == 32:
+        stats = _pending_stats[1]
+    _pending_stats = None
+    return GroupNormSwishFn.apply(x, norm.weight, norm.bias, swish, stats)
 
 
 def to_nhwc(x):

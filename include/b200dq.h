@@ -104,8 +104,12 @@ int b2dq_tapgemm(const b2dq_tapgemm_desc* desc, cudaStream_t stream);
  * each weight tile, epilogue overlapped through double-buffered TMEM.  Same maths as b2dq_tapgemm
  * with the 3x3 tap table; dgrad != 0 mirrors the taps (data gradient).  b: [128, 9*Cin] bf16. */
 int b2dq_pconv3x3(const void* a_bf16, const void* b_bf16, void* out_bf16, const float* bias,
-                  const void* residual_bf16, int NB, int H, int W, int Cin, int dgrad, int max_ctas,
-                  cudaStream_t stream);
+                  const void* residual_bf16, float* gn_part, int NB, int H, int W, int Cin, int dgrad,
+                  int max_ctas, cudaStream_t stream);
+/* gn_part (optional, [NB*H*W/128][32][2] floats): per-tile GroupNorm(32) partial sums of the OUTPUT, so the
+ * next GroupNorm needs no statistics pass; b2dq_gn_finalize_tiles turns them into stats [NB][32][2]. */
+int b2dq_gn_finalize_tiles(const float* gn_part, float* stats, int N, int H, int W, float eps,
+                           cudaStream_t stream);
 
 /* ------------------------------------------------------------------ batched / split-K GEMM
  * Weight gradients of the convolutions above (autograd of nn.Conv2d) and the attention
@@ -131,9 +135,14 @@ typedef struct b2dq_mm_desc {
   int block_n;            /* 0 = auto, 128 or 256 */
   int b_strip;            /* 1: the 3 taps of a CTA are 1-pixel shifts (3x3 filter row): B is loaded once
                              per k-block as a 66-pixel strip (needs a_mn = b_mn = 1, KW = 64, KH = KN = 1) */
+  float* colsum;          /* optional [splits][M] fp32 scratch: sum_k A[m,k] per split (the bias gradient when
+                             A = dY), computed on the tensor core as A x ones; 3-tap MN-major-A launches only */
 } b2dq_mm_desc;
 
 int b2dq_mmgemm(const b2dq_mm_desc* desc, cudaStream_t stream);
+
+/* out[m] = sum_splits part[split][m] (ordered) */
+int b2dq_colsum_reduce(const float* part, float* out, int splits, int M, cudaStream_t stream);
 
 /* partial [splits][taps][cout][cin] fp32 -> dw [cout][cin][taps] fp32 (OIHW); accumulate != 0: += */
 int b2dq_wgrad_reduce(const float* partial, float* dw, int splits, int taps, int cout, int cin,

@@ -127,11 +127,29 @@ def test_conv_fwd_dgrad_wgrad(nb, h, w, cin, cout, k, stride, mt, monkeypatch):
     dx = kn.conv_dgrad(dyd, kn.pack_weight_dgrad(wt.to(dev)), k, stride, cin, (h, w))
     e = rel_rms(dx.float().cpu(), xr.grad)
     assert e < 6e-3, f"dgrad rel rms {e}"
-    dw = kn.conv_wgrad(xd, dyd, k, stride)
+    dw, db_fused = kn.conv_wgrad(xd, dyd, k, stride, want_bias=True)   # 3x3: bias grad from the same GEMM
     e = rel_rms(dw.cpu(), wr.grad)
     assert e < 2e-3, f"wgrad rel rms {e}"
     db = kn.bias_grad(dyd)
     assert rel_rms(db.cpu(), dy.float().sum((0, 1, 2))) < 1e-4
+    assert rel_rms(db_fused.cpu(), dy.float().sum((0, 1, 2))) < 1e-4
+
+
+def test_pconv_emits_groupnorm_statistics():
+    """The persistent conv also returns (mean, rstd) of its output for the following GroupNorm(32)."""
+    from dynamicvectorquantization_b200 import kernels as kn
+    nb, h, w, c = 3, 64, 256, 128
+    x = _rand_bf(nb, h, w, c, seed=41)
+    wt = _rand_bf(c, c, 3, 3, scale=(c * 9) ** -0.5, seed=42).float()
+    bias = torch.randn(c, generator=torch.Generator().manual_seed(43))
+    res = _rand_bf(nb, h, w, c, seed=44)
+    y = kn.pconv3x3(x.cuda(), kn.pack_weight_fwd(wt.cuda()), bias.cuda(), res.cuda(), False, want_stats=True)
+    st = kn.last_conv_stats
+    ref = kn.gn_stats(y)                                   # statistics pass over the stored bf16 output
+    assert torch.allclose(st[..., 0], ref[..., 0], atol=2e-4, rtol=0)
+    assert torch.allclose(st[..., 1], ref[..., 1], rtol=2e-3)
+    y2 = kn.pconv3x3(x.cuda(), kn.pack_weight_fwd(wt.cuda()), bias.cuda(), res.cuda(), False, want_stats=True)
+    assert torch.equal(kn.last_conv_stats, st) and torch.equal(y, y2)      # deterministic
 
 
 # ------------------------------------------------------------------------------------------- GEMM

@@ -18,8 +18,8 @@ xb = xv.to(BF)
 which = sys.argv[1:] or ["conv", "wgrad", "vq"]
 for _ in range(3):
     if "conv" in which:
-        kn.FORCE_MT = 1; kn.conv_fwd(x, wp, bias, 3, 1, c)
-        kn.FORCE_MT = 2; kn.conv_fwd(x, wp, bias, 3, 1, c); kn.FORCE_MT = 0
+        kn.conv_fwd(x, wp, bias, 3, 1, c)                       # pconv3x3_kernel
+        kn.USE_PCONV = False; kn.conv_fwd(x, wp, bias, 3, 1, c); kn.USE_PCONV = True   # tapgemm_kernel
     if "wgrad" in which:
         kn.conv_wgrad(x, dy, 3, 1)
     if "vq" in which:
