@@ -197,10 +197,22 @@ def run_b200(args):
         p.requires_grad_(False)
     model.learning_rate = 4.5e-6 * world * args.batch
     ae_params = [p for n, p in model.named_parameters() if not n.startswith("loss.") and p.requires_grad]
-    use_graph = (world == 1) and not args.no_graph
+    use_graph = not args.no_graph
+    graph_ddp = use_graph and world > 1          # N > 1: graph-captured fwd+bwd, one flat gradient all-reduce
     opt = torch.optim.Adam(ae_params, lr=model.learning_rate, betas=(0.5, 0.9), capturable=use_graph)
     net = model
-    if world > 1:
+    flat_grad = None
+    if graph_ddp:
+        # every rank starts from rank 0's parameters / buffers (what DDP's constructor does)
+        for t in list(model.parameters()) + list(model.buffers()):
+            dist.broadcast(t.data, 0)
+        flat_grad = torch.zeros(sum(p.numel() for p in ae_params), device=dev)
+        off = 0
+        for p in ae_params:
+            p.grad = flat_grad[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        model.quantize.codebook.defer_ema = True
+    elif world > 1:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
     B = args.batch
     g = torch.Generator().manual_seed(2021 + rank)
@@ -208,13 +220,26 @@ def run_b200(args):
     x_dev = x_host.to(dev)
     loss_host = torch.zeros(1).pin_memory()
 
-    def step(x):
-        opt.zero_grad(set_to_none=True)
+    def fwd_bwd(x):
+        if flat_grad is not None:
+            flat_grad.zero_()                    # gradients stay views into one flat buffer
+        else:
+            opt.zero_grad(set_to_none=True)
         xrec, qloss, indices, gate = net(x)[:4]
         loss, _ = model.loss(qloss, x, xrec, 0, 0, last_layer=None, split="train", gate=gate)
         loss.backward()
+        return loss
+
+    def finish(loss):
+        if flat_grad is not None:
+            model.quantize.codebook.apply_deferred_ema()      # packed all-reduce + rank-0 restart rows
+            dist.all_reduce(flat_grad)                        # 192 MB over NVLink, then average like DDP
+            flat_grad.div_(world)
         opt.step()
         return loss
+
+    def step(x):
+        return finish(fwd_bwd(x))
 
     def barrier():
         if world > 1:
@@ -234,15 +259,18 @@ def run_b200(args):
             l0 = kn.launch_count()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                static_loss = step(static_x)
+                static_loss = fwd_bwd(static_x) if graph_ddp else step(static_x)
             launches_per_step = kn.launch_count() - l0
-            eager_step = step
+            if graph_ddp:                         # EMA finalize kernels run eagerly after each replay
+                l1 = kn.launch_count()
+                finish(static_loss)
+                launches_per_step += kn.launch_count() - l1
 
             def step(x):                          # noqa: F811  (graph replay with the eager signature)
                 if x is not static_x:
                     static_x.copy_(x, non_blocking=True)
                 graph.replay()
-                return static_loss
+                return finish(static_loss) if graph_ddp else static_loss
             for _ in range(2):
                 step(static_x)
             x_dev = static_x

@@ -95,6 +95,12 @@ class VQEmbedding(nn.Embedding):
         self._cb = None
         self._cb_key = None
         self._acc = None
+        # defer_ema: forward only accumulates the per-code statistics; the caller applies the EMA /
+        # restart / re-normalisation later with apply_deferred_ema().  Result-identical (the gather
+        # uses the pre-update codebook either way, :119-126) and lets a CUDA-graph-captured step keep
+        # the NCCL exchange outside the graph.
+        self.defer_ema = False
+        self._deferred = None
 
     # ---- derived search operands (bf16 codebook + squared norms), refreshed when weight changes
     def _codebook(self):
@@ -154,6 +160,19 @@ class VQEmbedding(nn.Embedding):
     def _ema_step(self, rows_f32_fn, n_vectors):
         """EMA + restart + re-normalisation after the search kernel has filled self._acc
         (:86-105 and :107-115).  rows_f32_fn(idx) returns fp32 input rows for the restart."""
+        if self.defer_ema:
+            self._deferred = (rows_f32_fn, n_vectors)
+            return
+        self._ema_step_now(rows_f32_fn, n_vectors)
+
+    @torch.no_grad()
+    def apply_deferred_ema(self):
+        if self._deferred is not None:
+            fn, n = self._deferred
+            self._ema_step_now(fn, n)
+
+    @torch.no_grad()
+    def _ema_step_now(self, rows_f32_fn, n_vectors):
         reduce_ema_stats(self._acc)
         sums, counts = self._acc_views()
         restart_rows = None
