@@ -61,7 +61,8 @@ SIGNATURES = {
     "b2dq_vq_bwd": [_vp, _vp, _vp, _vp, _vp, _f, _vp, _ll, _i, _vp],
     "b2dq_tapgemm": [C.POINTER(TapGemmDesc), _vp],
     "b2dq_mmgemm": [C.POINTER(MmDesc), _vp],
-    "b2dq_pconv3x3": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    "b2dq_pconv3x3": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    "b2dq_gn_bwd_reduce_tiles": [_vp, _vp, _i, _i, _i, _vp],
     "b2dq_gn_finalize_tiles": [_vp, _vp, _i, _i, _i, _f, _vp],
     "b2dq_colsum_reduce": [_vp, _vp, _i, _i, _vp],
     "b2dq_wgrad_reduce": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
@@ -69,7 +70,7 @@ SIGNATURES = {
     "b2dq_gn_stats": [_vp, _vp, _vp, _i, _i, _i, _i, _f, _vp],
     "b2dq_gn_apply": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "b2dq_gn_bwd_stats": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
-    "b2dq_gn_bwd_apply": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "b2dq_gn_bwd_apply": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "b2dq_gn_bwd_param": [_vp, _vp, _i, _i, _vp],
     "b2dq_nchw_f32_to_nhwc_bf16": [_vp, _vp, _i, _i, _i, _vp],
     "b2dq_nhwc_bf16_to_nchw_f32": [_vp, _vp, _i, _i, _i, _vp],

@@ -264,7 +264,8 @@ __global__ void gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy,
                                     const float* __restrict__ stats,
                                     const float* __restrict__ gamma, const float* __restrict__ beta,
                                     const float* __restrict__ ws_nc, __nv_bfloat16* __restrict__ dx,
-                                    int HW, int C, int G, int swish, int rows_per_block) {
+                                    const __nv_bfloat16* __restrict__ add, int HW, int C, int G,
+                                    int swish, int rows_per_block) {
   const int n = blockIdx.y;
   const int vecs = C >> 3;
   const int v = threadIdx.x % vecs;
@@ -313,6 +314,12 @@ __global__ void gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy,
         }
         o[k] = rstd[k] * (dz * gm[k] - k1[k] - xh * k2[k]);
       }
+      if (add) {
+        float fa[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(add + off + static_cast<long long>(r + j * rstep) * C)), fa);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] += fa[k];
+      }
       *reinterpret_cast<uint4*>(dx + off + static_cast<long long>(r + j * rstep) * C) = pack8(o);
     }
   }
@@ -331,6 +338,12 @@ __global__ void gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy,
         dz *= sg * (1.f + z * (1.f - sg));
       }
       o[k] = rstd[k] * (dz * gm[k] - k1[k] - xh * k2[k]);
+    }
+    if (add) {
+      float fa[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(add + off + static_cast<long long>(r) * C)), fa);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] += fa[k];
     }
     *reinterpret_cast<uint4*>(dx + off + static_cast<long long>(r) * C) = pack8(o);
   }
@@ -406,15 +419,16 @@ int b2dq_gn_bwd_stats(const void* dy, const void* x, const float* stats, const f
 
 // dgb: [2*C] floats: dgamma then dbeta (overwritten).
 int b2dq_gn_bwd_apply(const void* dy, const void* x, const float* stats, const float* gamma,
-                      const float* beta, const float* ws_nc, void* dx, float* dgb, int N, int HW,
-                      int C, int G, int swish, cudaStream_t stream) {
+                      const float* beta, const float* ws_nc, void* dx, float* dgb, const void* add,
+                      int N, int HW, int C, int G, int swish, cudaStream_t stream) {
   if (N <= 0 || HW <= 0) return 0;
   if (dgb) gn_bwd_param_kernel<<<(C + 127) / 128, 128, 0, stream>>>(ws_nc, dgb, N, C);
   const int rpb = pick_rows_per_block(HW, N);
   dim3 grid((HW + rpb - 1) / rpb, N);
   gn_bwd_apply_kernel<<<grid, 256, 0, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x), stats,
-      gamma, beta, ws_nc, reinterpret_cast<__nv_bfloat16*>(dx), HW, C, G, swish, rpb);
+      gamma, beta, ws_nc, reinterpret_cast<__nv_bfloat16*>(dx),
+      reinterpret_cast<const __nv_bfloat16*>(add), HW, C, G, swish, rpb);
   return (int)cudaGetLastError();
 }
 

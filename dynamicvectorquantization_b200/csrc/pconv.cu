@@ -28,7 +28,7 @@ constexpr uint32_t PC_STRIP_BYTES = PC_STRIP_ROWS * 128;           // 16,640
 constexpr uint32_t PC_STRIP_SLOT = 17 * 1024;                      // padded, keeps 1024 B alignment
 constexpr uint32_t PC_B_BYTES = PC_BN * 128;                       // 16 KB
 constexpr uint32_t PC_STAGE_BYTES = PC_MT * PC_STRIP_SLOT + 3 * PC_B_BYTES;   // 83,968
-constexpr uint32_t PC_SMEM = PC_STAGES * PC_STAGE_BYTES + 1024 + 256 + 1024 + 2048;   // + GN partials
+constexpr uint32_t PC_SMEM = PC_STAGES * PC_STAGE_BYTES + 1024 + 256 + 7168;   // + bias / GN scratch
 
 struct PconvParams {
   int kchunks;                 // Cin / 64
@@ -45,6 +45,14 @@ struct PconvParams {
   long long rN, rH, rW;
   float* gn_part;              // optional [num_tiles][32 groups][2]: per-tile (sum, sum of squares) of the
                                // OUTPUT per GroupNorm group of 4 channels (statistics for the next GroupNorm)
+  // Data-gradient mode, optional: the output d_a is the gradient wrt a = swish(GroupNorm(gnb_x)); emit
+  // the per-tile, per-channel sums the GroupNorm backward needs (sum dz, sum dz*xhat), so that its own
+  // reduction pass over (d_a, x) disappears.  gnb_x: [NB,H,W,128] like the output.
+  const __nv_bfloat16* gnb_x;
+  const float* gnb_stats;      // [NB][32][2] (mean, rstd)
+  const float* gnb_gamma;      // [128]
+  const float* gnb_beta;       // [128]
+  float* gnb_part;             // [num_tiles][128][2]
 };
 
 __global__ void __launch_bounds__(192, 1)
@@ -57,6 +65,9 @@ pconv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + (sBar + 64 - smem_u32(smem_raw)));
   float* bias_s = reinterpret_cast<float*>(smem_raw + (sBar + 256 - smem_u32(smem_raw)));
   float* gn_red = bias_s + 128;                  // [4 warps][64]
+  float* gsm = gn_red + 256;                     // GroupNorm gamma [128]
+  float* bsm = gsm + 128;                        // GroupNorm beta  [128]
+  float* red2 = bsm + 128;                       // [4 warps][128 ch][2]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_items = (p.num_tiles + PC_MT - 1) / PC_MT;
@@ -79,6 +90,10 @@ pconv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (threadIdx.x >= 64) {
     const int t = threadIdx.x - 64;
     bias_s[t] = (p.bias && t < p.Cout) ? p.bias[t] : 0.f;
+    if (p.gnb_part) {
+      gsm[t] = p.gnb_gamma[t];
+      bsm[t] = p.gnb_beta[t];
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -153,18 +168,22 @@ pconv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const uint32_t buf = it_item & 1;
       bool valid[PC_MT];
       long long ooff[PC_MT], roff[PC_MT];
+      int nimg[PC_MT];
 #pragma unroll
       for (int j = 0; j < PC_MT; ++j) {
         int ow0, oh, n;
         tile_coords(item * PC_MT + j, ow0, oh, n);
         const int ow = ow0 + m;
         valid[j] = (ow < p.W) && (n < p.NB);
+        nimg[j] = n < p.NB ? n : 0;
         ooff[j] = n * p.oN + oh * p.oH + ow * p.oW;
         roff[j] = n * p.rN + oh * p.rH + ow * p.rW;
       }
+      // row prefetched while the main loop runs: the residual (forward) or the GroupNorm input (dgrad)
+      const __nv_bfloat16* aux = p.gnb_part ? p.gnb_x : p.residual;
       uint4 res[PC_BN / 8];
-      if (p.residual && valid[0]) {
-        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + roff[0]);
+      if (aux && valid[0]) {
+        const uint4* rp = reinterpret_cast<const uint4*>(aux + roff[0]);
 #pragma unroll
         for (int i = 0; i < PC_BN / 8; ++i) res[i] = __ldg(rp + i);
       }
@@ -172,8 +191,8 @@ pconv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       tc_fence_after();
 #pragma unroll
       for (int j = 0; j < PC_MT; ++j) {
-        if (j > 0 && p.residual && valid[j]) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + roff[j]);
+        if (j > 0 && aux && valid[j]) {
+          const uint4* rp = reinterpret_cast<const uint4*>(aux + roff[j]);
 #pragma unroll
           for (int i = 0; i < PC_BN / 8; ++i) res[i] = __ldg(rp + i);
         }
@@ -183,7 +202,7 @@ pconv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           uint32_t r[32];
           tmem_ld_32x32(trow + c0, r);
           tmem_ld_wait();
-          if (!valid[j] && !p.gn_part) continue;
+          if (!valid[j] && !p.gn_part && !p.gnb_part) continue;
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + bias_s[c0 + i];
@@ -208,6 +227,63 @@ pconv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
               op[i] = u;
             }
+          }
+          if (p.gnb_part) {
+            // GroupNorm(+swish) backward partial sums for the 32 channels of this chunk:
+            //   A_c = sum_rows dz,  B_c = sum_rows dz * xhat,  dz = d_a * swish'(z), z = xhat*gamma + beta.
+            // First butterfly step (A_c / B_c pairs, lane bit 4) is fused into the production loop; four
+            // more halving steps leave lane l with entries 2l, 2l+1 of [A_0..A_31, B_0..B_31].
+            float w32[32];
+            const float* stp = p.gnb_stats + (static_cast<long long>(nimg[j]) * 32 + (c0 >> 2)) * 2;
+#pragma unroll
+            for (int g8 = 0; g8 < 8; ++g8) {
+              const float mean = __ldg(stp + 2 * g8), rstd = __ldg(stp + 2 * g8 + 1);
+              const uint4 u = res[(c0 >> 3) + (g8 >> 1)];
+              const uint32_t lo = (g8 & 1) ? u.z : u.x, hi = (g8 & 1) ? u.w : u.y;
+              const float xs[4] = {bf16_lo(lo), bf16_hi(lo), bf16_lo(hi), bf16_hi(hi)};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int i = 4 * g8 + e;
+                const float xh = (xs[e] - mean) * rstd;
+                const float z = fmaf(xh, gsm[c0 + i], bsm[c0 + i]);
+                const float sg = __fdividef(1.f, 1.f + __expf(-z));
+                const float dz = valid[j] ? v[i] * sg * (1.f + z * (1.f - sg)) : 0.f;
+                const float bz = valid[j] ? dz * xh : 0.f;
+                const float send = (lane & 16) ? dz : bz;
+                const float keep = (lane & 16) ? bz : dz;
+                w32[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+              }
+            }
+            float w16[16], w8[8], w4[4], w2[2];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float send = (lane & 8) ? w32[i] : w32[i + 16];
+              const float keep = (lane & 8) ? w32[i + 16] : w32[i];
+              w16[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float send = (lane & 4) ? w16[i] : w16[i + 8];
+              const float keep = (lane & 4) ? w16[i + 8] : w16[i];
+              w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float send = (lane & 2) ? w8[i] : w8[i + 4];
+              const float keep = (lane & 2) ? w8[i + 4] : w8[i];
+              w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const float send = (lane & 1) ? w4[i] : w4[i + 2];
+              const float keep = (lane & 1) ? w4[i + 2] : w4[i];
+              w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+            }
+            // lane l: entries 2l, 2l+1; entries 0..31 = A of channel c0+e, 32..63 = B of channel c0+e-32
+            const int e0 = 2 * lane;
+            const int kind = e0 >> 5, ch = c0 + (e0 & 31);
+            red2[q * 256 + ch * 2 + kind] = w2[0];
+            red2[q * 256 + (ch + 1) * 2 + kind] = w2[1];
           }
           if (p.gn_part) {
             // per-group (4 channels) sum / sum of squares of this row, then a fixed-order transposed
@@ -254,6 +330,20 @@ pconv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
           }
         }
+        if (p.gnb_part) {
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+          const int te = threadIdx.x - 64;
+          const int tile = item * PC_MT + j;
+          if (tile < p.num_tiles) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int i = 2 * te + e;
+              p.gnb_part[static_cast<long long>(tile) * 256 + i] =
+                  (red2[i] + red2[256 + i]) + (red2[512 + i] + red2[768 + i]);
+            }
+          }
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+        }
         if (p.gn_part) {
           asm volatile("bar.sync 2, 128;" ::: "memory");
           const int te = threadIdx.x - 64;
@@ -288,8 +378,9 @@ extern "C" {
 // W % 128 == 0, Cin % 64 == 0.  b_ptr: [128, 9*Cin] bf16, column = (r*3+s)*Cin + ci.
 // dgrad != 0: tap (r,s) reads the pixel at (+1-r, +1-s) instead of (r-1, s-1).
 int b2dq_pconv3x3(const void* a_ptr, const void* b_ptr, void* out, const float* bias,
-                  const void* residual, float* gn_part, int NB, int H, int W, int Cin, int dgrad,
-                  int max_ctas, cudaStream_t stream) {
+                  const void* residual, float* gn_part, const void* gnb_x, const float* gnb_stats,
+                  const float* gnb_gamma, const float* gnb_beta, float* gnb_part, int NB, int H, int W,
+                  int Cin, int dgrad, int max_ctas, cudaStream_t stream) {
   if (NB <= 0 || H <= 0 || W <= 0) return 0;
   if (W % 128 != 0 || Cin % 64 != 0 || Cin <= 0) return -1;
   CUtensorMap tmA, tmB;
@@ -328,6 +419,9 @@ int b2dq_pconv3x3(const void* a_ptr, const void* b_ptr, void* out, const float* 
   p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
   p.rN = p.oN; p.rH = p.oH; p.rW = p.oW;
   p.gn_part = gn_part;
+  if (gnb_part && (residual || !gnb_x || !gnb_stats || !gnb_gamma || !gnb_beta)) return -2;
+  p.gnb_x = reinterpret_cast<const __nv_bfloat16*>(gnb_x);
+  p.gnb_stats = gnb_stats; p.gnb_gamma = gnb_gamma; p.gnb_beta = gnb_beta; p.gnb_part = gnb_part;
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -357,6 +451,25 @@ __global__ void gn_finalize_tiles_kernel(const float* __restrict__ part, float* 
   if (var < 0) var = 0;
   stats[2 * i] = static_cast<float>(mean);
   stats[2 * i + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+}
+
+// ws_nc[n][c] = (sum dz, sum dz*xhat) over the tiles of image n, added in tile order (deterministic).
+__global__ void gn_bwd_reduce_tiles_kernel(const float* __restrict__ part, float* ws_nc, int N,
+                                           int tiles_per_image) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * 256) return;
+  const int n = i / 256, e = i % 256;
+  float a = 0.f;
+  const float* pp = part + (static_cast<long long>(n) * tiles_per_image) * 256 + e;
+  for (int t = 0; t < tiles_per_image; ++t) a += pp[static_cast<long long>(t) * 256];
+  ws_nc[i] = a;
+}
+
+int b2dq_gn_bwd_reduce_tiles(const float* gnb_part, float* ws_nc, int N, int H, int W, cudaStream_t stream) {
+  if (N <= 0) return 0;
+  if (W % 128) return -1;
+  gn_bwd_reduce_tiles_kernel<<<(N * 256 + 255) / 256, 256, 0, stream>>>(gnb_part, ws_nc, N, H * (W / 128));
+  return (int)cudaGetLastError();
 }
 
 int b2dq_gn_finalize_tiles(const float* gn_part, float* stats, int N, int H, int W, float eps,

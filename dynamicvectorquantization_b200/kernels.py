@@ -191,12 +191,16 @@ def conv_fwd(x, wpack, bias, ksize, stride, cout, residual=None, out_f32=False):
     return out
 
 
-def conv_dgrad(dy, wdpack, ksize, stride, cin, in_hw):
-    """dy NHWC bf16 [N,Ho,Wo,Cout] -> dx NHWC bf16 [N,H,W,Cin]."""
+def conv_dgrad(dy, wdpack, ksize, stride, cin, in_hw, gn_bwd=None):
+    """dy NHWC bf16 [N,Ho,Wo,Cout] -> dx NHWC bf16 [N,H,W,Cin].
+    gn_bwd = (gn_input, stats, gamma, beta): dx is the gradient wrt swish(GroupNorm(gn_input)); when the
+    persistent kernel runs, kernels.last_dgrad_gn_ws holds the GroupNorm-backward reduction afterwards."""
+    global last_dgrad_gn_ws
+    last_dgrad_gn_ws = None
     nb, ho, wo, cout = dy.shape
     assert cout % 64 == 0
     if _pconv_ok(ksize, stride, wo, cout, cin, nb, ho):
-        return pconv3x3(dy, wdpack, None, None, dgrad=True)
+        return pconv3x3(dy, wdpack, None, None, dgrad=True, gn_bwd=gn_bwd if FUSE_GN_BWD else None)
     kch = cout // 64
     h, w = in_hw
     dx = torch.empty(nb, h, w, cin, dtype=BF16, device=dy.device)
@@ -257,14 +261,28 @@ FUSE_GN_STATS = True     # pconv forward also emits the GroupNorm statistics of 
 last_conv_stats = None   # (mean, rstd) [N,32,2] of the most recent conv_fwd output, or None
 
 
-def pconv3x3(x, wpack, bias, residual, dgrad, want_stats=False):
-    global last_conv_stats
+FUSE_GN_BWD = True       # pconv data-gradient also emits the reduction of the GroupNorm backward it feeds
+last_dgrad_gn_ws = None  # ws_nc [N,128,2] produced by the most recent conv_dgrad(gn_bwd=...), or None
+
+
+def pconv3x3(x, wpack, bias, residual, dgrad, want_stats=False, gn_bwd=None):
+    """gn_bwd = (gn_input, stats, gamma, beta): dgrad launches only, see b2dq_pconv3x3."""
+    global last_conv_stats, last_dgrad_gn_ws
     nb, h, w, cin = x.shape
     lib = _cabi.lib()
     out = torch.empty(nb, h, w, 128, dtype=BF16, device=x.device)
     part = torch.empty(nb * h * (w // 128), 64, dtype=torch.float32, device=x.device) if want_stats else None
-    check(lib.b2dq_pconv3x3(_ptr(x), _ptr(wpack), _ptr(out), _ptr(bias), _ptr(residual), _ptr(part), nb, h, w, cin,
+    gx = gst = gg = gb = gpart = None
+    if gn_bwd is not None:
+        gx, gst, gg, gb = gn_bwd
+        gpart = torch.empty(nb * h * (w // 128), 256, dtype=torch.float32, device=x.device)
+    check(lib.b2dq_pconv3x3(_ptr(x), _ptr(wpack), _ptr(out), _ptr(bias), _ptr(residual), _ptr(part),
+                            _ptr(gx), _ptr(gst), _ptr(gg), _ptr(gb), _ptr(gpart), nb, h, w, cin,
                             int(dgrad), 0, _stream()), "pconv3x3")
+    if gn_bwd is not None:
+        ws = torch.empty(nb, 128, 2, dtype=torch.float32, device=x.device)
+        check(lib.b2dq_gn_bwd_reduce_tiles(_ptr(gpart), _ptr(ws), nb, h, w, _stream()), "gn_bwd_reduce_tiles")
+        last_dgrad_gn_ws = ws
     if want_stats:
         stats = torch.empty(nb, 32, 2, dtype=torch.float32, device=x.device)
         check(lib.b2dq_gn_finalize_tiles(_ptr(part), _ptr(stats), nb, h, w, 1e-6, _stream()), "gn_finalize_tiles")
@@ -396,10 +414,17 @@ def gn_forward(x, gamma, beta, swish, groups=32, eps=1e-6):
     return y, stats
 
 
-def gn_bwd(dy, x, stats, gamma, beta, swish, groups=32):
-    """Returns (dx bf16, dgamma f32, dbeta f32)."""
+def gn_bwd(dy, x, stats, gamma, beta, swish, groups=32, add=None, ws_nc=None):
+    """Returns (dx bf16, dgamma f32, dbeta f32); add (bf16, like x) is summed into dx (residual gradient);
+    ws_nc [N,C,2]: the reduction pass was already done by the producer of dy (pconv dgrad epilogue)."""
     nb, h, w, c = x.shape
     l = _cabi.lib()
+    if ws_nc is not None:
+        dx = torch.empty_like(x)
+        dgb = torch.empty(2, c, dtype=torch.float32, device=x.device)
+        check(l.b2dq_gn_bwd_apply(_ptr(dy), _ptr(x), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(ws_nc), _ptr(dx),
+                                  _ptr(dgb), _ptr(add), nb, h * w, c, groups, int(swish), _stream()), "gn_bwd_apply")
+        return dx, dgb[0], dgb[1]
     g = _gn_groups(nb, h * w * c * 2, 2)
     ws = torch.empty(nb, c, 2, dtype=torch.float32, device=x.device)
     part = torch.empty(g * l.b2dq_gn_chunks(g, h * w) * c * 2, dtype=torch.float32, device=x.device)
@@ -410,8 +435,9 @@ def gn_bwd(dy, x, stats, gamma, beta, swish, groups=32):
         dys, xs, ss, wss, dxs = dy[n0:n0 + n], x[n0:n0 + n], stats[n0:n0 + n], ws[n0:n0 + n], dx[n0:n0 + n]
         check(l.b2dq_gn_bwd_stats(_ptr(dys), _ptr(xs), _ptr(ss), _ptr(gamma), _ptr(beta), _ptr(part), _ptr(wss),
                                   n, h * w, c, groups, int(swish), _stream()), "gn_bwd_stats")
+        adds = None if add is None else add[n0:n0 + n]
         check(l.b2dq_gn_bwd_apply(_ptr(dys), _ptr(xs), _ptr(ss), _ptr(gamma), _ptr(beta), _ptr(wss), _ptr(dxs),
-                                  None, n, h * w, c, groups, int(swish), _stream()), "gn_bwd_apply_nodgb")
+                                  None, _ptr(adds), n, h * w, c, groups, int(swish), _stream()), "gn_bwd_apply_nodgb")
     check(l.b2dq_gn_bwd_param(_ptr(ws), _ptr(dgb), nb, c, _stream()), "gn_bwd_param")
     return dx, dgb[0], dgb[1]
 

@@ -90,12 +90,7 @@ class ResnetBlock(_Nhwc):
     def forward_nhwc(self, x):
         if self.training and self.dropout.p > 0:
             raise NotImplementedError("dropout > 0 is not used by the stage-1 configs")
-        h = ops.gn_swish(x, self.norm1)
-        h = ops.conv2d(h, self.conv1)
-        h = ops.gn_swish(h, self.norm2)
-        if self.in_channels != self.out_channels:
-            x = ops.conv2d(x, self.conv_shortcut if self.use_conv_shortcut else self.nin_shortcut)
-        return ops.conv2d(h, self.conv2, residual=x)          # x + conv2(...) fused in the epilogue
+        return ops.resnet_block(x, self)                       # one fused autograd node (ops.ResnetBlockFn)
 
 
 class AttnBlock(_Nhwc):

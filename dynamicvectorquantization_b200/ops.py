@@ -203,6 +203,80 @@ class GroupNormSwishFn(torch.autograd.Function):
         return dx, dg, db, None, None
 
 
+class ResnetBlockFn(torch.autograd.Function):
+    """x + conv2(swish(GN(conv1(swish(GN(x)))))) with an optional 1x1 / 3x3 shortcut convolution
+    (model.py:117-137) as ONE autograd node, so the backward can order and fuse its kernels:
+    the gradient arriving through the residual branch is added inside the last GroupNorm-backward
+    pass (no separate accumulation kernel), GroupNorm statistics come from the producing conv's
+    epilogue when available."""
+
+    @staticmethod
+    def forward(ctx, x, n1w, n1b, c1w, c1b, n2w, n2b, c2w, c2b, scw, scb, in_stats):
+        g1, b1, g2, b2 = _f32(n1w), _f32(n1b), _f32(n2w), _f32(n2b)
+        cout = c1w.shape[0]
+        if in_stats is not None:
+            st1 = in_stats
+            a1 = kn.gn_apply(x, st1, g1, b1, True)
+        else:
+            a1, st1 = kn.gn_forward(x, g1, b1, True)
+        h1 = kn.conv_fwd(a1, _packed(c1w, "fwd"), _f32(c1b), 3, 1, cout)
+        st2 = kn.last_conv_stats
+        if st2 is not None:
+            a2 = kn.gn_apply(h1, st2, g2, b2, True)
+        else:
+            a2, st2 = kn.gn_forward(h1, g2, b2, True)
+        sc = x if scw is None else kn.conv_fwd(x, _packed(scw, "fwd"), _f32(scb), scw.shape[-1], 1, cout)
+        out = kn.conv_fwd(a2, _packed(c2w, "fwd"), _f32(c2b), 3, 1, cout, residual=sc)
+        ctx.save_for_backward(x, a1, h1, a2, st1, st2, g1, b1, g2, b2, c1w, c2w, scw)
+        ctx.has_sc = scw is not None
+        ctx.bias_flags = (c1b is not None, c2b is not None, scb is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, a1, h1, a2, st1, st2, g1, b1, g2, b2, c1w, c2w, scw = ctx.saved_tensors
+        dout = dout.contiguous()
+        cin, cout = c1w.shape[1], c1w.shape[0]
+        hw = x.shape[1:3]
+        hb1, hb2, hbs = ctx.bias_flags
+        d_a2 = kn.conv_dgrad(dout, _packed(c2w, "dgrad"), 3, 1, cout, hw, gn_bwd=(h1, st2, g2, b2))
+        ws2 = kn.last_dgrad_gn_ws
+        dw2, db2 = kn.conv_wgrad(a2, dout, 3, 1, want_bias=True)
+        d_h1, dg2, dbt2 = kn.gn_bwd(d_a2, h1, st2, g2, b2, True, ws_nc=ws2)
+        d_a1 = kn.conv_dgrad(d_h1, _packed(c1w, "dgrad"), 3, 1, cin, hw, gn_bwd=(x, st1, g1, b1))
+        ws1 = kn.last_dgrad_gn_ws
+        dw1, db1 = kn.conv_wgrad(a1, d_h1, 3, 1, want_bias=True)
+        dws = dbs = None
+        if ctx.has_sc:
+            k = scw.shape[-1]
+            res_grad = kn.conv_dgrad(dout, _packed(scw, "dgrad"), k, 1, cin, hw)
+            dws, dbs = kn.conv_wgrad(x, dout, k, 1, want_bias=True)
+        else:
+            res_grad = dout
+        dx, dg1, dbt1 = kn.gn_bwd(d_a1, x, st1, g1, b1, True, add=res_grad, ws_nc=ws1)
+        return (dx, dg1, dbt1, dw1, db1 if hb1 else None, dg2, dbt2, dw2, db2 if hb2 else None,
+                dws, dbs if hbs else None, None)
+
+
+def resnet_block(x, blk):
+    """blk: nn.Module with norm1/conv1/norm2/conv2 (+ nin_shortcut / conv_shortcut)."""
+    global _pending_stats
+    in_stats = None
+    if _pending_stats is not None and _pending_stats[0]() is x:
+        in_stats = _pending_stats[1]
+    _pending_stats = None
+    sc = None
+    if blk.in_channels != blk.out_channels:
+        sc = blk.conv_shortcut if blk.use_conv_shortcut else blk.nin_shortcut
+    y = ResnetBlockFn.apply(x, blk.norm1.weight, blk.norm1.bias, blk.conv1.weight, blk.conv1.bias,
+                            blk.norm2.weight, blk.norm2.bias, blk.conv2.weight, blk.conv2.bias,
+                            None if sc is None else sc.weight, None if sc is None else sc.bias, in_stats)
+    stats = kn.last_conv_stats
+    kn.last_conv_stats = None
+    _pending_stats = (weakref.ref(y), stats) if stats is not None else None
+    return y
+
+
 class AttentionFn(torch.autograd.Function):
     """softmax(q k^T / sqrt(C)) v over the T = h*w positions of each image, single head of width C
     (model.py:176-188).  q, k, v: [B, T, C] bf16 (any row stride that is a multiple of 8)."""

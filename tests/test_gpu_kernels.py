@@ -152,6 +152,27 @@ def test_pconv_emits_groupnorm_statistics():
     assert torch.equal(kn.last_conv_stats, st) and torch.equal(y, y2)      # deterministic
 
 
+def test_pconv_dgrad_emits_groupnorm_backward_sums():
+    """conv data-gradient + the reduction of the GroupNorm(+swish) backward it feeds, in one kernel."""
+    from dynamicvectorquantization_b200 import kernels as kn
+    nb, h, w, c = 3, 48, 128, 128
+    dy = _rand_bf(nb, h, w, c, seed=51)
+    wt = _rand_bf(c, c, 3, 3, scale=(c * 9) ** -0.5, seed=52).float()
+    xg = (_rand_bf(nb, h, w, c, seed=53).float() * 1.3 + 0.2).to(BF)
+    gamma = (1 + 0.2 * torch.randn(c, generator=torch.Generator().manual_seed(54))).cuda()
+    beta = (0.1 * torch.randn(c, generator=torch.Generator().manual_seed(55))).cuda()
+    dyd, xd, wd = dy.cuda(), xg.cuda(), kn.pack_weight_dgrad(wt.cuda())
+    st = kn.gn_stats(xd)
+    da = kn.pconv3x3(dyd, wd, None, None, True, gn_bwd=(xd, st, gamma, beta))
+    ws = kn.last_dgrad_gn_ws
+    da_plain = kn.pconv3x3(dyd, wd, None, None, True)
+    assert torch.equal(da, da_plain)
+    dx_ref, dg_ref, db_ref = kn.gn_bwd(da, xd, st, gamma, beta, True)             # two-pass path
+    dx, dg, db = kn.gn_bwd(da, xd, st, gamma, beta, True, ws_nc=ws)               # fused reduction
+    assert rel_rms(dg, dg_ref) < 3e-3 and rel_rms(db, db_ref) < 3e-3
+    assert rel_rms(dx.float(), dx_ref.float()) < 6e-3
+
+
 # ------------------------------------------------------------------------------------------- GEMM
 @pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0), (1, 1)])
 @pytest.mark.parametrize("M,N,K,batch", [(1024, 1024, 256, 2), (256, 512, 256, 3), (64, 512, 64, 2)])
