@@ -261,7 +261,11 @@ FUSE_GN_STATS = True     # pconv forward also emits the GroupNorm statistics of 
 last_conv_stats = None   # (mean, rstd) [N,32,2] of the most recent conv_fwd output, or None
 
 
-FUSE_GN_BWD = True       # pconv data-gradient also emits the reduction of the GroupNorm backward it feeds
+# pconv data-gradient can also emit the reduction of the GroupNorm backward it feeds (correct, tested), but the
+# 512 MUFU ops + 500 shuffles per thread and tile pair make the 4 epilogue warps slower than the tensor core:
+# measured 86.9 ms/step with it vs 70.8 ms without (the separate gn_bwd_partial pass runs on all warps of
+# all SMs at HBM speed).  OFF by default.
+FUSE_GN_BWD = False
 last_dgrad_gn_ws = None  # ws_nc [N,128,2] produced by the most recent conv_dgrad(gn_bwd=...), or None
 
 

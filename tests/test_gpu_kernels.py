@@ -163,7 +163,7 @@ def test_pconv_dgrad_emits_groupnorm_backward_sums():
     beta = (0.1 * torch.randn(c, generator=torch.Generator().manual_seed(55))).cuda()
     dyd, xd, wd = dy.cuda(), xg.cuda(), kn.pack_weight_dgrad(wt.cuda())
     st = kn.gn_stats(xd)
-    da = kn.pconv3x3(dyd, wd, None, None, True, gn_bwd=(xd, st, gamma, beta))
+    da = kn.pconv3x3(dyd, wd, None, None, True, gn_bwd=(xd, st, gamma, beta))   # opt-in path (kn.FUSE_GN_BWD)
     ws = kn.last_dgrad_gn_ws
     da_plain = kn.pconv3x3(dyd, wd, None, None, True)
     assert torch.equal(da, da_plain)
