@@ -329,8 +329,8 @@ def run_b200(args):
                        "l2": "per-step working set (~40 GB of activations) >> 126 MB L2, no flush needed",
                        "model_tflops_per_step": 3 * FLOP_PER_IMAGE_FWD * B / 1e12},
             "clocks": clocks, "gpu_launches": launches,
-            "e2e": {"value": ips_e2e, "unit": "images/s", "h2d_bytes_per_step": x_host.numel() * 4 * 1,
-                    "d2h_bytes_per_step": 4},
+            "e2e": {"value": ips_e2e, "unit": "images/s", "h2d_bytes_per_step": x_host.numel() * 4 * world,
+                    "d2h_bytes_per_step": 4 * world},
             "model_flops_utilisation": {"achieved_tflops": 3 * FLOP_PER_IMAGE_FWD * ips / world / 1e12,
                                         "peak_tflops": peaks.get("bf16_tflops_sustained"),
                                         "note": "algorithmic conv+attention FLOPs (BASELINE.md) x3 for fwd+bwd, per GPU"},

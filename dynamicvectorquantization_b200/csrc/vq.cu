@@ -182,49 +182,71 @@ vq_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       s_best[(par * 2 + half) * 128 + row] = best;
       s_idx[(par * 2 + half) * 128 + row] = bi;
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      // gather / loss / EMA accumulation: each warp takes 16 rows, lanes span channels
-      for (int rr = 0; rr < 16; ++rr) {
-        const int r_in = ew * 16 + rr;
-        const long long grow = static_cast<long long>(tile) * VQ_BM + r_in;
-        if (grow >= p.N) break;
-        const float b0 = s_best[(par * 2 + 0) * 128 + r_in];
-        const float b1 = s_best[(par * 2 + 1) * 128 + r_in];
-        const int i0 = s_idx[(par * 2 + 0) * 128 + r_in];
-        const int i1 = s_idx[(par * 2 + 1) * 128 + r_in];
-        int idx = (b1 < b0) ? i1 : i0;
-        if (idx >= p.K) idx = 0;
-        float lsum = 0.f;
+      // gather / loss / EMA accumulation: each warp takes 16 rows, lanes span channels.  Four rows
+      // are in flight at a time (all loads of a group are issued before their first use): the
+      // phase is latency bound and sits between two tiles' searches.
+      constexpr int RG = 4;
+      for (int rr0 = 0; rr0 < 16; rr0 += RG) {
+        int idx[RG];
+        long long grow[RG];
+        bool ok[RG];
+#pragma unroll
+        for (int u = 0; u < RG; ++u) {
+          const int r_in = ew * 16 + rr0 + u;
+          grow[u] = static_cast<long long>(tile) * VQ_BM + r_in;
+          ok[u] = grow[u] < p.N;
+          const float b0 = s_best[(par * 2 + 0) * 128 + r_in];
+          const float b1 = s_best[(par * 2 + 1) * 128 + r_in];
+          const int i0 = s_idx[(par * 2 + 0) * 128 + r_in];
+          const int i1 = s_idx[(par * 2 + 1) * 128 + r_in];
+          idx[u] = (b1 < b0) ? i1 : i0;
+          if (idx[u] >= p.K) idx[u] = 0;
+        }
+        float lsum[RG] = {0.f, 0.f, 0.f, 0.f};
         for (int c = lane * 4; c < p.C; c += 128) {
-          float4 xv;
-          if (p.x_f32) {
-            xv = *reinterpret_cast<const float4*>(p.x_f32 + grow * p.C + c);
-          } else {
-            const uint2 u = *reinterpret_cast<const uint2*>(p.x_bf16 + grow * p.C + c);
-            xv = make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
+          float4 xv[RG], ev[RG];
+#pragma unroll
+          for (int u = 0; u < RG; ++u) {
+            xv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            ev[u] = xv[u];
+            if (!ok[u]) continue;
+            if (p.x_f32) {
+              xv[u] = *reinterpret_cast<const float4*>(p.x_f32 + grow[u] * p.C + c);
+            } else {
+              const uint2 w2 = *reinterpret_cast<const uint2*>(p.x_bf16 + grow[u] * p.C + c);
+              xv[u] = make_float4(bf16_lo(w2.x), bf16_hi(w2.x), bf16_lo(w2.y), bf16_hi(w2.y));
+            }
+            ev[u] = __ldg(reinterpret_cast<const float4*>(p.weight_f32 + static_cast<long long>(idx[u]) * p.C + c));
           }
-          const float4 ev = __ldg(reinterpret_cast<const float4*>(
-              p.weight_f32 + static_cast<long long>(idx) * p.C + c));
-          const float dx = ev.x - xv.x, dy = ev.y - xv.y, dz = ev.z - xv.z, dw = ev.w - xv.w;
-          lsum += dx * dx + dy * dy + dz * dz + dw * dw;
-          if (p.xq_f32) *reinterpret_cast<float4*>(p.xq_f32 + grow * p.C + c) = ev;
-          if (p.xq_bf16) {
-            uint2 o;
-            o.x = pack_bf16x2(ev.x, ev.y);
-            o.y = pack_bf16x2(ev.z, ev.w);
-            *reinterpret_cast<uint2*>(p.xq_bf16 + grow * p.C + c) = o;
-          }
-          if (p.sums) {
-            float* dst = p.sums + static_cast<long long>(idx) * p.C + c;
-            asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "f"(xv.x),
-                         "f"(xv.y), "f"(xv.z), "f"(xv.w)
-                         : "memory");
+#pragma unroll
+          for (int u = 0; u < RG; ++u) {
+            if (!ok[u]) continue;
+            const float dx = ev[u].x - xv[u].x, dy = ev[u].y - xv[u].y, dz = ev[u].z - xv[u].z,
+                        dw = ev[u].w - xv[u].w;
+            lsum[u] += dx * dx + dy * dy + dz * dz + dw * dw;
+            if (p.xq_f32) *reinterpret_cast<float4*>(p.xq_f32 + grow[u] * p.C + c) = ev[u];
+            if (p.xq_bf16) {
+              uint2 o;
+              o.x = pack_bf16x2(ev[u].x, ev[u].y);
+              o.y = pack_bf16x2(ev[u].z, ev[u].w);
+              *reinterpret_cast<uint2*>(p.xq_bf16 + grow[u] * p.C + c) = o;
+            }
+            if (p.sums) {
+              float* dst = p.sums + static_cast<long long>(idx[u]) * p.C + c;
+              asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "f"(xv[u].x),
+                           "f"(xv[u].y), "f"(xv[u].z), "f"(xv[u].w)
+                           : "memory");
+            }
           }
         }
-        lsum = warp_sum(lsum);
-        if (lane == 0) {
-          p.codes[grow] = idx;
-          if (p.counts) atomicAdd(p.counts + idx, 1.0f);
-          loss_local += lsum * (p.row_mask ? p.row_mask[grow] : 1.0f);
+#pragma unroll
+        for (int u = 0; u < RG; ++u) {
+          const float ls = warp_sum(lsum[u]);
+          if (lane == 0 && ok[u]) {
+            p.codes[grow[u]] = idx[u];
+            if (p.counts) atomicAdd(p.counts + idx[u], 1.0f);
+            loss_local += ls * (p.row_mask ? p.row_mask[grow[u]] : 1.0f);
+          }
         }
       }
     }
