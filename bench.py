@@ -23,7 +23,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "images/sec (256x256 DQ-VAE fwd+bwd)"
-WORKLOAD = "dqvae-dual-r-05 (F=16/F=8, K=1024) 256x256 bf16, batch 32 per GPU"
+WORKLOADS = {
+    "dqvae-dual-r-05": "dqvae-dual-r-05 (F=16/F=8, K=1024) 256x256 bf16, batch 32 per GPU",
+    "dqvae-entropy-dual-r05": "dqvae-entropy-dual-r05 (fixed entropy router) 256x256 bf16, batch 32 per GPU",
+    "dqvae-triple-r-03-03": "dqvae-triple-r-03-03 (F=32/16/8, K=1024) 256x256 bf16, batch 32 per GPU",
+}
+WORKLOAD = WORKLOADS["dqvae-dual-r-05"]
 FLOP_PER_IMAGE_FWD = 392.8e9 + 0.27e9          # BASELINE.md section 2 (2*MAC, attention included)
 
 
@@ -35,7 +40,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="images per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--config", default="dqvae-dual-r-05")
+    ap.add_argument("--config", default="dqvae-dual-r-05", choices=sorted(WORKLOADS),
+                    help="headline = dqvae-dual-r-05; the others are parity-test configs that can be timed too")
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph (N=1)")
     return ap.parse_args()
 
@@ -191,7 +197,19 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(2021)                      # the reference's default seed (train.py:41)
-    model = configs.build_model(configs.stage1_config(args.config)).to(dev)
+    global WORKLOAD
+    WORKLOAD = WORKLOADS[args.config]
+    cfg = configs.stage1_config(args.config)
+    if args.config == "dqvae-entropy-dual-r05":
+        # the router reads its threshold from a JSON of the reference tree (scripts/tools/thresholds/...);
+        # off the reference tree, write the one value it uses (key "50" = 1.6778)
+        jp = cfg["params"]["encoderconfig"]["params"]["router_config"]["params"]["json_path"]
+        if not os.path.exists(jp):
+            import tempfile
+            f = tempfile.NamedTemporaryFile("w", suffix=".json", delete=False)
+            json.dump({"50": 1.6778}, f); f.close()
+            cfg["params"]["encoderconfig"]["params"]["router_config"]["params"]["json_path"] = f.name
+    model = configs.build_model(cfg).to(dev)
     model.train()
     for p in model.loss.parameters():
         p.requires_grad_(False)

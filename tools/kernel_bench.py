@@ -74,12 +74,14 @@ def gn(nb, h, w, c):
     ms1 = timeit(lambda: kn.gn_stats(x)); st = kn.gn_stats(x)
     ms2 = timeit(lambda: kn.gn_apply(x, st, g, b, True))
     ms3 = timeit(lambda: kn.gn_bwd(dy, x, st, g, b, True))
-    ms4 = timeit(lambda: kn.gn_forward(x, g, b, True))
-    old = kn.GN_L2_BUDGET_BYTES; kn.GN_L2_BUDGET_BYTES = 1 << 40
-    ms3u = timeit(lambda: kn.gn_bwd(dy, x, st, g, b, True)); ms4u = timeit(lambda: kn.gn_forward(x, g, b, True))
+    old = kn.GN_L2_BUDGET_BYTES
+    res = {}
+    for mb in (70, 140, 280, 1 << 20):
+        kn.GN_L2_BUDGET_BYTES = mb << 20
+        res[f"bwd_{mb}MB"] = round(timeit(lambda: kn.gn_bwd(dy, x, st, g, b, True)), 3)
+        res[f"fwd_{mb}MB"] = round(timeit(lambda: kn.gn_forward(x, g, b, True)), 3)
     kn.GN_L2_BUDGET_BYTES = old
-    print(json.dumps(dict(k="gn_grouped_vs_whole", nb=nb, hw=h, c=c, fwd_grouped_ms=round(ms4, 3), fwd_whole_ms=round(ms4u, 3),
-                          bwd_grouped_ms=round(ms3, 3), bwd_whole_ms=round(ms3u, 3))))
+    print(json.dumps(dict(k="gn_image_groups", nb=nb, hw=h, c=c, **res)))
     print(json.dumps(dict(k="gn", nb=nb, hw=h, c=c, stats_ms=round(ms1, 3), stats_GBs=round(by / ms1 / 1e6), apply_ms=round(ms2, 3),
                           apply_GBs=round(2 * by / ms2 / 1e6), bwd_ms=round(ms3, 3), bwd_GBs=round(5 * by / ms3 / 1e6))))
 
