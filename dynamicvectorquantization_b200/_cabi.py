@@ -85,6 +85,7 @@ SIGNATURES = {
     "b2dq_bias_grad_blocks": [_ll],
     "b2dq_bias_grad": [_vp, _vp, _vp, _ll, _i, _vp],
     "b2dq_cast_f32_to_bf16": [_vp, _vp, _ll, _vp],
+    "b2dq_patch_entropy": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp],
 }
 
 

@@ -510,6 +510,17 @@ def add_bf16(a, b):
     return o
 
 
+def patch_entropy(x_nchw, bins, patch, sigma):
+    """x [B,3,H,W] fp32 NCHW -> [B, H/patch, W/patch] fp32 (dqvae_dual_entropy.py:25-63)."""
+    assert x_nchw.dtype == torch.float32 and x_nchw.dim() == 4 and x_nchw.shape[1] == 3
+    x_nchw = x_nchw.contiguous()
+    b, _, h, w = x_nchw.shape
+    out = torch.empty(b, h // patch, w // patch, dtype=torch.float32, device=x_nchw.device)
+    check(_cabi.lib().b2dq_patch_entropy(_ptr(x_nchw), _ptr(bins), _ptr(out), b, h, w, patch, bins.numel(),
+                                         float(sigma), _stream()), "patch_entropy")
+    return out
+
+
 def im2col3x3_small(x, flip=False):
     nb, h, w, cs = x.shape
     out = torch.empty(nb, h, w, 64, dtype=BF16, device=x.device)

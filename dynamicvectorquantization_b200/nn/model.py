@@ -15,6 +15,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .. import kernels as kn
 from .. import ops
 from .quantize import VectorQuantize2
 
@@ -68,7 +69,9 @@ def Scheduler_LinearWarmup_CosineDecay(warmup_steps, max_steps, multipler_min):
 
 class Entropy(nn.Sequential):
     """Per-patch grey-level entropy (dqvae_dual_entropy.py:13-63): soft histogram with 32 bins on
-    [-1,1], sigma 0.01.  fp32 PyTorch on purpose: eps = 1e-40 is subnormal (no FTZ allowed)."""
+    [-1,1], sigma 0.01, eps 1e-40.  forward() runs the fused CUDA kernel (csrc/entropy.cu: one read of
+    the image, no [B*patches, pixels, bins] intermediate); entropy() keeps the reference's helper
+    signature for callers that bring their own flattened patches."""
 
     def __init__(self, patch_size, image_width, image_height):
         super().__init__()
@@ -78,6 +81,7 @@ class Entropy(nn.Sequential):
         self.patch_num = int(self.width * self.height / self.psize ** 2)
         self.hw = int(self.width // self.psize)
         self.unfold = torch.nn.Unfold(kernel_size=(self.psize, self.psize), stride=self.psize)
+        self._bins = None
 
     def entropy(self, values, bins, sigma, batch):
         epsilon = 1e-40
@@ -89,13 +93,14 @@ class Entropy(nn.Sequential):
         ent = -torch.sum(pdf * torch.log(pdf), dim=1)
         return ent.reshape(batch, self.hw, self.hw)
 
+    @torch.no_grad()
     def forward(self, inputs):
-        b = inputs.shape[0]
-        gray = 0.2989 * inputs[:, 0:1] + 0.5870 * inputs[:, 1:2] + 0.1140 * inputs[:, 2:]
-        u = self.unfold(gray).transpose(1, 2)
-        u = torch.reshape(u.unsqueeze(2), (u.shape[0] * self.patch_num, u.shape[2]))
-        return self.entropy(u, bins=torch.linspace(-1, 1, 32).to(device=inputs.device),
-                            sigma=torch.tensor(0.01), batch=b)
+        if not inputs.is_cuda:
+            raise RuntimeError("Entropy (B200) needs CUDA tensors; there is no CPU fallback")
+        assert inputs.shape[-2] == self.height and inputs.shape[-1] == self.width
+        if self._bins is None or self._bins.device != inputs.device:
+            self._bins = torch.linspace(-1, 1, 32).to(device=inputs.device)
+        return kn.patch_entropy(inputs.float(), self._bins, self.psize, 0.01)
 
 
 def _disabled_train(self, mode=True):

@@ -22,13 +22,15 @@ BF16 = torch.bfloat16
 
 
 class _VQFn(torch.autograd.Function):
-    """rows [N,C] -> (x_q rows, sum_rows m*|e-x|^2 / (N*C) * (1+beta), codes).
+    """rows [N,C] -> (x_q rows, value_scale * sum_rows m*|e-x|^2 / (N*C), codes); the gradient of the
+    loss w.r.t. the rows is grad_scale * 2 m (x-e) / (N*C).  (value, grad) = (1+beta, beta) is the
+    EMA-frozen commitment loss of quantize2_mask.py:172-179.
 
     fp32 mode (x_f32 given): x_q = exact fp32 codebook rows, loss/EMA from the fp32 rows.
     bf16 mode: everything from the bf16 rows (fused-model path)."""
 
     @staticmethod
-    def forward(ctx, x_bf16, x_f32, row_mask, emb, beta, accumulate):
+    def forward(ctx, x_bf16, x_f32, row_mask, emb, value_scale, grad_scale, accumulate):
         n, c = x_bf16.shape
         loss_acc = torch.zeros(1, dtype=torch.float32, device=x_bf16.device)
         counts = sums = None
@@ -40,10 +42,10 @@ class _VQFn(torch.autograd.Function):
             x_bf16, emb._codebook(), w, x_f32=x_f32, row_mask=row_mask,
             want_xq_bf16=x_f32 is None, want_xq_f32=x_f32 is not None,
             counts=counts, sums=sums, loss_acc=loss_acc)
-        loss = loss_acc[0] * ((1.0 + beta) / float(n * c))
+        loss = loss_acc[0] * (value_scale / float(n * c))
         xq = xq_f if x_f32 is not None else xq_b
         ctx.save_for_backward(x_bf16 if x_f32 is None else x_f32, xq, row_mask)
-        ctx.coef = 2.0 * beta / float(n * c)
+        ctx.coef = 2.0 * grad_scale / float(n * c)
         ctx.mark_non_differentiable(codes)
         return xq, loss, codes
 
@@ -56,10 +58,10 @@ class _VQFn(torch.autograd.Function):
             g_xq = torch.zeros_like(xq)
         if x.dtype == BF16:
             g = kn.vq_bwd(g_xq.contiguous(), x, xq, row_mask, g_loss.reshape(1).float().contiguous(), ctx.coef)
-            return g, None, None, None, None, None
+            return g, None, None, None, None, None, None
         m = 1.0 if row_mask is None else row_mask.unsqueeze(1)
         g = g_xq + (ctx.coef * g_loss) * m * (x - xq)
-        return None, g, None, None, None, None
+        return None, g, None, None, None, None, None
 
 
 def reduce_ema_stats(acc):
@@ -77,30 +79,13 @@ def share_restart_rows(rows):
     return rows
 
 
-class VQEmbedding(nn.Embedding):
-    """VQ embedding module with EMA update (quantize2_mask.py:10-132)."""
-
-    def __init__(self, n_embed, embed_dim, ema=True, decay=0.99, restart_unused_codes=True, eps=1e-5):
-        super().__init__(n_embed + 1, embed_dim, padding_idx=n_embed)
-        self.ema = ema
-        self.decay = decay
-        self.eps = eps
-        self.restart_unused_codes = restart_unused_codes
-        self.n_embed = n_embed
-        if self.ema:
-            _ = [p.requires_grad_(False) for p in self.parameters()]
-            # padding index is not updated by EMA; embed_ema starts from the N(0,1) init (:27)
-            self.register_buffer("cluster_size_ema", torch.zeros(n_embed))
-            self.register_buffer("embed_ema", self.weight[:-1, :].detach().clone())
-        self._cb = None
-        self._cb_key = None
-        self._acc = None
-        # defer_ema: forward only accumulates the per-code statistics; the caller applies the EMA /
-        # restart / re-normalisation later with apply_deferred_ema().  Result-identical (the gather
-        # uses the pre-update codebook either way, :119-126) and lets a CUDA-graph-captured step keep
-        # the NCCL exchange outside the graph.
-        self.defer_ema = False
-        self._deferred = None
+class _SearchOperands:
+    """What the search kernel needs besides the rows, for any owner of a ``weight`` ([K(+1), C] fp32)
+    and ``n_embed``: the derived bf16 codebook + squared norms (refreshed when the weight changes) and
+    the packed [K*C sums | K counts] accumulator the kernel adds per-code statistics into."""
+    _cb = None
+    _cb_key = None
+    _acc = None
 
     # ---- derived search operands (bf16 codebook + squared norms), refreshed when weight changes
     def _codebook(self):
@@ -124,6 +109,32 @@ class VQEmbedding(nn.Embedding):
         k, c = self.n_embed, self.weight.shape[1]
         if self._acc is None or self._acc.device != self.weight.device:
             self._acc = torch.zeros(k * c + k, dtype=torch.float32, device=self.weight.device)
+
+
+class VQEmbedding(_SearchOperands, nn.Embedding):
+    """VQ embedding module with EMA update (quantize2_mask.py:10-132)."""
+
+    def __init__(self, n_embed, embed_dim, ema=True, decay=0.99, restart_unused_codes=True, eps=1e-5):
+        super().__init__(n_embed + 1, embed_dim, padding_idx=n_embed)
+        self.ema = ema
+        self.decay = decay
+        self.eps = eps
+        self.restart_unused_codes = restart_unused_codes
+        self.n_embed = n_embed
+        if self.ema:
+            _ = [p.requires_grad_(False) for p in self.parameters()]
+            # padding index is not updated by EMA; embed_ema starts from the N(0,1) init (:27)
+            self.register_buffer("cluster_size_ema", torch.zeros(n_embed))
+            self.register_buffer("embed_ema", self.weight[:-1, :].detach().clone())
+        self._cb = None
+        self._cb_key = None
+        self._acc = None
+        # defer_ema: forward only accumulates the per-code statistics; the caller applies the EMA /
+        # restart / re-normalisation later with apply_deferred_ema().  Result-identical (the gather
+        # uses the pre-update codebook either way, :119-126) and lets a CUDA-graph-captured step keep
+        # the NCCL exchange outside the graph.
+        self.defer_ema = False
+        self._deferred = None
 
     @torch.no_grad()
     def compute_distances(self, inputs):
@@ -196,7 +207,7 @@ class VQEmbedding(nn.Embedding):
         train = self.training and self.ema
         if train:
             self._ensure_acc()
-        xq, _, codes = _VQFn.apply(flat32.to(BF16), flat32, None, self, 0.0, train)
+        xq, _, codes = _VQFn.apply(flat32.to(BF16), flat32, None, self, 1.0, 0.0, train)
         if train:
             self._ema_step(lambda idx: flat32 if idx is None else flat32[idx], flat32.shape[0])
         return xq.detach().reshape(inputs.shape), codes.reshape(inputs.shape[:-1])
@@ -226,7 +237,7 @@ class VectorQuantize2(nn.Module):
         train = self.training and emb.ema
         if train:
             emb._ensure_acc()
-        xq, loss, codes = _VQFn.apply(rows_bf16, None, row_mask, emb, self.beta, train)
+        xq, loss, codes = _VQFn.apply(rows_bf16, None, row_mask, emb, 1.0 + self.beta, self.beta, train)
         if train:
             det = rows_bf16.detach()
             emb._ema_step(lambda idx: det if idx is None else det[idx], det.shape[0])
@@ -255,7 +266,8 @@ class VectorQuantize2(nn.Module):
         train = self.training and emb.ema
         if train:
             emb._ensure_acc()
-        xq, loss, codes = _VQFn.apply(flat32.detach().to(BF16), flat32, mask_rows, emb, self.beta, train)
+        xq, loss, codes = _VQFn.apply(flat32.detach().to(BF16), flat32, mask_rows, emb, 1.0 + self.beta, self.beta,
+                                      train)
         if train:
             det = flat32.detach()
             emb._ema_step(lambda idx: det if idx is None else det[idx], det.shape[0])

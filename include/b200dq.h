@@ -198,6 +198,14 @@ int b2dq_cast_f32_to_bf16(const float* a, void* out, long long n, cudaStream_t s
 int b2dq_im2col3x3_small(const void* src, void* dst, int N, int H, int W, int Cs, int flip,
                          cudaStream_t stream);
 
+
+/* ------------------------------------------------------------------ entropy router input
+ * Per-patch grey-level entropy (models/stage1_dynamic/dqvae_dual_entropy.py:25-63): x NCHW fp32
+ * [B,3,H,W] in [-1,1] -> out [B, H/patch, W/patch] fp32.  Soft histogram over `nbins` (= 32) bin
+ * centres `bins` (device, fp32) with Gaussian width sigma, eps 1e-40, -sum p log p. */
+int b2dq_patch_entropy(const float* x_nchw, const float* bins, float* out, int B, int H, int W, int patch,
+                       int nbins, float sigma, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -194,12 +194,145 @@ def triple_entropy_goldens():
     save("entropy_small.npz", x=xe, entropy=ent, gate=gate_e, threshold=1.5, budget=bud)
 
 
+# ----------------------------------------------------------------------------------- sibling quantizers
+def vq_family_goldens():
+    """quantize2 / quantize2_list / quantize_rqvae / quantize_vqgan of the reference.
+    Training passes store the restart rows each update drew (same replay trick as vq_goldens)."""
+    from modules.vector_quantization.quantize2 import VectorQuantize2 as VQ2
+    from modules.vector_quantization.quantize2_list import VectorQuantize2 as VQ2List
+    from modules.vector_quantization.quantize_rqvae import RQBottleneck
+    from modules.vector_quantization.quantize_vqgan import VectorQuantizer2
+    out = {}
+    g = torch.Generator().manual_seed(77)
+
+    def put(prefix, **kw):
+        for k, v in kw.items():
+            out[f"{prefix}_{k}"] = v.detach().clone() if torch.is_tensor(v) else v
+
+    # ---- quantize2.VectorQuantize2, both loss flavours
+    K, C = 64, 64
+    w = torch.randn(K + 1, C, generator=g)
+    x = torch.randn(2, C, 8, 8, generator=g)
+    gq = torch.randn(2, C, 8, 8, generator=g)
+    put("q2", weight=w, x=x, gq=gq)
+    for legacy in (True, False):
+        vq = VQ2(codebook_size=K, codebook_dim=C, commit_loss_legacy=legacy).eval()
+        with torch.no_grad():
+            vq.codebook.weight.copy_(w)
+        xin = x.clone().requires_grad_(True)
+        xq, loss, (_, _, codes) = vq(xin)
+        (xq * gq).sum().backward(retain_graph=True)
+        g_ste = xin.grad.clone()
+        xin.grad = None
+        loss.backward()
+        put(f"q2_legacy{int(legacy)}", xq=xq, loss=loss, codes=codes, gx_ste=g_ste, gx_loss=xin.grad)
+
+    # ---- quantize2_list.VectorQuantize2: ragged list, eval + one training pass
+    K = 16
+    wl = torch.randn(K + 1, C, generator=g)
+    xs = [torch.randn(n, C, generator=g) for n in (5, 77, 130)]
+    vq = VQ2List(codebook_size=K, codebook_dim=C).eval()
+    with torch.no_grad():
+        vq.codebook.weight.copy_(wl)
+        vq.codebook.embed_ema.copy_(wl[:-1])
+        vq.codebook.cluster_size_ema.fill_(1.0)
+    xin = [t.clone().requires_grad_(True) for t in xs]
+    xq_l, loss, (_, _, code_l) = vq(xin)
+    loss.backward()
+    put("ql", weight=wl, loss=loss, n_items=len(xs))
+    for i in range(len(xs)):
+        put(f"ql_{i}", x=xs[i], xq=xq_l[i], codes=code_l[i], gx=xin[i].grad)
+    vq.train()
+    # replay the RNG calls of _update_buffers item by item (quantize2_list.py:92-98)
+    torch.manual_seed(321)
+    restart = []
+    for t in xs:
+        v = t
+        if v.shape[0] < K:
+            v = vq.codebook._tile_with_noise(v, K)
+        restart.append(v[torch.randperm(v.shape[0])][:K].clone())
+    torch.manual_seed(321)
+    xq_t, loss_t, (_, _, code_t) = vq([t.clone() for t in xs])
+    put("ql_train", loss=loss_t, w=vq.codebook.weight, cs=vq.codebook.cluster_size_ema, em=vq.codebook.embed_ema)
+    for i in range(len(xs)):
+        put(f"ql_train_{i}", xq=xq_t[i], codes=code_t[i], restart=restart[i])
+
+    # ---- quantize_rqvae.RQBottleneck: separate codebooks (depth 3) and a shared one (2x2 patches, depth 2)
+    for tag, latent, code, shared, K in (("rq", (8, 8, 64), (8, 8, 3), False, 32),
+                                          ("rqs", (8, 8, 64), (4, 4, 2), True, 32)):
+        rq = RQBottleneck(latent_shape=latent, code_shape=code, n_embed=K, shared_codebook=shared).eval()
+        ws = []
+        with torch.no_grad():
+            for d, cb in enumerate(rq.codebooks):
+                if shared and d > 0:
+                    ws.append(ws[0])
+                    continue
+                wd = torch.randn(K + 1, cb.weight.shape[1], generator=g) * (0.6 ** d)
+                cb.weight.copy_(wd)
+                cb.embed_ema.copy_(wd[:-1])
+                cb.cluster_size_ema.fill_(1.0)
+                ws.append(wd)
+        xr = torch.randn(2, *latent, generator=g)
+        gqr = torch.randn(2, *latent, generator=g)
+        xin = xr.clone().requires_grad_(True)
+        q, loss, codes = rq(xin)
+        (q * gqr).sum().backward(retain_graph=True)
+        g_ste = xin.grad.clone()
+        xin.grad = None
+        loss.backward()
+        put(tag, x=xr, gq=gqr, quants=q, loss=loss, codes=codes, gx_ste=g_ste, gx_loss=xin.grad,
+            embed=rq.embed_code(codes), depth=code[2])
+        for d in range(code[2]):
+            put(f"{tag}_w{d}", v=ws[d])
+        rq.train()
+        xt = torch.randn(2, *latent, generator=g) * 1.5
+        # replay: depth d draws randperm over the residual rows entering depth d (quantize_rqvae.py:259-268)
+        torch.manual_seed(654)
+        n_rows = 2 * code[0] * code[1]
+        perms = [torch.randperm(n_rows) for _ in range(code[2])]
+        hooks, seen = [], []
+        for cb in (list(rq.codebooks) if not shared else [rq.codebooks[0]]):
+            hooks.append(cb.register_forward_pre_hook(lambda m, a: seen.append(a[0].detach().reshape(-1, a[0].shape[-1]).clone())))
+        torch.manual_seed(654)
+        q_t, loss_t, codes_t = rq(xt)
+        for h in hooks:
+            h.remove()
+        put(f"{tag}_train", x=xt, quants=q_t, loss=loss_t, codes=codes_t)
+        for d in range(code[2]):
+            cb = rq.codebooks[d]
+            put(f"{tag}_train_d{d}", restart=seen[d][perms[d]][:K], w=cb.weight, cs=cb.cluster_size_ema,
+                em=cb.embed_ema)
+
+    # ---- quantize_vqgan.VectorQuantizer2 (learnable codebook)
+    n_e = 64
+    we = torch.randn(n_e, C, generator=g) * 0.7
+    z = torch.randn(2, C, 8, 8, generator=g)
+    gz = torch.randn(2, C, 8, 8, generator=g)
+    put("vg", weight=we, z=z, gq=gz)
+    for legacy in (True, False):
+        q = VectorQuantizer2(n_e, C, beta=0.25, legacy=legacy, sane_index_shape=not legacy)
+        with torch.no_grad():
+            q.embedding.weight.copy_(we)
+        zin = z.clone().requires_grad_(True)
+        zq, loss, (_, _, idx) = q(zin)
+        (zq * gz).sum().backward(retain_graph=True)
+        g_ste = zin.grad.clone()
+        assert q.embedding.weight.grad is None or float(q.embedding.weight.grad.abs().max()) == 0.0
+        zin.grad = None
+        loss.backward()
+        put(f"vg_legacy{int(legacy)}", zq=zq, loss=loss, idx=idx, gz_ste=g_ste, gz_loss=zin.grad,
+            gw=q.embedding.weight.grad, entry=q.get_codebook_entry(idx.reshape(-1), (2, 8, 8, C)))
+    save("vq_family.npz", **out)
+
+
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["vq", "tiny", "dual", "variants"]
+    what = sys.argv[1:] or ["vq", "family", "tiny", "dual", "variants"]
     if "variants" in what:
         triple_entropy_goldens()
     if "vq" in what:
         vq_goldens()
+    if "family" in what:
+        vq_family_goldens()
     if "tiny" in what:
         model_goldens(orc.TINY_CFG, "tiny", batch=2, seed=3)
     if "dual" in what:

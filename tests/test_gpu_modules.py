@@ -200,7 +200,6 @@ def test_routers_budget_entropy_match_oracle_on_cpu():
     from modules.dynamic_modules.RouterTriple import TripleGrainFeatureRouter
     from modules.dynamic_modules.budget import (BudgetConstraint_NormedSeperateRatioMSE_TripleGrain,
                                                 BudgetConstraint_RatioMSE_DualGrain)
-    from models.stage1_dynamic.dqvae_dual_entropy import Entropy
     from oracle import dqvae_oracle as orc
     g = torch.Generator().manual_seed(0)
     r2 = DualGrainFeatureRouter(num_channels=64, normalization_type="group-32", gate_type="2layer-fc-SiLu")
@@ -220,5 +219,28 @@ def test_routers_budget_entropy_match_oracle_on_cpu():
     b3 = BudgetConstraint_NormedSeperateRatioMSE_TripleGrain(target_fine_ratio=0.3, target_median_ratio=0.3, gamma=1.0,
                                                              min_grain_size=8, median_grain_size=16, max_grain_size=32)
     assert torch.allclose(b3(gate3), orc.budget_loss_triple(gate3))
-    x = torch.rand(2, 3, 64, 64, generator=g) * 2 - 1
-    assert torch.allclose(Entropy(16, 64, 64)(x), orc.patch_entropy(x, 16), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("patch,size,batch", [(16, 256, 3), (16, 64, 2), (8, 64, 2), (4, 32, 1)])
+def test_patch_entropy_kernel_matches_oracle(patch, size, batch):
+    """csrc/entropy.cu vs the fp32 restatement of dqvae_dual_entropy.py:25-63: noise patches (entropy ~3),
+    constant patches (entropy ~0, every other bin at the 1e-40 floor) and smooth ramps."""
+    _overlay()
+    from models.stage1_dynamic.dqvae_dual_entropy import Entropy
+    from oracle import dqvae_oracle as orc
+    g = torch.Generator().manual_seed(patch * 1000 + size)
+    x = torch.rand(batch, 3, size, size, generator=g) * 2 - 1
+    n = size // patch
+    kind = torch.randint(0, 3, (batch, 1, n, n), generator=g).repeat_interleave(patch, 2).repeat_interleave(patch, 3)
+    const = (torch.rand(batch, 3, n, n, generator=g) * 2 - 1).repeat_interleave(patch, 2).repeat_interleave(patch, 3)
+    ramp = torch.linspace(-1, 1, size).view(1, 1, 1, size).expand(batch, 3, size, size)
+    x = torch.where(kind == 0, x, torch.where(kind == 1, const, ramp)).contiguous()
+    ref = orc.patch_entropy(x, patch)
+    mod = Entropy(patch, size, size)
+    got = mod(x.cuda())
+    assert got.shape == ref.shape and got.dtype == torch.float32
+    assert torch.allclose(got.cpu(), ref, rtol=2e-5, atol=2e-6), float((got.cpu() - ref).abs().max())
+    assert float(ref.min()) < 0.1 < 2.5 < float(ref.max()) or patch == 4      # both regimes are present
+    with pytest.raises(RuntimeError):
+        mod(x)                                                                 # no CPU fallback

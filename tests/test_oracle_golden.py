@@ -110,3 +110,97 @@ def test_entropy_oracle_matches_reference():
     assert 0 < int(gate[..., 1].sum()) < gate[..., 1].numel()          # both grains present
     b = orc.budget_loss_dual(gate.permute(0, 3, 1, 2).float(), min_grain=4, max_grain=8)
     assert abs(float(b) - float(g["budget"])) < 1e-6 * abs(float(g["budget"])) + 1e-9
+
+
+# --------------------------------------------------------------------------- sibling quantizers (8f row 2)
+from oracle import vq_family_oracle as vf  # noqa: E402
+
+
+def _unflat(rows, like_nchw):
+    b, c, h, w = like_nchw.shape
+    return rows.reshape(b, h, w, c).transpose(0, 3, 1, 2)
+
+
+@pytest.mark.parametrize("legacy", [True, False])
+def test_family_quantize2_oracle_matches_reference(legacy):
+    g = _load("vq_family.npz")
+    p = f"q2_legacy{int(legacy)}"
+    x = _flat(g["q2_x"])
+    xq, loss, idx, gx = vf.vq2_forward(x, g["q2_weight"], beta=0.25, legacy=legacy)
+    assert np.array_equal(idx, g[p + "_codes"].reshape(-1))
+    assert np.array_equal(_unflat(xq, g["q2_x"]), g[p + "_xq"])
+    assert abs(float(loss) - float(g[p + "_loss"])) <= 1e-6 * abs(float(g[p + "_loss"]))
+    assert np.array_equal(g[p + "_gx_ste"], g["q2_gq"])
+    assert np.allclose(_unflat(gx, g["q2_x"]), g[p + "_gx_loss"], rtol=1e-5, atol=1e-10)
+
+
+def test_family_quantize2_list_oracle_matches_reference():
+    g = _load("vq_family.npz")
+    n = int(g["ql_n_items"])
+    xs = [g[f"ql_{i}_x"] for i in range(n)]
+    xq, loss, idx, _ = vf.vq2_list_forward(xs, g["ql_weight"], beta=0.25)
+    for i in range(n):
+        assert np.array_equal(idx[i], g[f"ql_{i}_codes"])
+        assert np.array_equal(xq[i], g[f"ql_{i}_xq"])
+        e = g["ql_weight"][idx[i]]
+        assert np.allclose(g[f"ql_{i}_gx"], 2 * 0.25 * (xs[i] - e) / xs[i].size / n, rtol=1e-5, atol=1e-10)
+    assert abs(float(loss) - float(g["ql_loss"])) <= 1e-6 * abs(float(g["ql_loss"]))
+    # training: the codebook moves between items
+    k = g["ql_weight"].shape[0] - 1
+    xq, loss, idx, (w, cs, em) = vf.vq2_list_forward(
+        xs, g["ql_weight"], beta=0.25, train=True, cs=np.ones(k, np.float32), em=g["ql_weight"][:-1].copy(),
+        restart_rows=[g[f"ql_train_{i}_restart"] for i in range(n)])
+    for i in range(n):
+        assert np.array_equal(idx[i], g[f"ql_train_{i}_codes"])
+        assert np.allclose(xq[i], g[f"ql_train_{i}_xq"], rtol=0, atol=1e-6)
+    assert np.allclose(w, g["ql_train_w"], rtol=1e-5, atol=1e-6)
+    assert np.allclose(cs, g["ql_train_cs"], rtol=1e-6, atol=1e-7)
+    assert np.allclose(em, g["ql_train_em"], rtol=1e-5, atol=1e-6)
+    assert abs(float(loss) - float(g["ql_train_loss"])) <= 1e-5 * abs(float(g["ql_train_loss"]))
+
+
+@pytest.mark.parametrize("tag,latent,code,shared", [("rq", (8, 8, 64), (8, 8, 3), False),
+                                                     ("rqs", (8, 8, 64), (4, 4, 2), True)])
+def test_family_rq_oracle_matches_reference(tag, latent, code, shared):
+    g = _load("vq_family.npz")
+    depth = code[2]
+    ws = [g[f"{tag}_w{d}_v"].copy() for d in range(depth)]
+    if shared:
+        ws = [ws[0]] * depth
+    q, loss, codes, gx, _ = vf.rq_forward(g[f"{tag}_x"], ws, latent, code)
+    assert np.array_equal(codes, g[f"{tag}_codes"])
+    assert np.allclose(q, g[f"{tag}_quants"], rtol=0, atol=2e-6)
+    assert abs(float(loss) - float(g[f"{tag}_loss"])) <= 1e-6 * abs(float(g[f"{tag}_loss"]))
+    assert np.array_equal(g[f"{tag}_gx_ste"], g[f"{tag}_gq"])
+    assert np.allclose(vf.rq_to_latent_shape(gx, latent, code), g[f"{tag}_gx_loss"], rtol=1e-4, atol=1e-9)
+    assert np.allclose(vf.rq_embed_code(codes, ws, latent, code), g[f"{tag}_embed"], rtol=0, atol=2e-6)
+    # one training pass, every depth updating its codebook right after its own search
+    k = ws[0].shape[0] - 1
+    states = [(np.ones(k, np.float32), ws[d][:-1].copy()) for d in range(depth)]
+    if shared:
+        states = [states[0]] * depth
+    q, loss, codes, _, states = vf.rq_forward(
+        g[f"{tag}_train_x"], ws, latent, code, train=True, states=list(states),
+        restart_rows=[g[f"{tag}_train_d{d}_restart"] for d in range(depth)])
+    assert np.array_equal(codes, g[f"{tag}_train_codes"])
+    assert np.allclose(q, g[f"{tag}_train_quants"], rtol=0, atol=2e-6)
+    assert abs(float(loss) - float(g[f"{tag}_train_loss"])) <= 1e-5 * abs(float(g[f"{tag}_train_loss"]))
+    for d in range(depth):
+        assert np.allclose(ws[d], g[f"{tag}_train_d{d}_w"], rtol=1e-5, atol=1e-6), d
+        assert np.allclose(states[d][0], g[f"{tag}_train_d{d}_cs"], rtol=1e-6, atol=1e-7), d
+        assert np.allclose(states[d][1], g[f"{tag}_train_d{d}_em"], rtol=1e-5, atol=1e-6), d
+
+
+@pytest.mark.parametrize("legacy", [True, False])
+def test_family_vqgan_oracle_matches_reference(legacy):
+    g = _load("vq_family.npz")
+    p = f"vg_legacy{int(legacy)}"
+    z = _flat(g["vg_z"])
+    zq, loss, idx, gz, gw = vf.vqgan_forward(z, g["vg_weight"], beta=0.25, legacy=legacy)
+    assert np.array_equal(idx, g[p + "_idx"].reshape(-1))
+    assert np.array_equal(_unflat(zq, g["vg_z"]), g[p + "_zq"])
+    assert abs(float(loss) - float(g[p + "_loss"])) <= 1e-6 * abs(float(g[p + "_loss"]))
+    assert np.array_equal(g[p + "_gz_ste"], g["vg_gq"])
+    assert np.allclose(_unflat(gz, g["vg_z"]), g[p + "_gz_loss"], rtol=1e-5, atol=1e-10)
+    assert np.allclose(gw, g[p + "_gw"], rtol=1e-4, atol=1e-8)
+    assert np.allclose(_unflat(g["vg_weight"][idx], g["vg_z"]), g[p + "_entry"], rtol=0, atol=0)
