@@ -86,6 +86,9 @@ SIGNATURES = {
     "b2dq_bias_grad": [_vp, _vp, _vp, _ll, _i, _vp],
     "b2dq_cast_f32_to_bf16": [_vp, _vp, _ll, _vp],
     "b2dq_patch_entropy": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp],
+    "b2dq_permuter_forward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i,
+                              C.POINTER(C.c_longlong), _vp],
+    "b2dq_permuter_backward": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _ll, _ll, _vp],
 }
 
 

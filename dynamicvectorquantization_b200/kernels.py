@@ -521,6 +521,32 @@ def patch_entropy(x_nchw, bins, patch, sigma):
     return out
 
 
+def permuter_forward(indices, grain, coarse_hw, fine_hw, coarse_len, fine_len, region_first, codes6):
+    """permuter.py:50-109.  indices [B,F,F], grain [B,Hc,Hc] int64 -> six [B,L] int64 tensors."""
+    import ctypes
+    b = indices.shape[0]
+    dev = indices.device
+    outs = [torch.empty(b, n, dtype=torch.int64, device=dev) for n in (coarse_len,) * 3 + (fine_len,) * 3]
+    arr = (ctypes.c_longlong * 6)(*[int(c) for c in codes6])
+    check(_cabi.lib().b2dq_permuter_forward(_ptr(indices), _ptr(grain), *[_ptr(o) for o in outs], b, coarse_hw,
+                                            fine_hw, coarse_len, fine_len, int(bool(region_first)), arr,
+                                            _stream()), "permuter_forward")
+    return outs
+
+
+def permuter_backward(coarse_content, fine_content, coarse_position, fine_position, coarse_hw, fine_hw,
+                      coarse_position_eos, fine_position_eos):
+    """permuter.py:111-132 -> target [B,F,F] int64."""
+    b = coarse_content.shape[0]
+    out = torch.empty(b, fine_hw, fine_hw, dtype=torch.int64, device=coarse_content.device)
+    check(_cabi.lib().b2dq_permuter_backward(_ptr(coarse_content), _ptr(fine_content), _ptr(coarse_position),
+                                             _ptr(fine_position), _ptr(out), b, coarse_hw, fine_hw,
+                                             coarse_content.shape[1], fine_content.shape[1],
+                                             int(coarse_position_eos), int(fine_position_eos), _stream()),
+          "permuter_backward")
+    return out
+
+
 def im2col3x3_small(x, flip=False):
     nb, h, w, cs = x.shape
     out = torch.empty(nb, h, w, 64, dtype=BF16, device=x.device)

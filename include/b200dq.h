@@ -206,6 +206,24 @@ int b2dq_im2col3x3_small(const void* src, void* dst, int N, int H, int W, int Cs
 int b2dq_patch_entropy(const float* x_nchw, const float* bins, float* out, int B, int H, int W, int patch,
                        int nbins, float sigma, cudaStream_t stream);
 
+/* ------------------------------------------------------------------ stage-2 tokenisation: dual-grain permuter
+ * modules/dynamic_modules/permuter.py:50-109 (forward) and :111-132 (forward_back).  All tensors int64 on
+ * the device.  forward: indices [B,F,F] codes, grain [B,Hc,Hc] (0 coarse / 1 fine) -> content / position /
+ * segment rows of length coarse_len resp. fine_len (= longest sequence of the batch + 1 for the eos; the
+ * caller sizes them), eos then pad filled.  codes6 is a HOST array {content_pad, content_eos,
+ * coarse_position_pad, coarse_position_eos, fine_position_pad, fine_position_eos}.  region_first selects the
+ * fine ordering (:78-96).  backward: the inverse map -> target [B,F,F]; duplicate positions resolve to the
+ * last sequence element before the eos, positions outside the map are ignored (the reference raises). */
+int b2dq_permuter_forward(const long long* indices, const long long* grain, long long* coarse_content,
+                          long long* coarse_position, long long* coarse_segment, long long* fine_content,
+                          long long* fine_position, long long* fine_segment, int B, int coarse_hw, int fine_hw,
+                          int coarse_len, int fine_len, int region_first, const long long* codes6,
+                          cudaStream_t stream);
+int b2dq_permuter_backward(const long long* coarse_content, const long long* fine_content,
+                           const long long* coarse_position, const long long* fine_position, long long* target,
+                           int B, int coarse_hw, int fine_hw, int coarse_len, int fine_len,
+                           long long coarse_position_eos, long long fine_position_eos, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

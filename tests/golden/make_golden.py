@@ -325,14 +325,55 @@ def vq_family_goldens():
     save("vq_family.npz", **out)
 
 
+# ----------------------------------------------------------------------------------- stage-2 permuter
+def permuter_goldens():
+    """modules/dynamic_modules/permuter.py of the reference: both fine orderings, forward + forward_back,
+    on code maps whose coarse cells carry one code (what the dual-grain encoder emits), plus the edge cases
+    all-coarse / all-fine samples, a sequence with duplicate positions and one without eos."""
+    from modules.dynamic_modules.permuter import DualGrainSeperatePermuter
+    out = {}
+    g = torch.Generator().manual_seed(11)
+    for tag, hw1, fhw, b in (("p8", 4, 8, 5), ("p32", 16, 32, 3), ("p8b", 4, 8, 4), ("p32b", 16, 32, 2)):
+        grain = torch.randint(0, 2, (b, hw1, hw1), generator=g)
+        if not tag.endswith("b"):                                          # "b": padded length < full length
+            grain[0] = 0                                                   # all coarse: empty fine sequence
+            grain[1] = 1                                                   # all fine: empty coarse sequence
+        rep = grain.repeat_interleave(2, dim=-1).repeat_interleave(2, dim=-2)
+        fine_codes = torch.randint(0, 1024, (b, fhw, fhw), generator=g)
+        cell_codes = torch.randint(0, 1024, (b, hw1, hw1), generator=g).repeat_interleave(2, -1).repeat_interleave(2, -2)
+        indices = fine_codes * rep + cell_codes * (1 - rep)
+        out[f"{tag}_indices"], out[f"{tag}_grain"] = indices, grain
+        for order in ("region-first", "row-first"):
+            p = DualGrainSeperatePermuter(coarse_hw=hw1, fine_hw=fhw, coarse_position_pad_code=hw1 * hw1,
+                                          coarse_position_eos_code=hw1 * hw1 + 1, fine_position_order=order)
+            o = p(indices, grain)
+            back = p.forward_back(o["coarse_content"], o["fine_content"], o["coarse_position"], o["fine_position"])
+            assert torch.equal(back, indices)                              # the reference's own round-trip check
+            k = order[:3]
+            for name, v in o.items():
+                out[f"{tag}_{k}_{name}"] = v
+            out[f"{tag}_{k}_back"] = back
+    # forward_back on hand-made sequences: duplicates (last wins), garbage after the eos, a missing coarse eos
+    p = DualGrainSeperatePermuter(coarse_hw=4, fine_hw=8, coarse_position_pad_code=16, coarse_position_eos_code=17)
+    cc = torch.tensor([[5, 6, 7, 1025, 9, 1024], [1, 2, 3, 4, 5, 6]])
+    cp = torch.tensor([[0, 3, 0, 17, 2, 16], [0, 1, 2, 3, 4, 5]])           # sample 1 never reaches the eos
+    fc = torch.tensor([[40, 41, 42, 1025, 50], [60, 61, 1025, 1024, 1024]])
+    fp = torch.tensor([[9, 9, 63, 1025, 0], [0, 10, 1025, 1024, 1024]])
+    out["pb_cc"], out["pb_cp"], out["pb_fc"], out["pb_fp"] = cc, cp, fc, fp
+    out["pb_back"] = p.forward_back(cc, fc, cp, fp)
+    save("permuter.npz", **out)
+
+
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["vq", "family", "tiny", "dual", "variants"]
+    what = sys.argv[1:] or ["vq", "family", "permuter", "tiny", "dual", "variants"]
     if "variants" in what:
         triple_entropy_goldens()
     if "vq" in what:
         vq_goldens()
     if "family" in what:
         vq_family_goldens()
+    if "permuter" in what:
+        permuter_goldens()
     if "tiny" in what:
         model_goldens(orc.TINY_CFG, "tiny", batch=2, seed=3)
     if "dual" in what:

@@ -204,3 +204,31 @@ def test_family_vqgan_oracle_matches_reference(legacy):
     assert np.allclose(_unflat(gz, g["vg_z"]), g[p + "_gz_loss"], rtol=1e-5, atol=1e-10)
     assert np.allclose(gw, g[p + "_gw"], rtol=1e-4, atol=1e-8)
     assert np.allclose(_unflat(g["vg_weight"][idx], g["vg_z"]), g[p + "_entry"], rtol=0, atol=0)
+
+
+# --------------------------------------------------------------------------- stage-2 permuter (8f row 3)
+from oracle import permuter_oracle as po  # noqa: E402
+
+PERMUTER_CASES = [("p8", 4, 8), ("p32", 16, 32), ("p8b", 4, 8), ("p32b", 16, 32)]
+
+
+@pytest.mark.parametrize("tag,hw1,fhw", PERMUTER_CASES)
+@pytest.mark.parametrize("order", ["region-first", "row-first"])
+def test_permuter_oracle_matches_reference(tag, hw1, fhw, order):
+    g = _load("permuter.npz")
+    codes = dict(coarse_position_pad_code=hw1 * hw1, coarse_position_eos_code=hw1 * hw1 + 1)
+    o = po.forward(g[f"{tag}_indices"], g[f"{tag}_grain"], hw1, fhw, order, **codes)
+    k = order[:3]
+    for name, v in o.items():
+        assert np.array_equal(v, g[f"{tag}_{k}_{name}"]), name
+    back = po.forward_back(o["coarse_content"], o["fine_content"], o["coarse_position"], o["fine_position"],
+                           hw1, fhw, **codes)
+    assert np.array_equal(back, g[f"{tag}_{k}_back"]) and np.array_equal(back, g[f"{tag}_indices"])
+
+
+def test_permuter_oracle_backward_edge_cases_match_reference():
+    g = _load("permuter.npz")
+    back = po.forward_back(g["pb_cc"], g["pb_fc"], g["pb_cp"], g["pb_fp"], 4, 8,
+                           coarse_position_pad_code=16, coarse_position_eos_code=17)
+    assert np.array_equal(back, g["pb_back"])
+    assert back[0, 1, 1] == 41 and back[0, 0, 0] == 7 and back[1].sum() == 60 + 61   # last wins; no eos -> no spread
