@@ -43,6 +43,9 @@ def parse():
     ap.add_argument("--config", default="dqvae-dual-r-05", choices=sorted(WORKLOADS),
                     help="headline = dqvae-dual-r-05; the others are parity-test configs that can be timed too")
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph (N=1)")
+    ap.add_argument("--aux", action="store_true",
+                    help="instead of the headline step, time the widened rows (SURVEY 8f: patch entropy, stage-2 "
+                         "permuter, residual quantizer) on one GPU, one JSON line each with roofline + cpu_baseline")
     return ap.parse_args()
 
 
@@ -436,9 +439,116 @@ def cpu_baseline(args):
                       f"{threads} threads = fastest of the thread counts tried on the {cores} usable cores)"}
 
 
+def run_aux(args):
+    """each kernel timed alone with CUDA events (L2 flushed between launches), against the
+    measured HBM copy bandwidth, with the CPU oracle of the same op timed on a bounded sample beside it."""
+    import numpy as np
+    import torch
+    from dynamicvectorquantization_b200 import configs, kernels as kn
+    from oracle import dqvae_oracle as orc
+    from oracle import permuter_oracle as po
+    from oracle import vq_family_oracle as vf
+    configs.activate_overlay()
+    dev = torch.device("cuda:0")
+    torch.cuda.set_device(dev)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_h = peaks.get("hbm_gbs") or 6577.7
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    threads, cores = pick_threads(torch)
+
+    def gpu_ms(fn, iters=20):
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(iters):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); fn(); e.record(); torch.cuda.synchronize()
+            ts.append(s.elapsed_time(e))
+        return sorted(ts)[len(ts) // 2]
+
+    def cpu_s(fn, budget=5.0):
+        fn()
+        t0 = time.perf_counter(); n = 0
+        while n < 1 or (time.perf_counter() - t0 < budget and n < 20):
+            fn(); n += 1
+        return (time.perf_counter() - t0) / n
+
+    def emit(name, unit_name, units, ms, bytes_, cpu_units, cpu_sec, sample, launches=1):
+        print(json.dumps({
+            "metric": f"{unit_name}/sec ({name})", "value": units / ms * 1e3, "unit": f"{unit_name}/s", "n_gpus": 1,
+            "ms_per_call": ms, "higher_is_better": True, "data": "synthetic", "gpu_launches": launches,
+            "config": {"workload": name, "l2": "256 MB flush between launches"},
+            "roofline": {"bound": "hbm", "achieved": bytes_ / ms / 1e6, "peak": peak_h, "unit": "GB/s",
+                         "frac": bytes_ / ms / 1e6 / peak_h, "traffic": None,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks.get("hbm_gbs") else "fallback"},
+            "cpu_baseline": {"value": cpu_units / cpu_sec, "unit": f"{unit_name}/s", "cores": threads, "kind": "port",
+                             "sample": sample}}), flush=True)
+
+    # ---- patch entropy (a10): B=32 images 256x256, 16x16 patches; bytes = image once + 4 B per patch
+    from models.stage1_dynamic.dqvae_dual_entropy import Entropy
+    b = 32
+    x = torch.rand(b, 3, 256, 256, device=dev) * 2 - 1
+    ent = Entropy(16, 256, 256)
+    ms = gpu_ms(lambda: ent(x))
+    xc = x[:4].cpu()
+    sec = cpu_s(lambda: orc.patch_entropy(xc, 16))
+    emit("patch entropy 256x256, 16x16 patches, batch 32", "images", b, ms, b * 3 * 256 * 256 * 4 + b * 256 * 4,
+         4, sec, f"oracle (fp32 torch CPU, {threads} threads) on 4 images")
+    # ---- stage-2 permuter (8f row 3): B=256 code maps 32x32 + grain maps 16x16, ~50 % fine
+    b = 256
+    grain = torch.randint(0, 2, (b, 16, 16), device=dev)
+    idx = torch.randint(0, 1024, (b, 32, 32), device=dev)
+    from modules.dynamic_modules.permuter import DualGrainSeperatePermuter
+    perm = DualGrainSeperatePermuter()
+    out = perm(idx, grain)
+    lc, lf = out["coarse_content"].shape[1], out["fine_content"].shape[1]
+    ms = gpu_ms(lambda: perm(idx, grain))
+    gi, gg = idx[:8].cpu().numpy(), grain[:8].cpu().numpy()
+    sec = cpu_s(lambda: po.forward(gi, gg))
+    emit("dual-grain permuter forward, 256 code maps 32x32 (incl. the 2-int length read-back)", "maps", b, ms,
+         b * (1024 + 256) * 8 + b * 3 * (lc + lf) * 8, 8, sec, "numpy oracle on 8 maps, 1 thread", launches=1)
+    args4 = (out["coarse_content"], out["fine_content"], out["coarse_position"], out["fine_position"])
+    ms = gpu_ms(lambda: perm.forward_back(*args4))
+    a4 = [t[:8].cpu().numpy() for t in args4]
+    sec = cpu_s(lambda: po.forward_back(*a4))
+    emit("dual-grain permuter forward_back, 256 sequences -> 32x32 code maps", "maps", b, ms,
+         b * 2 * (lc + lf) * 8 + b * 1024 * 8, 8, sec, "numpy oracle (element loop like the reference) on 8 maps, 1 thread")
+    # ---- residual quantizer (8f row 2): B=32 latents 8x8x256, depth 4, K=16384 (RQ-VAE shape), eval forward
+    from modules.vector_quantization.quantize_rqvae import RQBottleneck
+    rq = RQBottleneck(latent_shape=(8, 8, 256), code_shape=(8, 8, 4), n_embed=16384, shared_codebook=True).to(dev).eval()
+    with torch.no_grad():
+        rq.codebooks[0].weight.normal_()
+    z = torch.randn(32, 8, 8, 256, device=dev)
+    with torch.no_grad():
+        ms = gpu_ms(lambda: rq(z))
+    n, c, k, d = 32 * 64, 256, 16384, 4
+    w = rq.codebooks[0].weight.detach().cpu().numpy()
+    zc = z[:4].cpu().numpy()
+    sec = cpu_s(lambda: vf.rq_forward(zc, [w] * d, (8, 8, 256), (8, 8, 4)))
+    flops = 2.0 * n * k * c * d
+    line_bytes = d * (2 * n * c + 2 * k * c + 8 * n + 4 * n * c)
+    print(json.dumps({
+        "metric": "latents/sec (RQ bottleneck 8x8x256, depth 4, K=16384, eval forward)", "value": 32 / ms * 1e3,
+        "unit": "latents/s", "n_gpus": 1, "ms_per_call": ms, "higher_is_better": True, "data": "synthetic",
+        "gpu_launches": 2 * d,
+        "roofline": {"bound": "tensor", "achieved": flops / ms / 1e9, "peak": peaks.get("bf16_tflops_sustained"),
+                     "unit": "TFLOP/s", "frac": (flops / ms / 1e9 / peaks["bf16_tflops_sustained"])
+                     if peaks.get("bf16_tflops_sustained") else None, "traffic": None,
+                     "note": f"N={n} rows per depth: 16 CTAs of work on 148 SMs, latency-bound; algorithmic bytes {line_bytes}"},
+        "cpu_baseline": {"value": 4 / sec, "unit": "latents/s", "cores": threads, "kind": "port",
+                         "sample": f"numpy oracle on 4 latents ({threads} BLAS threads)"}}), flush=True)
+
+
 if __name__ == "__main__":
     a = parse()
-    if a.impl == "reference":
+    if a.aux:
+        run_aux(a)
+    elif a.impl == "reference":
         run_reference(a)
     else:
         run_b200(a)
