@@ -9,11 +9,23 @@
 //   :172-179 masked commitment loss       -> sum_rows m * sum_c (e - x)^2
 // The [N,K] distance matrix never leaves the SM: x.e^T tiles are produced by tcgen05.mma
 // into TMEM (two 256-column buffers) and reduced to a running (min, argmin) per row by
-// the epilogue warps while the tensor core works on the next codebook tile.
+// the search warps while the tensor core works on the next codebook tile.
 //
-// CTA = 320 threads: warp 0 TMA producer, warp 1 MMA issuer (+TMEM owner), warps 2..9 epilogue.
-// Persistent over 128-row tiles of x; the x tile stays resident in shared memory (<= 64 KB)
-// while the codebook streams through a 4-stage 32 KB ring.
+// CTA = 576 threads, four roles that only meet through mbarriers:
+//   warp 0        TMA producer: x tile in four 16 KB channel chunks (each chunk is re-loaded for the
+//                 next tile as soon as the last MMA that reads it has retired; the next tile's rows
+//                 are prefetched into L2 a tile ahead) + the codebook through a 4-stage 32 KB ring
+//   warp 1        MMA issuer (+ TMEM owner)
+//   warps 2..9    search: TMEM -> registers, d = ||e||^2 - 2 x.e, running (min, argmin); ||e||^2 of
+//                 the NEXT codebook tile is fetched while the current one is reduced and read back
+//                 from a per-warp shared-memory slot (no global-load latency inside the loop)
+//   warps 10..17  gather: codes -> fp32 codebook rows, loss, EMA sums; works on tile t while the
+//                 search warps and the tensor core are already on tile t+1
+// Small N (residual quantizer, stage-2 sampling): the codebook is split over `splits` CTAs per row
+// tile; the partial minima meet in a 64-bit atomicMin (ordered distance bits | index, so the lowest
+// index still wins ties) and the last CTA of a tile to arrive runs its gather.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tmap.h"
 
@@ -22,10 +34,13 @@ namespace b2 {
 constexpr int VQ_BM = 128;        // latent rows per tile
 constexpr int VQ_BN = 256;        // codebook entries per MMA tile
 constexpr int VQ_STAGES = 4;      // codebook ring depth
-constexpr int VQ_THREADS = 320;
+constexpr int VQ_SEARCH_WARPS = 8;
+constexpr int VQ_GATHER_WARPS = 8;
+constexpr int VQ_THREADS = 32 * (2 + VQ_SEARCH_WARPS + VQ_GATHER_WARPS);
 constexpr uint32_t VQ_A_CHUNK = VQ_BM * 128;   // 16 KB: 128 rows x 64 bf16
 constexpr uint32_t VQ_B_CHUNK = VQ_BN * 128;   // 32 KB
-constexpr uint32_t VQ_SMEM = 4 * VQ_A_CHUNK + VQ_STAGES * VQ_B_CHUNK + 1024 /*align*/ + 8192;
+constexpr uint32_t VQ_SCRATCH = 16384;         // barriers, argmin hand-off, ||e||^2 slots
+constexpr uint32_t VQ_SMEM = 4 * VQ_A_CHUNK + VQ_STAGES * VQ_B_CHUNK + 1024 /*align*/ + VQ_SCRATCH;
 
 struct VqParams {
   const __nv_bfloat16* x_bf16;   // [N,C] search operand (and loss/EMA operand when x_f32 == null)
@@ -39,11 +54,347 @@ struct VqParams {
   float* loss_acc;               // [1] += sum m*(e-x)^2   (null: skip)
   float* counts;                 // [K] += 1 per assigned row   (null: no EMA accumulation)
   float* sums;                   // [K,C] += x row
+  unsigned long long* keys;      // [tiles*128] split mode: running min of (ordered d | index), preset to ~0
+  unsigned int* tile_done;       // [tiles]     split mode: arrival counter, preset to 0xFFFFFFFF
   int N, C, K;
+  int splits;                    // CTAs sharing one row tile (1 = no split)
+  int ntiles_per_split;          // codebook tiles of 256 entries per split
 };
+
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* tm, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tm), "r"(c0),
+               "r"(c1)
+               : "memory");
+}
+// fp32 -> uint32 whose unsigned order is the float order (for the split-mode atomicMin key)
+__device__ __forceinline__ uint32_t ordered_bits(float d) {
+  const uint32_t u = __float_as_uint(d);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
 
 __global__ void __launch_bounds__(VQ_THREADS, 1)
 vq_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const VqParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = base;
+  const uint32_t sB = base + 4 * VQ_A_CHUNK;
+  const uint32_t sX = sB + VQ_STAGES * VQ_B_CHUNK;  // barriers + scratch
+  uint8_t* gen = smem_raw + (sX - smem_u32(smem_raw));
+  // barrier slots (8 B each)
+  const uint32_t bar_full = sX;                          // [VQ_STAGES] codebook stage landed
+  const uint32_t bar_empty = bar_full + 8 * VQ_STAGES;   // [VQ_STAGES] codebook stage consumed
+  const uint32_t bar_afull = bar_empty + 8 * VQ_STAGES;  // [4] x chunk landed
+  const uint32_t bar_aempty = bar_afull + 32;            // [4] x chunk no longer read by any MMA
+  const uint32_t bar_tfull = bar_aempty + 32;            // [2] accumulator buffer complete
+  const uint32_t bar_tempty = bar_tfull + 16;            // [2] accumulator buffer drained
+  const uint32_t bar_cfull = bar_tempty + 16;            // [2] argmin of a tile published
+  const uint32_t bar_cempty = bar_cfull + 16;            // [2] argmin slot consumed by the gather warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + 256);
+  volatile int* s_flag = reinterpret_cast<volatile int*>(gen + 272);   // [2] split mode: "this CTA gathers"
+  float* s_best = reinterpret_cast<float*>(gen + 512);                  // [2 parity][2 half][128]
+  int* s_idx = reinterpret_cast<int*>(gen + 512 + 2048);                // [2][2][128]
+  float* s_sq = reinterpret_cast<float*>(gen + 512 + 4096);             // [8 warps][2 slots][128]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KC = p.C >> 6;
+  const int num_m_tiles = (p.N + VQ_BM - 1) / VQ_BM;
+  const int num_n_tiles = (p.K + VQ_BN - 1) / VQ_BN;
+  const int S = p.splits, per = p.ntiles_per_split;
+  const int total = num_m_tiles * S;                     // work items: (row tile, codebook split)
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < VQ_STAGES; ++i) {
+      mbar_init(bar_full + 8 * i, 1);
+      mbar_init(bar_empty + 8 * i, 1);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(bar_afull + 8 * i, 1);
+      mbar_init(bar_aempty + 8 * i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_tfull + 8 * i, 1);
+      mbar_init(bar_tempty + 8 * i, VQ_SEARCH_WARPS);
+      mbar_init(bar_cfull + 8 * i, VQ_SEARCH_WARPS);
+      mbar_init(bar_cempty + 8 * i, VQ_GATHER_WARPS);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) tmem_alloc<512>(smem_u32(tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------ TMA producer
+      uint32_t stage = 0, phase = 0, it = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+        const int tile = w / S, sp = w - tile * S;
+        const int j0 = sp * per, j1 = min(num_n_tiles, j0 + per);
+        {  // rows of the next work item: HBM -> L2 now, L2 -> shared memory when the chunk frees up
+          const int wn = w + gridDim.x;
+          if (wn < total && wn / S != tile)
+            for (int kc = 0; kc < KC; ++kc) tma_prefetch_l2_2d(&tmA, kc * 64, (wn / S) * VQ_BM);
+        }
+        for (int j = j0; j < j1; ++j)
+          for (int kc = 0; kc < KC; ++kc) {
+            if (j == j0) {
+              mbar_wait(bar_aempty + 8 * kc, (it & 1) ^ 1);
+              mbar_arrive_expect_tx(bar_afull + 8 * kc, VQ_A_CHUNK);
+              tma_load_2d(sA + kc * VQ_A_CHUNK, &tmA, bar_afull + 8 * kc, kc * 64, tile * VQ_BM);
+            }
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+            mbar_arrive_expect_tx(bar_full + 8 * stage, VQ_B_CHUNK);
+            tma_load_2d(sB + stage * VQ_B_CHUNK, &tmB, bar_full + 8 * stage, kc * 64, j * VQ_BN);
+            if (++stage == VQ_STAGES) { stage = 0; phase ^= 1; }
+          }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------------------------ MMA issuer
+      constexpr uint32_t idesc = make_idesc_bf16(VQ_BM, VQ_BN, 0, 0);
+      uint32_t stage = 0, phase = 0, it = 0, jj = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+        const int tile = w / S, sp = w - tile * S;
+        const int j0 = sp * per, j1 = min(num_n_tiles, j0 + per);
+        for (int j = j0; j < j1; ++j, ++jj) {
+          const uint32_t buf = jj & 1;
+          mbar_wait(bar_tempty + 8 * buf, ((jj >> 1) & 1) ^ 1);
+          tc_fence_after();
+          for (int kc = 0; kc < KC; ++kc) {
+            if (j == j0) mbar_wait(bar_afull + 8 * kc, it & 1);
+            mbar_wait(bar_full + 8 * stage, phase);
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t da = make_smem_desc(sA + kc * VQ_A_CHUNK + k * 32, 0, 1024);
+              const uint64_t db = make_smem_desc(sB + stage * VQ_B_CHUNK + k * 32, 0, 1024);
+              umma_bf16(tmem_base + buf * VQ_BN, da, db, idesc, (kc | k) ? 1u : 0u);
+            }
+            umma_commit(bar_empty + 8 * stage);
+            if (j == j1 - 1) umma_commit(bar_aempty + 8 * kc);   // last reader of this x chunk
+            if (++stage == VQ_STAGES) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(bar_tfull + 8 * buf);
+        }
+      }
+    }
+  } else if (warp < 2 + VQ_SEARCH_WARPS) {
+    // ------------------------------------------------ search: running argmin over the codebook
+    const int ew = warp - 2;          // 0..7
+    const int q = warp & 3;           // TMEM lane quadrant this warp may read
+    const int half = ew >> 2;         // which 128 columns of each 256-column tile
+    const int row = q * 32 + lane;    // row of the tile owned by this thread
+    float* my_sq = s_sq + ew * 256;   // two slots of 128 squared norms, private to this warp
+    uint32_t jj = 0, it = 0;
+    {
+      const int sp0 = blockIdx.x % S;   // blockIdx.x < total: the first work item always exists
+      const float4 v = __ldg(reinterpret_cast<const float4*>(p.cb_sqnorm + sp0 * per * VQ_BN + half * 128) + lane);
+      *reinterpret_cast<float4*>(my_sq + lane * 4) = v;
+      __syncwarp();
+    }
+    for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+      const int tile = w / S, sp = w - tile * S;
+      const int j0 = sp * per, j1 = min(num_n_tiles, j0 + per);
+      const int wn = w + gridDim.x;
+      const int jnext_item = (wn < total) ? (wn % S) * per : -1;
+      float best = __int_as_float(0x7f800000);
+      int bi = 0;
+      for (int j = j0; j < j1; ++j, ++jj) {
+        const uint32_t buf = jj & 1;
+        // squared norms of the codebook tile after this one: in flight while this one is reduced
+        const int nj = (j + 1 < j1) ? j + 1 : jnext_item;
+        float4 nsq = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (nj >= 0) nsq = __ldg(reinterpret_cast<const float4*>(p.cb_sqnorm + nj * VQ_BN + half * 128) + lane);
+        mbar_wait(bar_tfull + 8 * buf, (jj >> 1) & 1);
+        tc_fence_after();
+        const uint32_t tcol = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * VQ_BN +
+                              half * 128;
+        const int colbase = j * VQ_BN + half * 128;
+        const float* sq = my_sq + (jj & 1) * 128;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(tcol + c0, r);
+          float4 s[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) s[i] = *reinterpret_cast<const float4*>(sq + c0 + 4 * i);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float d0 = fmaf(-2.f, __uint_as_float(r[4 * i + 0]), s[i].x);
+            const float d1 = fmaf(-2.f, __uint_as_float(r[4 * i + 1]), s[i].y);
+            const float d2 = fmaf(-2.f, __uint_as_float(r[4 * i + 2]), s[i].z);
+            const float d3 = fmaf(-2.f, __uint_as_float(r[4 * i + 3]), s[i].w);
+            const int c = colbase + c0 + 4 * i;
+            if (d0 < best) { best = d0; bi = c; }
+            if (d1 < best) { best = d1; bi = c + 1; }
+            if (d2 < best) { best = d2; bi = c + 2; }
+            if (d3 < best) { best = d3; bi = c + 3; }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+        if (nj >= 0) *reinterpret_cast<float4*>(my_sq + ((jj + 1) & 1) * 128 + lane * 4) = nsq;
+        __syncwarp();
+      }
+      // publish (min, argmin) of this work item to the gather warps
+      const int par = it & 1;
+      mbar_wait(bar_cempty + 8 * par, ((it >> 1) & 1) ^ 1);
+      if (S == 1) {
+        s_best[(par * 2 + half) * 128 + row] = best;
+        s_idx[(par * 2 + half) * 128 + row] = bi;
+      } else {
+        const long long grow = static_cast<long long>(tile) * VQ_BM + row;
+        if (grow < p.N)
+          atomicMin(p.keys + grow, (static_cast<unsigned long long>(ordered_bits(best)) << 32) |
+                                       static_cast<unsigned int>(bi));
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_cfull + 8 * par);
+    }
+  } else {
+    // ------------------------------------------------ gather / loss / EMA accumulation
+    // Each warp takes 16 rows of the tile, four at a time (all loads of a group are issued before
+    // their first use); a lane covers 8 consecutive channels.
+    const int gw = warp - (2 + VQ_SEARCH_WARPS);   // 0..7
+    uint32_t it = 0;
+    float loss_local = 0.f;
+    for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+      const int tile = w / S;
+      const int par = it & 1;
+      mbar_wait(bar_cfull + 8 * par, (it >> 1) & 1);
+      bool gather_here = true;
+      if (S > 1) {
+        // the CTA that completes a tile's set of codebook splits gathers for it
+        if (gw == 0 && lane == 0) {
+          __threadfence();
+          const unsigned int prev = atomicAdd(p.tile_done + tile, 1u);   // preset 0xFFFFFFFF
+          s_flag[par] = (prev == static_cast<unsigned int>(S - 2)) ? 1 : 0;
+          __threadfence();
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        gather_here = s_flag[par] != 0;
+      }
+      if (gather_here) {
+        constexpr int RG = 4;
+        for (int rr0 = 0; rr0 < 16; rr0 += RG) {
+          int idx[RG];
+          long long grow[RG];
+          bool ok[RG];
+#pragma unroll
+          for (int u = 0; u < RG; ++u) {
+            const int r_in = gw * 16 + rr0 + u;
+            grow[u] = static_cast<long long>(tile) * VQ_BM + r_in;
+            ok[u] = grow[u] < p.N;
+            if (S == 1) {
+              const float b0 = s_best[(par * 2 + 0) * 128 + r_in];
+              const float b1 = s_best[(par * 2 + 1) * 128 + r_in];
+              const int i0 = s_idx[(par * 2 + 0) * 128 + r_in];
+              const int i1 = s_idx[(par * 2 + 1) * 128 + r_in];
+              idx[u] = (b1 < b0) ? i1 : i0;   // lower column half wins ties
+            } else {
+              idx[u] = ok[u] ? static_cast<int>(__ldcg(p.keys + grow[u]) & 0xFFFFFFFFull) : 0;
+            }
+            if (idx[u] >= p.K || idx[u] < 0) idx[u] = 0;
+          }
+          float lsum[RG] = {0.f, 0.f, 0.f, 0.f};
+          for (int c = lane * 8; c < p.C; c += 256) {
+            float4 xa[RG], xb[RG], ea[RG], eb[RG];
+#pragma unroll
+            for (int u = 0; u < RG; ++u) {
+              xa[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+              xb[u] = xa[u]; ea[u] = xa[u]; eb[u] = xa[u];
+              if (!ok[u]) continue;
+              if (p.x_f32) {
+                const float4* xp = reinterpret_cast<const float4*>(p.x_f32 + grow[u] * p.C + c);
+                xa[u] = xp[0];
+                xb[u] = xp[1];
+              } else {
+                const uint4 w4 = *reinterpret_cast<const uint4*>(p.x_bf16 + grow[u] * p.C + c);
+                xa[u] = make_float4(bf16_lo(w4.x), bf16_hi(w4.x), bf16_lo(w4.y), bf16_hi(w4.y));
+                xb[u] = make_float4(bf16_lo(w4.z), bf16_hi(w4.z), bf16_lo(w4.w), bf16_hi(w4.w));
+              }
+              const float4* ep = reinterpret_cast<const float4*>(p.weight_f32 + static_cast<long long>(idx[u]) * p.C + c);
+              ea[u] = __ldg(ep);
+              eb[u] = __ldg(ep + 1);
+            }
+#pragma unroll
+            for (int u = 0; u < RG; ++u) {
+              if (!ok[u]) continue;
+              {
+                const float dx = ea[u].x - xa[u].x, dy = ea[u].y - xa[u].y, dz = ea[u].z - xa[u].z,
+                            dw = ea[u].w - xa[u].w;
+                lsum[u] += dx * dx + dy * dy + dz * dz + dw * dw;
+              }
+              {
+                const float dx = eb[u].x - xb[u].x, dy = eb[u].y - xb[u].y, dz = eb[u].z - xb[u].z,
+                            dw = eb[u].w - xb[u].w;
+                lsum[u] += dx * dx + dy * dy + dz * dz + dw * dw;
+              }
+              if (p.xq_f32) {
+                float4* op = reinterpret_cast<float4*>(p.xq_f32 + grow[u] * p.C + c);
+                op[0] = ea[u];
+                op[1] = eb[u];
+              }
+              if (p.xq_bf16) {
+                uint4 o;
+                o.x = pack_bf16x2(ea[u].x, ea[u].y);
+                o.y = pack_bf16x2(ea[u].z, ea[u].w);
+                o.z = pack_bf16x2(eb[u].x, eb[u].y);
+                o.w = pack_bf16x2(eb[u].z, eb[u].w);
+                *reinterpret_cast<uint4*>(p.xq_bf16 + grow[u] * p.C + c) = o;
+              }
+              if (p.sums) {
+                float* dst = p.sums + static_cast<long long>(idx[u]) * p.C + c;
+                asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "f"(xa[u].x),
+                             "f"(xa[u].y), "f"(xa[u].z), "f"(xa[u].w)
+                             : "memory");
+                asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst + 4), "f"(xb[u].x),
+                             "f"(xb[u].y), "f"(xb[u].z), "f"(xb[u].w)
+                             : "memory");
+              }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < RG; ++u) {
+            const float ls = warp_sum(lsum[u]);
+            if (lane == 0 && ok[u]) {
+              p.codes[grow[u]] = idx[u];
+              if (p.counts) atomicAdd(p.counts + idx[u], 1.0f);
+              loss_local += ls * (p.row_mask ? p.row_mask[grow[u]] : 1.0f);
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_cempty + 8 * par);
+    }
+    if (lane == 0 && p.loss_acc && loss_local != 0.f) atomicAdd(p.loss_acc, loss_local);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// First version of the search kernel (8 warps do search AND gather, single-buffered x tile); kept
+// behind B2DQ_VQ_V1=1 for A/B timing against the role-split kernel above.
+constexpr int VQ1_THREADS = 320;
+constexpr uint32_t VQ1_SMEM = 4 * VQ_A_CHUNK + VQ_STAGES * VQ_B_CHUNK + 1024 /*align*/ + 8192;
+
+__global__ void __launch_bounds__(VQ1_THREADS, 1)
+vq_search_kernel_v1(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const VqParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -376,11 +727,34 @@ int b2dq_vq_prepare_codebook(const float* weight_f32, void* cb_bf16, float* cb_s
   return (int)cudaGetLastError();
 }
 
+// Split plan for small N: `splits` CTAs share one row tile, each searching a slice of the codebook.
+static void vq_split_plan(int N, int K, int max_ctas, int* splits, int* per) {
+  const int tiles = (N + VQ_BM - 1) / VQ_BM;
+  const int nn = (K + VQ_BN - 1) / VQ_BN;
+  int ctas = num_sms();
+  if (max_ctas > 0 && max_ctas < ctas) ctas = max_ctas;
+  int s = 1;
+  if (tiles * 2 <= ctas && nn >= 2) s = ctas / tiles < nn ? ctas / tiles : nn;
+  int pr = (nn + s - 1) / s;
+  s = (nn + pr - 1) / pr;               // no empty split
+  *splits = s;
+  *per = pr;
+}
+
+int b2dq_vq_search_workspace_bytes(int N, int K) {
+  if (N <= 0 || K <= 0) return 0;
+  int s, per;
+  vq_split_plan(N, K, 0, &s, &per);
+  if (s <= 1) return 0;
+  const int tiles = (N + VQ_BM - 1) / VQ_BM;
+  return tiles * VQ_BM * 8 + tiles * 4;
+}
+
 int b2dq_vq_search_gather(const void* x_bf16, const float* x_f32, const void* cb_bf16,
                           const float* cb_sqnorm, const float* weight_f32, const float* row_mask,
                           long long* codes, void* xq_bf16, float* xq_f32, float* loss_acc,
                           float* counts, float* sums, int N, int C, int K, int max_ctas,
-                          cudaStream_t stream) {
+                          void* workspace, int workspace_bytes, cudaStream_t stream) {
   if (N <= 0) return 0;
   if (C % 64 != 0 || C > 256 || C <= 0 || K <= 0) return -1;
   CUtensorMap tmA, tmB;
@@ -398,10 +772,18 @@ int b2dq_vq_search_gather(const void* x_bf16, const float* x_f32, const void* cb
     int r = make_tmap_bf16(&tmB, cb_bf16, 2, dims, str, box);
     if (r) return r;
   }
+  static int use_v1 = -1;
+  if (use_v1 < 0) {
+    const char* e = getenv("B2DQ_VQ_V1");
+    use_v1 = (e && e[0] == '1') ? 1 : 0;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(vq_search_kernel,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, VQ_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(vq_search_kernel_v1, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             VQ1_SMEM);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
@@ -417,11 +799,37 @@ int b2dq_vq_search_gather(const void* x_bf16, const float* x_f32, const void* cb
   p.loss_acc = loss_acc;
   p.counts = counts;
   p.sums = sums;
+  p.keys = nullptr;
+  p.tile_done = nullptr;
   p.N = N; p.C = C; p.K = K;
   const int tiles = (N + VQ_BM - 1) / VQ_BM;
+  p.splits = 1;
+  p.ntiles_per_split = (K + VQ_BN - 1) / VQ_BN;
   int grid = num_sms();
   if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
-  if (tiles < grid) grid = tiles;
+  if (use_v1) {
+    if (tiles < grid) grid = tiles;
+    vq_search_kernel_v1<<<grid, VQ1_THREADS, VQ1_SMEM, stream>>>(tmA, tmB, p);
+    return (int)cudaGetLastError();
+  }
+  if (workspace) {
+    int s, per;
+    vq_split_plan(N, K, max_ctas, &s, &per);
+    const int need = tiles * VQ_BM * 8 + tiles * 4;
+    if (s > 1) {
+      if (workspace_bytes < need) return -3;
+      if (reinterpret_cast<uintptr_t>(workspace) & 7) return -4;
+      p.splits = s;
+      p.ntiles_per_split = per;
+      p.keys = reinterpret_cast<unsigned long long*>(workspace);
+      p.tile_done = reinterpret_cast<unsigned int*>(p.keys + (size_t)tiles * VQ_BM);
+      // keys start at the largest key, arrival counters at 0xFFFFFFFF (first arrival reads it back)
+      cudaError_t e = cudaMemsetAsync(workspace, 0xFF, need, stream);
+      if (e != cudaSuccess) return (int)e;
+    }
+  }
+  const int items = tiles * p.splits;
+  if (items < grid) grid = items;
   vq_search_kernel<<<grid, VQ_THREADS, VQ_SMEM, stream>>>(tmA, tmB, p);
   return (int)cudaGetLastError();
 }

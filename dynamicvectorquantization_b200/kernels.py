@@ -68,17 +68,23 @@ class Codebook:
 
 
 def vq_search_gather(x_bf16, codebook, weight_f32, x_f32=None, row_mask=None, want_xq_bf16=True,
-                     want_xq_f32=False, counts=None, sums=None, loss_acc=None, max_ctas=0):
-    """x_bf16 [N,C].  Returns (codes int64 [N], xq_bf16 | None, xq_f32 | None)."""
+                     want_xq_f32=False, counts=None, sums=None, loss_acc=None, max_ctas=0, split=True):
+    """x_bf16 [N,C].  Returns (codes int64 [N], xq_bf16 | None, xq_f32 | None).
+    split=True lets small-N calls spread the codebook over several CTAs per row tile (same results)."""
     N, Cd = x_bf16.shape
     dev = x_bf16.device
+    ws, ws_bytes = None, 0
+    if split and N > 0:
+        ws_bytes = _cabi.lib().b2dq_vq_search_workspace_bytes(N, codebook.K)
+        if ws_bytes > 0:
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     codes = torch.empty(N, dtype=torch.int64, device=dev)
     xq_b = torch.empty(N, Cd, dtype=BF16, device=dev) if want_xq_bf16 else None
     xq_f = torch.empty(N, Cd, dtype=torch.float32, device=dev) if want_xq_f32 else None
     check(_cabi.lib().b2dq_vq_search_gather(
         _ptr(x_bf16), _ptr(x_f32), _ptr(codebook.cb), _ptr(codebook.sqnorm), _ptr(weight_f32),
         _ptr(row_mask), _ptr(codes), _ptr(xq_b), _ptr(xq_f), _ptr(loss_acc), _ptr(counts), _ptr(sums),
-        N, Cd, codebook.K, max_ctas, _stream()), "vq_search_gather")
+        N, Cd, codebook.K, max_ctas, _ptr(ws), ws_bytes, _stream()), "vq_search_gather")
     return codes, xq_b, xq_f
 
 

@@ -43,12 +43,17 @@ int b2dq_vq_prepare_codebook(const float* weight_f32, void* cb_bf16, float* cb_s
  *   codes      [N] int64;  xq_bf16 / xq_f32: optional gathered rows of weight_f32 (pre-update)
  *   loss_acc   optional [1], += sum_rows mask * sum_c (e - x)^2
  *   counts [K] / sums [K,C]: optional, += per-code row count / row sum (training mode)
- *   max_ctas   0 = one CTA per SM */
+ *   max_ctas   0 = one CTA per SM
+ *   workspace  optional scratch of b2dq_vq_search_workspace_bytes(N, K) bytes (8 B aligned).  With
+ *              it, a call whose row tiles would leave more than half of the SMs idle (residual
+ *              quantizer depth loop quantize_rqvae.py:237-271, stage-2 sampling) splits the
+ *              codebook over several CTAs per row tile; results are identical. */
+int b2dq_vq_search_workspace_bytes(int N, int K);   /* 0: a split would not help */
 int b2dq_vq_search_gather(const void* x_bf16, const float* x_f32, const void* cb_bf16,
                           const float* cb_sqnorm, const float* weight_f32, const float* row_mask,
                           long long* codes, void* xq_bf16, float* xq_f32, float* loss_acc,
                           float* counts, float* sums, int N, int C, int K, int max_ctas,
-                          cudaStream_t stream);
+                          void* workspace, int workspace_bytes, cudaStream_t stream);
 
 /* EMA update of cluster_size_ema [K] / embed_ema [K,C], dead-code restart from restart_rows [K,C]
  * (rows the reference draws with randperm, :97), and weight[:K] = embed_ema / smoothed size.

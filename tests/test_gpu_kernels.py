@@ -72,6 +72,100 @@ def test_vq_search_matches_oracle(N, K, C):
     assert torch.allclose(sums.cpu(), ref_sums, rtol=1e-4, atol=1e-4)
 
 
+def _vq_case(N, K, C, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(N, C, generator=g)
+    src = x[torch.randint(0, N, (K,), generator=g)]
+    w = torch.cat([src + 0.1 * torch.randn(K, C, generator=g), torch.zeros(1, C)], 0).contiguous()
+    mask = (torch.rand(N, generator=g) > 0.5).float() * 0.75 + 0.25
+    return x, w, mask
+
+
+def _vq_run(kn, x, w, mask, K, C, x_f32=False, **kw):
+    dev = "cuda"
+    cb = kn.Codebook(K, C, dev)
+    wd = w.to(dev)
+    cb.refresh(wd)
+    counts = torch.zeros(K, device=dev)
+    sums = torch.zeros(K, C, device=dev)
+    loss = torch.zeros(1, device=dev)
+    xb = x.to(BF).to(dev)
+    codes, xq_b, xq_f = kn.vq_search_gather(xb, cb, wd, x_f32=x.to(dev) if x_f32 else None, row_mask=mask.to(dev),
+                                            want_xq_f32=True, counts=counts, sums=sums, loss_acc=loss, **kw)
+    torch.cuda.synchronize()
+    return codes.cpu(), xq_b.cpu(), xq_f.cpu(), counts.cpu(), sums.cpu(), float(loss.item())
+
+
+def _vq_check(x, w, mask, K, C, out, x_f32=False):
+    from oracle import vq_oracle as vo
+    codes, xq_b, xq_f, counts, sums, loss = out
+    N = x.shape[0]
+    xr = x.to(BF).float().numpy()
+    wr = np.concatenate([vo.bf16_round(w[:-1].numpy()), np.zeros((1, C), np.float32)], 0)
+    ref = vo.find_nearest_embedding(xr, wr)
+    got = codes.numpy()
+    mism = np.nonzero(ref != got)[0]
+    if len(mism):
+        d64 = (wr[:-1].astype(np.float64) ** 2).sum(1)[None, :] - 2 * xr[mism].astype(np.float64) @ wr[:-1].T.astype(np.float64)
+        gap = np.abs(d64[np.arange(len(mism)), got[mism]] - d64[np.arange(len(mism)), ref[mism]])
+        scale = (xr[mism].astype(np.float64) ** 2).sum(1) + 1.0
+        assert np.all(gap < 1e-6 * scale * 256), f"{len(mism)} real mismatches, max gap {gap.max()}"
+    assert len(mism) <= max(1, N // 2000), f"{len(mism)} near-tie mismatches of {N}"
+    assert torch.equal(xq_f, w[got])
+    assert torch.equal(xq_b, w[got].to(BF))
+    rows = x if x_f32 else x.to(BF).float()           # loss / EMA sums use the fp32 rows when given
+    d2 = ((w[got] - rows) ** 2).sum(1) * mask
+    assert abs(loss - float(d2.sum())) <= 1e-4 * float(d2.sum())
+    assert torch.equal(counts, torch.bincount(torch.from_numpy(got), minlength=K).float())
+    ref_sums = torch.zeros(K, C).index_add_(0, torch.from_numpy(got), rows)
+    assert torch.allclose(sums, ref_sums, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("N,K,C,max_ctas,x_f32", [
+    (4096, 1024, 256, 7, False),      # 32 row tiles on 7 CTAs: 4-5 tiles per CTA (every ring / parity wraps)
+    (40000, 1024, 256, 0, True),      # 313 tiles on all SMs, ragged last tile, fp32 rows for loss / sums
+    (5000, 700, 192, 3, False),       # ragged rows and codes, 3 channel chunks
+    (2304, 256, 64, 2, True),         # one codebook tile, one channel chunk
+])
+def test_vq_search_many_tiles_per_cta(N, K, C, max_ctas, x_f32):
+    from dynamicvectorquantization_b200 import kernels as kn
+    x, w, mask = _vq_case(N, K, C, N + K + C)
+    out = _vq_run(kn, x, w, mask, K, C, x_f32=x_f32, max_ctas=max_ctas, split=False)
+    _vq_check(x, w, mask, K, C, out, x_f32=x_f32)
+
+
+@pytest.mark.parametrize("N,K,C", [(2048, 16384, 256), (300, 4096, 256), (64, 1024, 128), (1, 512, 64),
+                                   (1100, 5000, 192)])
+def test_vq_search_codebook_split(N, K, C):
+    """Small N: the codebook is split over several CTAs per row tile (64-bit atomicMin of ordered distance |
+    index); codes, gathered rows and statistics must equal the unsplit search and the oracle."""
+    from dynamicvectorquantization_b200 import _cabi, kernels as kn
+    assert _cabi.lib().b2dq_vq_search_workspace_bytes(N, K) > 0, "case does not exercise the split"
+    x, w, mask = _vq_case(N, K, C, N + K)
+    a = _vq_run(kn, x, w, mask, K, C, split=True)
+    b = _vq_run(kn, x, w, mask, K, C, split=False)
+    assert torch.equal(a[0], b[0]), "split and unsplit searches disagree"
+    _vq_check(x, w, mask, K, C, a)
+    for _ in range(3):                                 # arrival order of the splits must not matter
+        c = _vq_run(kn, x, w, mask, K, C, split=True)
+        assert torch.equal(a[0], c[0]) and torch.equal(a[3], c[3])
+
+
+def test_vq_search_exact_ties_lowest_index_wins():
+    """Duplicate codebook rows (exact ties) in different 256-code tiles, column halves and splits."""
+    from dynamicvectorquantization_b200 import kernels as kn
+    K, C = 2048, 256
+    for N, split in ((512, True), (20000, False)):
+        x, w, mask = _vq_case(N, K, C, 5)
+        w[1500] = w[3]; w[700] = w[3]; w[130] = w[3]      # copies of code 3
+        w[2047] = w[300]; w[301] = w[300]
+        out = _vq_run(kn, x, w, mask, K, C, split=split)
+        codes = out[0]
+        for dup in (1500, 700, 130, 2047, 301):
+            assert int((codes == dup).sum()) == 0, f"code {dup} chosen over its lower-index duplicate"
+        _vq_check(x, w, mask, K, C, out)
+
+
 # ------------------------------------------------------------------------------------------- conv
 CONV_CASES = [
     # nb, h, w, cin, cout, k, stride

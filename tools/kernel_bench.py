@@ -86,10 +86,26 @@ def gn(nb, h, w, c):
                           apply_GBs=round(2 * by / ms2 / 1e6), bwd_ms=round(ms3, 3), bwd_GBs=round(5 * by / ms3 / 1e6))))
 
 
+def vq_small():
+    """Small-N calls (residual quantizer depth step, stage-2 sampling): codebook split on / off."""
+    C = 256
+    for N, K in ((2048, 16384), (2048, 1024), (256, 16384), (32768, 1024)):
+        g = torch.Generator(device=dev).manual_seed(0)
+        x = torch.randn(N, C, device=dev, generator=g)
+        w = torch.cat([torch.randn(K, C, device=dev, generator=g), torch.zeros(1, C, device=dev)])
+        cb = kn.Codebook(K, C, dev); cb.refresh(w)
+        xb = x.to(BF)
+        fl = 2.0 * N * K * C
+        for split in (False, True):
+            ms = timeit(lambda: kn.vq_search_gather(xb, cb, w, split=split), iters=20)
+            print(json.dumps(dict(k="vq_search_gather", N=N, K=K, split=split, ms=round(ms, 4), tflops=round(fl / ms / 1e9, 1))))
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["vq", "conv", "gn"]
     if "vq" in what:
         vq()
+        vq_small()
     if "conv" in what:
         for c in [(32, 256, 256, 128, 128, 3, 1), (32, 128, 128, 128, 128, 3, 1), (32, 64, 64, 256, 256, 3, 1), (32, 32, 32, 256, 256, 3, 1),
                   (32, 16, 16, 512, 512, 3, 1), (32, 32, 32, 256, 256, 1, 1), (32, 256, 256, 128, 128, 3, 2), (32, 128, 128, 256, 256, 3, 1)]:
