@@ -402,22 +402,51 @@ def kernel_rooflines(torch, kn, dev, peaks):
             "ms_per_launch": ms, "traffic": prof.get("pconv_dram_bytes_per_launch"),
             "burst_peak": peaks.get("bf16_tflops"),
             "frac_of_burst_peak": (flops / ms / 1e9 / peaks["bf16_tflops"]) if peaks.get("bf16_tflops") else None}
-    # VQ search (+gather) at N=65536, C=256, K=1024: algorithmic bytes = 2NC + 2KC + 8N + 2NC
-    N, C, K = 65536, 256, 1024
-    xv = torch.randn(N, C, device=dev)
-    wv = torch.cat([xv[torch.randperm(N, device=dev)[:K]] + 0.1 * torch.randn(K, C, device=dev),
-                    torch.zeros(1, C, device=dev)])
-    cb = kn.Codebook(K, C, dev); cb.refresh(wv)
-    xb = xv.to(BF)
-    msv = timed(lambda: kn.vq_search_gather(xb, cb, wv), 50)
-    by = 2 * N * C + 2 * K * C + 8 * N + 2 * N * C
+    # VQ search (+gather) at N=65536, C=256: algorithmic bytes = 2NC + 2KC + 8N + 2NC.  The kernel (tens of
+    # microseconds) is shorter than the host side of one launch, so 20 launches are captured in a CUDA
+    # graph and the replay is timed (CUDA events, L2 flushed before each replay).
+    N, C = 65536, 256
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     peak_h = peaks.get("hbm_gbs")
+
+    def graph_ms(fn, launches=20, reps=7):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(launches):
+                fn()
+        ts = []
+        for _ in range(reps):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); g.replay(); e.record(); torch.cuda.synchronize()
+            ts.append(s.elapsed_time(e) / launches)
+        return sorted(ts)[len(ts) // 2]
+
+    sweep = []
+    for K in (256, 1024, 8192, 16384):
+        gen = torch.Generator(device=dev).manual_seed(0)
+        xv = torch.randn(N, C, device=dev, generator=gen)
+        wv = torch.cat([xv[torch.randperm(N, device=dev, generator=gen)[:K]] +
+                        0.1 * torch.randn(K, C, device=dev, generator=gen), torch.zeros(1, C, device=dev)])
+        cb = kn.Codebook(K, C, dev); cb.refresh(wv)
+        xb = xv.to(BF)
+        msv = graph_ms(lambda: kn.vq_search_gather(xb, cb, wv))
+        by = 2 * N * C + 2 * K * C + 8 * N + 2 * N * C
+        sweep.append({"K": K, "ms_per_launch": msv, "GBps": by / msv / 1e6,
+                      "hbm_frac": (by / msv / 1e6 / peak_h) if peak_h else None,
+                      "tensor_tflops": 2.0 * N * K * C / msv / 1e9,
+                      "tensor_frac": (2.0 * N * K * C / msv / 1e9 / peak_t) if peak_t else None})
+    k1 = sweep[1]
     roof_vq = {"kernel": "vq_search_kernel (N=65536, C=256, K=1024, search+gather)", "bound": "tensor",
-               "note": "dense [N,C]x[C,K] contraction above the ridge: tensor-bound (SURVEY 8d); HBM fraction reported as the metric asks",
-               "achieved": by / msv / 1e6, "peak": peak_h, "unit": "GB/s",
-               "frac": (by / msv / 1e6 / peak_h) if peak_h else None,
-               "tensor_tflops": 2.0 * N * K * C / msv / 1e9, "ms_per_launch": msv,
-               "traffic": prof.get("vq_dram_bytes_per_launch")}
+               "note": "dense [N,C]x[C,K] contraction above the ridge for K >= 1024: tensor-bound (SURVEY 8d); the HBM "
+                       "fraction is reported as the metric asks; K=256 is the memory-leaning point of the sweep",
+               "achieved": k1["GBps"], "peak": peak_h, "unit": "GB/s", "frac": k1["hbm_frac"],
+               "tensor_tflops": k1["tensor_tflops"], "tensor_frac": k1["tensor_frac"],
+               "ms_per_launch": k1["ms_per_launch"], "timing": "20 launches per CUDA-graph replay, median of 7, L2 flushed",
+               "traffic": prof.get("vq_dram_bytes_per_launch"), "sweep": sweep}
     return roof, roof_vq
 
 

@@ -24,8 +24,6 @@
 // Small N (residual quantizer, stage-2 sampling): the codebook is split over `splits` CTAs per row
 // tile; the partial minima meet in a 64-bit atomicMin (ordered distance bits | index, so the lowest
 // index still wins ties) and the last CTA of a tile to arrive runs its gather.
-#include <stdlib.h>
-
 #include "common.cuh"
 #include "tmap.h"
 
@@ -70,6 +68,101 @@ __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* tm, int c0
 __device__ __forceinline__ uint32_t ordered_bits(float d) {
   const uint32_t u = __float_as_uint(d);
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+constexpr int VQ_RG = 4;          // rows a gather warp keeps in flight
+
+// Gather / loss / EMA sums for VQ_RG consecutive rows (row0 ..) of the latent; a lane covers 8 channels
+// (C <= 256).  Every load of the group is issued before the first use - rows past N re-read row N-1 and
+// are masked at the stores only - so a group costs one memory round trip, not one per row.  The loss is
+// accumulated per LANE (sum over its 8 channels, weighted by the row mask); the caller reduces it over
+// the warp once at the end of the kernel, so there is no shuffle in here.
+//   X32   the rows for loss / EMA sums come from x_f32 (else from x_bf16)
+//   NEEDX loss or EMA sums requested (a plain eval gather never touches x)
+template <bool X32, bool NEEDX>
+__device__ __forceinline__ void vq_gather_group(const VqParams& p, const int (&idx)[VQ_RG], int row0,
+                                                int lane, float& loss_lane) {
+  const int c = lane * 8;
+  if (c < p.C) {
+    float4 ea[VQ_RG], eb[VQ_RG];
+    float4 xa[(X32 && NEEDX) ? VQ_RG : 1], xb[(X32 && NEEDX) ? VQ_RG : 1];
+    uint4 raw[(!X32 && NEEDX) ? VQ_RG : 1];
+    float mk[VQ_RG];
+#pragma unroll
+    for (int u = 0; u < VQ_RG; ++u) {
+      const int lrow = min(row0 + u, p.N - 1);
+      mk[u] = 1.0f;
+      if (NEEDX) {
+        if (p.row_mask) mk[u] = __ldg(p.row_mask + lrow);
+        const long long off = static_cast<long long>(lrow) * p.C + c;
+        if (X32) {
+          const float4* xp = reinterpret_cast<const float4*>(p.x_f32 + off);
+          xa[(X32 && NEEDX) ? u : 0] = xp[0];
+          xb[(X32 && NEEDX) ? u : 0] = xp[1];
+        } else {
+          raw[(!X32 && NEEDX) ? u : 0] = *reinterpret_cast<const uint4*>(p.x_bf16 + off);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < VQ_RG; ++u) {
+      const float4* ep = reinterpret_cast<const float4*>(p.weight_f32 + static_cast<long long>(idx[u]) * p.C + c);
+      ea[u] = __ldg(ep);
+      eb[u] = __ldg(ep + 1);
+    }
+#pragma unroll
+    for (int u = 0; u < VQ_RG; ++u) {
+      const bool live = row0 + u < p.N;
+      float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
+      if (NEEDX) {
+        if (X32) {
+          va = xa[(X32 && NEEDX) ? u : 0];
+          vb = xb[(X32 && NEEDX) ? u : 0];
+        } else {
+          const uint4 w4 = raw[(!X32 && NEEDX) ? u : 0];
+          va = make_float4(bf16_lo(w4.x), bf16_hi(w4.x), bf16_lo(w4.y), bf16_hi(w4.y));
+          vb = make_float4(bf16_lo(w4.z), bf16_hi(w4.z), bf16_lo(w4.w), bf16_hi(w4.w));
+        }
+        if (p.loss_acc) {
+          const float d0 = ea[u].x - va.x, d1 = ea[u].y - va.y, d2 = ea[u].z - va.z, d3 = ea[u].w - va.w;
+          const float d4 = eb[u].x - vb.x, d5 = eb[u].y - vb.y, d6 = eb[u].z - vb.z, d7 = eb[u].w - vb.w;
+          const float s0 = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+          const float s1 = d4 * d4 + d5 * d5 + d6 * d6 + d7 * d7;
+          loss_lane += (live ? mk[u] : 0.f) * (s0 + s1);
+        }
+      }
+      if (!live) continue;
+      const long long off = static_cast<long long>(row0 + u) * p.C + c;
+      if (p.xq_f32) {
+        float4* op = reinterpret_cast<float4*>(p.xq_f32 + off);
+        op[0] = ea[u];
+        op[1] = eb[u];
+      }
+      if (p.xq_bf16) {
+        uint4 o;
+        o.x = pack_bf16x2(ea[u].x, ea[u].y);
+        o.y = pack_bf16x2(ea[u].z, ea[u].w);
+        o.z = pack_bf16x2(eb[u].x, eb[u].y);
+        o.w = pack_bf16x2(eb[u].z, eb[u].w);
+        *reinterpret_cast<uint4*>(p.xq_bf16 + off) = o;
+      }
+      if (NEEDX && p.sums) {
+        float* dst = p.sums + static_cast<long long>(idx[u]) * p.C + c;
+        asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "f"(va.x), "f"(va.y), "f"(va.z),
+                     "f"(va.w)
+                     : "memory");
+        asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst + 4), "f"(vb.x), "f"(vb.y),
+                     "f"(vb.z), "f"(vb.w)
+                     : "memory");
+      }
+    }
+  }
+  // lanes 0..3 publish the code (and the per-code count) of one row each
+  if (lane < VQ_RG && row0 + lane < p.N) {
+    const int mine = lane == 0 ? idx[0] : lane == 1 ? idx[1] : lane == 2 ? idx[2] : idx[3];
+    p.codes[row0 + lane] = mine;
+    if (p.counts) atomicAdd(p.counts + mine, 1.0f);
+  }
 }
 
 __global__ void __launch_bounds__(VQ_THREADS, 1)
@@ -283,16 +376,13 @@ vq_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         gather_here = s_flag[par] != 0;
       }
       if (gather_here) {
-        constexpr int RG = 4;
-        for (int rr0 = 0; rr0 < 16; rr0 += RG) {
-          int idx[RG];
-          long long grow[RG];
-          bool ok[RG];
+        for (int rr0 = 0; rr0 < 16; rr0 += VQ_RG) {
+          int idx[VQ_RG];
+          const int r_in0 = gw * 16 + rr0;
+          const int row0 = tile * VQ_BM + r_in0;
 #pragma unroll
-          for (int u = 0; u < RG; ++u) {
-            const int r_in = gw * 16 + rr0 + u;
-            grow[u] = static_cast<long long>(tile) * VQ_BM + r_in;
-            ok[u] = grow[u] < p.N;
+          for (int u = 0; u < VQ_RG; ++u) {
+            const int r_in = r_in0 + u;
             if (S == 1) {
               const float b0 = s_best[(par * 2 + 0) * 128 + r_in];
               const float b1 = s_best[(par * 2 + 1) * 128 + r_in];
@@ -300,308 +390,22 @@ vq_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               const int i1 = s_idx[(par * 2 + 1) * 128 + r_in];
               idx[u] = (b1 < b0) ? i1 : i0;   // lower column half wins ties
             } else {
-              idx[u] = ok[u] ? static_cast<int>(__ldcg(p.keys + grow[u]) & 0xFFFFFFFFull) : 0;
+              idx[u] = (row0 + u < p.N) ? static_cast<int>(__ldcg(p.keys + row0 + u) & 0xFFFFFFFFull) : 0;
             }
             if (idx[u] >= p.K || idx[u] < 0) idx[u] = 0;
           }
-          float lsum[RG] = {0.f, 0.f, 0.f, 0.f};
-          for (int c = lane * 8; c < p.C; c += 256) {
-            float4 xa[RG], xb[RG], ea[RG], eb[RG];
-#pragma unroll
-            for (int u = 0; u < RG; ++u) {
-              xa[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-              xb[u] = xa[u]; ea[u] = xa[u]; eb[u] = xa[u];
-              if (!ok[u]) continue;
-              if (p.x_f32) {
-                const float4* xp = reinterpret_cast<const float4*>(p.x_f32 + grow[u] * p.C + c);
-                xa[u] = xp[0];
-                xb[u] = xp[1];
-              } else {
-                const uint4 w4 = *reinterpret_cast<const uint4*>(p.x_bf16 + grow[u] * p.C + c);
-                xa[u] = make_float4(bf16_lo(w4.x), bf16_hi(w4.x), bf16_lo(w4.y), bf16_hi(w4.y));
-                xb[u] = make_float4(bf16_lo(w4.z), bf16_hi(w4.z), bf16_lo(w4.w), bf16_hi(w4.w));
-              }
-              const float4* ep = reinterpret_cast<const float4*>(p.weight_f32 + static_cast<long long>(idx[u]) * p.C + c);
-              ea[u] = __ldg(ep);
-              eb[u] = __ldg(ep + 1);
-            }
-#pragma unroll
-            for (int u = 0; u < RG; ++u) {
-              if (!ok[u]) continue;
-              {
-                const float dx = ea[u].x - xa[u].x, dy = ea[u].y - xa[u].y, dz = ea[u].z - xa[u].z,
-                            dw = ea[u].w - xa[u].w;
-                lsum[u] += dx * dx + dy * dy + dz * dz + dw * dw;
-              }
-              {
-                const float dx = eb[u].x - xb[u].x, dy = eb[u].y - xb[u].y, dz = eb[u].z - xb[u].z,
-                            dw = eb[u].w - xb[u].w;
-                lsum[u] += dx * dx + dy * dy + dz * dz + dw * dw;
-              }
-              if (p.xq_f32) {
-                float4* op = reinterpret_cast<float4*>(p.xq_f32 + grow[u] * p.C + c);
-                op[0] = ea[u];
-                op[1] = eb[u];
-              }
-              if (p.xq_bf16) {
-                uint4 o;
-                o.x = pack_bf16x2(ea[u].x, ea[u].y);
-                o.y = pack_bf16x2(ea[u].z, ea[u].w);
-                o.z = pack_bf16x2(eb[u].x, eb[u].y);
-                o.w = pack_bf16x2(eb[u].z, eb[u].w);
-                *reinterpret_cast<uint4*>(p.xq_bf16 + grow[u] * p.C + c) = o;
-              }
-              if (p.sums) {
-                float* dst = p.sums + static_cast<long long>(idx[u]) * p.C + c;
-                asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "f"(xa[u].x),
-                             "f"(xa[u].y), "f"(xa[u].z), "f"(xa[u].w)
-                             : "memory");
-                asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst + 4), "f"(xb[u].x),
-                             "f"(xb[u].y), "f"(xb[u].z), "f"(xb[u].w)
-                             : "memory");
-              }
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < RG; ++u) {
-            const float ls = warp_sum(lsum[u]);
-            if (lane == 0 && ok[u]) {
-              p.codes[grow[u]] = idx[u];
-              if (p.counts) atomicAdd(p.counts + idx[u], 1.0f);
-              loss_local += ls * (p.row_mask ? p.row_mask[grow[u]] : 1.0f);
-            }
-          }
+          if (!p.loss_acc && !p.sums) vq_gather_group<false, false>(p, idx, row0, lane, loss_local);
+          else if (p.x_f32) vq_gather_group<true, true>(p, idx, row0, lane, loss_local);
+          else vq_gather_group<false, true>(p, idx, row0, lane, loss_local);
         }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_cempty + 8 * par);
     }
-    if (lane == 0 && p.loss_acc && loss_local != 0.f) atomicAdd(p.loss_acc, loss_local);
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
-  }
-}
-
-// ---------------------------------------------------------------------------------
-// First version of the search kernel (8 warps do search AND gather, single-buffered x tile); kept
-// behind B2DQ_VQ_V1=1 for A/B timing against the role-split kernel above.
-constexpr int VQ1_THREADS = 320;
-constexpr uint32_t VQ1_SMEM = 4 * VQ_A_CHUNK + VQ_STAGES * VQ_B_CHUNK + 1024 /*align*/ + 8192;
-
-__global__ void __launch_bounds__(VQ1_THREADS, 1)
-vq_search_kernel_v1(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const VqParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sA = base;
-  const uint32_t sB = base + 4 * VQ_A_CHUNK;
-  const uint32_t sX = sB + VQ_STAGES * VQ_B_CHUNK;  // barriers + scratch (8 KB)
-  uint8_t* gen = smem_raw + (sX - smem_u32(smem_raw));
-  // barrier slots (8 B each)
-  const uint32_t bar_full = sX;                 // [VQ_STAGES]
-  const uint32_t bar_empty = sX + 8 * VQ_STAGES;
-  const uint32_t bar_tfull = sX + 16 * VQ_STAGES;        // [2]
-  const uint32_t bar_tempty = bar_tfull + 16;            // [2]
-  const uint32_t bar_afull = bar_tempty + 16;
-  const uint32_t bar_aempty = bar_afull + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + 256);
-  float* s_best = reinterpret_cast<float*>(gen + 512);    // [2 parity][2 half][128]
-  int* s_idx = reinterpret_cast<int*>(gen + 512 + 2048);  // [2][2][128]
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int KC = p.C >> 6;
-  const int num_m_tiles = (p.N + VQ_BM - 1) / VQ_BM;
-  const int num_n_tiles = (p.K + VQ_BN - 1) / VQ_BN;
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < VQ_STAGES; ++i) {
-      mbar_init(bar_full + 8 * i, 1);
-      mbar_init(bar_empty + 8 * i, 1);
+    if (p.loss_acc) {
+      loss_local = warp_sum(loss_local);
+      if (lane == 0 && loss_local != 0.f) atomicAdd(p.loss_acc, loss_local);
     }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(bar_tfull + 8 * i, 1);
-      mbar_init(bar_tempty + 8 * i, 8);
-    }
-    mbar_init(bar_afull, 1);
-    mbar_init(bar_aempty, 1);
-    fence_barrier_init();
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-  }
-  if (warp == 1) tmem_alloc<512>(smem_u32(tmem_slot));
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      // ------------------------------------------------ TMA producer
-      uint32_t stage = 0, phase = 0, it = 0;
-      for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x, ++it) {
-        mbar_wait(bar_aempty, (it & 1) ^ 1);
-        mbar_arrive_expect_tx(bar_afull, KC * VQ_A_CHUNK);
-        for (int kc = 0; kc < KC; ++kc)
-          tma_load_2d(sA + kc * VQ_A_CHUNK, &tmA, bar_afull, kc * 64, tile * VQ_BM);
-        for (int j = 0; j < num_n_tiles; ++j)
-          for (int kc = 0; kc < KC; ++kc) {
-            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-            mbar_arrive_expect_tx(bar_full + 8 * stage, VQ_B_CHUNK);
-            tma_load_2d(sB + stage * VQ_B_CHUNK, &tmB, bar_full + 8 * stage, kc * 64, j * VQ_BN);
-            if (++stage == VQ_STAGES) { stage = 0; phase ^= 1; }
-          }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // ------------------------------------------------ MMA issuer
-      constexpr uint32_t idesc = make_idesc_bf16(VQ_BM, VQ_BN, 0, 0);
-      uint32_t stage = 0, phase = 0, it = 0, jj = 0;
-      for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x, ++it) {
-        mbar_wait(bar_afull, it & 1);
-        tc_fence_after();
-        for (int j = 0; j < num_n_tiles; ++j, ++jj) {
-          const uint32_t buf = jj & 1;
-          mbar_wait(bar_tempty + 8 * buf, ((jj >> 1) & 1) ^ 1);
-          tc_fence_after();
-          for (int kc = 0; kc < KC; ++kc) {
-            mbar_wait(bar_full + 8 * stage, phase);
-            tc_fence_after();
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t da = make_smem_desc(sA + kc * VQ_A_CHUNK + k * 32, 0, 1024);
-              const uint64_t db = make_smem_desc(sB + stage * VQ_B_CHUNK + k * 32, 0, 1024);
-              umma_bf16(tmem_base + buf * VQ_BN, da, db, idesc, (kc | k) ? 1u : 0u);
-            }
-            umma_commit(bar_empty + 8 * stage);
-            if (++stage == VQ_STAGES) { stage = 0; phase ^= 1; }
-          }
-          umma_commit(bar_tfull + 8 * buf);
-        }
-        umma_commit(bar_aempty);
-      }
-    }
-  } else {
-    // ------------------------------------------------ epilogue: running argmin, then gather
-    const int ew = warp - 2;          // 0..7
-    const int q = warp & 3;           // TMEM lane quadrant this warp may read
-    const int half = ew >> 2;         // which 128 columns of each 256-column tile
-    const int row = q * 32 + lane;    // row of the tile owned in the argmin phase
-    uint32_t jj = 0, it = 0;
-    float loss_local = 0.f;
-    for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x, ++it) {
-      float best = __int_as_float(0x7f800000);
-      int bi = 0;
-      for (int j = 0; j < num_n_tiles; ++j, ++jj) {
-        const uint32_t buf = jj & 1;
-        mbar_wait(bar_tfull + 8 * buf, (jj >> 1) & 1);
-        tc_fence_after();
-        const uint32_t tcol = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * VQ_BN +
-                              half * 128;
-        const int colbase = j * VQ_BN + half * 128;
-#pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld_32x32(tcol + c0, r);
-          tmem_ld_wait();
-          const float4* sq4 = reinterpret_cast<const float4*>(p.cb_sqnorm + colbase + c0);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 s = __ldg(sq4 + i);
-            const float d0 = fmaf(-2.f, __uint_as_float(r[4 * i + 0]), s.x);
-            const float d1 = fmaf(-2.f, __uint_as_float(r[4 * i + 1]), s.y);
-            const float d2 = fmaf(-2.f, __uint_as_float(r[4 * i + 2]), s.z);
-            const float d3 = fmaf(-2.f, __uint_as_float(r[4 * i + 3]), s.w);
-            const int c = colbase + c0 + 4 * i;
-            if (d0 < best) { best = d0; bi = c; }
-            if (d1 < best) { best = d1; bi = c + 1; }
-            if (d2 < best) { best = d2; bi = c + 2; }
-            if (d3 < best) { best = d3; bi = c + 3; }
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
-      }
-      // combine the two column halves (lower column index wins ties)
-      const int par = it & 1;
-      s_best[(par * 2 + half) * 128 + row] = best;
-      s_idx[(par * 2 + half) * 128 + row] = bi;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      // gather / loss / EMA accumulation: each warp takes 16 rows, lanes span channels.  Four rows
-      // are in flight at a time (all loads of a group are issued before their first use): the
-      // phase is latency bound and sits between two tiles' searches.
-      constexpr int RG = 4;
-      for (int rr0 = 0; rr0 < 16; rr0 += RG) {
-        int idx[RG];
-        long long grow[RG];
-        bool ok[RG];
-#pragma unroll
-        for (int u = 0; u < RG; ++u) {
-          const int r_in = ew * 16 + rr0 + u;
-          grow[u] = static_cast<long long>(tile) * VQ_BM + r_in;
-          ok[u] = grow[u] < p.N;
-          const float b0 = s_best[(par * 2 + 0) * 128 + r_in];
-          const float b1 = s_best[(par * 2 + 1) * 128 + r_in];
-          const int i0 = s_idx[(par * 2 + 0) * 128 + r_in];
-          const int i1 = s_idx[(par * 2 + 1) * 128 + r_in];
-          idx[u] = (b1 < b0) ? i1 : i0;
-          if (idx[u] >= p.K) idx[u] = 0;
-        }
-        float lsum[RG] = {0.f, 0.f, 0.f, 0.f};
-        for (int c = lane * 4; c < p.C; c += 128) {
-          float4 xv[RG], ev[RG];
-#pragma unroll
-          for (int u = 0; u < RG; ++u) {
-            xv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            ev[u] = xv[u];
-            if (!ok[u]) continue;
-            if (p.x_f32) {
-              xv[u] = *reinterpret_cast<const float4*>(p.x_f32 + grow[u] * p.C + c);
-            } else {
-              const uint2 w2 = *reinterpret_cast<const uint2*>(p.x_bf16 + grow[u] * p.C + c);
-              xv[u] = make_float4(bf16_lo(w2.x), bf16_hi(w2.x), bf16_lo(w2.y), bf16_hi(w2.y));
-            }
-            ev[u] = __ldg(reinterpret_cast<const float4*>(p.weight_f32 + static_cast<long long>(idx[u]) * p.C + c));
-          }
-#pragma unroll
-          for (int u = 0; u < RG; ++u) {
-            if (!ok[u]) continue;
-            const float dx = ev[u].x - xv[u].x, dy = ev[u].y - xv[u].y, dz = ev[u].z - xv[u].z,
-                        dw = ev[u].w - xv[u].w;
-            lsum[u] += dx * dx + dy * dy + dz * dz + dw * dw;
-            if (p.xq_f32) *reinterpret_cast<float4*>(p.xq_f32 + grow[u] * p.C + c) = ev[u];
-            if (p.xq_bf16) {
-              uint2 o;
-              o.x = pack_bf16x2(ev[u].x, ev[u].y);
-              o.y = pack_bf16x2(ev[u].z, ev[u].w);
-              *reinterpret_cast<uint2*>(p.xq_bf16 + grow[u] * p.C + c) = o;
-            }
-            if (p.sums) {
-              float* dst = p.sums + static_cast<long long>(idx[u]) * p.C + c;
-              asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "f"(xv[u].x),
-                           "f"(xv[u].y), "f"(xv[u].z), "f"(xv[u].w)
-                           : "memory");
-            }
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < RG; ++u) {
-          const float ls = warp_sum(lsum[u]);
-          if (lane == 0 && ok[u]) {
-            p.codes[grow[u]] = idx[u];
-            if (p.counts) atomicAdd(p.counts + idx[u], 1.0f);
-            loss_local += ls * (p.row_mask ? p.row_mask[grow[u]] : 1.0f);
-          }
-        }
-      }
-    }
-    if (lane == 0 && p.loss_acc) atomicAdd(p.loss_acc, loss_local);
   }
 
   tc_fence_before();
@@ -772,18 +576,10 @@ int b2dq_vq_search_gather(const void* x_bf16, const float* x_f32, const void* cb
     int r = make_tmap_bf16(&tmB, cb_bf16, 2, dims, str, box);
     if (r) return r;
   }
-  static int use_v1 = -1;
-  if (use_v1 < 0) {
-    const char* e = getenv("B2DQ_VQ_V1");
-    use_v1 = (e && e[0] == '1') ? 1 : 0;
-  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(vq_search_kernel,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, VQ_SMEM);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(vq_search_kernel_v1, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             VQ1_SMEM);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
@@ -807,11 +603,6 @@ int b2dq_vq_search_gather(const void* x_bf16, const float* x_f32, const void* cb
   p.ntiles_per_split = (K + VQ_BN - 1) / VQ_BN;
   int grid = num_sms();
   if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
-  if (use_v1) {
-    if (tiles < grid) grid = tiles;
-    vq_search_kernel_v1<<<grid, VQ1_THREADS, VQ1_SMEM, stream>>>(tmA, tmB, p);
-    return (int)cudaGetLastError();
-  }
   if (workspace) {
     int s, per;
     vq_split_plan(N, K, max_ctas, &s, &per);

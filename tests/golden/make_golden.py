@@ -364,8 +364,79 @@ def permuter_goldens():
     save("permuter.npz", **out)
 
 
+def loss_goldens():
+    """Stage-1 training loss of the reference (LPIPS + PatchGAN + adaptive weight) on seeded
+    weights: torchvision's VGG16 is built WITHOUT the pretrained file (offline) and every tensor of the loss
+    module is overwritten from oracle.loss_oracle.make_loss_weights.  xrec is a seeded toy "decoder tail"
+    conv3x3(feat, w_last) so that the adaptive weight has a last layer to differentiate."""
+    import torchvision
+    import torch.nn.functional as F
+    import modules.losses.lpips as ref_lpips
+    from oracle import loss_oracle as lo
+    tv_vgg16 = torchvision.models.vgg16
+
+    class _Models:                       # what `from torchvision import models` gives lpips.py, minus the download
+        @staticmethod
+        def vgg16(pretrained=True):
+            return tv_vgg16(weights=None)
+    ref_lpips.models = _Models
+    from modules.losses.vqperceptual_multidisc import VQLPIPSWithDiscriminator
+    disc_cfg = {"target": "modules.discriminator.model.NLayerDiscriminator",
+                "params": {"input_nc": 3, "ndf": 64, "n_layers": 3, "use_actnorm": False}}
+    budget_cfg = {"target": "modules.dynamic_modules.budget.BudgetConstraint_RatioMSE_DualGrain",
+                  "params": {"target_ratio": 0.5, "gamma": 10.0, "min_grain_size": 16, "max_grain_size": 32,
+                             "calculate_all": True}}
+    loss = VQLPIPSWithDiscriminator(disc_start=0, disc_config=disc_cfg, disc_init=True, codebook_weight=1.0,
+                                    pixelloss_weight=1.0, disc_factor=1.0, disc_weight=1.0, perceptual_weight=1.0,
+                                    disc_conditional=False, disc_adaptive_loss=True, disc_loss="hinge",
+                                    disc_weight_max=0.75, budget_loss_config=budget_cfg)
+    sd = lo.make_loss_weights(seed=21)
+    ref_sd = loss.state_dict()
+    mine = {k[len("loss."):]: v for k, v in sd.items()}
+    missing = [k for k in ref_sd if k not in mine and "num_batches" not in k and "scaling_layer" not in k]
+    extra = [k for k in mine if k not in ref_sd]
+    assert not missing and not extra, (missing, extra)
+    for k, v in mine.items():
+        assert ref_sd[k].shape == v.shape, k
+    loss.load_state_dict(mine, strict=False)
+    out = {}
+    for mode in ("eval", "train"):
+        # "train" = what Lightning's model.train() leaves: BatchNorm uses batch statistics.  The Dropout in
+        # front of every LPIPS lin head would also turn on (LPIPS().eval() at :74 does not survive
+        # model.train()); it is switched off here so that the fixture is deterministic - the product keeps
+        # the reference behaviour and the GPU test checks the dropout statistics separately.
+        loss.train(mode == "train")
+        loss.perceptual_loss.eval()
+        loss.load_state_dict(mine, strict=False)                     # reset BatchNorm running statistics
+        x, feat, w_last, qloss, gate = lo.toy_inputs()
+        w_last.requires_grad_(True)
+        feat.requires_grad_(True)
+        xrec = F.conv2d(feat, w_last, padding=1)
+        l0, log0 = loss(qloss, x, xrec, 0, 0, last_layer=w_last, split="train", gate=gate)
+        g_w, g_feat = torch.autograd.grad(l0, [w_last, feat])
+        bn_after0 = {k: v.clone() for k, v in loss.state_dict().items() if "running" in k}
+        l1, log1 = loss(qloss, x, xrec.detach(), 1, 0, last_layer=w_last, split="train")
+        dparams = dict(loss.discriminator.named_parameters())
+        g_d = torch.autograd.grad(l1, list(dparams.values()))
+        bn_after1 = {k: v.clone() for k, v in loss.state_dict().items() if "running" in k}
+        p = mode + "_"
+        out.update({p + "loss0": l0, p + "g_w_last": g_w, p + "g_feat": g_feat, p + "loss1": l1, p + "xrec": xrec})
+        out.update({p + "log0_" + k.replace("train_", ""): v for k, v in log0.items()})
+        out.update({p + "log1_" + k.replace("train_", ""): v for k, v in log1.items()})
+        out.update({p + "gd_norm_" + k: g.norm() for k, g in zip(dparams, g_d)})
+        out[p + "gd_main.0.weight"] = g_d[list(dparams).index("main.0.weight")]
+        out[p + "gd_main.11.weight"] = g_d[list(dparams).index("main.11.weight")]
+        out.update({p + "bn0_" + k: v for k, v in bn_after0.items()})
+        out.update({p + "bn1_" + k: v for k, v in bn_after1.items()})
+        # LPIPS alone, per image
+        out[p + "lpips"] = loss.perceptual_loss(x, xrec.detach())
+    save("loss_small.npz", **out)
+
+
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["vq", "family", "permuter", "tiny", "dual", "variants"]
+    what = sys.argv[1:] or ["vq", "family", "permuter", "tiny", "dual", "variants", "loss"]
+    if "loss" in what:
+        loss_goldens()
     if "variants" in what:
         triple_entropy_goldens()
     if "vq" in what:

@@ -110,7 +110,8 @@ def _vq_check(x, w, mask, K, C, out, x_f32=False):
         gap = np.abs(d64[np.arange(len(mism)), got[mism]] - d64[np.arange(len(mism)), ref[mism]])
         scale = (xr[mism].astype(np.float64) ** 2).sum(1) + 1.0
         assert np.all(gap < 1e-6 * scale * 256), f"{len(mism)} real mismatches, max gap {gap.max()}"
-    assert len(mism) <= max(1, N // 2000), f"{len(mism)} near-tie mismatches of {N}"
+    # rounding-level near-ties scale with the number of candidates per row
+    assert len(mism) <= max(1, N // 2000) * max(1, K // 1024), f"{len(mism)} near-tie mismatches of {N}"
     assert torch.equal(xq_f, w[got])
     assert torch.equal(xq_b, w[got].to(BF))
     rows = x if x_f32 else x.to(BF).float()           # loss / EMA sums use the fp32 rows when given

@@ -22,6 +22,26 @@ def timeit(fn, iters=10, warm=3):
     return ts[len(ts) // 2]
 
 
+def timeit_graph(fn, launches=20, reps=5):
+    """Kernel-only time of a launch-bound call: `launches` calls captured in one CUDA graph (no host work
+    between them), best of `reps` replays, L2 flushed before each replay."""
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(launches):
+            fn()
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); g.replay(); e.record(); torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e) / launches)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
 def vq(N=65536, C=256):
     for K in (256, 1024, 8192, 16384):
         g = torch.Generator(device=dev).manual_seed(0)
@@ -30,11 +50,13 @@ def vq(N=65536, C=256):
         cb = kn.Codebook(K, C, dev); cb.refresh(w)
         xb = x.to(BF)
         ms = timeit(lambda: kn.vq_search_gather(xb, cb, w))
+        msg = timeit_graph(lambda: kn.vq_search_gather(xb, cb, w))
         fl = 2.0 * N * K * C
         by = 2 * N * C + 2 * K * C + 8 * N + 2 * N * C
-        print(json.dumps(dict(k="vq_search_gather", N=N, K=K, ms=round(ms, 4), tflops=round(fl / ms / 1e9, 1), alg_GBs=round(by / ms / 1e6, 1))))
+        print(json.dumps(dict(k="vq_search_gather", N=N, K=K, ms_eager=round(ms, 4), ms=round(msg, 4), tflops=round(fl / msg / 1e9, 1),
+                              alg_GBs=round(by / msg / 1e6, 1))))
         counts = torch.zeros(K, device=dev); sums = torch.zeros(K, C, device=dev); loss = torch.zeros(1, device=dev)
-        ms = timeit(lambda: kn.vq_search_gather(xb, cb, w, counts=counts, sums=sums, loss_acc=loss))
+        ms = timeit_graph(lambda: kn.vq_search_gather(xb, cb, w, counts=counts, sums=sums, loss_acc=loss))
         print(json.dumps(dict(k="vq_search_gather+ema", N=N, K=K, ms=round(ms, 4), tflops=round(fl / ms / 1e9, 1))))
 
 
@@ -97,7 +119,7 @@ def vq_small():
         xb = x.to(BF)
         fl = 2.0 * N * K * C
         for split in (False, True):
-            ms = timeit(lambda: kn.vq_search_gather(xb, cb, w, split=split), iters=20)
+            ms = timeit_graph(lambda: kn.vq_search_gather(xb, cb, w, split=split))
             print(json.dumps(dict(k="vq_search_gather", N=N, K=K, split=split, ms=round(ms, 4), tflops=round(fl / ms / 1e9, 1))))
 
 
