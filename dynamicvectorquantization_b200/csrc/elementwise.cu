@@ -151,30 +151,75 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ a, __nv_bfloat16*
 // dst[pixel][t*Cs + c] = src[pixel + off_t][c], zero padded to 64 columns.
 // flip = 0: off_t = (r-1, s-1)   (forward / weight gradient);  flip = 1: off_t = (1-r, 1-s) (dgrad).
 // One thread produces 8 columns (one 16 B store).
+// CS > 0: channel count known at compile time (RGB: 3): the column -> (tap, channel) divisions become
+// multiply-shifts (the runtime-Cs version spends its time in integer division sequences).
+template <int CS>
 __global__ void im2col3x3_small_kernel(const __nv_bfloat16* __restrict__ src,
-                                       __nv_bfloat16* __restrict__ dst, int H, int W, int Cs,
+                                       __nv_bfloat16* __restrict__ dst, int H, int W, int Cs_rt,
                                        int flip, long long total_vecs) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total_vecs) return;
+  const int Cs = CS > 0 ? CS : Cs_rt;
   const int cv = static_cast<int>(i & 7);
   const long long pix = i >> 3;
   const int w = static_cast<int>(pix % W);
   const int h = static_cast<int>((pix / W) % H);
   const long long n = pix / (static_cast<long long>(W) * H);
+  const __nv_bfloat16* img = src + n * H * W * Cs;
+  const int sgn = flip ? -1 : 1;
   __align__(16) __nv_bfloat16 vals[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int col = cv * 8 + k;
     __nv_bfloat16 v = __float2bfloat16_rn(0.f);
     if (col < 9 * Cs) {
-      const int t = col / Cs, c = col - t * Cs;
-      const int r = t / 3, s = t - 3 * r;
-      const int hh = h + (flip ? 1 - r : r - 1), ww = w + (flip ? 1 - s : s - 1);
-      if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = src[((n * H + hh) * W + ww) * Cs + c];
+      const int t = col / Cs, c = col - t * Cs;     // divisions by a literal when CS > 0
+      const int r = t / 3, sx = t - 3 * r;
+      const int hh = h + sgn * (r - 1), ww = w + sgn * (sx - 1);
+      if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = img[(hh * W + ww) * Cs + c];
     }
     vals[k] = v;
   }
   reinterpret_cast<uint4*>(dst)[i] = *reinterpret_cast<const uint4*>(vals);
+}
+
+// Three-channel case (RGB image in, RGB gradient out): ONE thread builds the whole 64-column row of a
+// pixel - 27 two-byte loads that hit L1 (neighbouring pixels share them), eight 16 B stores - instead of
+// eight threads each resolving (tap, channel) per element.
+__global__ void im2col3x3_c3_kernel(const unsigned short* __restrict__ src, uint4* __restrict__ dst, int H,
+                                    int W, int flip, long long npix) {
+  const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (pix >= npix) return;
+  const int w = static_cast<int>(pix % W);
+  const int h = static_cast<int>((pix / W) % H);
+  const long long n = pix / (static_cast<long long>(W) * H);
+  const unsigned short* img = src + n * H * W * 3;
+  const int sgn = flip ? -1 : 1;
+  unsigned short v[32];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int r = t / 3, sx = t - 3 * r;
+    const int hh = h + sgn * (r - 1), ww = w + sgn * (sx - 1);
+    const bool ok = hh >= 0 && hh < H && ww >= 0 && ww < W;
+    const unsigned short* q = img + (hh * W + ww) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[t * 3 + c] = ok ? __ldg(q + c) : static_cast<unsigned short>(0);
+  }
+#pragma unroll
+  for (int k = 27; k < 32; ++k) v[k] = 0;
+  uint4* out = dst + pix * 8;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 o;
+    o.x = v[8 * j + 0] | (static_cast<uint32_t>(v[8 * j + 1]) << 16);
+    o.y = v[8 * j + 2] | (static_cast<uint32_t>(v[8 * j + 3]) << 16);
+    o.z = v[8 * j + 4] | (static_cast<uint32_t>(v[8 * j + 5]) << 16);
+    o.w = v[8 * j + 6] | (static_cast<uint32_t>(v[8 * j + 7]) << 16);
+    out[j] = o;
+  }
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+  for (int j = 4; j < 8; ++j) out[j] = z;
 }
 
 // part[block][c] = sum over the block's rows of dy[row][c] (bias gradient), dy bf16 [rows][C],
@@ -319,7 +364,10 @@ int b2dq_im2col3x3_small(const void* src, void* dst, int N, int H, int W, int Cs
                          cudaStream_t st) {
   if (9 * Cs > 64) return -1;
   const long long total = (long long)N * H * W * 8;
-  return launch1d(im2col3x3_small_kernel, total, st, reinterpret_cast<const __nv_bfloat16*>(src),
+  if (Cs == 3)
+    return launch1d(im2col3x3_c3_kernel, total / 8, st, reinterpret_cast<const unsigned short*>(src),
+                    reinterpret_cast<uint4*>(dst), H, W, flip, total / 8);
+  return launch1d(im2col3x3_small_kernel<0>, total, st, reinterpret_cast<const __nv_bfloat16*>(src),
                   reinterpret_cast<__nv_bfloat16*>(dst), H, W, Cs, flip, total);
 }
 

@@ -275,6 +275,20 @@ __global__ void gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy,
   const int r1 = min(HW, r0 + rows_per_block);
   const int cg = C / G;
   const float inv_cnt = 1.f / (static_cast<float>(HW) * cg);
+  // per-group constants once per CTA (thread g sums its group's channels in channel order), not once
+  // per thread: for the small late-stage tensors the old per-thread loop cost more than the rows
+  __shared__ float s_k[64][2];
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    float S1 = 0.f, S2 = 0.f;
+    for (int cc = g * cg; cc < (g + 1) * cg; ++cc) {
+      const float gmm = gamma[cc];
+      S1 = fmaf(gmm, ws_nc[(static_cast<long long>(n) * C + cc) * 2 + 0], S1);
+      S2 = fmaf(gmm, ws_nc[(static_cast<long long>(n) * C + cc) * 2 + 1], S2);
+    }
+    s_k[g][0] = S1 * inv_cnt;
+    s_k[g][1] = S2 * inv_cnt;
+  }
+  __syncthreads();
   float mean[8], rstd[8], gm[8], bt[8], k1[8], k2[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
@@ -282,13 +296,7 @@ __global__ void gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy,
     const int g = c / cg;
     mean[k] = stats[(n * G + g) * 2]; rstd[k] = stats[(n * G + g) * 2 + 1];
     gm[k] = gamma[c]; bt[k] = beta[c];
-    float S1 = 0.f, S2 = 0.f;
-    for (int cc = g * cg; cc < (g + 1) * cg; ++cc) {
-      const float gmm = gamma[cc];
-      S1 = fmaf(gmm, ws_nc[(static_cast<long long>(n) * C + cc) * 2 + 0], S1);
-      S2 = fmaf(gmm, ws_nc[(static_cast<long long>(n) * C + cc) * 2 + 1], S2);
-    }
-    k1[k] = S1 * inv_cnt; k2[k] = S2 * inv_cnt;
+    k1[k] = s_k[g][0]; k2[k] = s_k[g][1];
   }
   const long long off = (static_cast<long long>(n) * HW) * C + v * 8;
   int r = r0 + rlane;
@@ -422,6 +430,7 @@ int b2dq_gn_bwd_apply(const void* dy, const void* x, const float* stats, const f
                       const float* beta, const float* ws_nc, void* dx, float* dgb, const void* add,
                       int N, int HW, int C, int G, int swish, cudaStream_t stream) {
   if (N <= 0 || HW <= 0) return 0;
+  if (G > 64 || C % 8 || C % G || 256 % (C / 8)) return -1;
   if (dgb) gn_bwd_param_kernel<<<(C + 127) / 128, 128, 0, stream>>>(ws_nc, dgb, N, C);
   const int rpb = pick_rows_per_block(HW, N);
   dim3 grid((HW + rpb - 1) / rpb, N);

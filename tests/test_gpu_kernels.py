@@ -378,3 +378,12 @@ def test_layout_upsample_softmax():
     for t, (r, s_) in enumerate([(r, s_) for r in range(3) for s_ in range(3)]):
         assert torch.equal(col[..., t * 3:(t + 1) * 3], pad[:, :, r:r + 6, s_:s_ + 5].permute(0, 2, 3, 1))
     assert float(col[..., 27:].abs().sum()) == 0.0
+    # flipped taps (data-gradient form) and a channel count that takes the generic kernel
+    for cs, flip in ((3, True), (5, False), (5, True), (3, False)):
+        img = _rand_bf(3, 7, 9, cs, seed=10 + cs)
+        col = kn.im2col3x3_small(img.to(dev), flip=flip).cpu().float()
+        pad = F.pad(img.float().permute(0, 3, 1, 2), (1, 1, 1, 1))
+        for t, (r, s_) in enumerate([(r, s_) for r in range(3) for s_ in range(3)]):
+            rr, ss = (2 - r, 2 - s_) if flip else (r, s_)
+            assert torch.equal(col[..., t * cs:(t + 1) * cs], pad[:, :, rr:rr + 7, ss:ss + 9].permute(0, 2, 3, 1)), (cs, flip, t)
+        assert float(col[..., 9 * cs:].abs().sum()) == 0.0
