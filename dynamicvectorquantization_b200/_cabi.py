@@ -83,6 +83,7 @@ SIGNATURES = {
     "b2dq_softmax_bwd_rows": [_vp, _vp, _vp, _ll, _i, _f, _vp],
     "b2dq_add_bf16": [_vp, _vp, _vp, _ll, _vp],
     "b2dq_im2col3x3_small": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "b2dq_pack_weights": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "b2dq_bias_grad_blocks": [_ll],
     "b2dq_bias_grad": [_vp, _vp, _vp, _ll, _i, _vp],
     "b2dq_cast_f32_to_bf16": [_vp, _vp, _ll, _vp],

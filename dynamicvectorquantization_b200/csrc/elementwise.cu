@@ -272,12 +272,45 @@ __global__ void bias_grad_generic_kernel(const __nv_bfloat16* __restrict__ dy, f
     part[static_cast<long long>(blockIdx.x) * C + c] = s;
   }
 }
+// out[c] = sum_b part[b][c].  256 threads = 32 channels x 8 block lanes: lane l adds blocks l, l+8, ... in
+// order, the eight lane sums are then added in lane order - a fixed order for a given `blocks`, so the
+// result is reproducible (the old one-thread-per-channel loop was ~1200 dependent loads long).
 __global__ void bias_grad_reduce_kernel(const float* __restrict__ part, float* out, int blocks, int C) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float a = 0.f;
-  for (int b = 0; b < blocks; ++b) a += part[static_cast<long long>(b) * C + c];
-  out[c] = a;
+  __shared__ float sh[8][32];
+  const int cl = threadIdx.x & 31, seg = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  float a0 = 0.f, a1 = 0.f;
+  if (c < C) {
+    int b = seg;
+    for (; b + 8 < blocks; b += 16) {
+      a0 += part[static_cast<long long>(b) * C + c];
+      a1 += part[static_cast<long long>(b + 8) * C + c];
+    }
+    if (b < blocks) a0 += part[static_cast<long long>(b) * C + c];
+  }
+  sh[seg][cl] = a0 + a1;
+  __syncthreads();
+  if (seg == 0 && c < C) {
+    float a = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a += sh[k][cl];
+    out[c] = a;
+  }
+}
+
+// OIHW fp32 -> the two bf16 GEMM packings of a convolution weight in one pass:
+//   fwd  [Cout][R*S*Cin]  (tap-major, Cin contiguous)     dgr  [Cin][R*S*Cout]  (contraction over Cout)
+// Either output may be null.  One thread per weight element, read in memory order.
+__global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* fwd, __nv_bfloat16* dgr,
+                                    int Cout, int Cin, int RS, long long total) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int t = static_cast<int>(i % RS);
+  const int ci = static_cast<int>((i / RS) % Cin);
+  const int co = static_cast<int>(i / (static_cast<long long>(RS) * Cin));
+  const __nv_bfloat16 v = __float2bfloat16_rn(w[i]);
+  if (fwd) fwd[(static_cast<long long>(co) * RS + t) * Cin + ci] = v;
+  if (dgr) dgr[(static_cast<long long>(ci) * RS + t) * Cout + co] = v;
 }
 
 }  // namespace b2
@@ -391,8 +424,17 @@ int b2dq_bias_grad(const void* dy, float* out, float* part, long long rows, int 
     bias_grad_generic_kernel<<<blocks, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dy), part,
                                                      rows, C, (int)rpb);
   }
-  bias_grad_reduce_kernel<<<(C + 127) / 128, 128, 0, st>>>(part, out, (int)blocks, C);
+  bias_grad_reduce_kernel<<<(C + 31) / 32, 256, 0, st>>>(part, out, (int)blocks, C);
   return (int)cudaGetLastError();
+}
+
+// weight [Cout,Cin,R,S] fp32 -> fwd [Cout, R*S*Cin] and/or dgrad [Cin, R*S*Cout] bf16 (null = skip).
+int b2dq_pack_weights(const float* weight, void* fwd, void* dgrad, int Cout, int Cin, int R, int S,
+                      cudaStream_t st) {
+  if (Cout <= 0 || Cin <= 0 || R <= 0 || S <= 0) return -1;
+  const long long total = (long long)Cout * Cin * R * S;
+  return launch1d(pack_weights_kernel, total, st, weight, reinterpret_cast<__nv_bfloat16*>(fwd),
+                  reinterpret_cast<__nv_bfloat16*>(dgrad), Cout, Cin, R * S, total);
 }
 
 }  // extern "C"

@@ -435,22 +435,38 @@ int b2dq_pconv3x3(const void* a_ptr, const void* b_ptr, void* out, const float* 
 
 // stats[n][g] = (mean, rstd) from the per-tile partials written by b2dq_pconv3x3 (tiles of an image are
 // contiguous; added in tile order: deterministic).  count = H*W*4 elements per group.
+__device__ __forceinline__ double shfl_xor_f64(double v, int m) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_xor_sync(0xffffffffu, lo, m);
+  hi = __shfl_xor_sync(0xffffffffu, hi, m);
+  return __hiloint2double(hi, lo);
+}
+// One warp per (image, group): lane l adds tiles l, l+32, ... in order, then a fixed butterfly.
 __global__ void gn_finalize_tiles_kernel(const float* __restrict__ part, float* stats, int N,
                                          int tiles_per_image, double inv_count, float eps) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (i >= N * 32) return;
   const int n = i / 32, g = i % 32;
   double a = 0.0, b = 0.0;
   const float* pp = part + (static_cast<long long>(n) * tiles_per_image) * 64 + g * 2;
-  for (int t = 0; t < tiles_per_image; ++t) {
-    a += pp[static_cast<long long>(t) * 64];
-    b += pp[static_cast<long long>(t) * 64 + 1];
+  for (int t = lane; t < tiles_per_image; t += 32) {
+    const float2 v = *reinterpret_cast<const float2*>(pp + static_cast<long long>(t) * 64);
+    a += v.x;
+    b += v.y;
   }
-  const double mean = a * inv_count;
-  double var = b * inv_count - mean * mean;
-  if (var < 0) var = 0;
-  stats[2 * i] = static_cast<float>(mean);
-  stats[2 * i + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += shfl_xor_f64(a, o);
+    b += shfl_xor_f64(b, o);
+  }
+  if (lane == 0) {
+    const double mean = a * inv_count;
+    double var = b * inv_count - mean * mean;
+    if (var < 0) var = 0;
+    stats[2 * i] = static_cast<float>(mean);
+    stats[2 * i + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
 }
 
 // ws_nc[n][c] = (sum dz, sum dz*xhat) over the tiles of image n, added in tile order (deterministic).
@@ -477,7 +493,7 @@ int b2dq_gn_finalize_tiles(const float* gn_part, float* stats, int N, int H, int
   if (N <= 0) return 0;
   if (W % 128) return -1;
   const int tpi = H * (W / 128);
-  gn_finalize_tiles_kernel<<<(N * 32 + 127) / 128, 128, 0, stream>>>(
+  gn_finalize_tiles_kernel<<<(N * 32 * 32 + 255) / 256, 256, 0, stream>>>(
       gn_part, stats, N, tpi, 1.0 / (static_cast<double>(H) * W * 4), eps);
   return (int)cudaGetLastError();
 }

@@ -169,6 +169,16 @@ def pack_weight_dgrad(w):
     return w.detach().permute(1, 2, 3, 0).reshape(ci, r * s * co).to(BF16).contiguous()
 
 
+def pack_weights(w, want_fwd=True, want_dgrad=True):
+    """Both bf16 packings of an OIHW fp32 weight in ONE launch -> (fwd | None, dgrad | None)."""
+    co, ci, r, s = w.shape
+    w = w.detach().contiguous()
+    fwd = torch.empty(co, r * s * ci, dtype=BF16, device=w.device) if want_fwd else None
+    dgr = torch.empty(ci, r * s * co, dtype=BF16, device=w.device) if want_dgrad else None
+    check(_cabi.lib().b2dq_pack_weights(_ptr(w), _ptr(fwd), _ptr(dgr), co, ci, r, s, _stream()), "pack_weights")
+    return fwd, dgr
+
+
 def conv_fwd(x, wpack, bias, ksize, stride, cout, residual=None, out_f32=False):
     """x NHWC bf16; wpack from pack_weight_fwd; stride-2 uses pad (0,1,0,1) like Downsample."""
     global last_conv_stats

@@ -29,7 +29,17 @@ def _packed(weight, kind):
         return ent[1]
     w = weight.detach()
     co, ci, r, s = w.shape
-    if kind == "fwd":
+    if kind in ("fwd", "dgrad") and w.is_cuda and w.dtype == torch.float32:
+        # one launch makes both packings when the data gradient will be wanted too (training)
+        other = "dgrad" if kind == "fwd" else "fwd"
+        both = weight.requires_grad or kind == "dgrad"   # (grad mode is off inside Function.forward)
+        oent = cache.get(other)
+        need_other = both and not (oent is not None and oent[0] == stamp)
+        fwd, dgr = kn.pack_weights(w, want_fwd=(kind == "fwd" or need_other), want_dgrad=(kind == "dgrad" or need_other))
+        if need_other:
+            cache[other] = (stamp, dgr if other == "dgrad" else fwd)
+        p = fwd if kind == "fwd" else dgr
+    elif kind == "fwd":
         p = kn.pack_weight_fwd(w)
     elif kind == "dgrad":
         p = kn.pack_weight_dgrad(w)

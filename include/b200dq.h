@@ -159,6 +159,11 @@ int b2dq_colsum_reduce(const float* part, float* out, int splits, int M, cudaStr
 int b2dq_wgrad_reduce(const float* partial, float* dw, int splits, int taps, int cout, int cin,
                       int accumulate, cudaStream_t stream);
 
+/* weight [Cout,Cin,R,S] fp32 (the nn.Conv2d parameter, model.py:43-47 etc.) -> the bf16 GEMM packings
+ * fwd [Cout, R*S*Cin] and/or dgrad [Cin, R*S*Cout] in one pass (null = skip that packing). */
+int b2dq_pack_weights(const float* weight, void* fwd, void* dgrad, int Cout, int Cin, int R, int S,
+                      cudaStream_t stream);
+
 /* out[c] = sum_rows dy[row][c]; deterministic two-stage sum, part = b2dq_bias_grad_blocks(rows)*C floats */
 int b2dq_bias_grad_blocks(long long rows);
 int b2dq_bias_grad(const void* dy_bf16, float* out, float* part, long long rows, int C, cudaStream_t stream);

@@ -387,3 +387,23 @@ def test_layout_upsample_softmax():
             rr, ss = (2 - r, 2 - s_) if flip else (r, s_)
             assert torch.equal(col[..., t * cs:(t + 1) * cs], pad[:, :, rr:rr + 7, ss:ss + 9].permute(0, 2, 3, 1)), (cs, flip, t)
         assert float(col[..., 9 * cs:].abs().sum()) == 0.0
+
+
+def test_fused_weight_packing_matches_the_torch_packings():
+    from dynamicvectorquantization_b200 import kernels as kn
+    g = torch.Generator().manual_seed(3)
+    for co, ci, k in ((128, 64, 3), (256, 512, 1), (3, 128, 3), (64, 3, 3), (192, 320, 3)):
+        w = torch.randn(co, ci, k, k, generator=g).cuda()
+        fwd, dgr = kn.pack_weights(w)
+        assert torch.equal(fwd, kn.pack_weight_fwd(w)) and torch.equal(dgr, kn.pack_weight_dgrad(w))
+        only_f, none_d = kn.pack_weights(w, want_dgrad=False)
+        assert none_d is None and torch.equal(only_f, fwd)
+
+
+def test_bias_grad_matches_fp32_sum():
+    from dynamicvectorquantization_b200 import kernels as kn
+    for rows, c in ((32 * 32 * 32, 256), (70001, 128), (300, 512), (32 * 256 * 64, 128)):
+        dy = _rand_bf(rows, c, seed=rows % 97)
+        got = kn.bias_grad(dy.cuda().view(1, rows, 1, c)).cpu()
+        ref = dy.double().sum(0)
+        assert float((got.double() - ref).abs().max()) <= 2e-4 * float(dy.double().abs().sum(0).max())
