@@ -212,3 +212,16 @@ def loss_forward(sd, codebook_loss, inputs, reconstructions, optimizer_idx, glob
     d_loss = factor * hinge_d_loss(logits_real, logits_fake)
     return d_loss, {"disc_loss": d_loss.detach(), "logits_real": logits_real.detach().mean(),
                     "logits_fake": logits_fake.detach().mean()}
+
+
+def toy_inputs(seed=11, b=2, res=64, cfeat=8):
+    """Seeded stand-in for "decoder output as a function of its last layer": xrec = conv3x3(feat, w_last).
+    Shared by tests/golden/make_golden.py::loss_goldens and the tests, so the fixture stores outputs only."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(b, 3, res, res, generator=g) * 2 - 1
+    feat = torch.randn(b, cfeat, res, res, generator=g) * 0.5
+    w_last = torch.randn(3, cfeat, 3, 3, generator=g) * 0.1
+    qloss = torch.rand((), generator=g) * 0.1
+    fine = (torch.rand(b, 1, 4, 4, generator=g) > 0.4).float()
+    gate = torch.cat([1 - fine, fine], 1)
+    return x, feat, w_last, qloss, gate

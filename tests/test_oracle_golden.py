@@ -232,3 +232,53 @@ def test_permuter_oracle_backward_edge_cases_match_reference():
                            coarse_position_pad_code=16, coarse_position_eos_code=17)
     assert np.array_equal(back, g["pb_back"])
     assert back[0, 1, 1] == 41 and back[0, 0, 0] == 7 and back[1].sum() == 60 + 61   # last wins; no eos -> no spread
+
+
+# ------------------------------------------------------------------------------------ training loss
+@pytest.mark.parametrize("mode", ["eval", "train"])
+def test_loss_oracle_matches_reference(mode):
+    """oracle.loss_oracle (LPIPS + PatchGAN + adaptive weight) vs the reference's VQLPIPSWithDiscriminator run in
+    the build container on the same seeded weights (tests/golden/make_golden.py::loss_goldens)."""
+    import torch.nn.functional as F
+    from oracle import loss_oracle as lo
+    g = np.load(os.path.join(G, "loss_small.npz"))
+    sd = lo.make_loss_weights(seed=21)
+    x, feat, w_last, qloss, gate = lo.toy_inputs()
+    w_last.requires_grad_(True)
+    feat.requires_grad_(True)
+    xrec = F.conv2d(feat, w_last, padding=1)
+    assert np.allclose(xrec.detach().numpy(), g[mode + "_xrec"], atol=1e-6)
+    train = mode == "train"
+    stats0 = {}
+    l0, log0 = lo.loss_forward(sd, qloss, x, xrec, 0, 0, last_layer=w_last, gate=gate, disc_weight_max=0.75,
+                               train=train, budget=lo.budget_loss_dual, new_stats=stats0)
+    gw, gf = torch.autograd.grad(l0, [w_last, feat])
+
+    def close(a, key, rtol=2e-4, atol=1e-7):
+        b = g[mode + "_" + key]
+        a = a.detach().numpy() if torch.is_tensor(a) else np.asarray(a)
+        assert np.allclose(a, b, rtol=rtol, atol=atol), (key, float(np.abs(a - b).max()), float(np.abs(b).max()))
+    close(l0, "loss0")
+    close(log0["p_loss"], "log0_p_loss")
+    close(log0["d_weight"], "log0_d_weight", rtol=1e-3)
+    close(log0["g_loss"], "log0_g_loss")
+    close(log0["budget_loss"], "log0_budget_loss")
+    close(gw, "g_w_last", rtol=2e-3, atol=1e-6 * float(np.abs(g[mode + "_g_w_last"]).max()) + 1e-9)
+    close(gf, "g_feat", rtol=2e-3, atol=2e-3 * float(np.abs(g[mode + "_g_feat"]).max()))
+    close(lo.lpips(sd, x, xrec.detach()), "lpips")
+    if train:
+        for k, v in stats0.items():
+            close(v, "bn0_" + k[len("loss."):], rtol=1e-4, atol=1e-6)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if "discriminator" in k and "running" not in k}
+    sd1 = dict(sd); sd1.update(params)
+    l1, log1 = lo.loss_forward(sd1, qloss, x, xrec.detach(), 1, 0, train=train)
+    close(l1, "loss1")
+    close(log1["logits_real"], "log1_logits_real", atol=1e-6)
+    close(log1["logits_fake"], "log1_logits_fake", atol=1e-6)
+    names = list(params)
+    gd = torch.autograd.grad(l1, [params[k] for k in names])
+    for k, gr in zip(names, gd):
+        short = k[len("loss.discriminator."):]
+        close(gr.norm(), "gd_norm_" + short, rtol=2e-3, atol=1e-7)
+    close(gd[names.index("loss.discriminator.main.0.weight")], "gd_main.0.weight", rtol=2e-3,
+          atol=2e-3 * float(np.abs(g[mode + "_gd_main.0.weight"]).max()))
