@@ -43,6 +43,9 @@ def parse():
     ap.add_argument("--config", default="dqvae-dual-r-05", choices=sorted(WORKLOADS),
                     help="headline = dqvae-dual-r-05; the others are parity-test configs that can be timed too")
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph (N=1)")
+    ap.add_argument("--loss", default="surrogate", choices=["surrogate", "real"],
+                    help="real: time the reference's full training_step (both optimizer passes, LPIPS + PatchGAN + "
+                         "adaptive weight; SURVEY 8f row 1) on one GPU instead of the headline fwd+bwd step")
     ap.add_argument("--aux", action="store_true",
                     help="instead of the headline step, time the widened rows (SURVEY 8f: patch entropy, stage-2 "
                          "permuter, residual quantizer) on one GPU, one JSON line each with roofline + cpu_baseline")
@@ -589,9 +592,109 @@ def run_aux(args):
                          "sample": f"numpy oracle on 4 latents ({threads} BLAS threads)"}}), flush=True)
 
 
+def run_real_loss(args):
+    """training_step of dqvae_dual_feat.py:88-119 as Lightning drives it with two optimizers -
+    pass 0: AE forward, L1 + LPIPS + adaptive-weight GAN + codebook + budget loss, backward, Adam(AE);
+    pass 1: AE forward again, hinge loss of the PatchGAN on real / reconstructed images, backward, Adam(D).
+    VGG16 / lin heads are randomly initialised (no pretrained files offline): identical arithmetic."""
+    os.environ.setdefault("B200DQ_ALLOW_RANDOM_VGG", "1")
+    import torch
+    from dynamicvectorquantization_b200 import configs, kernels as kn
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    torch.manual_seed(2021)
+    cfg = configs.stage1_config("dqvae-dual-r-05")
+    cfg["params"]["lossconfig"] = configs.real_loss_config(configs._BUDGET_DUAL)
+    model = configs.build_model(cfg).to(dev).train()
+    B = args.batch
+    model.learning_rate = 4.5e-6 * B
+    ae = [p for n, p in model.named_parameters() if not n.startswith("loss.") and p.requires_grad]
+    dp = list(model.loss.discriminator.parameters())
+    mk = lambda ps: torch.optim.Adam(ps, lr=model.learning_rate, betas=(0.5, 0.9), capturable=True, fused=True)
+    opt_ae, opt_d = mk(ae), mk(dp)
+    g = torch.Generator().manual_seed(2021)
+    x_host = (torch.rand(B, 3, 256, 256, generator=g) * 2 - 1).pin_memory()
+    x_dev = x_host.to(dev)
+    loss_host = torch.zeros(2).pin_memory()
+
+    def step(x):
+        opt_ae.zero_grad(set_to_none=True)
+        xrec, qloss, indices, gate = model(x)[:4]
+        l0, _ = model.loss(qloss, x, xrec, 0, 0, last_layer=model.get_last_layer(), split="train", gate=gate)
+        l0.backward()
+        opt_ae.step()
+        opt_d.zero_grad(set_to_none=True)
+        xrec, qloss, indices, gate = model(x)[:4]
+        l1, _ = model.loss(qloss, x, xrec, 1, 0, last_layer=model.get_last_layer(), split="train")
+        l1.backward()
+        opt_d.step()
+        return torch.stack([l0.detach(), l1.detach()])
+
+    for _ in range(max(args.warmup, 3)):
+        step(x_dev)
+    torch.cuda.synchronize()
+    graph, launches_per_step = None, None
+    if not args.no_graph:
+        try:
+            static_x = x_dev.clone()
+            l0c = kn.launch_count()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = step(static_x)
+            launches_per_step = kn.launch_count() - l0c
+            eager = step
+
+            def step(x):                              # noqa: F811
+                if x is not static_x:
+                    static_x.copy_(x, non_blocking=True)
+                graph.replay()
+                return static_out
+            step(static_x)
+            x_dev = static_x
+        except Exception as e:
+            sys.stderr.write(f"[bench --loss real] CUDA graph capture failed ({type(e).__name__}: {e}); eager\n")
+            graph = None
+            torch.cuda.synchronize()
+    sampler = ClockSampler(0); sampler.start()
+    c0 = kn.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(args.steps):
+        step(x_dev)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    launches = launches_per_step * args.steps if graph is not None else kn.launch_count() - c0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = step(x_host.to(dev, non_blocking=True))
+        loss_host.copy_(out, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_e2e = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    print(json.dumps({
+        "metric": "images/sec (256x256 DQ-VAE training_step, LPIPS + PatchGAN loss, both optimizer passes)",
+        "value": B * args.steps / (ms / 1e3), "unit": "images/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOADS["dqvae-dual-r-05"] + ", lossconfig of the reference YAML", "global_batch": B,
+                   "step": "2 AE forwards + AE backward + LPIPS fwd/bwd + 3 discriminator forwards + backwards + 2 Adam",
+                   "cuda_graph": graph is not None, "weights": "random init (VGG16 / lin heads / AE / D)",
+                   "discriminator": "PyTorch CUDA ops (cuDNN, TF32) - not yet on the hand-written kernels"},
+        "clocks": clocks, "gpu_launches": launches,
+        "e2e": {"value": B * args.steps / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": x_host.numel() * 4,
+                "d2h_bytes_per_step": 8},
+        "last_losses": [float(v) for v in loss_host]}), flush=True)
+
+
 if __name__ == "__main__":
     a = parse()
-    if a.aux:
+    if a.loss == "real":
+        run_real_loss(a)
+    elif a.aux:
         run_aux(a)
     elif a.impl == "reference":
         run_reference(a)

@@ -28,6 +28,7 @@ class TapGemmDesc(C.Structure):
         ("bias", C.c_void_p),
         ("residual", C.c_void_p), ("rN", C.c_longlong), ("rH", C.c_longlong), ("rW", C.c_longlong),
         ("alpha", C.c_float), ("out_f32", C.c_int), ("block_n", C.c_int), ("m_tiles_per_cta", C.c_int),
+        ("relu", C.c_int),
     ]
 
 
@@ -84,6 +85,9 @@ SIGNATURES = {
     "b2dq_add_bf16": [_vp, _vp, _vp, _ll, _vp],
     "b2dq_im2col3x3_small": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
     "b2dq_pack_weights": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "b2dq_maxpool2x2": [_vp, _vp, _i, _i, _i, _i, _vp],
+    "b2dq_maxpool2x2_bwd": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "b2dq_relu_bwd": [_vp, _vp, _vp, _ll, _vp],
     "b2dq_bias_grad_blocks": [_ll],
     "b2dq_bias_grad": [_vp, _vp, _vp, _ll, _i, _vp],
     "b2dq_cast_f32_to_bf16": [_vp, _vp, _ll, _vp],

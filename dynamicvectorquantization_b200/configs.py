@@ -42,6 +42,18 @@ def _surrogate(budget):
     return dict(target="dynamicvectorquantization_b200.nn.model.SurrogateAELoss", params=p)
 
 
+def real_loss_config(budget):
+    """lossconfig of configs/stage1/dqvae-dual-r-05_imagenet.yml:36-63 (LPIPS + PatchGAN + adaptive weight)."""
+    p = dict(disc_start=0,
+             disc_config=dict(target="modules.discriminator.model.NLayerDiscriminator",
+                              params=dict(input_nc=3, ndf=64, n_layers=3, use_actnorm=False)),
+             disc_init=True, codebook_weight=1.0, pixelloss_weight=1.0, disc_factor=1.0, disc_weight=1.0,
+             perceptual_weight=1.0, disc_conditional=False, disc_loss="hinge", disc_weight_max=0.75)
+    if budget is not None:
+        p["budget_loss_config"] = budget
+    return dict(target="modules.losses.vqperceptual_multidisc.VQLPIPSWithDiscriminator", params=p)
+
+
 def _enc_dual(router):
     return dict(target="modules.dynamic_modules.EncoderDual.DualGrainEncoder",
                 params=dict(ch=128, ch_mult=[1, 1, 2, 2, 4], num_res_blocks=2, attn_resolutions=[16, 32],

@@ -313,6 +313,76 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
   if (dgr) dgr[(static_cast<long long>(ci) * RS + t) * Cout + co] = v;
 }
 
+// 2x2 / stride 2 max pooling, NHWC bf16, one thread per 8 output channels.
+__device__ __forceinline__ void max8(float (&m)[8], const uint4& u) {
+  float f[8];
+  unpack8(u, f);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], f[k]);
+}
+__global__ void maxpool2x2_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int H, int W, int CV,
+                                  long long total) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int cv = static_cast<int>(i % CV);
+  const long long pix = i / CV;
+  const int Wo = W >> 1, Ho = H >> 1;
+  const int wo = static_cast<int>(pix % Wo);
+  const int ho = static_cast<int>((pix / Wo) % Ho);
+  const long long n = pix / (static_cast<long long>(Wo) * Ho);
+  const uint4* p00 = x + ((n * H + 2 * ho) * W + 2 * wo) * CV + cv;
+  const uint4 a = __ldg(p00), b = __ldg(p00 + CV), c = __ldg(p00 + static_cast<long long>(W) * CV),
+              d = __ldg(p00 + static_cast<long long>(W) * CV + CV);
+  float m[8];
+  unpack8(a, m);
+  max8(m, b); max8(m, c); max8(m, d);
+  y[i] = pack8(m);
+}
+// dx[window position] = dy if that position holds the FIRST maximum of its window in scan order
+// (0,0),(0,1),(1,0),(1,1) - ATen's max_pool2d keeps the first index on ties (ReLU outputs tie at 0 a lot).
+__global__ void maxpool2x2_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x,
+                                      uint4* __restrict__ dx, int H, int W, int CV, long long total) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int cv = static_cast<int>(i % CV);
+  const long long pix = i / CV;
+  const int Wo = W >> 1, Ho = H >> 1;
+  const int wo = static_cast<int>(pix % Wo);
+  const int ho = static_cast<int>((pix / Wo) % Ho);
+  const long long n = pix / (static_cast<long long>(Wo) * Ho);
+  const long long o00 = ((n * H + 2 * ho) * W + 2 * wo) * CV + cv;
+  const long long offs[4] = {o00, o00 + CV, o00 + static_cast<long long>(W) * CV,
+                             o00 + static_cast<long long>(W) * CV + CV};
+  float f[4][8], g[8], o[4][8];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) unpack8(__ldg(x + offs[q]), f[q]);
+  unpack8(__ldg(dy + i), g);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    int best = 0;
+    float m = f[0][k];
+#pragma unroll
+    for (int q = 1; q < 4; ++q)
+      if (f[q][k] > m) { m = f[q][k]; best = q; }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) o[q][k] = (q == best) ? g[k] : 0.f;
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) dx[offs[q]] = pack8(o[q]);
+}
+// dx = dy where the ReLU output y is positive, else 0 (8 bf16 per thread).
+__global__ void relu_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ y, uint4* __restrict__ dx,
+                                long long total) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  float g[8], v[8];
+  unpack8(__ldg(dy + i), g);
+  unpack8(__ldg(y + i), v);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) g[k] = v[k] > 0.f ? g[k] : 0.f;
+  dx[i] = pack8(g);
+}
+
 }  // namespace b2
 
 using namespace b2;
@@ -426,6 +496,27 @@ int b2dq_bias_grad(const void* dy, float* out, float* part, long long rows, int 
   }
   bias_grad_reduce_kernel<<<(C + 31) / 32, 256, 0, st>>>(part, out, (int)blocks, C);
   return (int)cudaGetLastError();
+}
+
+int b2dq_maxpool2x2(const void* x, void* y, int N, int H, int W, int C, cudaStream_t st) {
+  if (N <= 0) return 0;
+  if (H % 2 || W % 2 || C % 8) return -1;
+  const long long total = (long long)N * (H / 2) * (W / 2) * (C / 8);
+  return launch1d(maxpool2x2_kernel, total, st, reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), H, W,
+                  C / 8, total);
+}
+int b2dq_maxpool2x2_bwd(const void* dy, const void* x, void* dx, int N, int H, int W, int C, cudaStream_t st) {
+  if (N <= 0) return 0;
+  if (H % 2 || W % 2 || C % 8) return -1;
+  const long long total = (long long)N * (H / 2) * (W / 2) * (C / 8);
+  return launch1d(maxpool2x2_bwd_kernel, total, st, reinterpret_cast<const uint4*>(dy),
+                  reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(dx), H, W, C / 8, total);
+}
+int b2dq_relu_bwd(const void* dy, const void* y, void* dx, long long n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  if (n % 8) return -1;
+  return launch1d(relu_bwd_kernel, n / 8, st, reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(y),
+                  reinterpret_cast<uint4*>(dx), n / 8);
 }
 
 // weight [Cout,Cin,R,S] fp32 -> fwd [Cout, R*S*Cin] and/or dgrad [Cin, R*S*Cout] bf16 (null = skip).

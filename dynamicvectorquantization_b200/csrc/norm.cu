@@ -10,17 +10,6 @@
 namespace b2 {
 
 __device__ __forceinline__ float sigmoidf_(float z) { return __fdividef(1.f, 1.f + __expf(-z)); }
-__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
-  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
-  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
-}
-__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
-  uint4 o;
-  o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
-  o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
-  return o;
-}
-
 // ------------------------------------------------------------------ forward statistics
 // grid (chunks, N); block 256.  Thread t owns channel vector (8 ch) v = t % (C/8) and walks rows.
 // Deterministic: per-thread sums are combined in a fixed order in shared memory, every CTA writes its

@@ -44,6 +44,7 @@ struct TapGemmParams {
   const __nv_bfloat16* residual; // same indexing as out via rN/rH/rW, or null
   long long rN, rH, rW;
   float alpha;                   // scale applied to the accumulator before bias/residual
+  int relu;                      // clamp the result at zero (VGG feature stack of the perceptual loss)
   int out_f32;
 };
 
@@ -217,6 +218,10 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int i = 0; i < CW; ++i) v[i] += __bfloat162float(p.residual[roff[j] + col + i]);
             }
           }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < CW; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
           if (p.out_f32) {
             float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + ooff[j] + col);
 #pragma unroll
@@ -242,6 +247,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (c < p.Cout) {
               float o = v[i];
               if (p.residual) o += __bfloat162float(p.residual[roff[j] + c]);
+              if (p.relu) o = fmaxf(o, 0.f);
               if (p.out_f32) static_cast<float*>(p.out)[ooff[j] + c] = o;
               else static_cast<__nv_bfloat16*>(p.out)[ooff[j] + c] = __float2bfloat16_rn(o);
             }
@@ -304,6 +310,7 @@ struct b2dq_tapgemm_desc {
   int out_f32;
   int block_n;                   // 0 = auto
   int m_tiles_per_cta;           // 0 = auto, 1 or 2
+  int relu;                      // != 0: out = max(out, 0)
 };
 
 int b2dq_tapgemm(const b2dq_tapgemm_desc* d, cudaStream_t stream) {
@@ -343,7 +350,7 @@ int b2dq_tapgemm(const b2dq_tapgemm_desc* d, cudaStream_t stream) {
   p.bias = d->bias;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(d->residual);
   p.rN = d->rN; p.rH = d->rH; p.rW = d->rW;
-  p.alpha = d->alpha; p.out_f32 = d->out_f32;
+  p.alpha = d->alpha; p.out_f32 = d->out_f32; p.relu = d->relu;
   dim3 grid((unsigned)(p.tiles_w * p.tiles_h * tiles_n), (unsigned)((d->Cout + bn - 1) / bn));
   // two 128-pixel tiles per CTA once there are enough tiles for >= 2 waves of 2 CTAs/SM
   const bool mt2 = d->m_tiles_per_cta == 2 || (d->m_tiles_per_cta == 0 && grid.x * grid.y >= 8 * 148);

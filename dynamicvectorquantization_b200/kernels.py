@@ -116,7 +116,7 @@ def _fill(arr, vals):
 
 def tapgemm(a, a_dims, a_strides, b, b_rows, b_k, taps, kchunks, out, out_off, ostr, wout, hout, nb,
             cout, bias=None, residual=None, res_off=0, rstr=(0, 0, 0), alpha=1.0, out_f32=False,
-            block_n=0, b_batch=1, b_batch_stride=0, m_tiles_per_cta=0):
+            block_n=0, b_batch=1, b_batch_stride=0, m_tiles_per_cta=0, relu=False):
     """taps: list of (dc, dw, dp, dh, bk)."""
     d = TapGemmDesc()
     d.a_ptr = a.data_ptr()
@@ -139,6 +139,7 @@ def tapgemm(a, a_dims, a_strides, b, b_rows, b_k, taps, kchunks, out, out_off, o
         m_tiles = -(-wout // d.TW) * -(-hout // d.TH) * -(-nb // d.TN)
         block_n = _pick_block_n(m_tiles, cout)
     d.alpha, d.out_f32, d.block_n, d.m_tiles_per_cta = alpha, int(out_f32), block_n, (m_tiles_per_cta or FORCE_MT)
+    d.relu = int(bool(relu))
     check(_cabi.lib().b2dq_tapgemm(C.byref(d), _stream()), "tapgemm")
 
 
@@ -179,13 +180,14 @@ def pack_weights(w, want_fwd=True, want_dgrad=True):
     return fwd, dgr
 
 
-def conv_fwd(x, wpack, bias, ksize, stride, cout, residual=None, out_f32=False):
-    """x NHWC bf16; wpack from pack_weight_fwd; stride-2 uses pad (0,1,0,1) like Downsample."""
+def conv_fwd(x, wpack, bias, ksize, stride, cout, residual=None, out_f32=False, relu=False):
+    """x NHWC bf16; wpack from pack_weight_fwd; stride-2 uses pad (0,1,0,1) like Downsample.
+    relu: clamp the output at zero in the epilogue (tap-GEMM path only)."""
     global last_conv_stats
     last_conv_stats = None
     nb, h, w, cin = x.shape
     assert cin % 64 == 0, "Cin must be a multiple of 64 (edge layers use the im2col path)"
-    if not out_f32 and _pconv_ok(ksize, stride, w, cin, cout, nb, h):
+    if not out_f32 and not relu and _pconv_ok(ksize, stride, w, cin, cout, nb, h):
         return pconv3x3(x, wpack, bias, residual, dgrad=False, want_stats=FUSE_GN_STATS)
     kch = cin // 64
     if stride == 1:
@@ -203,7 +205,7 @@ def conv_fwd(x, wpack, bias, ksize, stride, cout, residual=None, out_f32=False):
     out = torch.empty(nb, ho, wo, cout, dtype=torch.float32 if out_f32 else BF16, device=x.device)
     ostr = (ho * wo * cout, wo * cout, cout)
     tapgemm(x, dims, strs, wpack, wpack.shape[0], wpack.shape[1], taps, kch, out, 0, ostr, wo, ho, nb,
-            cout, bias=bias, residual=residual, rstr=ostr, out_f32=out_f32)
+            cout, bias=bias, residual=residual, rstr=ostr, out_f32=out_f32, relu=relu)
     return out
 
 
@@ -569,3 +571,27 @@ def im2col3x3_small(x, flip=False):
     check(_cabi.lib().b2dq_im2col3x3_small(_ptr(x), _ptr(out), nb, h, w, cs, int(flip), _stream()),
           "im2col3x3_small")
     return out
+
+
+# ------------------------------------------------------------------------------------------ VGG pieces
+def maxpool2x2(x):
+    """2x2 / stride 2 max pooling of NHWC bf16."""
+    nb, h, w, c = x.shape
+    y = torch.empty(nb, h // 2, w // 2, c, dtype=BF16, device=x.device)
+    check(_cabi.lib().b2dq_maxpool2x2(_ptr(x), _ptr(y), nb, h, w, c, _stream()), "maxpool2x2")
+    return y
+
+
+def maxpool2x2_bwd(dy, x):
+    """Gradient of maxpool2x2 w.r.t. its input x (first maximum of a window gets the gradient)."""
+    nb, h, w, c = x.shape
+    dx = torch.empty_like(x)
+    check(_cabi.lib().b2dq_maxpool2x2_bwd(_ptr(dy), _ptr(x), _ptr(dx), nb, h, w, c, _stream()), "maxpool2x2_bwd")
+    return dx
+
+
+def relu_bwd(dy, y):
+    """dy * (y > 0) for a ReLU whose OUTPUT is y (bf16, same shape)."""
+    dx = torch.empty_like(dy)
+    check(_cabi.lib().b2dq_relu_bwd(_ptr(dy), _ptr(y), _ptr(dx), dy.numel(), _stream()), "relu_bwd")
+    return dx

@@ -100,6 +100,7 @@ typedef struct b2dq_tapgemm_desc {
   int out_f32;            /* 0: bf16 output, 1: fp32 output */
   int block_n;            /* 0 = auto (16/64/128/256) */
   int m_tiles_per_cta;    /* 0 = auto, 1 or 2 (two 128-pixel tiles share each weight tile) */
+  int relu;               /* != 0: clamp the result at zero (conv + ReLU of the VGG16 stack, lpips.py:88-97) */
 } b2dq_tapgemm_desc;
 
 int b2dq_tapgemm(const b2dq_tapgemm_desc* desc, cudaStream_t stream);
@@ -158,6 +159,14 @@ int b2dq_colsum_reduce(const float* part, float* out, int splits, int M, cudaStr
 /* partial [splits][taps][cout][cin] fp32 -> dw [cout][cin][taps] fp32 (OIHW); accumulate != 0: += */
 int b2dq_wgrad_reduce(const float* partial, float* dw, int splits, int taps, int cout, int cin,
                       int accumulate, cudaStream_t stream);
+
+/* Perceptual-loss feature stack (modules/losses/lpips.py:78-113, torchvision VGG16): 2x2/2 max pooling of
+ * NHWC bf16 [N,H,W,C] (H, W even, C % 8 == 0) and its gradient (first maximum in window scan order gets
+ * the gradient, like ATen), and the gradient of a ReLU given its OUTPUT y: dx = dy * (y > 0). */
+int b2dq_maxpool2x2(const void* x_bf16, void* y_bf16, int N, int H, int W, int C, cudaStream_t stream);
+int b2dq_maxpool2x2_bwd(const void* dy_bf16, const void* x_bf16, void* dx_bf16, int N, int H, int W, int C,
+                        cudaStream_t stream);
+int b2dq_relu_bwd(const void* dy_bf16, const void* y_bf16, void* dx_bf16, long long n, cudaStream_t stream);
 
 /* weight [Cout,Cin,R,S] fp32 (the nn.Conv2d parameter, model.py:43-47 etc.) -> the bf16 GEMM packings
  * fwd [Cout, R*S*Cin] and/or dgrad [Cin, R*S*Cout] in one pass (null = skip that packing). */

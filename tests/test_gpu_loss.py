@@ -1,0 +1,177 @@
+"""GPU parity of the stage-1 training loss: LPIPS on the tensor-core convolution kernels, the
+PatchGAN discriminator and the adaptive-weight loss, against oracle/loss_oracle.py (fp32, CPU) and the fixtures
+minted from the reference's own classes (tests/golden/loss_small.npz).
+
+Tolerances: the VGG16 stack runs in bf16 (13 convolution layers, fp32 accumulation), so LPIPS values are compared
+at 2e-2 relative and its gradients at 6e-2 relative RMS; everything that does not pass through the bf16 stack
+(discriminator terms) at 2e-3 (TF32 convolutions are torch's cuDNN default)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def rel_rms(a, b):
+    a, b = a.double().flatten().cpu(), b.double().flatten().cpu()
+    return float(((a - b).pow(2).mean() / b.pow(2).mean().clamp_min(1e-30)).sqrt())
+
+
+def _loss_module(monkeypatch, seed=21, budget=True):
+    monkeypatch.setenv("B200DQ_ALLOW_RANDOM_VGG", "1")
+    from dynamicvectorquantization_b200 import configs
+    configs.activate_overlay()
+    from modules.losses.vqperceptual_multidisc import VQLPIPSWithDiscriminator
+    from oracle import loss_oracle as lo
+    disc_cfg = {"target": "modules.discriminator.model.NLayerDiscriminator",
+                "params": {"input_nc": 3, "ndf": 64, "n_layers": 3, "use_actnorm": False}}
+    loss = VQLPIPSWithDiscriminator(disc_start=0, disc_config=disc_cfg, disc_init=True, disc_weight_max=0.75,
+                                    budget_loss_config=configs._BUDGET_DUAL if budget else None)
+    sd = lo.make_loss_weights(seed)
+    loss.load_state_dict({k[len("loss."):]: v for k, v in sd.items()}, strict=False)
+    return loss.cuda(), sd
+
+
+def test_maxpool_and_relu_gradients_match_torch():
+    from dynamicvectorquantization_b200 import kernels as kn
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(3, 12, 20, 64, generator=g).clamp_min(0).to(BF)       # ReLU output: many exact ties at 0
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    yr = F.max_pool2d(xr, 2, 2)
+    y = kn.maxpool2x2(x.cuda())
+    assert torch.equal(y.cpu().float(), yr.detach().permute(0, 2, 3, 1))
+    dy = torch.randn(3, 6, 10, 64, generator=g).to(BF)
+    yr.backward(dy.float().permute(0, 3, 1, 2))
+    dx = kn.maxpool2x2_bwd(dy.cuda(), x.cuda())
+    assert torch.equal(dx.cpu().float(), xr.grad.permute(0, 2, 3, 1))
+    d2 = torch.randn(3, 12, 20, 64, generator=g).to(BF)
+    got = kn.relu_bwd(d2.cuda(), x.cuda()).cpu()
+    assert torch.equal(got, torch.where(x > 0, d2, torch.zeros_like(d2)))
+
+
+@pytest.mark.parametrize("res,batch", [(64, 2), (128, 3)])
+def test_lpips_matches_oracle(monkeypatch, res, batch):
+    from oracle import loss_oracle as lo
+    loss, sd = _loss_module(monkeypatch)
+    lp = loss.perceptual_loss.eval()
+    g = torch.Generator().manual_seed(res)
+    x = torch.rand(batch, 3, res, res, generator=g) * 2 - 1
+    y = (x + 0.3 * torch.randn(batch, 3, res, res, generator=g)).clamp(-1, 1)
+    yr = y.clone().requires_grad_(True)
+    ref = lo.lpips(sd, x, yr)
+    ref.sum().backward()
+    yd = y.cuda().requires_grad_(True)
+    got = lp(x.cuda(), yd)
+    got.sum().backward()
+    assert got.shape == (batch, 1, 1, 1)
+    assert torch.allclose(got.detach().cpu(), ref.detach(), rtol=2e-2, atol=1e-4), (got.flatten(), ref.flatten())
+    assert rel_rms(yd.grad, yr.grad) < 6e-2
+    # gradient w.r.t. the first argument too (both sides are differentiable in the reference)
+    xd = x.cuda().requires_grad_(True)
+    lp(xd, y.cuda()).sum().backward()
+    xr = x.clone().requires_grad_(True)
+    lo.lpips(sd, xr, y).sum().backward()
+    assert rel_rms(xd.grad, xr.grad) < 6e-2
+    # features through the reference-facing NCHW interface
+    feats = lp.net(lp.scaling_layer(x.cuda()))
+    shift = torch.tensor(lo.SHIFT)[None, :, None, None]
+    scale = torch.tensor(lo.SCALE)[None, :, None, None]
+    ref_feats = lo.vgg_features(sd, (x - shift) / scale)
+    for a, b in zip(feats, ref_feats):
+        assert a.shape == b.shape and rel_rms(a, b) < 2e-2
+
+
+def test_lpips_training_mode_dropout_is_live_and_unbiased(monkeypatch):
+    loss, _ = _loss_module(monkeypatch)
+    lp = loss.perceptual_loss
+    g = torch.Generator().manual_seed(1)
+    x = (torch.rand(2, 3, 64, 64, generator=g) * 2 - 1).cuda()
+    y = (x + 0.3 * torch.randn(2, 3, 64, 64, generator=g).cuda()).clamp(-1, 1)
+    with torch.no_grad():
+        ref = lp.eval()(x, y)
+        lp.train()                                    # what Lightning's model.train() does to the frozen metric
+        torch.manual_seed(0)
+        draws = torch.stack([lp(x, y) for _ in range(24)])
+    assert float(draws.std(0).max()) > 0, "dropout in front of the lin heads should be active in training mode"
+    assert torch.allclose(draws.mean(0), ref, rtol=0.1), (draws.mean(0).flatten(), ref.flatten())
+
+
+@pytest.mark.parametrize("mode", ["eval", "train"])
+def test_full_loss_matches_oracle_and_reference_golden(monkeypatch, mode):
+    from oracle import loss_oracle as lo
+    gold = np.load(os.path.join(GOLD, "loss_small.npz"))
+    loss, sd = _loss_module(monkeypatch)
+    loss.train(mode == "train")
+    loss.perceptual_loss.eval()                       # deterministic comparison (see the dropout test)
+    x, feat, w_last, qloss, gate = lo.toy_inputs()
+    xd, gd, qd = x.cuda(), gate.cuda(), qloss.cuda()
+    wl = w_last.cuda().requires_grad_(True)
+    ft = feat.cuda().requires_grad_(True)
+    xrec = F.conv2d(ft, wl, padding=1)
+    l0, log0 = loss(qd, xd, xrec, 0, 0, last_layer=wl, split="train", gate=gd)
+    gw, gf = torch.autograd.grad(l0, [wl, ft])
+    # oracle on the CPU, same inputs
+    w2 = w_last.clone().requires_grad_(True)
+    f2 = feat.clone().requires_grad_(True)
+    xrec2 = F.conv2d(f2, w2, padding=1)
+    r0, rlog = lo.loss_forward(sd, qloss, x, xrec2, 0, 0, last_layer=w2, gate=gate, disc_weight_max=0.75,
+                               train=(mode == "train"), budget=lo.budget_loss_dual)
+    rgw, rgf = torch.autograd.grad(r0, [w2, f2])
+    p = mode + "_"
+    for got, ref, key, tol in ((l0, r0, "loss0", 2e-2), (log0["train_p_loss"], rlog["p_loss"], "log0_p_loss", 2e-2),
+                               (log0["train_g_loss"], rlog["g_loss"], "log0_g_loss", 2e-3),
+                               (log0["train_d_weight"], rlog["d_weight"], "log0_d_weight", 5e-2),
+                               (log0["train_budget_loss"], rlog["budget_loss"], "log0_budget_loss", 1e-5)):
+        assert abs(float(got) - float(ref)) <= tol * abs(float(ref)) + 1e-6, (key, float(got), float(ref))
+        assert abs(float(got) - float(gold[p + key])) <= tol * abs(float(gold[p + key])) + 1e-6, (key, "golden")
+    assert rel_rms(gw, rgw) < 6e-2 and rel_rms(gw, torch.from_numpy(gold[p + "g_w_last"])) < 6e-2
+    assert rel_rms(gf, rgf) < 6e-2 and rel_rms(gf, torch.from_numpy(gold[p + "g_feat"])) < 6e-2
+    # discriminator pass
+    l1, log1 = loss(qd, xd, xrec.detach(), 1, 0, last_layer=wl, split="train")
+    assert abs(float(l1) - float(gold[p + "loss1"])) <= 2e-3 * abs(float(gold[p + "loss1"])) + 1e-6
+    dparams = dict(loss.discriminator.named_parameters())
+    gds = torch.autograd.grad(l1, list(dparams.values()))
+    for k, gr in zip(dparams, gds):
+        ref = float(gold[p + "gd_norm_" + k])
+        assert abs(float(gr.norm()) - ref) <= 1e-2 * ref + 1e-7, (k, float(gr.norm()), ref)
+    if mode == "train":
+        for k, v in loss.state_dict().items():
+            if "running" in k:
+                # TF32 convolutions (torch's cuDNN default) feed these statistics
+                assert torch.allclose(v.cpu(), torch.from_numpy(gold[p + "bn1_" + k]), rtol=2e-2, atol=3e-4), k
+
+
+def test_training_step_under_the_real_loss(monkeypatch):
+    """Both optimizer passes of training_step (dqvae_dual_feat.py:88-119) with the reference's loss config on the
+    reduced-width dual-grain model: finite losses, gradients where the reference has them."""
+    monkeypatch.setenv("B200DQ_ALLOW_RANDOM_VGG", "1")
+    from dynamicvectorquantization_b200 import configs
+    cfg = configs.scaled_dual_config()
+    cfg["params"]["lossconfig"] = configs.real_loss_config(cfg["params"]["lossconfig"]["params"]["budget_loss_config"])
+    torch.manual_seed(0)
+    model = configs.build_model(cfg).cuda().train()
+    model.learning_rate, model.min_learning_rate = 1e-4, 1e-6          # what train.py:243-267 injects
+    model.steps_per_epoch, model.training_steps, model.max_epoch = 10, 100, 10
+    (opt_ae, opt_disc), scheds = model.configure_optimizers()
+    assert len(scheds) == 2
+    x = torch.rand(4, 3, 64, 64, device="cuda") * 2 - 1
+    batch = {"image": x.permute(0, 2, 3, 1).contiguous()}
+    for it in range(2):
+        opt_ae.zero_grad(set_to_none=True)
+        l0 = model.training_step(batch, it, 0)
+        l0.backward()
+        assert torch.isfinite(l0)
+        assert model.decoder.conv_out.weight.grad is not None and model.encoder.conv_in.weight.grad is not None
+        assert all(p.grad is None for p in model.loss.perceptual_loss.parameters())
+        opt_ae.step()
+        opt_disc.zero_grad(set_to_none=True)
+        l1 = model.training_step(batch, it, 1)
+        l1.backward()
+        assert torch.isfinite(l1)
+        assert all(p.grad is not None for p in model.loss.discriminator.parameters())
+        opt_disc.step()

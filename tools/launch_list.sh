@@ -2,7 +2,7 @@
 # ncu launch list (gpu__time_duration only) of ONE training step -> gpurun_out/step_launches.csv
 mkdir -p gpurun_out
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
-  --log-file gpurun_out/step_launches_ncu.csv python tools/profile_step.py 32 2>&1 | tail -2
+  --log-file gpurun_out/step_launches_ncu.csv python tools/profile_step.py 32 $1 2>&1 | tail -2
 python - <<'PY'
 import csv, collections
 rows = list(csv.reader(l for l in open("gpurun_out/step_launches_ncu.csv") if l.startswith('"')))
