@@ -85,6 +85,9 @@ SIGNATURES = {
     "b2dq_add_bf16": [_vp, _vp, _vp, _ll, _vp],
     "b2dq_im2col3x3_small": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
     "b2dq_pack_weights": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "b2dq_lpips_head_chunks": [_i, _i],              # returns a count, not a status
+    "b2dq_lpips_head_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _f, _vp],
+    "b2dq_lpips_head_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _f, _vp],
     "b2dq_maxpool2x2": [_vp, _vp, _i, _i, _i, _i, _vp],
     "b2dq_maxpool2x2_bwd": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "b2dq_relu_bwd": [_vp, _vp, _vp, _ll, _vp],

@@ -595,3 +595,25 @@ def relu_bwd(dy, y):
     dx = torch.empty_like(dy)
     check(_cabi.lib().b2dq_relu_bwd(_ptr(dy), _ptr(y), _ptr(dx), dy.numel(), _stream()), "relu_bwd")
     return dx
+
+
+def lpips_head_fwd(f0, f1, w, seed=None, p_drop=0.0):
+    """f0, f1 NHWC bf16 [N,H,W,C]; w fp32 [C]; seed: int64 CUDA tensor [1] (dropout) or None.
+    Returns the per-image spatial mean [N] (fp32)."""
+    nb, h, wd, c = f0.shape
+    lib = _cabi.lib()
+    chunks = lib.b2dq_lpips_head_chunks(nb, h * wd)
+    part = torch.empty(nb, chunks, dtype=torch.float32, device=f0.device)
+    check(lib.b2dq_lpips_head_fwd(_ptr(f0), _ptr(f1), _ptr(w), _ptr(part), nb, h * wd, c, _ptr(seed), float(p_drop),
+                                  _stream()), "lpips_head_fwd")
+    return part.sum(1) / float(h * wd)
+
+
+def lpips_head_bwd(f0, f1, w, g, want0, want1, seed=None, p_drop=0.0):
+    """g fp32 [N] = gradient w.r.t. the spatial means.  Returns (df0 | None, df1 | None) in bf16."""
+    nb, h, wd, c = f0.shape
+    d0 = torch.empty_like(f0) if want0 else None
+    d1 = torch.empty_like(f1) if want1 else None
+    check(_cabi.lib().b2dq_lpips_head_bwd(_ptr(f0), _ptr(f1), _ptr(w), _ptr(g), _ptr(d0), _ptr(d1), nb, h * wd, c,
+                                          _ptr(seed), float(p_drop), _stream()), "lpips_head_bwd")
+    return d0, d1

@@ -9,7 +9,8 @@ What differs is how it is computed: the 13 VGG16 convolutions (40 GFLOP per 256x
 the loss) run as NHWC bf16 tap GEMMs on the tensor cores with the ReLU in the GEMM epilogue, max pooling
 and the ReLU / pooling gradients are small CUDA kernels, and only the gradient the training step needs
 (w.r.t. the reconstruction, no weight gradients - the network is frozen) is computed.  The per-level
-head (channel normalisation, squared difference, 1x1 ``lin``, spatial mean) is evaluated in fp32.
+head (channel normalisation, squared difference, dropout, 1x1 ``lin``, spatial mean) is one fused kernel per
+direction (csrc/lpips.cu) that reads the two feature maps once.
 
 Weights: like the reference, the constructor wants torchvision's pretrained VGG16 and
 ``modules/lpips/vgg.pth`` (the five ``lin`` heads that ship with the reference tree).  Offline, set
@@ -115,6 +116,25 @@ class _MaxPoolFn(torch.autograd.Function):
     def backward(ctx, dy):
         (x,) = ctx.saved_tensors
         return kn.maxpool2x2_bwd(dy.contiguous(), x)
+
+
+class _HeadFn(torch.autograd.Function):
+    """One LPIPS level: mean_hw sum_c w_c drop_c (f0/|f0| - f1/|f1|)^2 -> [N] fp32, fused (csrc/lpips.cu)."""
+
+    @staticmethod
+    def forward(ctx, f0, f1, w, seed, p_drop):
+        f0, f1 = f0.contiguous(), f1.contiguous()
+        w = w.detach().reshape(-1).float().contiguous()
+        ctx.save_for_backward(f0, f1, w, seed)
+        ctx.p_drop = p_drop
+        return kn.lpips_head_fwd(f0, f1, w, seed, p_drop)
+
+    @staticmethod
+    def backward(ctx, g):
+        f0, f1, w, seed = ctx.saved_tensors
+        d0, d1 = kn.lpips_head_bwd(f0, f1, w, g.float().contiguous(), ctx.needs_input_grad[0], ctx.needs_input_grad[1],
+                                   seed, ctx.p_drop)
+        return d0, d1, None, None, None
 
 
 # ---------------------------------------------------------------------------------------- modules
@@ -272,15 +292,13 @@ class LPIPS(nn.Module):
         of the lin head is live whenever the module is in training mode, as in the reference (LPIPS().eval() at
         vqperceptual_multidisc.py:74 does not survive the LightningModule's .train())."""
         lin = getattr(self, f"lin{k}").model
-        a, b = f0.float(), f1.float()
-        a = a / (a.pow(2).sum(-1, keepdim=True).sqrt() + 1e-10)
-        b = b / (b.pow(2).sum(-1, keepdim=True).sqrt() + 1e-10)
-        d = (a - b) ** 2
+        seed, p_drop = None, 0.0
         for m in lin:
-            if isinstance(m, nn.Dropout):
-                d = F.dropout(d, m.p, m.training)
-        w = lin[-1].weight.reshape(1, 1, 1, -1).float()
-        return (d * w).sum(-1).mean((1, 2))
+            if isinstance(m, nn.Dropout) and m.training and m.p > 0:
+                # drawn on the device so that a captured CUDA graph gets a fresh mask at every replay
+                seed = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64, device=f0.device)
+                p_drop = float(m.p)
+        return _HeadFn.apply(f0, f1, lin[-1].weight, seed, p_drop)
 
     def forward(self, input, target):
         if not input.is_cuda:

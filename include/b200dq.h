@@ -168,6 +168,19 @@ int b2dq_maxpool2x2_bwd(const void* dy_bf16, const void* x_bf16, void* dx_bf16, 
                         cudaStream_t stream);
 int b2dq_relu_bwd(const void* dy_bf16, const void* y_bf16, void* dx_bf16, long long n, cudaStream_t stream);
 
+/* LPIPS level head (lpips.py:44-55,116-122): f0, f1 = NHWC bf16 features [N,HW,C] (C in {64,128,256,512}),
+ * w = lin weights [C].  fwd: part[n*chunks + j] = partial sums over pixel chunks of
+ * sum_c w_c drop_c (f0_c/(|f0|+1e-10) - f1_c/(|f1|+1e-10))^2 (divide the per-image sum by HW for the spatial mean;
+ * chunks = b2dq_lpips_head_chunks).  bwd: g[n] = gradient w.r.t. the spatial mean; writes the gradient w.r.t.
+ * f0 and/or f1 (bf16, null = skip).  seed: device pointer to the dropout seed of this call, or null for no
+ * dropout; p_drop = drop probability (nn.Dropout in front of the lin head, live in training mode). */
+int b2dq_lpips_head_chunks(int N, int HW);
+int b2dq_lpips_head_fwd(const void* f0_bf16, const void* f1_bf16, const float* w, float* part, int N, int HW, int C,
+                        const unsigned long long* seed, float p_drop, cudaStream_t stream);
+int b2dq_lpips_head_bwd(const void* f0_bf16, const void* f1_bf16, const float* w, const float* g, void* df0_bf16,
+                        void* df1_bf16, int N, int HW, int C, const unsigned long long* seed, float p_drop,
+                        cudaStream_t stream);
+
 /* weight [Cout,Cin,R,S] fp32 (the nn.Conv2d parameter, model.py:43-47 etc.) -> the bf16 GEMM packings
  * fwd [Cout, R*S*Cin] and/or dgrad [Cin, R*S*Cout] in one pass (null = skip that packing). */
 int b2dq_pack_weights(const float* weight, void* fwd, void* dgrad, int Cout, int Cin, int R, int S,
