@@ -605,7 +605,9 @@ def run_real_loss(args):
     torch.manual_seed(2021)
     cfg = configs.stage1_config("dqvae-dual-r-05")
     cfg["params"]["lossconfig"] = configs.real_loss_config(configs._BUDGET_DUAL)
-    model = configs.build_model(cfg).to(dev).train()
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):      # the loss module prints a banner like the reference's
+        model = configs.build_model(cfg).to(dev).train()
     B = args.batch
     model.learning_rate = 4.5e-6 * B
     ae = [p for n, p in model.named_parameters() if not n.startswith("loss.") and p.requires_grad]
