@@ -175,6 +175,78 @@ print("CONFORMANCE_OK")
     assert "CONFORMANCE_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not mounted")
+def test_loss_overlay_conforms_to_the_reference_loss_module():
+    """modules.losses.vqperceptual_multidisc.VQLPIPSWithDiscriminator through the overlay, built from the
+    reference's own YAML lossconfig: same state_dict keys / shapes as the reference class (torchvision VGG16
+    without the pretrained file), same seeded discriminator initialisation, same loss helpers on CPU tensors."""
+    import subprocess
+    code = r'''
+import os, sys, yaml, torch
+os.environ["B200DQ_ALLOW_RANDOM_VGG"] = "1"
+sys.path.insert(0, %r); sys.path.insert(0, %r + "/dynamicvectorquantization_b200/overlay"); sys.path.append(%r)
+os.chdir(%r)
+from utils.utils import instantiate_from_config
+conf = yaml.safe_load(open("configs/stage1/dqvae-dual-r-05_imagenet.yml"))["model"]["params"]["lossconfig"]
+torch.manual_seed(3)
+mine = instantiate_from_config(conf)
+assert type(mine).__module__.startswith("dynamicvectorquantization_b200"), type(mine)
+assert type(mine.perceptual_loss).__module__.startswith("dynamicvectorquantization_b200")
+assert type(mine.discriminator).__module__.startswith("dynamicvectorquantization_b200")
+assert not mine.perceptual_loss.training and all(not p.requires_grad for p in mine.perceptual_loss.parameters())
+mk = {k: tuple(v.shape) for k, v in mine.state_dict().items()}
+md = {k: v.clone() for k, v in mine.discriminator.state_dict().items()}
+import dynamicvectorquantization_b200.nn.losses as L
+x, y = torch.randn(4, 1, 6, 6), torch.randn(4, 1, 6, 6)
+mine_vals = [float(L.hinge_d_loss(x, y)), float(L.vanilla_d_loss(x, y)), float(L.bce_discr_loss(x, y)),
+             float(L.hinge_g_loss(y)), float(L.bce_gen_loss(y)), L.adopt_weight(1.0, 3, threshold=5), L.adopt_weight(1.0, 7, threshold=5)]
+# the reference classes themselves
+sys.path = [p for p in sys.path if "overlay" not in p]
+for k in [k for k in sys.modules if k.split(".")[0] in ("modules", "models")]:
+    del sys.modules[k]
+import torchvision
+import modules.losses.lpips as ref_lpips
+tv = torchvision.models.vgg16
+class _M:
+    @staticmethod
+    def vgg16(pretrained=True):
+        return tv(weights=None)
+ref_lpips.models = _M
+torch.manual_seed(3)
+ref = instantiate_from_config(conf)
+assert type(ref).__module__ == "modules.losses.vqperceptual_multidisc"
+rk = {k: tuple(v.shape) for k, v in ref.state_dict().items()}
+assert mk == rk, sorted(set(mk.items()) ^ set(rk.items()))[:10]
+# lin heads come from the reference tree's modules/lpips/vgg.pth in both
+for k in range(5):
+    assert torch.equal(getattr(mine.perceptual_loss, "lin%%d" %% k).model[1].weight, getattr(ref.perceptual_loss, "lin%%d" %% k).model[1].weight)
+import modules.losses.vqperceptual_multidisc as R
+ref_vals = [float(R.hinge_d_loss(x, y)), float(R.vanilla_d_loss(x, y)), float(R.bce_discr_loss(x, y)),
+            float(R.hinge_g_loss(y)), float(R.bce_gen_loss(y)), R.adopt_weight(1.0, 3, threshold=5), R.adopt_weight(1.0, 7, threshold=5)]
+assert mine_vals == ref_vals, (mine_vals, ref_vals)
+# discriminator: identical module structure and init distribution (weights_init); same forward on CPU given same weights
+ref.discriminator.load_state_dict(md)
+from dynamicvectorquantization_b200.nn.discriminator import NLayerDiscriminator
+d2 = NLayerDiscriminator(input_nc=3, ndf=64, n_layers=3); d2.load_state_dict(md)
+img = torch.randn(2, 3, 64, 64)
+assert torch.equal(ref.discriminator.eval()(img), d2.eval()(img))
+print("LOSS_CONFORMANCE_OK")
+''' % (ROOT, ROOT, REF, REF)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900)
+    assert "LOSS_CONFORMANCE_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_lpips_refuses_to_run_without_weights_unless_told(monkeypatch, tmp_path):
+    """No silent random perceptual metric: without the pretrained files the constructor raises."""
+    import subprocess
+    code = "import os, sys; sys.path.insert(0, %r); os.chdir(%r); os.environ.pop('B200DQ_ALLOW_RANDOM_VGG', None)\n" \
+           "os.environ['TORCH_HOME'] = %r\n" \
+           "from dynamicvectorquantization_b200.nn.lpips import LPIPS\n" \
+           "try:\n    LPIPS()\n    print('BUILT')\nexcept RuntimeError as e:\n    print('RAISED', str(e)[:60])\n" % (ROOT, str(tmp_path), str(tmp_path))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert "RAISED" in r.stdout, r.stdout[-1000:] + r.stderr[-2000:]
+
+
 # ------------------------------------------------------------------------------- data parallel (gloo)
 def _ddp_worker(rank, world, port, q):
     import torch.distributed as dist
