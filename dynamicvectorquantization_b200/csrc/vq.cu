@@ -55,8 +55,45 @@ struct VqParams {
   unsigned long long* keys;      // [tiles*128] split mode: running min of (ordered d | index), preset to ~0
   unsigned int* tile_done;       // [tiles]     split mode: arrival counter, preset to 0xFFFFFFFF
   int N, C, K;
-  int splits;                    // CTAs sharing one row tile (1 = no split)
-  int ntiles_per_split;          // codebook tiles of 256 entries per split
+  // Work schedule (VqSched): `full_rounds` whole row tiles per CTA (tile = round * gridDim.x + blockIdx.x), then
+  // the remaining `tail_tiles` row tiles are cut stream-K style into runs of `tail_q` codebook tiles per CTA
+  // (a run may cover the end of one row tile and the start of the next).  tail_q == codebook tiles per row
+  // tile means "no split".  keys / tile_done are indexed by the tail-local tile.
+  int full_rounds, tail_tiles, tail_q;
+};
+
+struct VqItem {
+  int tile;      // row tile
+  int j0, j1;    // codebook tiles [j0, j1) of 256 entries
+  int nsplit;    // CTAs that share this row tile (1: this CTA owns it and gathers directly)
+  int tl;        // tail-local tile index (keys / tile_done slot) when nsplit > 1
+};
+// The same pure function of (blockIdx, ordinal) in every role of the CTA.
+struct VqSched {
+  int G, b, R, nn, q, tailbase, U, i, u, uend;
+  __device__ VqSched(const VqParams& p, int nn_)
+      : G(gridDim.x), b(blockIdx.x), R(p.full_rounds), nn(nn_), q(p.tail_q), tailbase(p.full_rounds * gridDim.x),
+        U(p.tail_tiles * nn_), i(0), u(0), uend(0) {}
+  __device__ bool next(VqItem& it) {
+    if (i < R) {
+      it.tile = i * G + b; it.j0 = 0; it.j1 = nn; it.nsplit = 1; it.tl = 0;
+      ++i;
+      return true;
+    }
+    if (i == R) {                       // enter the tail: this CTA's run of codebook-tile units
+      const long long u0 = static_cast<long long>(b) * q;
+      u = u0 < U ? static_cast<int>(u0) : U;
+      uend = min(U, u + q);
+      ++i;
+    }
+    if (u >= uend) return false;
+    const int tl = u / nn, j0 = u - tl * nn;
+    const int j1 = min(nn, j0 + (uend - u));
+    it.tile = tailbase + tl; it.j0 = j0; it.j1 = j1; it.tl = tl;
+    it.nsplit = ((tl + 1) * nn - 1) / q - (tl * nn) / q + 1;
+    u += j1 - j0;
+    return true;
+  }
 };
 
 __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* tm, int c0, int c1) {
@@ -193,8 +230,6 @@ vq_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int KC = p.C >> 6;
   const int num_m_tiles = (p.N + VQ_BM - 1) / VQ_BM;
   const int num_n_tiles = (p.K + VQ_BN - 1) / VQ_BN;
-  const int S = p.splits, per = p.ntiles_per_split;
-  const int total = num_m_tiles * S;                     // work items: (row tile, codebook split)
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < VQ_STAGES; ++i) {
@@ -225,13 +260,15 @@ vq_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       // ------------------------------------------------ TMA producer
       uint32_t stage = 0, phase = 0, it = 0;
-      for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
-        const int tile = w / S, sp = w - tile * S;
-        const int j0 = sp * per, j1 = min(num_n_tiles, j0 + per);
+      VqSched sched(p, num_n_tiles);
+      VqItem wi;
+      for (; sched.next(wi); ++it) {
+        const int tile = wi.tile, j0 = wi.j0, j1 = wi.j1;
         {  // rows of the next work item: HBM -> L2 now, L2 -> shared memory when the chunk frees up
-          const int wn = w + gridDim.x;
-          if (wn < total && wn / S != tile)
-            for (int kc = 0; kc < KC; ++kc) tma_prefetch_l2_2d(&tmA, kc * 64, (wn / S) * VQ_BM);
+          VqSched peek = sched;
+          VqItem nx;
+          if (peek.next(nx) && nx.tile != tile)
+            for (int kc = 0; kc < KC; ++kc) tma_prefetch_l2_2d(&tmA, kc * 64, nx.tile * VQ_BM);
         }
         for (int j = j0; j < j1; ++j)
           for (int kc = 0; kc < KC; ++kc) {
@@ -252,9 +289,10 @@ vq_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // ------------------------------------------------ MMA issuer
       constexpr uint32_t idesc = make_idesc_bf16(VQ_BM, VQ_BN, 0, 0);
       uint32_t stage = 0, phase = 0, it = 0, jj = 0;
-      for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
-        const int tile = w / S, sp = w - tile * S;
-        const int j0 = sp * per, j1 = min(num_n_tiles, j0 + per);
+      VqSched sched(p, num_n_tiles);
+      VqItem wi;
+      for (; sched.next(wi); ++it) {
+        const int j0 = wi.j0, j1 = wi.j1;
         for (int j = j0; j < j1; ++j, ++jj) {
           const uint32_t buf = jj & 1;
           mbar_wait(bar_tempty + 8 * buf, ((jj >> 1) & 1) ^ 1);
@@ -285,17 +323,25 @@ vq_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int row = q * 32 + lane;    // row of the tile owned by this thread
     float* my_sq = s_sq + ew * 256;   // two slots of 128 squared norms, private to this warp
     uint32_t jj = 0, it = 0;
+    VqSched sched(p, num_n_tiles);
+    VqItem wi;
     {
-      const int sp0 = blockIdx.x % S;   // blockIdx.x < total: the first work item always exists
-      const float4 v = __ldg(reinterpret_cast<const float4*>(p.cb_sqnorm + sp0 * per * VQ_BN + half * 128) + lane);
-      *reinterpret_cast<float4*>(my_sq + lane * 4) = v;
+      VqSched peek = sched;
+      VqItem first;
+      if (peek.next(first)) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(p.cb_sqnorm + first.j0 * VQ_BN + half * 128) + lane);
+        *reinterpret_cast<float4*>(my_sq + lane * 4) = v;
+      }
       __syncwarp();
     }
-    for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
-      const int tile = w / S, sp = w - tile * S;
-      const int j0 = sp * per, j1 = min(num_n_tiles, j0 + per);
-      const int wn = w + gridDim.x;
-      const int jnext_item = (wn < total) ? (wn % S) * per : -1;
+    for (; sched.next(wi); ++it) {
+      const int tile = wi.tile, j0 = wi.j0, j1 = wi.j1;
+      int jnext_item = -1;
+      {
+        VqSched peek = sched;
+        VqItem nx;
+        if (peek.next(nx)) jnext_item = nx.j0;
+      }
       float best = __int_as_float(0x7f800000);
       int bi = 0;
       for (int j = j0; j < j1; ++j, ++jj) {
@@ -340,14 +386,13 @@ vq_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // publish (min, argmin) of this work item to the gather warps
       const int par = it & 1;
       mbar_wait(bar_cempty + 8 * par, ((it >> 1) & 1) ^ 1);
-      if (S == 1) {
+      if (wi.nsplit == 1) {
         s_best[(par * 2 + half) * 128 + row] = best;
         s_idx[(par * 2 + half) * 128 + row] = bi;
       } else {
-        const long long grow = static_cast<long long>(tile) * VQ_BM + row;
-        if (grow < p.N)
-          atomicMin(p.keys + grow, (static_cast<unsigned long long>(ordered_bits(best)) << 32) |
-                                       static_cast<unsigned int>(bi));
+        if (static_cast<long long>(tile) * VQ_BM + row < p.N)
+          atomicMin(p.keys + static_cast<long long>(wi.tl) * VQ_BM + row,
+                    (static_cast<unsigned long long>(ordered_bits(best)) << 32) | static_cast<unsigned int>(bi));
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_cfull + 8 * par);
@@ -359,8 +404,11 @@ vq_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int gw = warp - (2 + VQ_SEARCH_WARPS);   // 0..7
     uint32_t it = 0;
     float loss_local = 0.f;
-    for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
-      const int tile = w / S;
+    VqSched sched(p, num_n_tiles);
+    VqItem wi;
+    for (; sched.next(wi); ++it) {
+      const int tile = wi.tile;
+      const int S = wi.nsplit;
       const int par = it & 1;
       mbar_wait(bar_cfull + 8 * par, (it >> 1) & 1);
       bool gather_here = true;
@@ -368,7 +416,7 @@ vq_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // the CTA that completes a tile's set of codebook splits gathers for it
         if (gw == 0 && lane == 0) {
           __threadfence();
-          const unsigned int prev = atomicAdd(p.tile_done + tile, 1u);   // preset 0xFFFFFFFF
+          const unsigned int prev = atomicAdd(p.tile_done + wi.tl, 1u);   // preset 0xFFFFFFFF
           s_flag[par] = (prev == static_cast<unsigned int>(S - 2)) ? 1 : 0;
           __threadfence();
         }
@@ -390,7 +438,9 @@ vq_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               const int i1 = s_idx[(par * 2 + 1) * 128 + r_in];
               idx[u] = (b1 < b0) ? i1 : i0;   // lower column half wins ties
             } else {
-              idx[u] = (row0 + u < p.N) ? static_cast<int>(__ldcg(p.keys + row0 + u) & 0xFFFFFFFFull) : 0;
+              idx[u] = (row0 + u < p.N)
+                           ? static_cast<int>(__ldcg(p.keys + static_cast<long long>(wi.tl) * VQ_BM + r_in) & 0xFFFFFFFFull)
+                           : 0;
             }
             if (idx[u] >= p.K || idx[u] < 0) idx[u] = 0;
           }
@@ -531,27 +581,53 @@ int b2dq_vq_prepare_codebook(const float* weight_f32, void* cb_bf16, float* cb_s
   return (int)cudaGetLastError();
 }
 
-// Split plan for small N: `splits` CTAs share one row tile, each searching a slice of the codebook.
-static void vq_split_plan(int N, int K, int max_ctas, int* splits, int* per) {
+// Work schedule (see VqSched): whole row tiles for `rounds` full waves of the grid, then the leftover row tiles
+// stream-K split into runs of `q` codebook tiles so that the last wave keeps every SM busy.  Covers both
+// "512 row tiles on 148 SMs" (3 full rounds + 68 tiles cut in halves: 3.5 rounds instead of 4) and the small-N
+// calls of the residual quantizer / stage-2 sampling (16 row tiles, 64 codebook tiles each -> 147 CTAs).
+struct VqPlan {
+  int grid, rounds, tail_tiles, q, split;   // split: some row tile is shared between CTAs (needs the workspace)
+};
+static VqPlan vq_plan(int N, int K, int max_ctas, bool allow_split) {
+  VqPlan pl;
   const int tiles = (N + VQ_BM - 1) / VQ_BM;
   const int nn = (K + VQ_BN - 1) / VQ_BN;
-  int ctas = num_sms();
-  if (max_ctas > 0 && max_ctas < ctas) ctas = max_ctas;
-  int s = 1;
-  if (tiles * 2 <= ctas && nn >= 2) s = ctas / tiles < nn ? ctas / tiles : nn;
-  int pr = (nn + s - 1) / s;
-  s = (nn + pr - 1) / pr;               // no empty split
-  *splits = s;
-  *per = pr;
+  int G = num_sms();
+  if (max_ctas > 0 && max_ctas < G) G = max_ctas;
+  if (G < 1) G = 1;
+  pl.rounds = tiles / G;
+  pl.tail_tiles = tiles - pl.rounds * G;
+  pl.q = nn;
+  pl.split = 0;
+  // a split tail costs tail_tiles/G of a round (plus the re-load of shared row tiles and the atomics)
+  // instead of a whole one: worth it when the tail leaves at least ~15 % of the SMs idle
+  // ... and when a row tile has enough codebook tiles to amortise what a shared tile costs (second load of its
+  // rows, 128 atomics per sharer, the workspace memset): measured on B200, K = 1024 (4 codebook tiles) loses
+  // (N = 32768: 38.8 vs 25.7 us), K >= 8192 gains 8-15 % and small-N calls 3.5-6x
+  if (allow_split && nn >= 8 && pl.tail_tiles > 0 && pl.tail_tiles * 20 <= G * 17) {
+    const long long U = (long long)pl.tail_tiles * nn;
+    int q = (int)((U + G - 1) / G);
+    if (q < 1) q = 1;
+    if (q < nn || q % nn) {
+      pl.q = q;
+      pl.split = 1;
+    }
+  }
+  if (pl.rounds > 0) {
+    pl.grid = G;
+  } else {
+    const long long U = (long long)pl.tail_tiles * nn;
+    pl.grid = (int)((U + pl.q - 1) / pl.q);
+  }
+  return pl;
 }
 
+// Scratch for the shared row tiles: an upper bound that holds for any max_ctas (0: never needed).
 int b2dq_vq_search_workspace_bytes(int N, int K) {
-  if (N <= 0 || K <= 0) return 0;
-  int s, per;
-  vq_split_plan(N, K, 0, &s, &per);
-  if (s <= 1) return 0;
+  if (N <= 0 || K <= 7 * VQ_BN) return 0;
   const int tiles = (N + VQ_BM - 1) / VQ_BM;
-  return tiles * VQ_BM * 8 + tiles * 4;
+  const int cap = tiles < 1024 ? tiles : 1024;   // the tail is shorter than one wave of the grid
+  return cap * VQ_BM * 8 + cap * 4;
 }
 
 int b2dq_vq_search_gather(const void* x_bf16, const float* x_f32, const void* cb_bf16,
@@ -598,29 +674,21 @@ int b2dq_vq_search_gather(const void* x_bf16, const float* x_f32, const void* cb
   p.keys = nullptr;
   p.tile_done = nullptr;
   p.N = N; p.C = C; p.K = K;
-  const int tiles = (N + VQ_BM - 1) / VQ_BM;
-  p.splits = 1;
-  p.ntiles_per_split = (K + VQ_BN - 1) / VQ_BN;
-  int grid = num_sms();
-  if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
-  if (workspace) {
-    int s, per;
-    vq_split_plan(N, K, max_ctas, &s, &per);
-    const int need = tiles * VQ_BM * 8 + tiles * 4;
-    if (s > 1) {
-      if (workspace_bytes < need) return -3;
-      if (reinterpret_cast<uintptr_t>(workspace) & 7) return -4;
-      p.splits = s;
-      p.ntiles_per_split = per;
-      p.keys = reinterpret_cast<unsigned long long*>(workspace);
-      p.tile_done = reinterpret_cast<unsigned int*>(p.keys + (size_t)tiles * VQ_BM);
-      // keys start at the largest key, arrival counters at 0xFFFFFFFF (first arrival reads it back)
-      cudaError_t e = cudaMemsetAsync(workspace, 0xFF, need, stream);
-      if (e != cudaSuccess) return (int)e;
-    }
+  VqPlan pl = vq_plan(N, K, max_ctas, workspace != nullptr);
+  if (pl.split) {
+    const int need = pl.tail_tiles * VQ_BM * 8 + pl.tail_tiles * 4;
+    if (workspace_bytes < need) return -3;
+    if (reinterpret_cast<uintptr_t>(workspace) & 7) return -4;
+    p.keys = reinterpret_cast<unsigned long long*>(workspace);
+    p.tile_done = reinterpret_cast<unsigned int*>(p.keys + (size_t)pl.tail_tiles * VQ_BM);
+    // keys start at the largest key, arrival counters at 0xFFFFFFFF (first arrival reads it back)
+    cudaError_t e = cudaMemsetAsync(workspace, 0xFF, need, stream);
+    if (e != cudaSuccess) return (int)e;
   }
-  const int items = tiles * p.splits;
-  if (items < grid) grid = items;
+  p.full_rounds = pl.rounds;
+  p.tail_tiles = pl.tail_tiles;
+  p.tail_q = pl.q;
+  const int grid = pl.grid;
   vq_search_kernel<<<grid, VQ_THREADS, VQ_SMEM, stream>>>(tmA, tmB, p);
   return (int)cudaGetLastError();
 }

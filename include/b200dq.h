@@ -44,11 +44,12 @@ int b2dq_vq_prepare_codebook(const float* weight_f32, void* cb_bf16, float* cb_s
  *   loss_acc   optional [1], += sum_rows mask * sum_c (e - x)^2
  *   counts [K] / sums [K,C]: optional, += per-code row count / row sum (training mode)
  *   max_ctas   0 = one CTA per SM
- *   workspace  optional scratch of b2dq_vq_search_workspace_bytes(N, K) bytes (8 B aligned).  With
- *              it, a call whose row tiles would leave more than half of the SMs idle (residual
- *              quantizer depth loop quantize_rqvae.py:237-271, stage-2 sampling) splits the
- *              codebook over several CTAs per row tile; results are identical. */
-int b2dq_vq_search_workspace_bytes(int N, int K);   /* 0: a split would not help */
+ *   workspace  optional scratch of b2dq_vq_search_workspace_bytes(N, K) bytes (8 B aligned).  With it and
+ *              K >= 2048, the row tiles left over after the full waves of the grid - all of them for the small
+ *              N of the residual quantizer depth loop (quantize_rqvae.py:237-271) or stage-2 sampling - are cut
+ *              stream-K style into runs of codebook tiles shared between CTAs (64-bit atomicMin of ordered
+ *              distance | index, the last CTA of a row tile gathers); results are identical. */
+int b2dq_vq_search_workspace_bytes(int N, int K);   /* 0: K < 2048, a shared row tile would not pay */
 int b2dq_vq_search_gather(const void* x_bf16, const float* x_f32, const void* cb_bf16,
                           const float* cb_sqnorm, const float* weight_f32, const float* row_mask,
                           long long* codes, void* xq_bf16, float* xq_f32, float* loss_acc,

@@ -135,7 +135,7 @@ def test_vq_search_many_tiles_per_cta(N, K, C, max_ctas, x_f32):
     _vq_check(x, w, mask, K, C, out, x_f32=x_f32)
 
 
-@pytest.mark.parametrize("N,K,C", [(2048, 16384, 256), (300, 4096, 256), (64, 1024, 128), (1, 512, 64),
+@pytest.mark.parametrize("N,K,C", [(2048, 16384, 256), (300, 4096, 256), (64, 2048, 128), (1, 1800, 64),
                                    (1100, 5000, 192)])
 def test_vq_search_codebook_split(N, K, C):
     """Small N: the codebook is split over several CTAs per row tile (64-bit atomicMin of ordered distance |
@@ -150,6 +150,23 @@ def test_vq_search_codebook_split(N, K, C):
     for _ in range(3):                                 # arrival order of the splits must not matter
         c = _vq_run(kn, x, w, mask, K, C, split=True)
         assert torch.equal(a[0], c[0]) and torch.equal(a[3], c[3])
+
+
+@pytest.mark.parametrize("N,K,C,x_f32", [(65536, 2048, 256, False), (32768, 2304, 256, True), (32768, 2048, 128, False),
+                                         (40000, 8192, 64, False), (19000, 4096, 64, True)])
+def test_vq_search_stream_k_tail(N, K, C, x_f32):
+    """Large N: the row tiles left over after the full waves are cut into runs of codebook tiles (a run may span
+    two row tiles), so that the last wave keeps every SM busy.  Codes, gathered rows and statistics must equal the
+    unsplit search and the oracle."""
+    from dynamicvectorquantization_b200 import kernels as kn
+    x, w, mask = _vq_case(N, K, C, N + K + 1)
+    a = _vq_run(kn, x, w, mask, K, C, x_f32=x_f32, split=True)
+    b = _vq_run(kn, x, w, mask, K, C, x_f32=x_f32, split=False)
+    assert torch.equal(a[0], b[0]), "stream-K and unsplit searches disagree"
+    assert torch.equal(a[3], b[3])
+    _vq_check(x, w, mask, K, C, a, x_f32=x_f32)
+    c = _vq_run(kn, x, w, mask, K, C, x_f32=x_f32, split=True, max_ctas=37)     # a different cut of the same work
+    assert torch.equal(a[0], c[0])
 
 
 def test_vq_search_exact_ties_lowest_index_wins():
