@@ -376,6 +376,113 @@ def conv_wgrad(x, dy, ksize, stride, want_bias=False):
     return dw, db
 
 
+# ------------------------------------------------------------------------------------------ upsample + conv
+# nearest-neighbour x2 followed by a 3x3 convolution (model.py:49-53) = four 2x2 convolutions of the LOW-resolution
+# input, one per output parity class (ph, pw): output row 2i+ph reads low-res rows {i-1: r=0 | i: r=1,2} for ph = 0
+# and {i: r=0,1 | i+1: r=2} for ph = 1 (same for columns), so the nine taps collapse onto four whose weights are
+# sums of the original ones.  16 tap-GEMM steps per low-res pixel instead of 36, and the upsampled tensor is never
+# written.  _UP_M[ph, a, r] = 1 when filter row r lands on low-res offset a of parity ph.
+_UP_M = ((( 1, 0, 0), (0, 1, 1)), ((1, 1, 0), (0, 0, 1)))
+_UP_OFF = ((-1, 0), (0, 1))                     # low-res offset of slot a for parity ph
+
+
+_up_m_cache = {}
+
+
+def _up_m(ref):
+    """_UP_M as a tensor on ref's device (cached: no host-to-device copy inside a CUDA-graph capture)."""
+    key = (ref.device, ref.dtype)
+    if key not in _up_m_cache:
+        _up_m_cache[key] = torch.tensor(_UP_M, dtype=ref.dtype, device=ref.device)
+    return _up_m_cache[key]
+
+
+def upconv_fold(w):
+    """OIHW fp32 [Cout,Cin,3,3] -> folded weights [2(ph),2(pw),2(a),2(b),Cout,Cin] (fp32)."""
+    m = _up_m(w)
+    return torch.einsum("par,qbs,oirs->pqaboi", m, m, w)
+
+
+def upconv_unfold_grad(dwf):
+    """Gradient w.r.t. the folded weights [2,2,2,2,Cout,Cin] -> gradient w.r.t. the 3x3 weights (OIHW)."""
+    m = _up_m(dwf)
+    return torch.einsum("par,qbs,pqaboi->oirs", m, m, dwf).contiguous()
+
+
+def upconv_pack(w):
+    """-> (fwd [Cout, 16*Cin], dgrad [Cin, 16*Cout]) bf16; column block ((ph*2+pw)*2+a)*2+b."""
+    wf = upconv_fold(w.detach().float())
+    co, ci = w.shape[0], w.shape[1]
+    fwd = wf.permute(4, 0, 1, 2, 3, 5).reshape(co, 16 * ci).to(BF16).contiguous()
+    dgr = wf.permute(5, 0, 1, 2, 3, 4).reshape(ci, 16 * co).to(BF16).contiguous()
+    return fwd, dgr
+
+
+def upconv_fwd(x, wpack_fwd, bias, cout):
+    """x NHWC bf16 [N,H,W,Cin] -> conv3x3(upsample2x(x)) [N,2H,2W,Cout] as four parity-class tap GEMMs."""
+    nb, h, w, cin = x.shape
+    assert cin % 64 == 0
+    out = torch.empty(nb, 2 * h, 2 * w, cout, dtype=BF16, device=x.device)
+    dims, strs = nhwc_view(x)
+    for ph in (0, 1):
+        for pw in (0, 1):
+            cls = ph * 2 + pw
+            taps = [(0, _UP_OFF[pw][b], 0, _UP_OFF[ph][a], ((cls * 2 + a) * 2 + b) * cin)
+                    for a in (0, 1) for b in (0, 1)]
+            tapgemm(x, dims, strs, wpack_fwd, cout, 16 * cin, taps, cin // 64, out, (ph * 2 * w + pw) * cout,
+                    (4 * h * w * cout, 4 * w * cout, 2 * cout), w, h, nb, cout, bias=bias)
+    return out
+
+
+def upconv_dgrad(dy, wpack_dgrad, cin):
+    """dy NHWC bf16 [N,2H,2W,Cout] -> gradient w.r.t. the low-resolution input [N,H,W,Cin]: one 16-tap GEMM
+    over the parity view of dy."""
+    nb, h2, w2, cout = dy.shape
+    h, w = h2 // 2, w2 // 2
+    assert cout % 64 == 0
+    dx = torch.empty(nb, h, w, cin, dtype=BF16, device=dy.device)
+    dims, strs = parity_view(dy)
+    taps = []
+    for ph in (0, 1):
+        for pw in (0, 1):
+            cls = ph * 2 + pw
+            for a in (0, 1):
+                for b in (0, 1):
+                    # y[2i+ph, 2j+pw] reads x[i+dh, j+dw]  =>  dx[i, j] gathers dy[2(i-dh)+ph, 2(j-dw)+pw]
+                    taps.append((pw * cout, -_UP_OFF[pw][b], ph, -_UP_OFF[ph][a], ((cls * 2 + a) * 2 + b) * cout))
+    tapgemm(dy, dims, strs, wpack_dgrad, cin, 16 * cout, taps, cout // 64, dx, 0, (h * w * cin, w * cin, cin), w, h,
+            nb, cin)
+    return dx
+
+
+def upconv_wgrad(x, dy, want_bias=False):
+    """dW (fp32 OIHW [Cout,Cin,3,3]) [+ db] of conv3x3(upsample2x(x)): per parity class a 4-tap weight-gradient
+    GEMM of the strided class view of dy against the low-resolution x, unfolded onto the nine filter taps."""
+    nb, h, w, cin = x.shape
+    cout = dy.shape[-1]
+    bdims, bstrs = nhwc_view(x)
+    kw, kh, kn = tile_shape(w, h, nb, pixels=64)
+    ktw, kth = (w + kw - 1) // kw, (h + kh - 1) // kh
+    kblocks = ktw * kth * ((nb + kn - 1) // kn)
+    mt, nt = (cout + 127) // 128, (cin + 127) // 128
+    splits = _wgrad_splits(kblocks, mt * nt * 4)
+    dy6 = dy.view(nb, h, 2, w, 2, cout)
+    dwf = torch.empty(2, 2, 2, 2, cout, cin, dtype=torch.float32, device=x.device)
+    for ph in (0, 1):
+        for pw in (0, 1):
+            dyc = dy6[:, :, ph, :, pw, :]                     # [N,H,W,Cout] view, pixel stride 2*Cout
+            adims = (cout, w, 1, h, nb)
+            astrs = (1, 2 * cout, 2 * w * cout, 4 * w * cout, 4 * h * w * cout)
+            taps = [(0, _UP_OFF[pw][b], 0, _UP_OFF[ph][a]) for a in (0, 1) for b in (0, 1)]
+            partial = torch.empty(splits, 4, cout, cin, dtype=torch.float32, device=x.device)
+            mmgemm(dyc, adims, astrs, True, x, bdims, bstrs, True, cout, cin, kblocks, partial,
+                   (4 * cout * cin, cout * cin, cin), taps=taps, kbox=(kw, kh, kn), ktiles=(ktw, kth), splits=splits,
+                   out_f32=True, block_n=128, taps_per_cta=1)
+            dwf[ph, pw] = partial.sum(0).view(2, 2, cout, cin)
+    dw = upconv_unfold_grad(dwf)
+    return (dw, bias_grad(dy)) if want_bias else dw
+
+
 def bias_grad(dy):
     cch = dy.shape[-1]
     rows = dy.numel() // cch

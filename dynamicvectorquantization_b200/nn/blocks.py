@@ -42,6 +42,9 @@ class Upsample(_Nhwc):
             self.conv = torch.nn.Conv2d(in_channels, in_channels, kernel_size=3, stride=1, padding=1)
 
     def forward_nhwc(self, x):
+        if self.with_conv and ops.FOLD_UPSAMPLE and x.shape[-1] % 64 == 0 and self.conv.out_channels % 64 == 0:
+            # nearest x2 + conv3x3 as four 2x2 convolutions of the low-resolution input (2.25x fewer FLOPs)
+            return ops.UpsampleConvFn.apply(x, self.conv.weight, self.conv.bias)
         x = ops.Upsample2xFn.apply(x)
         if self.with_conv:
             x = ops.conv2d(x, self.conv)

@@ -15,6 +15,8 @@ from . import kernels as kn
 
 BF16 = torch.bfloat16
 
+FOLD_UPSAMPLE = True   # Upsample(with_conv): four parity-class 2x2 convolutions instead of upsample + conv3x3
+
 # GroupNorm statistics produced by the epilogue of the conv that made a tensor: (weakref(tensor), stats).
 # Consumed by the very next gn_swish on THAT tensor object; anything else recomputes them.
 _pending_stats = None
@@ -39,6 +41,11 @@ def _packed(weight, kind):
         if need_other:
             cache[other] = (stamp, dgr if other == "dgrad" else fwd)
         p = fwd if kind == "fwd" else dgr
+    elif kind in ("up_fwd", "up_dgrad"):            # nearest x2 + conv3x3 folded to four 2x2 parity convolutions
+        fwd, dgr = kn.upconv_pack(w)
+        other = "up_dgrad" if kind == "up_fwd" else "up_fwd"
+        cache[other] = (stamp, dgr if other == "up_dgrad" else fwd)
+        p = fwd if kind == "up_fwd" else dgr
     elif kind == "fwd":
         p = kn.pack_weight_fwd(w)
     elif kind == "dgrad":
@@ -347,6 +354,35 @@ class Upsample2xFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         return kn.upsample2x_bwd(g.contiguous())
+
+
+class UpsampleConvFn(torch.autograd.Function):
+    """conv3x3(nearest_upsample_x2(x)) + bias (Upsample.forward, model.py:49-53) without materialising the
+    upsampled tensor: four 2x2 parity-class convolutions of the low-resolution input (kernels.upconv_*)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        y = kn.upconv_fwd(x, _packed(weight, "up_fwd"), _f32(bias), weight.shape[0])
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = kn.upconv_dgrad(dy, _packed(weight, "up_dgrad"), weight.shape[1])
+        want_db = ctx.has_bias and ctx.needs_input_grad[2]
+        if ctx.needs_input_grad[1]:
+            if want_db:
+                dw, db = kn.upconv_wgrad(x, dy, want_bias=True)
+            else:
+                dw = kn.upconv_wgrad(x, dy)
+        elif want_db:
+            db = kn.bias_grad(dy)
+        return dx, dw, db
 
 
 class ToNHWCFn(torch.autograd.Function):

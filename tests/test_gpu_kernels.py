@@ -424,3 +424,37 @@ def test_bias_grad_matches_fp32_sum():
         got = kn.bias_grad(dy.cuda().view(1, rows, 1, c)).cpu()
         ref = dy.double().sum(0)
         assert float((got.double() - ref).abs().max()) <= 2e-4 * float(dy.double().abs().sum(0).max())
+
+
+@pytest.mark.parametrize("nb,h,w,cin,cout", [(2, 16, 16, 256, 256), (1, 32, 32, 128, 128), (2, 8, 24, 64, 128),
+                                             (3, 64, 64, 128, 128)])
+def test_folded_upsample_conv_matches_upsample_then_conv(nb, h, w, cin, cout):
+    """Upsample(with_conv) as four 2x2 parity-class convolutions of the low-resolution input (kernels.upconv_*)
+    against fp32 F.conv2d(F.interpolate(x, 2, 'nearest')) on the same bf16-rounded operands: output, dX, dW, db."""
+    from dynamicvectorquantization_b200 import ops
+    g = torch.Generator().manual_seed(nb * h + cin)
+    x = _rand_bf(nb, h, w, cin, seed=1)
+    wt = (torch.randn(cout, cin, 3, 3, generator=g) * (cin * 9) ** -0.5)
+    b = torch.randn(cout, generator=g) * 0.1
+    dy = _rand_bf(nb, 2 * h, 2 * w, cout, seed=2)
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = wt.to(BF).float().requires_grad_(True)          # the 3x3 taps as the unfolded bf16 path would see them
+    br = b.clone().requires_grad_(True)
+    ref = F.conv2d(F.interpolate(xr, scale_factor=2.0, mode="nearest"), wr, br, padding=1)
+    ref.backward(dy.float().permute(0, 3, 1, 2))
+    xd = x.cuda().requires_grad_(True)
+    wd = wt.cuda().requires_grad_(True)
+    bd = b.cuda().requires_grad_(True)
+    y = ops.UpsampleConvFn.apply(xd, wd, bd)
+    y.backward(dy.cuda())
+    assert y.shape == (nb, 2 * h, 2 * w, cout)
+    assert rel_rms(y, ref.detach().permute(0, 2, 3, 1)) < 1e-2
+    assert rel_rms(xd.grad, xr.grad.permute(0, 2, 3, 1)) < 1e-2
+    assert rel_rms(wd.grad, wr.grad) < 1e-2
+    assert rel_rms(bd.grad, br.grad) < 1e-2
+    # and against the unfolded kernels (upsample2x + conv3x3): same result up to bf16 rounding
+    x2 = x.cuda().requires_grad_(True)
+    w2 = wt.cuda().requires_grad_(True)
+    y2 = ops.Conv2dFn.apply(ops.Upsample2xFn.apply(x2), w2, b.cuda(), None, 3, 1)
+    y2.backward(dy.cuda())
+    assert rel_rms(y, y2) < 1e-2 and rel_rms(xd.grad, x2.grad) < 1.5e-2 and rel_rms(wd.grad, w2.grad) < 1e-2
