@@ -12,6 +12,7 @@ those files.
 """
 import math
 
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -272,20 +273,29 @@ def entropy_router(entropy, threshold):
     return torch.cat([coarse, fine], dim=-1)
 
 
-def patch_entropy(x, patch=16):
-    """models/stage1_dynamic/dqvae_dual_entropy.py:25-63 (32 bins on [-1,1], sigma 0.01, eps 1e-40)."""
+def patch_entropy(x, patch=16, lo=-1.0):
+    """models/stage1_dynamic/dqvae_dual_entropy.py:25-63 (32 bins on [-1,1], sigma 0.01, eps 1e-40).  lo=0.0 gives
+    the variant of scripts/tools/calculate_entropy_thresholds.py:65-79, whose bins span [0,1]."""
     b = x.shape[0]
     gray = 0.2989 * x[:, 0:1] + 0.5870 * x[:, 1:2] + 0.1140 * x[:, 2:]
     u = F.unfold(gray, kernel_size=patch, stride=patch).transpose(1, 2)      # [b, P, patch*patch]
     nper = u.shape[1]
     u = u.reshape(b * nper, -1)
-    bins = torch.linspace(-1, 1, 32, device=x.device)
+    bins = torch.linspace(lo, 1, 32, device=x.device)
     k = torch.exp(-0.5 * ((u.unsqueeze(2) - bins.view(1, 1, -1)) / torch.tensor(0.01)).pow(2))
     pdf = k.mean(dim=1)
     pdf = pdf / (pdf.sum(dim=1, keepdim=True) + 1e-40) + 1e-40
     ent = -(pdf * torch.log(pdf)).sum(dim=1)
     hw = x.shape[-1] // patch
     return ent.reshape(b, hw, hw)
+
+
+def entropy_thresholds(batches, patch=16):
+    """scripts/tools/calculate_entropy_thresholds.py:95-117: patch entropies (bins on [0,1]) of every batch, sorted;
+    threshold "i" (i = 1..99) = sorted[(size * i) // 100]."""
+    ent = np.sort(np.concatenate([patch_entropy(b, patch, lo=0.0).reshape(-1).numpy() for b in batches]))
+    size = ent.shape[0]
+    return {str(i + 1): float(ent[int((size * (i + 1)) // 100)]) for i in range(99)}
 
 
 def dual_encoder(sd, cfg, x, x_entropy=None, forced_gate=None, entropy_threshold=None, p="encoder"):

@@ -433,8 +433,43 @@ def loss_goldens():
     save("loss_small.npz", **out)
 
 
+def threshold_inputs(seed=3, n_batches=3, b=4, res=64, patch=16):
+    """Seeded image batches in [0,1] mixing noise and flat patches (regenerated by the tests)."""
+    g = torch.Generator().manual_seed(seed)
+    k = res // patch
+    out = []
+    for _ in range(n_batches):
+        x = torch.rand(b, 3, res, res, generator=g)
+        flat = torch.rand(b, 3, k, k, generator=g).repeat_interleave(patch, 2).repeat_interleave(patch, 3)
+        pick = (torch.rand(b, 1, k, k, generator=g) > 0.5).float().repeat_interleave(patch, 2).repeat_interleave(patch, 3)
+        out.append(pick * x + (1 - pick) * flat)
+    return out
+
+
+def threshold_goldens():
+    """scripts/tools/calculate_entropy_thresholds.py of the reference: its Entropy class (bins on [0,1]) and its
+    percentile procedure (:95-117), run on seeded batches (the data-set loaders are not importable offline)."""
+    src = open(os.path.join(REF, "scripts/tools/calculate_entropy_thresholds.py")).read().split("if __name__")[0]
+    src = src.replace("from data.imagenet_lmdb import Imagenet_LMDB", "").replace("from data.ffhq_lmdb import FFHQ_LMDB", "")
+    ns = {}
+    exec(compile(src, "calculate_entropy_thresholds", "exec"), ns)
+    model = ns["Entropy"](16, 64, 64)
+    with torch.no_grad():
+        for i, image in enumerate(threshold_inputs()):
+            if i == 0:
+                entropy_numpy = model(image).view(-1).cpu().numpy()
+            else:
+                entropy_numpy = np.concatenate((entropy_numpy, model(image).view(-1).cpu().numpy()))
+    entropy_numpy = np.sort(entropy_numpy)
+    size = entropy_numpy.shape[0]
+    th = np.array([entropy_numpy[int((size * (i + 1)) // 100)] for i in range(99)], dtype=np.float32)
+    save("entropy_thresholds.npz", thresholds=th, entropies=entropy_numpy)
+
+
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["vq", "family", "permuter", "tiny", "dual", "variants", "loss"]
+    what = sys.argv[1:] or ["vq", "family", "permuter", "tiny", "dual", "variants", "loss", "thresholds"]
+    if "thresholds" in what:
+        threshold_goldens()
     if "loss" in what:
         loss_goldens()
     if "variants" in what:

@@ -244,3 +244,28 @@ def test_patch_entropy_kernel_matches_oracle(patch, size, batch):
     assert float(ref.min()) < 0.1 < 2.5 < float(ref.max()) or patch == 4      # both regimes are present
     with pytest.raises(RuntimeError):
         mod(x)                                                                 # no CPU fallback
+
+
+def test_entropy_threshold_tool_matches_the_reference_procedure(tmp_path):
+    """nn/thresholds.py (fused entropy kernel, bins on [0,1], device-side sort) against the oracle restatement of
+    scripts/tools/calculate_entropy_thresholds.py and the fixture minted from the reference tool itself, on images
+    that mix flat and noise patches."""
+    import json
+    import os
+    import numpy as np
+    from dynamicvectorquantization_b200.nn.thresholds import EntropyThresholds
+    from oracle import dqvae_oracle as orc
+    from test_oracle_golden import _threshold_inputs
+    batches = _threshold_inputs()
+    acc = EntropyThresholds(patch_size=16, image_size=64)
+    for b in batches:
+        acc.update(b.cuda())
+    got = acc.thresholds()
+    ref = orc.entropy_thresholds(batches, patch=16)
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "entropy_thresholds.npz"))["thresholds"]
+    assert list(got) == [str(i) for i in range(1, 100)]
+    for i, k in enumerate(ref):
+        assert abs(got[k] - ref[k]) <= 2e-4 * abs(ref[k]) + 2e-5, (k, got[k], ref[k])
+        assert abs(got[k] - float(gold[i])) <= 2e-4 * abs(float(gold[i])) + 2e-5, (k, got[k], float(gold[i]))
+    acc.save(str(tmp_path / "t.json"))
+    assert json.load(open(tmp_path / "t.json"))["50"] == got["50"]

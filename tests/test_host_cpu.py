@@ -247,6 +247,73 @@ def test_lpips_refuses_to_run_without_weights_unless_told(monkeypatch, tmp_path)
     assert "RAISED" in r.stdout, r.stdout[-1000:] + r.stderr[-2000:]
 
 
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not mounted")
+def test_reference_checkpoint_loads_through_init_from_ckpt(tmp_path):
+    """Checkpoint I/O conformance: a Lightning-style checkpoint {"state_dict": ...} written from
+    the REFERENCE's modules (encoder, decoder, quantizer, 1x1 convs, loss incl. LPIPS + discriminator) loads into
+    the overlay model through the reference's own ckpt_path / ignore_keys arguments (dqvae_dual_feat.py:36-57),
+    tensor for tensor, and round-trips back into the reference modules."""
+    import subprocess
+    code = r'''
+import os, sys, types, yaml, torch, torch.nn as nn
+os.environ["B200DQ_ALLOW_RANDOM_VGG"] = "1"
+ROOT, REF, TMP = %r, %r, %r
+sys.path.insert(0, ROOT); sys.path.append(REF); os.chdir(REF)
+pl = types.ModuleType("pytorch_lightning"); pl.LightningModule = nn.Module; sys.modules["pytorch_lightning"] = pl
+import torchvision
+import modules.losses.lpips as ref_lpips
+tv = torchvision.models.vgg16
+class _M:
+    @staticmethod
+    def vgg16(pretrained=True):
+        return tv(weights=None)
+ref_lpips.models = _M
+from utils.utils import instantiate_from_config
+conf = yaml.safe_load(open("configs/stage1/dqvae-dual-r-05_imagenet.yml"))["model"]
+p = conf["params"]
+torch.manual_seed(11)
+parts = {"encoder": instantiate_from_config(p["encoderconfig"]), "decoder": instantiate_from_config(p["decoderconfig"]),
+         "quantize": instantiate_from_config(p["vqconfig"]), "loss": instantiate_from_config(p["lossconfig"]),
+         "quant_conv": nn.Conv2d(256, 256, 1), "post_quant_conv": nn.Conv2d(256, 256, 1)}
+assert type(parts["encoder"]).__module__ == "modules.dynamic_modules.EncoderDual"          # the reference's classes
+sd = {}
+for name, m in parts.items():
+    with torch.no_grad():
+        for t in m.state_dict().values():
+            if t.dtype.is_floating_point:
+                t.add_(torch.randn_like(t) * 0.01)                                           # a "trained" state
+    sd.update({name + "." + k: v.clone() for k, v in m.state_dict().items()})
+ckpt = os.path.join(TMP, "last.ckpt")
+torch.save({"state_dict": sd, "epoch": 3, "global_step": 1234}, ckpt)
+# ---- now the overlay
+for k in [k for k in sys.modules if k.split(".")[0] in ("modules", "models")]:
+    del sys.modules[k]
+sys.path.insert(0, ROOT + "/dynamicvectorquantization_b200/overlay")
+conf2 = yaml.safe_load(open("configs/stage1/dqvae-dual-r-05_imagenet.yml"))["model"]
+conf2["params"]["ckpt_path"] = ckpt
+model = instantiate_from_config(conf2)
+assert type(model).__module__.startswith("dynamicvectorquantization_b200")
+mine = model.state_dict()
+assert set(mine) == set(sd), sorted(set(mine) ^ set(sd))[:10]
+bad = [k for k in sd if not torch.equal(mine[k], sd[k])]
+assert not bad, bad[:10]
+# ignore_keys drops whole sub-trees, as in the reference
+conf3 = yaml.safe_load(open("configs/stage1/dqvae-dual-r-05_imagenet.yml"))["model"]
+conf3["params"].update(ckpt_path=ckpt, ignore_keys=["loss.discriminator", "quantize"])
+torch.manual_seed(5)
+m3 = instantiate_from_config(conf3).state_dict()
+assert torch.equal(m3["encoder.conv_in.weight"], sd["encoder.conv_in.weight"])
+assert not torch.equal(m3["loss.discriminator.main.0.weight"], sd["loss.discriminator.main.0.weight"])
+assert not torch.equal(m3["quantize.codebook.weight"], sd["quantize.codebook.weight"])
+# and back: the overlay's state_dict loads into the reference modules strictly
+for name, m in parts.items():
+    m.load_state_dict({k[len(name) + 1:]: v for k, v in mine.items() if k.startswith(name + ".")}, strict=True)
+print("CKPT_CONFORMANCE_OK")
+''' % (ROOT, REF, str(tmp_path))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900)
+    assert "CKPT_CONFORMANCE_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
 # ------------------------------------------------------------------------------- data parallel (gloo)
 def _ddp_worker(rank, world, port, q):
     import torch.distributed as dist

@@ -282,3 +282,23 @@ def test_loss_oracle_matches_reference(mode):
         close(gr.norm(), "gd_norm_" + short, rtol=2e-3, atol=1e-7)
     close(gd[names.index("loss.discriminator.main.0.weight")], "gd_main.0.weight", rtol=2e-3,
           atol=2e-3 * float(np.abs(g[mode + "_gd_main.0.weight"]).max()))
+
+
+def _threshold_inputs(seed=3, n_batches=3, b=4, res=64, patch=16):
+    g = torch.Generator().manual_seed(seed)
+    k = res // patch
+    out = []
+    for _ in range(n_batches):
+        x = torch.rand(b, 3, res, res, generator=g)
+        flat = torch.rand(b, 3, k, k, generator=g).repeat_interleave(patch, 2).repeat_interleave(patch, 3)
+        pick = (torch.rand(b, 1, k, k, generator=g) > 0.5).float().repeat_interleave(patch, 2).repeat_interleave(patch, 3)
+        out.append(pick * x + (1 - pick) * flat)
+    return out
+
+
+def test_entropy_threshold_oracle_matches_reference_tool():
+    """orc.entropy_thresholds vs the reference's scripts/tools/calculate_entropy_thresholds.py procedure."""
+    g = np.load(os.path.join(G, "entropy_thresholds.npz"))
+    th = orc.entropy_thresholds(_threshold_inputs(), patch=16)
+    got = np.array([th[str(i)] for i in range(1, 100)], dtype=np.float32)
+    assert np.allclose(got, g["thresholds"], rtol=1e-6, atol=1e-7)
