@@ -246,6 +246,7 @@ def test_patch_entropy_kernel_matches_oracle(patch, size, batch):
         mod(x)                                                                 # no CPU fallback
 
 
+@pytest.mark.gpu
 def test_entropy_threshold_tool_matches_the_reference_procedure(tmp_path):
     """nn/thresholds.py (fused entropy kernel, bins on [0,1], device-side sort) against the oracle restatement of
     scripts/tools/calculate_entropy_thresholds.py and the fixture minted from the reference tool itself, on images
