@@ -10,8 +10,6 @@ none of which the hand-written kernels cover yet; it runs on PyTorch's CUDA ops 
 torch's cuDNN default).  The perceptual term - the FLOP-heavy part of the loss - is on the tensor-core
 path (``nn/lpips.py``).
 """
-import functools
-
 import torch.nn as nn
 
 
@@ -25,35 +23,32 @@ def weights_init(m):
 
 
 class NLayerDiscriminator(nn.Module):
-    """PatchGAN discriminator as in Pix2Pix (discriminator/model.py:17-67)."""
+    """PatchGAN discriminator as in Pix2Pix (discriminator/model.py:17-67): a stem convolution, `n_layers - 1`
+    stride-2 stages and one stride-1 stage of conv4x4 -> norm -> LeakyReLU(0.2) with widths ndf * min(2^n, 8), and a
+    one-channel conv4x4 head.  ``main`` holds the same modules at the same indices as the reference's Sequential."""
 
     def __init__(self, input_nc=3, ndf=64, n_layers=3, use_actnorm=False):
         super().__init__()
-        if not use_actnorm:
-            norm_layer = nn.BatchNorm2d
-        else:
+        if use_actnorm:
             try:
                 from utils.utils import ActNorm          # reference tree (falls through the overlay)
             except Exception as e:
                 raise NotImplementedError("use_actnorm=True needs the reference's utils.utils.ActNorm on sys.path") from e
             norm_layer = ActNorm
-        if type(norm_layer) == functools.partial:
-            use_bias = norm_layer.func != nn.BatchNorm2d
         else:
-            use_bias = norm_layer != nn.BatchNorm2d
-        kw, padw = 4, 1
-        sequence = [nn.Conv2d(input_nc, ndf, kernel_size=kw, stride=2, padding=padw), nn.LeakyReLU(0.2, True)]
-        nf_mult = 1
-        for n in range(1, n_layers):
-            nf_mult_prev, nf_mult = nf_mult, min(2 ** n, 8)
-            sequence += [nn.Conv2d(ndf * nf_mult_prev, ndf * nf_mult, kernel_size=kw, stride=2, padding=padw,
-                                   bias=use_bias),
-                         norm_layer(ndf * nf_mult), nn.LeakyReLU(0.2, True)]
-        nf_mult_prev, nf_mult = nf_mult, min(2 ** n_layers, 8)
-        sequence += [nn.Conv2d(ndf * nf_mult_prev, ndf * nf_mult, kernel_size=kw, stride=1, padding=padw, bias=use_bias),
-                     norm_layer(ndf * nf_mult), nn.LeakyReLU(0.2, True)]
-        sequence += [nn.Conv2d(ndf * nf_mult, 1, kernel_size=kw, stride=1, padding=padw)]
-        self.main = nn.Sequential(*sequence)
+            norm_layer = nn.BatchNorm2d
+        conv_bias = norm_layer is not nn.BatchNorm2d      # BatchNorm brings its own shift (:30-33)
+        widths = [ndf * min(2 ** n, 8) for n in range(n_layers + 1)]
+        strides = [2] * (n_layers - 1) + [1]
+
+        def conv(cin, cout, stride, bias=True):
+            return nn.Conv2d(cin, cout, kernel_size=4, stride=stride, padding=1, bias=bias)
+
+        layers = [conv(input_nc, widths[0], 2), nn.LeakyReLU(0.2, True)]
+        for cin, cout, stride in zip(widths[:-1], widths[1:], strides):
+            layers += [conv(cin, cout, stride, bias=conv_bias), norm_layer(cout), nn.LeakyReLU(0.2, True)]
+        layers.append(conv(widths[-1], 1, 1))             # one prediction per receptive-field patch
+        self.main = nn.Sequential(*layers)
 
     def forward(self, input):
         return self.main(input)

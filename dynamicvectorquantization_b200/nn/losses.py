@@ -1,14 +1,23 @@
 """Stage-1 training loss: L1 + LPIPS + adaptive-weight PatchGAN + codebook + budget terms.
 
-Mirror of ``modules/losses/vqperceptual_multidisc.py`` (reference): helper losses (:17-47) and
-``VQLPIPSWithDiscriminator`` (:50-194) with the same constructor arguments, attribute / sub-module names
-(``perceptual_loss``, ``discriminator``, ``budget_loss``) and ``forward`` contract
-``forward(codebook_loss, inputs, reconstructions, optimizer_idx, global_step, last_layer=None, cond=None,
-split="train", gate=None) -> (loss, log dict)``.
+Public surface of ``modules/losses/vqperceptual_multidisc.py`` (reference): the GAN loss helpers (:17-47) and
+``VQLPIPSWithDiscriminator`` (:50-194) - same constructor arguments, same attribute / sub-module names
+(``perceptual_loss``, ``discriminator``, ``budget_loss`` ...), same call contract
 
-Differences in HOW (results identical): the perceptual term runs on the tensor-core kernels
-(``nn/lpips.py``); in the discriminator pass (``optimizer_idx == 1``) the reference also evaluates L1 +
-LPIPS and then discards them (:116-124 run before the branch) - here they are skipped.
+    loss, log = module(codebook_loss, inputs, reconstructions, optimizer_idx, global_step,
+                       last_layer=None, cond=None, split="train", gate=None)
+
+and the same keys in the returned log dict.  The body is organised around the two passes Lightning drives
+(``optimizer_idx`` 0 = autoencoder, 1 = discriminator) instead of one long branch:
+
+* ``_autoencoder_pass``: nll = mean(|x - xrec| + w_p * LPIPS(x, xrec)) (:116-124), g = GAN loss of D(xrec)
+  (:127-135), adaptive weight |d nll / d last_layer| / (|d g / d last_layer| + 1e-4) clamped to [0, 1e4] and to
+  ``disc_weight_max`` (:102-113,137-146), total = nll + d_weight * disc_factor * g + codebook_weight *
+  mean(codebook_loss) [+ budget(gate)] (:148-153);
+* ``_discriminator_pass``: disc_factor * GAN loss of D(x.detach()), D(xrec.detach()) (:178-187).  The reference
+  evaluates L1 + LPIPS before branching and discards them in this pass; they are not computed here.
+
+The perceptual term runs on the tensor-core kernels (``nn/lpips.py``).
 """
 import torch
 import torch.nn as nn
@@ -24,40 +33,46 @@ except Exception:
 
 
 class DummyLoss(nn.Module):
-    def __init__(self):
-        super().__init__()
+    """Placeholder loss (vqperceptual_multidisc.py:13-15)."""
 
 
 def adopt_weight(weight, global_step, threshold=0, value=0.):
-    if global_step < threshold:
-        weight = value
-    return weight
+    """`value` until `threshold` steps have passed, `weight` afterwards (:17-20)."""
+    return value if global_step < threshold else weight
 
 
 def log(t, eps=1e-10):
-    return torch.log(t + eps)
+    return (t + eps).log()
 
 
+# ---- GAN objectives (:25-47); *_d_* take (logits_real, logits_fake), *_g_* / *_gen_* take logits_fake
 def hinge_d_loss(logits_real, logits_fake):
-    loss_real = torch.mean(F.relu(1. - logits_real))
-    loss_fake = torch.mean(F.relu(1. + logits_fake))
-    return 0.5 * (loss_real + loss_fake)
+    real_term = F.relu(1. - logits_real).mean()
+    fake_term = F.relu(1. + logits_fake).mean()
+    return 0.5 * (real_term + fake_term)
 
 
 def hinge_g_loss(logits_fake):
-    return -torch.mean(logits_fake)
+    return -logits_fake.mean()
 
 
 def vanilla_d_loss(logits_real, logits_fake):
-    return 0.5 * (torch.mean(F.softplus(-logits_real)) + torch.mean(F.softplus(logits_fake)))
+    return 0.5 * (F.softplus(-logits_real).mean() + F.softplus(logits_fake).mean())
 
 
 def bce_discr_loss(logits_real, logits_fake):
-    return (-log(1 - torch.sigmoid(logits_fake)) - log(torch.sigmoid(logits_real))).mean()
+    return (-log(1 - logits_fake.sigmoid()) - log(logits_real.sigmoid())).mean()
 
 
 def bce_gen_loss(logits_fake):
-    return -log(torch.sigmoid(logits_fake)).mean()
+    return -log(logits_fake.sigmoid()).mean()
+
+
+_GAN_OBJECTIVES = {                      # name -> (discriminator objective, generator objective)   (:78-88)
+    "hinge": (hinge_d_loss, hinge_g_loss),
+    "vanilla": (vanilla_d_loss, hinge_g_loss),
+    "bce": (bce_discr_loss, bce_gen_loss),
+}
 
 
 class VQLPIPSWithDiscriminator(nn.Module):
@@ -65,95 +80,97 @@ class VQLPIPSWithDiscriminator(nn.Module):
                  disc_factor=1.0, disc_weight=1.0, perceptual_weight=1.0, disc_conditional=False,
                  disc_adaptive_loss=True, disc_loss="hinge", disc_weight_max=None, budget_loss_config=None):
         super().__init__()
-        assert disc_loss in ["hinge", "vanilla", "bce"]
-        self.codebook_weight = codebook_weight
+        if disc_loss not in _GAN_OBJECTIVES:
+            raise AssertionError(f"Unknown GAN loss '{disc_loss}'.")
+        self.disc_loss, self.gen_loss = _GAN_OBJECTIVES[disc_loss]
+        # reconstruction / perceptual term
         self.pixel_weight = pixelloss_weight
-        self.perceptual_loss = LPIPS().eval()
         self.perceptual_weight = perceptual_weight
-        self.discriminator_iter_start = disc_start
+        self.perceptual_loss = LPIPS().eval()
+        self.codebook_weight = codebook_weight
+        # adversarial term
         self.discriminator = instantiate_from_config(disc_config)
         if disc_init:
             self.discriminator = self.discriminator.apply(weights_init)
-        if disc_loss == "hinge":
-            self.disc_loss, self.gen_loss = hinge_d_loss, hinge_g_loss
-        elif disc_loss == "vanilla":
-            self.disc_loss, self.gen_loss = vanilla_d_loss, hinge_g_loss
-        else:
-            self.disc_loss, self.gen_loss = bce_discr_loss, bce_gen_loss
-        print(f"VQLPIPSWithDiscriminator running with {disc_loss} loss.")
+        self.discriminator_iter_start = disc_start
         self.disc_factor = disc_factor
         self.discriminator_weight = disc_weight
-        self.disc_conditional = disc_conditional
-        self.disc_adaptive_loss = disc_adaptive_loss
         self.disc_weight_max = disc_weight_max
+        self.disc_adaptive_loss = disc_adaptive_loss
+        self.disc_conditional = disc_conditional
+        # grain budget term
         self.budget_loss_config = budget_loss_config
         if budget_loss_config is not None:
             self.budget_loss = instantiate_from_config(budget_loss_config)
+        print(f"VQLPIPSWithDiscriminator running with {disc_loss} loss.")
 
+    # ------------------------------------------------------------------ pieces
     def calculate_adaptive_weight(self, nll_loss, g_loss, last_layer=None):
-        if last_layer is not None:
-            nll_grads = torch.autograd.grad(nll_loss, last_layer, retain_graph=True)[0]
-            g_grads = torch.autograd.grad(g_loss, last_layer, retain_graph=True)[0]
+        """Balance of the two gradients that reach the decoder's last layer (:102-113)."""
+        layer = last_layer if last_layer is not None else self.last_layer[0]
+        nll_grads, g_grads = (torch.autograd.grad(term, layer, retain_graph=True)[0] for term in (nll_loss, g_loss))
+        ratio = nll_grads.norm() / (g_grads.norm() + 1e-4)
+        return ratio.clamp(0.0, 1e4).detach() * self.discriminator_weight
+
+    def _logits(self, images, cond):
+        if cond is None:
+            assert not self.disc_conditional
+            return self.discriminator(images)
+        assert self.disc_conditional
+        return self.discriminator(torch.cat((images, cond), dim=1))
+
+    def _disc_factor(self, global_step):
+        return adopt_weight(self.disc_factor, global_step, threshold=self.discriminator_iter_start)
+
+    # ------------------------------------------------------------------ optimizer_idx == 0
+    def _autoencoder_pass(self, codebook_loss, inputs, reconstructions, global_step, last_layer, cond, split, gate):
+        inputs, reconstructions = inputs.contiguous(), reconstructions.contiguous()
+        rec_loss = (inputs - reconstructions).abs()
+        if self.perceptual_weight > 0:
+            p_loss = self.perceptual_loss(inputs, reconstructions)
+            rec_loss = rec_loss + self.perceptual_weight * p_loss
         else:
-            nll_grads = torch.autograd.grad(nll_loss, self.last_layer[0], retain_graph=True)[0]
-            g_grads = torch.autograd.grad(g_loss, self.last_layer[0], retain_graph=True)[0]
-        d_weight = torch.norm(nll_grads) / (torch.norm(g_grads) + 1e-4)
-        d_weight = torch.clamp(d_weight, 0.0, 1e4).detach()
-        return d_weight * self.discriminator_weight
+            p_loss = torch.tensor([0.0])
+        nll_loss = rec_loss.mean()
+        g_loss = self.gen_loss(self._logits(reconstructions, cond))
+
+        if self.disc_adaptive_loss:
+            try:
+                d_weight = self.calculate_adaptive_weight(nll_loss, g_loss, last_layer=last_layer)
+            except RuntimeError:                      # no graph to differentiate (evaluation)
+                assert not self.training
+                d_weight = torch.tensor(0.0)
+            if self.disc_weight_max is not None:
+                d_weight.clamp_max_(self.disc_weight_max)
+        else:
+            d_weight = torch.tensor(self.disc_weight_max)
+
+        disc_factor = self._disc_factor(global_step)
+        quant_loss = codebook_loss.mean()
+        loss = nll_loss + d_weight * disc_factor * g_loss + self.codebook_weight * quant_loss
+        terms = dict(quant_loss=quant_loss.detach(), nll_loss=nll_loss.detach().mean(),
+                     rec_loss=rec_loss.detach().mean(), p_loss=p_loss.detach().mean(), d_weight=d_weight.detach(),
+                     disc_factor=torch.tensor(disc_factor), g_loss=g_loss.detach().mean())
+        if gate is not None and self.budget_loss_config is not None:
+            budget_loss = self.budget_loss(gate=gate)
+            loss = loss + budget_loss
+            terms["budget_loss"] = budget_loss.detach().mean()
+        terms["total_loss"] = loss.clone().detach().mean()
+        return loss, {f"{split}_{name}": value for name, value in terms.items()}
+
+    # ------------------------------------------------------------------ optimizer_idx == 1
+    def _discriminator_pass(self, inputs, reconstructions, global_step, cond, split):
+        logits_real = self._logits(inputs.contiguous().detach(), cond)
+        logits_fake = self._logits(reconstructions.contiguous().detach(), cond)
+        d_loss = self._disc_factor(global_step) * self.disc_loss(logits_real, logits_fake)
+        terms = dict(disc_loss=d_loss.clone().detach().mean(), logits_real=logits_real.detach().mean(),
+                     logits_fake=logits_fake.detach().mean())
+        return d_loss, {f"{split}_{name}": value for name, value in terms.items()}
 
     def forward(self, codebook_loss, inputs, reconstructions, optimizer_idx, global_step, last_layer=None,
                 cond=None, split="train", gate=None):
         if optimizer_idx == 0:
-            rec_loss = torch.abs(inputs.contiguous() - reconstructions.contiguous())
-            if self.perceptual_weight > 0:
-                p_loss = self.perceptual_loss(inputs.contiguous(), reconstructions.contiguous())
-                rec_loss = rec_loss + self.perceptual_weight * p_loss
-            else:
-                p_loss = torch.tensor([0.0])
-            nll_loss = torch.mean(rec_loss)
-            if cond is None:
-                assert not self.disc_conditional
-                logits_fake = self.discriminator(reconstructions.contiguous())
-            else:
-                assert self.disc_conditional
-                logits_fake = self.discriminator(torch.cat((reconstructions.contiguous(), cond), dim=1))
-            g_loss = self.gen_loss(logits_fake)
-            if self.disc_adaptive_loss:
-                try:
-                    d_weight = self.calculate_adaptive_weight(nll_loss, g_loss, last_layer=last_layer)
-                except RuntimeError:
-                    assert not self.training
-                    d_weight = torch.tensor(0.0)
-                if self.disc_weight_max is not None:
-                    d_weight.clamp_max_(self.disc_weight_max)
-            else:
-                d_weight = torch.tensor(self.disc_weight_max)
-            disc_factor = adopt_weight(self.disc_factor, global_step, threshold=self.discriminator_iter_start)
-            loss = nll_loss + d_weight * disc_factor * g_loss + self.codebook_weight * codebook_loss.mean()
-            log_d = {"{}_quant_loss".format(split): codebook_loss.detach().mean(),
-                     "{}_nll_loss".format(split): nll_loss.detach().mean(),
-                     "{}_rec_loss".format(split): rec_loss.detach().mean(),
-                     "{}_p_loss".format(split): p_loss.detach().mean(),
-                     "{}_d_weight".format(split): d_weight.detach(),
-                     "{}_disc_factor".format(split): torch.tensor(disc_factor),
-                     "{}_g_loss".format(split): g_loss.detach().mean()}
-            if gate is not None and self.budget_loss_config is not None:
-                budget_loss = self.budget_loss(gate=gate)
-                loss = loss + budget_loss
-                log_d["{}_budget_loss".format(split)] = budget_loss.detach().mean()
-            log_d["{}_total_loss".format(split)] = loss.clone().detach().mean()
-            return loss, log_d
-
+            return self._autoencoder_pass(codebook_loss, inputs, reconstructions, global_step, last_layer, cond,
+                                          split, gate)
         if optimizer_idx == 1:
-            if cond is None:
-                logits_real = self.discriminator(inputs.contiguous().detach())
-                logits_fake = self.discriminator(reconstructions.contiguous().detach())
-            else:
-                logits_real = self.discriminator(torch.cat((inputs.contiguous().detach(), cond), dim=1))
-                logits_fake = self.discriminator(torch.cat((reconstructions.contiguous().detach(), cond), dim=1))
-            disc_factor = adopt_weight(self.disc_factor, global_step, threshold=self.discriminator_iter_start)
-            d_loss = disc_factor * self.disc_loss(logits_real, logits_fake)
-            log_d = {"{}_disc_loss".format(split): d_loss.clone().detach().mean(),
-                     "{}_logits_real".format(split): logits_real.detach().mean(),
-                     "{}_logits_fake".format(split): logits_fake.detach().mean()}
-            return d_loss, log_d
+            return self._discriminator_pass(inputs, reconstructions, global_step, cond, split)

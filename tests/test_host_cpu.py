@@ -314,6 +314,67 @@ print("CKPT_CONFORMANCE_OK")
     assert "CKPT_CONFORMANCE_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
+@pytest.mark.parametrize("mode", ["eval", "train"])
+def test_loss_module_host_logic_matches_reference_golden(monkeypatch, mode):
+    """The loss module's own logic (adaptive weight, clamps, hinge terms, budget, BatchNorm bookkeeping, log keys)
+    on CPU: the perceptual term - the only part that needs the CUDA kernels - is replaced by the pinned fp32 oracle,
+    everything else runs as shipped and must reproduce the fixture minted from the reference's class."""
+    monkeypatch.setenv("B200DQ_ALLOW_RANDOM_VGG", "1")
+    import torch.nn.functional as F
+    from dynamicvectorquantization_b200 import configs
+    from dynamicvectorquantization_b200.nn.losses import VQLPIPSWithDiscriminator
+    from oracle import loss_oracle as lo
+    configs.activate_overlay()
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "loss_small.npz"))
+    disc_cfg = {"target": "modules.discriminator.model.NLayerDiscriminator",
+                "params": {"input_nc": 3, "ndf": 64, "n_layers": 3, "use_actnorm": False}}
+    loss = VQLPIPSWithDiscriminator(disc_start=0, disc_config=disc_cfg, disc_init=True, disc_weight_max=0.75,
+                                    budget_loss_config=configs._BUDGET_DUAL)
+    sd = lo.make_loss_weights(seed=21)
+    loss.load_state_dict({k[len("loss."):]: v for k, v in sd.items()}, strict=False)
+    loss.train(mode == "train")
+    monkeypatch.setattr(loss.perceptual_loss, "forward", lambda a, b: lo.lpips(sd, a, b))
+    x, feat, w_last, qloss, gate = lo.toy_inputs()
+    w_last.requires_grad_(True)
+    feat.requires_grad_(True)
+    xrec = F.conv2d(feat, w_last, padding=1)
+    l0, log0 = loss(qloss, x, xrec, 0, 0, last_layer=w_last, split="train", gate=gate)
+    gw, gf = torch.autograd.grad(l0, [w_last, feat])
+    p = mode + "_"
+
+    def close(a, key, rtol=2e-4, atol=1e-7):
+        b = gold[p + key]
+        a = a.detach().numpy() if torch.is_tensor(a) else np.asarray(a)
+        assert np.allclose(a, b, rtol=rtol, atol=atol), (key, float(np.abs(a - b).max()))
+    close(l0, "loss0")
+    assert sorted(log0) == sorted("train_" + k[len(p + "log0_"):] for k in gold.files if k.startswith(p + "log0_"))
+    for k in gold.files:
+        if k.startswith(p + "log0_"):
+            close(log0["train_" + k[len(p + "log0_"):]], k[len(p):], rtol=1e-3)
+    close(gw, "g_w_last", rtol=2e-3, atol=1e-6 * float(np.abs(gold[p + "g_w_last"]).max()) + 1e-9)
+    close(gf, "g_feat", rtol=2e-3, atol=2e-3 * float(np.abs(gold[p + "g_feat"]).max()))
+    l1, log1 = loss(qloss, x, xrec.detach(), 1, 0, last_layer=w_last, split="train")
+    close(l1, "loss1")
+    assert sorted(log1) == ["train_disc_loss", "train_logits_fake", "train_logits_real"]
+    close(log1["train_logits_real"], "log1_logits_real", atol=1e-6)
+    dparams = dict(loss.discriminator.named_parameters())
+    for k, gr in zip(dparams, torch.autograd.grad(l1, list(dparams.values()))):
+        close(gr.norm(), "gd_norm_" + k, rtol=2e-3, atol=1e-7)
+    if mode == "train":
+        for k, v in loss.state_dict().items():
+            if "running" in k:
+                close(v, "bn1_" + k, rtol=1e-4, atol=1e-6)
+    # evaluation without a graph: the adaptive weight falls back to 0 like the reference (:139-142)
+    loss.eval()
+    with torch.no_grad():
+        lv, logv = loss(qloss, x, xrec.detach(), 0, 0, last_layer=w_last, split="val", gate=gate)
+    assert float(logv["val_d_weight"]) == 0.0 and torch.isfinite(lv)
+    # discriminator warm-up: before disc_start the adversarial factor is 0
+    loss.discriminator_iter_start = 10
+    _, logw = loss(qloss, x, F.conv2d(feat, w_last, padding=1), 0, 3, last_layer=w_last, split="train", gate=gate)
+    assert float(logw["train_disc_factor"]) == 0.0
+
+
 # ------------------------------------------------------------------------------- data parallel (gloo)
 def _ddp_worker(rank, world, port, q):
     import torch.distributed as dist
