@@ -56,6 +56,7 @@ _vp, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 SIGNATURES = {
     "b2dq_version": [],
     "b2dq_vq_prepare_codebook": [_vp, _vp, _vp, _i, _i, _vp],
+    "b2dq_vq_search_plan": [_i, _i, _i, _i, C.POINTER(C.c_int)],
     "b2dq_vq_search_workspace_bytes": [_i, _i],      # returns a byte count, not a status
     "b2dq_vq_search_gather": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                               _i, _i, _i, _i, _vp, _i, _vp],

@@ -588,12 +588,10 @@ int b2dq_vq_prepare_codebook(const float* weight_f32, void* cb_bf16, float* cb_s
 struct VqPlan {
   int grid, rounds, tail_tiles, q, split;   // split: some row tile is shared between CTAs (needs the workspace)
 };
-static VqPlan vq_plan(int N, int K, int max_ctas, bool allow_split) {
+static VqPlan vq_plan_for(int N, int K, int G, bool allow_split) {
   VqPlan pl;
   const int tiles = (N + VQ_BM - 1) / VQ_BM;
   const int nn = (K + VQ_BN - 1) / VQ_BN;
-  int G = num_sms();
-  if (max_ctas > 0 && max_ctas < G) G = max_ctas;
   if (G < 1) G = 1;
   pl.rounds = tiles / G;
   pl.tail_tiles = tiles - pl.rounds * G;
@@ -620,6 +618,21 @@ static VqPlan vq_plan(int N, int K, int max_ctas, bool allow_split) {
     pl.grid = (int)((U + pl.q - 1) / pl.q);
   }
   return pl;
+}
+
+static VqPlan vq_plan(int N, int K, int max_ctas, bool allow_split) {
+  int G = num_sms();
+  if (max_ctas > 0 && max_ctas < G) G = max_ctas;
+  return vq_plan_for(N, K, G, allow_split);
+}
+
+// The schedule a launch on `num_ctas` CTAs would use: out5 = {grid, full_rounds, tail_tiles, tail_q, split}.
+// Host-only (no device needed): lets callers and tests inspect the stream-K cut.
+int b2dq_vq_search_plan(int N, int K, int num_ctas, int allow_split, int* out5) {
+  if (N <= 0 || K <= 0 || num_ctas <= 0 || !out5) return -1;
+  const VqPlan pl = vq_plan_for(N, K, num_ctas, allow_split != 0);
+  out5[0] = pl.grid; out5[1] = pl.rounds; out5[2] = pl.tail_tiles; out5[3] = pl.q; out5[4] = pl.split;
+  return 0;
 }
 
 // Scratch for the shared row tiles: an upper bound that holds for any max_ctas (0: never needed).

@@ -49,6 +49,8 @@ int b2dq_vq_prepare_codebook(const float* weight_f32, void* cb_bf16, float* cb_s
  *              N of the residual quantizer depth loop (quantize_rqvae.py:237-271) or stage-2 sampling - are cut
  *              stream-K style into runs of codebook tiles shared between CTAs (64-bit atomicMin of ordered
  *              distance | index, the last CTA of a row tile gathers); results are identical. */
+int b2dq_vq_search_plan(int N, int K, int num_ctas, int allow_split, int* out5 /* host: grid, full rounds,
+                        tail row tiles, codebook tiles per tail run, split flag */);
 int b2dq_vq_search_workspace_bytes(int N, int K);   /* 0: K < 2048, a shared row tile would not pay */
 int b2dq_vq_search_gather(const void* x_bf16, const float* x_f32, const void* cb_bf16,
                           const float* cb_sqnorm, const float* weight_f32, const float* row_mask,

@@ -375,6 +375,70 @@ def test_loss_module_host_logic_matches_reference_golden(monkeypatch, mode):
     assert float(logw["train_disc_factor"]) == 0.0
 
 
+# ------------------------------------------------------------------------------- VQ work schedule
+def _vq_items(n_tiles_codebook, plan, cta):
+    """Python mirror of VqSched::next (csrc/vq.cu): the (row tile, j0, j1, nsplit, tail slot) items of one CTA."""
+    grid, rounds, tail_tiles, q, _ = plan
+    nn = n_tiles_codebook
+    items = [(r * grid + cta, 0, nn, 1, 0) for r in range(rounds)]
+    U = tail_tiles * nn
+    u = min(cta * q, U)
+    uend = min(U, u + q)
+    while u < uend:
+        tl, j0 = divmod(u, nn)
+        j1 = min(nn, j0 + (uend - u))
+        nsplit = ((tl + 1) * nn - 1) // q - (tl * nn) // q + 1
+        items.append((rounds * grid + tl, j0, j1, nsplit, tl))
+        u += j1 - j0
+    return items
+
+
+@pytest.mark.parametrize("G", [148, 132, 37, 7, 1])
+def test_vq_stream_k_schedule_covers_every_tile_exactly_once(G):
+    """The schedule b2dq_vq_search_plan hands the kernel: every (row tile, codebook tile) unit is searched exactly
+    once, a CTA never sees a row tile twice, nsplit equals the number of CTAs that really share the tile (the
+    arrival counter's target), tail slots stay inside the workspace, and a split is only planned where it pays."""
+    import ctypes
+    from dynamicvectorquantization_b200 import _cabi, build
+    build.build()
+    lib = _cabi.lib()
+    out = (ctypes.c_int * 5)()
+    cases = [(65536, 1024), (65536, 8192), (65536, 16384), (32768, 2048), (32768, 2304), (40000, 8192), (2048, 16384),
+             (256, 16384), (1, 1800), (300, 4096), (1100, 5000), (19000, 4096), (128 * G, 4096), (128 * G + 1, 4096),
+             (128 * (2 * G - 1), 2048), (5000, 256), (77, 300)]
+    for N, K in cases:
+        for allow in (0, 1):
+            assert lib.b2dq_vq_search_plan(N, K, G, allow, out) == 0
+            plan = tuple(out)
+            grid, rounds, tail_tiles, q, split = plan
+            tiles, nn = -(-N // 128), -(-K // 256)
+            assert 1 <= grid <= G and rounds * grid + tail_tiles == tiles, (N, K, G, plan)
+            if not allow or nn < 8:
+                assert not split and q == nn
+            seen = {}
+            sharers = {}
+            for cta in range(grid):
+                mine = _vq_items(nn, plan, cta)
+                assert len({it[0] for it in mine}) == len(mine), "a CTA got the same row tile twice"
+                for tile, j0, j1, nsplit, tl in mine:
+                    assert 0 <= j0 < j1 <= nn and tile < tiles
+                    for j in range(j0, j1):
+                        assert (tile, j) not in seen, (N, K, G, tile, j)
+                        seen[(tile, j)] = cta
+                    sharers.setdefault(tile, []).append((nsplit, tl))
+                    if nsplit > 1:
+                        assert split and 0 <= tl < tail_tiles
+                        assert lib.b2dq_vq_search_workspace_bytes(N, K) >= tail_tiles * 128 * 8 + tail_tiles * 4
+                    else:
+                        assert (j0, j1) == (0, nn), "an unshared tile must be searched whole by its CTA"
+            assert len(seen) == tiles * nn, (N, K, G, plan, len(seen))
+            for tile, lst in sharers.items():
+                assert all(ns == len(lst) for ns, _ in lst), (N, K, G, tile, lst)
+            if split:                                  # the cut must shorten the last wave
+                longest = max(sum(j1 - j0 for _, j0, j1, _, _ in _vq_items(nn, plan, c)) for c in range(grid))
+                assert longest < (rounds + 1) * nn
+
+
 # ------------------------------------------------------------------------------- data parallel (gloo)
 def _ddp_worker(rank, world, port, q):
     import torch.distributed as dist
