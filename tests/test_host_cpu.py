@@ -375,6 +375,49 @@ def test_loss_module_host_logic_matches_reference_golden(monkeypatch, mode):
     assert float(logw["train_disc_factor"]) == 0.0
 
 
+# ------------------------------------------------------------------------------- folded upsample + conv
+def test_upsample_conv_fold_is_exact_in_fp32():
+    """The algebra behind kernels.upconv_*: conv3x3(nearest_upsample_x2(x)) equals, per output parity class, a 2x2
+    convolution of the low-resolution input with the folded weights and offsets _UP_OFF (fp32 identity), the
+    un-fold maps gradients back onto the 3x3 taps, and the bf16 packings address the blocks the tap tables name."""
+    import torch.nn.functional as F
+    from dynamicvectorquantization_b200 import kernels as kn
+    g = torch.Generator().manual_seed(0)
+    n, ci, co, h, w = 2, 5, 4, 6, 7
+    x = torch.randn(n, ci, h, w, generator=g)
+    wt = torch.randn(co, ci, 3, 3, generator=g, requires_grad=True)
+    ref = F.conv2d(F.interpolate(x, scale_factor=2.0, mode="nearest"), wt, padding=1)
+    wf = kn.upconv_fold(wt)
+    wf.retain_grad()
+    xp = F.pad(x, (1, 1, 1, 1))
+    out = torch.zeros_like(ref)
+    for ph in (0, 1):
+        for pw in (0, 1):
+            acc = 0
+            for a in (0, 1):
+                for b in (0, 1):
+                    dh, dw = kn._UP_OFF[ph][a], kn._UP_OFF[pw][b]
+                    acc = acc + torch.einsum("nihw,oi->nohw", xp[:, :, 1 + dh:1 + dh + h, 1 + dw:1 + dw + w], wf[ph, pw, a, b])
+            out[:, :, ph::2, pw::2] = acc
+    assert torch.allclose(out, ref, atol=1e-5)
+    up = torch.randn(ref.shape, generator=g)
+    (gref,) = torch.autograd.grad((ref * up).sum(), wt, retain_graph=True)
+    (out * up).sum().backward()
+    assert torch.allclose(kn.upconv_unfold_grad(wf.grad), gref, atol=1e-4)
+    assert torch.allclose(wt.grad, gref, atol=1e-4)
+    # packings: column block ((ph*2+pw)*2+a)*2+b of the forward pack is wf[ph,pw,a,b] (Cout x Cin), of the data-gradient
+    # pack its transpose
+    fwd, dgr = kn.upconv_pack(wt)
+    assert fwd.shape == (co, 16 * ci) and dgr.shape == (ci, 16 * co) and fwd.dtype == torch.bfloat16
+    for ph in (0, 1):
+        for pw in (0, 1):
+            for a in (0, 1):
+                for b in (0, 1):
+                    blk = ((ph * 2 + pw) * 2 + a) * 2 + b
+                    assert torch.equal(fwd[:, blk * ci:(blk + 1) * ci], wf[ph, pw, a, b].detach().to(torch.bfloat16))
+                    assert torch.equal(dgr[:, blk * co:(blk + 1) * co], wf[ph, pw, a, b].detach().t().to(torch.bfloat16))
+
+
 # ------------------------------------------------------------------------------- VQ work schedule
 def _vq_items(n_tiles_codebook, plan, cta):
     """Python mirror of VqSched::next (csrc/vq.cu): the (row tile, j0, j1, nsplit, tail slot) items of one CTA."""
