@@ -347,7 +347,7 @@ def run_b200(args):
         pass
     ips = world * B * args.steps / (ms / 1e3)
     ips_e2e = world * B * args.steps / (ms_e2e / 1e3)
-    roof, roof_vq = kernel_rooflines(torch, kn, dev, peaks)
+    roof, roof_vq = kernel_rooflines(torch, kn, dev, peaks, with_cpu=(world == 1 and not args.no_cpu_baseline))
     line = {"metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -370,7 +370,7 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-def kernel_rooflines(torch, kn, dev, peaks):
+def kernel_rooflines(torch, kn, dev, peaks, with_cpu=False):
     """Live CUDA-event timing (current stream) of the dominant kernel of the step - the 3x3
     128->128 convolution at 256x256, batch 32 (77 + 135 GF/img of the 393 GF/img forward are this
     shape) - and of the VQ search kernel at the microbench shape."""
@@ -453,6 +453,8 @@ def kernel_rooflines(torch, kn, dev, peaks):
     # distances + argmin of a bounded row sample against the K=1024 codebook, scaled to rows/s
     vq_cpu = None
     try:
+        if not with_cpu:
+            raise RuntimeError("skipped (N > 1 or --no-cpu-baseline)")
         import numpy as np
         from oracle import vq_oracle as vo
         rows = 8192
