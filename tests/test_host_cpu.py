@@ -127,6 +127,13 @@ def test_configs_match_reference_yaml(name, yml):
     for key in ("quant_before_dim", "quant_after_dim", "quant_sample_temperature", "image_key", "monitor",
                 "warmup_epochs", "scheduler_type"):
         assert mine["params"][key] == ref["params"][key], key
+    # the real loss (bench.py --loss real, tests/test_gpu_loss.py) is the YAML's lossconfig, budget term included
+    budget = ref["params"]["lossconfig"]["params"].get("budget_loss_config")
+    assert configs.real_loss_config(budget) == ref["params"]["lossconfig"], name
+    if name == "dqvae-dual-r-05":
+        assert configs._BUDGET_DUAL == budget
+    if name == "dqvae-triple-r-03-03":
+        assert configs._BUDGET_TRIPLE == budget
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not mounted")
