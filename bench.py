@@ -40,8 +40,12 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="images per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget-s", type=float, default=150.0, help="--impl reference: wall-clock bound of the run")
+    ap.add_argument("--cpu-sample-batch", type=int, default=2, help="--impl reference: images per CPU step")
     ap.add_argument("--config", default="dqvae-dual-r-05", choices=sorted(WORKLOADS),
                     help="headline = dqvae-dual-r-05; the others are parity-test configs that can be timed too")
+    ap.add_argument("--no-real-loss", action="store_true",
+                    help="N=1: do not append the `real_loss_step` object (a short `--loss real` run in a child process)")
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph (N=1)")
     ap.add_argument("--loss", default="surrogate", choices=["surrogate", "real"],
                     help="real: time the reference's full training_step (both optimizer passes, LPIPS + PatchGAN + "
@@ -137,6 +141,76 @@ def pick_threads(torch):
     return best[0], cores
 
 
+REF_YAML = {"dqvae-dual-r-05": "dqvae-dual-r-05_imagenet.yml",
+            "dqvae-entropy-dual-r05": "dqvae-entropy-dual-r05_imagenet.yml",
+            "dqvae-triple-r-03-03": "dqvae-triple-r-03-03_imagenet.yml"}
+
+
+def find_reference_tree():
+    """The reference's own source tree, if one travelled with the repo: baseline/_ref (git-ignored copy made by
+    __graft_entry__.build() in the build container, or dropped there by the driver), else /root/reference."""
+    for cand in (os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+        if os.path.isfile(os.path.join(cand, "modules", "dynamic_modules", "EncoderDual.py")):
+            return cand
+    return None
+
+
+def reference_step_fn(cfg_name, batch, ref_root):
+    """One fwd+bwd of the REFERENCE's own modules (encoder, quantizer, 1x1 convs, decoder built from the
+    reference's YAML by its own instantiate_from_config, fp32, torch CPU) under the surrogate loss of the B200 arm.
+    Only pytorch_lightning is shimmed (LightningModule = nn.Module; it is not installed here)."""
+    import types
+    import torch
+    import torch.nn as nn
+    import yaml
+    if "pytorch_lightning" not in sys.modules:
+        pl = types.ModuleType("pytorch_lightning")
+        pl.LightningModule = nn.Module
+        sys.modules["pytorch_lightning"] = pl
+    sys.path.insert(0, ref_root)                  # before the repo root: `modules`, `models`, `utils` = reference's
+    cwd = os.getcwd()
+    os.chdir(ref_root)                            # the reference resolves relative paths (threshold JSON) from its root
+    try:
+        from utils.utils import instantiate_from_config
+        conf = yaml.safe_load(open(os.path.join(ref_root, "configs", "stage1", REF_YAML[cfg_name])))["model"]["params"]
+        torch.manual_seed(2021)
+        m = nn.Module()
+        m.encoder = instantiate_from_config(conf["encoderconfig"])
+        m.decoder = instantiate_from_config(conf["decoderconfig"])
+        m.quantize = instantiate_from_config(conf["vqconfig"])
+        m.quant_conv = nn.Conv2d(conf["quant_before_dim"], conf["quant_after_dim"], 1)
+        m.post_quant_conv = nn.Conv2d(conf["quant_after_dim"], conf["quant_before_dim"], 1)
+        budget = instantiate_from_config(conf["lossconfig"]["params"]["budget_loss_config"]) \
+            if "budget_loss_config" in conf["lossconfig"]["params"] else None
+        entropy = None
+        if cfg_name == "dqvae-entropy-dual-r05":
+            from models.stage1_dynamic.dqvae_dual_entropy import Entropy
+            entropy = Entropy(conf.get("entropy_patch_size", 16), conf.get("image_size", 256), conf.get("image_size", 256))
+    finally:
+        os.chdir(cwd)
+    for mod in (m.encoder, m.decoder, m.quantize):
+        assert type(mod).__module__.split(".")[0] == "modules" and ref_root in sys.modules[type(mod).__module__].__file__
+    m.train()
+    hkey = "h_triple" if "triple" in cfg_name else "h_dual"
+    g = torch.Generator().manual_seed(2021)
+    x = torch.rand(batch, 3, 256, 256, generator=g) * 2 - 1
+    params = [p for p in m.parameters() if p.requires_grad]
+
+    def step():
+        for p in params:
+            p.grad = None
+        hd = m.encoder(x, entropy(x) if entropy is not None else None)
+        h = m.quant_conv(hd[hkey])
+        quant, qloss, _ = m.quantize(x=h, temp=0.0, codebook_mask=hd["codebook_mask"])
+        xrec = m.decoder(m.post_quant_conv(quant), hd["indices"])
+        loss = (xrec - x).abs().mean() + qloss
+        if budget is not None:
+            loss = loss + budget(hd["gate"])
+        loss.backward()
+        return float(loss.detach())
+    return step
+
+
 def oracle_step_fn(cfg_name, batch, seed=0):
     """One fwd+bwd of the fp32 oracle port (reference algorithm) on the host cores."""
     import torch
@@ -154,20 +228,45 @@ def oracle_step_fn(cfg_name, batch, seed=0):
         out = orc.model_forward(full, ocfg, x)
         loss = (out["xrec"] - x).abs().mean() + out["qloss"] + orc.budget_loss_dual(out["gate"].float())
         loss.backward()
-        return float(loss)
+        return float(loss.detach())
     return step
+
+
+def cpu_step_fn(cfg_name, batch):
+    """-> (step, kind, what): the reference's own modules when its tree is available, else the oracle port."""
+    import contextlib
+    ref_root = find_reference_tree()
+    if ref_root is not None:
+        try:
+            with contextlib.redirect_stdout(sys.stderr):      # the reference's constructors print banners
+                fn = reference_step_fn(cfg_name, batch, ref_root)
+            return (fn, "reference",
+                    f"the reference's own modules imported from {os.path.relpath(ref_root, ROOT) if ref_root.startswith(ROOT) else ref_root} "
+                    f"(built from configs/stage1/{REF_YAML[cfg_name]}; training mode: gumbel routing + EMA codebook update)")
+        except Exception as e:
+            sys.stderr.write(f"[bench] reference modules unusable ({type(e).__name__}: {e}); timing the oracle port\n")
+    return (oracle_step_fn(cfg_name, batch), "port",
+            "fp32 oracle port of the reference modules (no reference tree next to the repo)")
+
+
+def workload_config(args, world):
+    """The `config` object - identical in both arms (the reference arm times a bounded per-step sample of it)."""
+    return {"workload": WORKLOADS[args.config], "global_batch": world * args.batch, "parallelism": f"dp{world}",
+            "step": "fwd + bwd (surrogate L1 + qloss + budget loss) + DDP all-reduce + Adam",
+            "l2": "per-step working set (~40 GB of activations) >> 126 MB L2, no flush needed"}
 
 
 def run_reference(args):
     import torch
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     threads, cores = pick_threads(torch)
-    sample_b = 1
-    step = oracle_step_fn(args.config, sample_b)
+    sample_b = max(1, args.cpu_sample_batch)
+    step, kind, what = cpu_step_fn(args.config, sample_b)
     t0 = time.perf_counter(); step(); first = time.perf_counter() - t0
-    budget_s = 150.0
+    budget_s = args.cpu_budget_s
     warm = max(0, min(args.warmup - 1, int(budget_s * 0.2 / max(first, 1e-3))))
     for _ in range(warm):
         step()
@@ -177,15 +276,15 @@ def run_reference(args):
         step()
     dt = time.perf_counter() - t0
     ips = sample_b * steps / dt
+    sample = (f"{steps} x fwd+bwd of {sample_b} images per step (of the {world * args.batch}-image batch of the config: "
+              f"a CPU step of the full batch needs ~25 fp32 activations of 2 GiB each per 32 images and minutes per "
+              f"step; the per-image cost of the convolutions does not depend on the batch) - {what}; {threads} "
+              f"threads = fastest of the thread counts tried on the {cores} usable cores")
     line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warm + 1, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": f"{sample_b} image per step (bounded CPU sample)"},
-            "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
-                             "sample": f"{steps} x fwd+bwd of {sample_b} image, dual config, fp32 oracle port "
-                                       f"of the reference modules (reference is pure PyTorch; not installable "
-                                       f"offline as a package); {threads} threads = fastest of the thread counts "
-                                       f"tried on the {cores} usable cores"},
+            "config": workload_config(args, world),
+            "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -234,6 +333,8 @@ def run_b200(args):
         # every rank starts from rank 0's parameters / buffers (what DDP's constructor does)
         for t in list(model.parameters()) + list(model.buffers()):
             dist.broadcast(t.data, 0)
+        from dynamicvectorquantization_b200 import ops as b2ops
+        b2ops.invalidate_caches(model)          # writes through .data do not bump the version the caches key on
         flat_grad = torch.zeros(sum(p.numel() for p in ae_params), device=dev)
         off = 0
         for p in ae_params:
@@ -258,9 +359,17 @@ def run_b200(args):
         loss.backward()
         return loss
 
+    exchange_note = None
+    if graph_ddp:
+        exchange_note = ("fwd+bwd replayed from one CUDA graph; after it: packed VQ-statistics all-reduce + restart-row "
+                         "broadcast (1 MiB), ONE flat fp32 gradient all-reduce (%d MB, NCCL over NVLink, not overlapped "
+                         "with the backward), Adam" % (sum(p.numel() for p in ae_params) * 4 // 2 ** 20))
+    elif world > 1:
+        exchange_note = "torch DistributedDataParallel (bucketed all-reduce overlapped with the backward), eager launches"
+
     def finish(loss):
         if flat_grad is not None:
-            model.quantize.codebook.apply_deferred_ema()      # packed all-reduce + rank-0 restart rows
+            model.quantize.codebook.apply_deferred_ema(keep=True)   # packed all-reduce + rank-0 restart rows
             dist.all_reduce(flat_grad)                        # 192 MB over NVLink, then average like DDP
             flat_grad.div_(world)
         opt.step()
@@ -347,24 +456,25 @@ def run_b200(args):
         pass
     ips = world * B * args.steps / (ms / 1e3)
     ips_e2e = world * B * args.steps / (ms_e2e / 1e3)
-    roof, roof_vq = kernel_rooflines(torch, kn, dev, peaks, with_cpu=(world == 1 and not args.no_cpu_baseline))
+    roof, roof_vq, roof_gn = kernel_rooflines(torch, kn, dev, peaks, with_cpu=(world == 1 and not args.no_cpu_baseline))
     line = {"metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": world * B, "parallelism": f"dp{world}",
-                       "step": "fwd + bwd (surrogate L1 + qloss + budget loss) + DDP all-reduce + Adam",
-                       "cuda_graph": graph is not None,
-                       "l2": "per-step working set (~40 GB of activations) >> 126 MB L2, no flush needed",
-                       "model_tflops_per_step": 3 * FLOP_PER_IMAGE_FWD * B / 1e12},
+            "config": workload_config(args, world), "cuda_graph": graph is not None,
+            "model_tflops_per_step": 3 * FLOP_PER_IMAGE_FWD * B / 1e12,
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": ips_e2e, "unit": "images/s", "h2d_bytes_per_step": x_host.numel() * 4 * world,
                     "d2h_bytes_per_step": 4 * world},
             "model_flops_utilisation": {"achieved_tflops": 3 * FLOP_PER_IMAGE_FWD * ips / world / 1e12,
                                         "peak_tflops": peaks.get("bf16_tflops_sustained"),
                                         "note": "algorithmic conv+attention FLOPs (BASELINE.md) x3 for fwd+bwd, per GPU"},
-            "roofline": roof, "roofline_vq": roof_vq}
+            "roofline": roof, "roofline_vq": roof_vq, "roofline_gn": roof_gn}
+    if world > 1:
+        line["exchange"] = exchange_note
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(args)
+    if world == 1 and not args.no_real_loss:
+        line["real_loss_step"] = real_loss_line(args)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -400,21 +510,48 @@ def kernel_rooflines(torch, kn, dev, peaks, with_cpu=False):
         prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))
     except Exception:
         pass
-    peak_t = peaks.get("bf16_tflops_sustained")
+    from dynamicvectorquantization_b200.build import source_sha
+
+    def traffic(key):
+        """DRAM bytes per launch from the committed ncu capture - only if it was taken from THESE kernel sources."""
+        if prof.get(key + "_csrc_sha16") == source_sha(key):
+            return prof.get(key + "_dram_bytes_per_launch")
+        return None
+
+    burst, sustained = peaks.get("bf16_tflops"), peaks.get("bf16_tflops_sustained")
     roof = {"kernel": "pconv3x3_kernel (conv3x3 128->128 @256x256, batch 32, forward)", "bound": "tensor",
-            "achieved": flops / ms / 1e9, "peak": peak_t, "unit": "TFLOP/s",
-            "frac": (flops / ms / 1e9 / peak_t) if peak_t else None,
-            "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed back-to-back inside a long run)"
-            if peak_t else "unavailable",
-            "ms_per_launch": ms, "traffic": prof.get("pconv_dram_bytes_per_launch"),
-            "burst_peak": peaks.get("bf16_tflops"),
-            "frac_of_burst_peak": (flops / ms / 1e9 / peaks["bf16_tflops"]) if peaks.get("bf16_tflops") else None}
+            "achieved": flops / ms / 1e9, "peak": burst, "unit": "TFLOP/s",
+            "frac": (flops / ms / 1e9 / burst) if burst else None,
+            "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst: the kernel is timed alone, 3 warm-up + 20 launches)"
+            if burst else "unavailable",
+            "ms_per_launch": ms, "traffic": traffic("pconv"),
+            "traffic_source": "profiles/ncu_summary.json (ncu --set full of the same kernel sources; null if the sources changed)",
+            "algorithmic_bytes": 2 * 2 * nb * hw * hw * c + 2 * 9 * c * c,
+            "sustained_peak": sustained,
+            "frac_of_sustained_peak": (flops / ms / 1e9 / sustained) if sustained else None}
+    peak_t = burst
+    del x, w, wp
+    # GroupNorm(+swish) backward on the largest activation of the step ([32,256,256,128] bf16: 15 of the 69
+    # GroupNorm layers, most of the family's bytes).  Algorithmic traffic = read dy, read x, write dx.
+    peak_h = peaks.get("hbm_gbs")
+    xg = torch.randn(nb, hw, hw, c, device=dev).to(BF)
+    dyg = torch.randn(nb, hw, hw, c, device=dev).to(BF)
+    gam, bet = torch.ones(c, device=dev), torch.zeros(c, device=dev)
+    _, st = kn.gn_forward(xg, gam, bet, True)
+    ms_gn = timed(lambda: kn.gn_bwd(dyg, xg, st, gam, bet, True), 20)
+    by_gn = 3 * xg.numel() * 2
+    roof_gn = {"kernel": "GroupNorm(32)+swish backward on [32,256,256,128] bf16 (" + kn.gn_bwd_kernel_name() + ")",
+               "bound": "hbm", "achieved": by_gn / ms_gn / 1e6, "peak": peak_h, "unit": "GB/s",
+               "frac": (by_gn / ms_gn / 1e6 / peak_h) if peak_h else None, "ms_per_launch": ms_gn,
+               "algorithmic_bytes": by_gn, "traffic": traffic("gn"),
+               "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peak_h else "unavailable",
+               "timing": "3 warm-up + 20 back-to-back launches, CUDA events; 1.6 GB per launch >> 126 MB L2"}
+    del xg, dyg
     # VQ search (+gather) at N=65536, C=256: algorithmic bytes = 2NC + 2KC + 8N + 2NC.  The kernel (tens of
     # microseconds) is shorter than the host side of one launch, so 20 launches are captured in a CUDA
     # graph and the replay is timed (CUDA events, L2 flushed before each replay).
     N, C = 65536, 256
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    peak_h = peaks.get("hbm_gbs")
 
     def graph_ms(fn, launches=20, reps=7):
         for _ in range(3):
@@ -444,10 +581,22 @@ def kernel_rooflines(torch, kn, dev, peaks, with_cpu=False):
             wv_k1024 = wv
         msv = graph_ms(lambda: kn.vq_search_gather(xb, cb, wv))
         by = 2 * N * C + 2 * K * C + 8 * N + 2 * N * C
-        sweep.append({"K": K, "ms_per_launch": msv, "GBps": by / msv / 1e6,
+        parity = None
+        if with_cpu:
+            # the codes of the very buffers just timed, audited on a row sample against the fp64 search of the
+            # oracle on the same bf16 operands (SURVEY 8d tie policy); a real mismatch fails the bench
+            from oracle import vq_oracle as vo
+            codes = kn.vq_search_gather(xb, cb, wv)[0]
+            rows = torch.arange(0, N, N // 4096, device=dev)[:4096]
+            wr = torch.cat([wv[:-1].to(BF).float(), wv[-1:]]).cpu().numpy()
+            parity = vo.audit_codes(xb[rows].float().cpu().numpy(), wr, codes[rows].cpu().numpy())
+            parity["rows_checked"] = int(rows.numel())
+            assert parity["real"] == 0, f"VQ codes of the timed buffers differ from the oracle at K={K}: {parity}"
+        sweep.append({"K": K, "ms_per_launch": msv, "GBps": by / msv / 1e6, "codes_vs_fp64_oracle": parity,
                       "hbm_frac": (by / msv / 1e6 / peak_h) if peak_h else None,
                       "tensor_tflops": 2.0 * N * K * C / msv / 1e9,
-                      "tensor_frac": (2.0 * N * K * C / msv / 1e9 / peak_t) if peak_t else None})
+                      "tensor_frac": (2.0 * N * K * C / msv / 1e9 / peak_t) if peak_t else None,
+                      "tensor_frac_of_sustained": (2.0 * N * K * C / msv / 1e9 / sustained) if sustained else None})
     k1 = sweep[1]
     # the reference algorithm of the same op on the host cores (numpy oracle port, quantize2_mask.py:29-55):
     # distances + argmin of a bounded row sample against the K=1024 codebook, scaled to rows/s
@@ -476,27 +625,54 @@ def kernel_rooflines(torch, kn, dev, peaks, with_cpu=False):
                        "fraction is reported as the metric asks; K=256 is the memory-leaning point of the sweep",
                "achieved": k1["GBps"], "peak": peak_h, "unit": "GB/s", "frac": k1["hbm_frac"],
                "tensor_tflops": k1["tensor_tflops"], "tensor_frac": k1["tensor_frac"],
+               "tensor_peak_source": "MEASURED_PEAKS.json bf16_tflops (burst: kernel timed alone)",
                "ms_per_launch": k1["ms_per_launch"], "timing": "20 launches per CUDA-graph replay, median of 7, L2 flushed",
-               "traffic": prof.get("vq_dram_bytes_per_launch"), "sweep": sweep, "cpu_baseline": vq_cpu}
-    return roof, roof_vq
+               "traffic": traffic("vq"), "sweep": sweep, "cpu_baseline": vq_cpu,
+               "codes_vs_fp64_oracle": k1.get("codes_vs_fp64_oracle"),
+               "burst_peak_tflops": burst, "tensor_frac_of_burst": (k1["tensor_tflops"] / burst) if burst else None}
+    # the training shape of every stage-1 config: 32 images -> N = 32768 rows, K = 1024, search + gather + statistics
+    try:
+        Nt, K = 32768, 1024
+        xt = xb[:Nt].contiguous()
+        cbt = kn.Codebook(K, C, dev); cbt.refresh(wv_k1024)
+        counts, sums = torch.zeros(K, device=dev), torch.zeros(K, C, device=dev)
+        lacc = torch.zeros(1, device=dev)
+        mst = graph_ms(lambda: kn.vq_search_gather(xt, cbt, wv_k1024, counts=counts, sums=sums, loss_acc=lacc))
+        roof_vq["training_shape"] = {"N": Nt, "K": K, "ms_per_launch": mst, "tensor_tflops": 2.0 * Nt * K * C / mst / 1e9,
+                                     "tensor_frac_of_burst": (2.0 * Nt * K * C / mst / 1e9 / burst) if burst else None,
+                                     "what": "search + gather + loss + in-kernel EMA counts/sums"}
+    except Exception as e:
+        roof_vq["training_shape"] = {"unavailable": f"{type(e).__name__}: {e}"}
+    return roof, roof_vq, roof_gn
 
 
 def cpu_baseline(args):
-    import torch
-    threads, cores = pick_threads(torch)
-    step = oracle_step_fn(args.config, 1)
-    t0 = time.perf_counter(); step(); first = time.perf_counter() - t0   # also warms pools / allocator
-    if first > 20.0:                              # slow host: the first step is the bounded sample
-        n, dt = 1, first
-    else:
-        t0 = time.perf_counter()
-        n = 0
-        while n < 1 or (time.perf_counter() - t0 < 15 and n < 6):
-            step(); n += 1
-        dt = time.perf_counter() - t0
-    return {"value": n / dt, "unit": "images/s", "cores": threads, "kind": "port",
-            "sample": f"{n} x fwd+bwd of 1 image (dual config, fp32 oracle port of the reference modules, torch CPU, "
-                      f"{threads} threads = fastest of the thread counts tried on the {cores} usable cores)"}
+    """The reported CPU baseline of the B200 arm = a short run of the reference arm in its OWN process (this one
+    has the overlay on sys.path, so `modules.*` would resolve to the B200 classes here)."""
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
+    env["CUDA_VISIBLE_DEVICES"] = ""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--config", args.config, "--steps", "6",
+           "--warmup", "1", "--cpu-budget-s", "25", "--cpu-sample-batch", "1", "--batch", str(args.batch)]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
+        line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+        return line["cpu_baseline"]
+    except Exception as e:                        # a reported baseline, never a reason to fail the bench
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+
+
+def real_loss_line(args):
+    """`--loss real` (the reference's full training_step: LPIPS + PatchGAN + adaptive weight, both optimizer passes)
+    timed in a child process after the headline run; carried in the headline line as `real_loss_step`."""
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
+    cmd = [sys.executable, os.path.abspath(__file__), "--loss", "real", "--steps", str(min(args.steps, 10)), "--warmup", "3",
+           "--batch", str(args.batch)]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=900)
+        d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+        return {k: d.get(k) for k in ("metric", "value", "unit", "ms_per_step", "steps", "gpu_launches", "e2e", "config")}
+    except Exception as e:
+        return {"unavailable": f"{type(e).__name__}: {e}"}
 
 
 def run_aux(args):

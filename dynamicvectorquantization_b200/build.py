@@ -11,6 +11,19 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-shared", "-Xcompiler", "-fPIC"]
 
 
+KERNEL_SOURCES = {"pconv": "pconv.cu", "vq": "vq.cu", "wgrad": "mmgemm.cu", "tapgemm": "tapgemm.cu", "gn": "norm.cu"}
+
+
+def source_sha(kernel):
+    """sha256[:16] of the sources a kernel family is built from (its .cu + the shared headers): profiles/ncu_summary.json
+    records it next to the DRAM traffic it measured, bench.py reports that traffic only for the same sources."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in (KERNEL_SOURCES[kernel], "common.cuh", "tmap.h"):
+        h.update(open(os.path.join(CSRC, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
 def needs_build():
     if not os.path.exists(OUT):
         return True

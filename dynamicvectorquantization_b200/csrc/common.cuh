@@ -199,6 +199,28 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return o;
 }
 
+// ---------------------------------------------------------------- per-device launch state (host)
+// cudaFuncAttributeMaxDynamicSharedMemorySize and the SM count are properties of a DEVICE: a process that
+// touches a second GPU must set / query them again there.  `mask` is one bit per device ordinal.
+template <class F>
+static inline int set_max_smem_once(F* fn, int bytes, unsigned long long& mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && ((mask >> dev) & 1ull)) return 0;
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return (int)e;
+  if (dev >= 0 && dev < 64) mask |= 1ull << dev;
+  return 0;
+}
+static inline int device_sm_count() {
+  static int sms[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!sms[dev]) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+  return sms[dev];
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -273,13 +273,8 @@ template <int BN, int STAGES, int MAXTAPS, bool STRIP = false>
 static int launch_mm(const CUtensorMap& tmA, const CUtensorMap& tmB, const MmParams& p, dim3 grid,
                      cudaStream_t stream) {
   using Cfg = MmCfg<BN, STAGES, MAXTAPS, STRIP>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(mmgemm_kernel<BN, STAGES, MAXTAPS, STRIP>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
+  static unsigned long long attr_mask = 0;
+  if (int e = set_max_smem_once(mmgemm_kernel<BN, STAGES, MAXTAPS, STRIP>, Cfg::SMEM, attr_mask)) return e;
   mmgemm_kernel<BN, STAGES, MAXTAPS, STRIP><<<grid, 192, Cfg::SMEM, stream>>>(tmA, tmB, p);
   return (int)cudaGetLastError();
 }

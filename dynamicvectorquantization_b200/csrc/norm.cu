@@ -3,7 +3,7 @@
 // :119-127 (ResnetBlock), :170 (AttnBlock, no swish), EncoderDual.py:116-117,126-127,
 // DecoderPositional.py:142-143.  HBM-bound: forward = 2 reads + 1 write of the tensor
 // (statistics pass + apply pass), backward = 2 reads of (dy, x) + 1 write.
-// Statistics are accumulated per CTA in fp32 and across CTAs in fp64 (atomicAdd double), so the
+// Statistics are accumulated per CTA in fp32 and combined across CTAs in a fixed order in fp64 (no atomics), so the
 // E[x^2]-E[x]^2 form does not lose the variance.
 #include "common.cuh"
 

@@ -398,12 +398,8 @@ int b2dq_pconv3x3(const void* a_ptr, const void* b_ptr, void* out, const float* 
     int r = make_tmap_bf16(&tmB, b_ptr, 2, dims, str, box);
     if (r) return r - 1000;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(pconv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_SMEM);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
+  static unsigned long long attr_mask = 0;
+  if (int e = set_max_smem_once(pconv3x3_kernel, PC_SMEM, attr_mask)) return e;
   PconvParams p;
   p.kchunks = Cin / 64; p.cin = Cin;
   for (int i = 0; i < 3; ++i) {

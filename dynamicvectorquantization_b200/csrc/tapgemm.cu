@@ -269,13 +269,8 @@ template <int BN, int STAGES, int MT>
 static int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const TapGemmParams& p,
                           dim3 grid, cudaStream_t stream) {
   using Cfg = TgCfg<BN, STAGES, MT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel<BN, STAGES, MT>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
+  static unsigned long long attr_mask = 0;
+  if (int e = set_max_smem_once(tapgemm_kernel<BN, STAGES, MT>, Cfg::SMEM, attr_mask)) return e;
   grid.x = (grid.x + MT - 1) / MT;
   tapgemm_kernel<BN, STAGES, MT><<<grid, 192, Cfg::SMEM, stream>>>(tmA, tmB, p);
   return (int)cudaGetLastError();

@@ -558,15 +558,7 @@ __global__ void vq_bwd_kernel(const __nv_bfloat16* __restrict__ g_xq,
 // =================================================================================== C ABI
 using namespace b2;
 
-static int g_num_sms = 0;
-static int num_sms() {
-  if (!g_num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return g_num_sms;
-}
+static int num_sms() { return device_sm_count(); }
 
 extern "C" {
 
@@ -665,13 +657,8 @@ int b2dq_vq_search_gather(const void* x_bf16, const float* x_f32, const void* cb
     int r = make_tmap_bf16(&tmB, cb_bf16, 2, dims, str, box);
     if (r) return r;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(vq_search_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, VQ_SMEM);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
+  static unsigned long long attr_mask = 0;
+  if (int e = set_max_smem_once(vq_search_kernel, VQ_SMEM, attr_mask)) return e;
   VqParams p;
   p.x_bf16 = reinterpret_cast<const __nv_bfloat16*>(x_bf16);
   p.x_f32 = x_f32;

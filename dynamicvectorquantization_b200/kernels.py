@@ -543,6 +543,11 @@ def gn_forward(x, gamma, beta, swish, groups=32, eps=1e-6):
     return y, stats
 
 
+def gn_bwd_kernel_name():
+    """Which kernels gn_bwd launches (for bench.py's roofline_gn label)."""
+    return "gn_bwd_partial + gn_bwd_reduce + gn_bwd_apply"
+
+
 def gn_bwd(dy, x, stats, gamma, beta, swish, groups=32, add=None, ws_nc=None):
     """Returns (dx bf16, dgamma f32, dbeta f32); add (bf16, like x) is summed into dx (residual gradient);
     ws_nc [N,C,2]: the reduction pass was already done by the producer of dy (pconv dgrad epilogue)."""

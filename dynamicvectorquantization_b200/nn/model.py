@@ -122,6 +122,13 @@ class _GrainVQModelBase(_Base):
         self.quant_conv = torch.nn.Conv2d(quant_before_dim, quant_after_dim, 1)
         self.post_quant_conv = torch.nn.Conv2d(quant_after_dim, quant_before_dim, 1)
         self.quant_sample_temperature = quant_sample_temperature
+        for name in ("encoder", "decoder", "quantize"):
+            mod = type(getattr(self, name)).__module__
+            if not mod.startswith("dynamicvectorquantization_b200"):
+                import warnings
+                warnings.warn(f"{name} resolved to {mod}, not to the B200 overlay: the reference tree is ahead of the "
+                              f"overlay on sys.path (start the job with `python -m dynamicvectorquantization_b200.launch "
+                              f"<script> ...`) or the config names a class this package does not provide")
 
     def _finish_init(self, ckpt_path, ignore_keys, monitor, warmup_epochs, loss_with_epoch, scheduler_type):
         if ckpt_path is not None:
@@ -272,6 +279,13 @@ class _GrainVQModelBase(_Base):
         return log
 
     def get_code_emb_with_depth(self, code):
+        """dqvae_dual_feat.py:191-192 / dqvae_triple_feat.py:217-218 delegate to the quantizer's
+        embed_code_with_depth (a (tensor, None)-style return for the quantizers that define it); the entropy model
+        (dqvae_dual_entropy.py:258-262) uses get_codebook_entry.  quantize2_mask.VectorQuantize2 - the quantizer of
+        every stage-1 config - has no embed_code_with_depth (the reference raises AttributeError there): fall back
+        to get_codebook_entry instead of failing."""
+        if not self._uses_entropy and hasattr(self.quantize, "embed_code_with_depth"):
+            return self.quantize.embed_code_with_depth(code)
         return self.quantize.get_codebook_entry(code)
 
 

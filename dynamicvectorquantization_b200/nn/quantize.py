@@ -121,6 +121,14 @@ class VQEmbedding(_SearchOperands, nn.Embedding):
         self.eps = eps
         self.restart_unused_codes = restart_unused_codes
         self.n_embed = n_embed
+        if not ema:
+            # the reference trains a non-EMA codebook through the (x_q - sg(x))^2 term (:177-179); this class only
+            # implements the EMA-frozen codebook every stage-1 config uses (learnable codebooks: quantize_vqgan)
+            raise NotImplementedError("VQEmbedding(ema=False) is not implemented on the B200 path; use "
+                                      "modules.vector_quantization.quantize_vqgan.VectorQuantizer2 for a learnable codebook")
+        if embed_dim % 64 != 0 or embed_dim > 256:
+            raise ValueError(f"VQEmbedding (B200): embed_dim must be a multiple of 64 and <= 256 (the search kernel "
+                             f"stages the rows in 64-channel chunks), got {embed_dim}")
         if self.ema:
             _ = [p.requires_grad_(False) for p in self.parameters()]
             # padding index is not updated by EMA; embed_ema starts from the N(0,1) init (:27)
@@ -172,15 +180,21 @@ class VQEmbedding(_SearchOperands, nn.Embedding):
         """EMA + restart + re-normalisation after the search kernel has filled self._acc
         (:86-105 and :107-115).  rows_f32_fn(idx) returns fp32 input rows for the restart."""
         if self.defer_ema:
-            self._deferred = (rows_f32_fn, n_vectors)
+            self._deferred = (rows_f32_fn(None), n_vectors)     # the rows tensor itself (no closure: picklable)
             return
         self._ema_step_now(rows_f32_fn, n_vectors)
 
     @torch.no_grad()
-    def apply_deferred_ema(self):
-        if self._deferred is not None:
-            fn, n = self._deferred
-            self._ema_step_now(fn, n)
+    def apply_deferred_ema(self, keep=False):
+        """Apply the EMA / restart / re-normalisation of the last deferred training forward, once: a second call
+        without a new forward raises.  keep=True leaves it pending (a CUDA-graph replay refills the SAME rows
+        buffer and statistics in place, so the owner of the graph re-applies it after every replay)."""
+        if self._deferred is None:
+            raise RuntimeError("apply_deferred_ema(): no deferred codebook update is pending")
+        rows, n = self._deferred
+        if not keep:
+            self._deferred = None
+        self._ema_step_now(lambda idx: rows if idx is None else rows[idx], n)
 
     @torch.no_grad()
     def _ema_step_now(self, rows_f32_fn, n_vectors):

@@ -65,6 +65,19 @@ def _packed(weight, kind):
     return p
 
 
+def invalidate_caches(module):
+    """Drop every derived bf16 copy (GEMM weight packings, VQ search codebook + norms) held for `module`'s
+    parameters.  The caches are validated by (data_ptr, tensor._version), and a write THROUGH `.data`
+    (`p.data.copy_(...)`, `dist.broadcast(p.data, 0)`, `nn.init.*_(p.data)`, EMA weight swaps such as LitEma) does
+    not bump the parameter's version counter: call this after any such write that happens after the first forward.
+    Ordinary optimizer steps, `load_state_dict` and `p.copy_()` under no_grad do bump it and need nothing."""
+    for p in module.parameters():
+        p.__dict__.pop("_b2_packs", None)
+    for m in module.modules():
+        if hasattr(m, "_cb_key"):
+            m._cb_key = None
+
+
 def _f32(t):
     return None if t is None else t.detach().float().contiguous()
 

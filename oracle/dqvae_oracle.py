@@ -67,6 +67,7 @@ SMALL_TRIPLE_CFG = dict(
     router="feature", grains=3,
 )
 # entropy-routed dual model (dqvae-entropy-dual-r05_imagenet.yml): no router parameters
+ENTROPY_CFG = dict(DUAL_CFG, router="entropy")
 SMALL_ENTROPY_CFG = dict(SMALL_CFG, router="entropy")
 TINY_ENTROPY_CFG = dict(TINY_CFG, router="entropy")
 
@@ -298,9 +299,23 @@ def entropy_thresholds(batches, patch=16):
     return {str(i + 1): float(ent[int((size * (i + 1)) // 100)]) for i in range(99)}
 
 
-def dual_encoder(sd, cfg, x, x_entropy=None, forced_gate=None, entropy_threshold=None, p="encoder"):
-    """EncoderDual.py:89-156 in eval mode (no gumbel noise; `forced_gate` [B,h,w,2] overrides the
-    router output, which is how the train-mode one-hot sample is replayed deterministically)."""
+def gumbel_softmax_hard(logits, noise, forced_index=None):
+    """torch.nn.functional.gumbel_softmax(logits, tau=1, hard=True, dim=-1) with the Gumbel noise given
+    (noise = -log(Exp(1)) drawn by the caller; EncoderDual.py:132-133, EncoderTriple.py:157-158): the value is
+    the one-hot of argmax(softmax(logits + noise)), the gradient is that of the soft sample.
+    forced_index replays the arg-max of another run (teacher forcing across a near-tie)."""
+    y_soft = torch.softmax(logits + noise, dim=-1)
+    index = y_soft.argmax(dim=-1, keepdim=True) if forced_index is None else forced_index.unsqueeze(-1)
+    y_hard = torch.zeros_like(logits).scatter_(-1, index, 1.0)
+    return y_hard - y_soft.detach() + y_soft
+
+
+def dual_encoder(sd, cfg, x, x_entropy=None, forced_gate=None, entropy_threshold=None, p="encoder",
+                 gumbel_noise=None, forced_index=None):
+    """EncoderDual.py:89-156.  Default = eval mode (no gumbel noise; `forced_gate` [B,h,w,2] overrides the
+    router output).  `gumbel_noise` [B,h,w,2] switches to the TRAINING-mode routing of a feature router
+    (update_router and self.training, :132-133 and :142-145): hard gumbel-softmax sample with that noise, and
+    h_dual multiplied by gate.max(dim=1) - value 1, but it carries the gradient that trains the router."""
     nlev = len(cfg["ch_mult"])
     res = cfg["resolution"]
     h = conv2d(sd, p + ".conv_in", x)
@@ -329,11 +344,16 @@ def dual_encoder(sd, cfg, x, x_entropy=None, forced_gate=None, entropy_threshold
         gate = feature_router(sd, p + ".router", h_fine, h_coarse)
     else:
         gate = entropy_router(x_entropy, entropy_threshold)
+    if gumbel_noise is not None:
+        gate = gumbel_softmax_hard(gate, gumbel_noise, forced_index)
     gate = gate.permute(0, 3, 1, 2)
     indices = gate.argmax(dim=1)
     up = h_coarse.repeat_interleave(2, dim=-1).repeat_interleave(2, dim=-2)
     idx_rep = indices.repeat_interleave(2, dim=-1).repeat_interleave(2, dim=-2).unsqueeze(1)
     h_dual = torch.where(idx_rep == 0, up, h_fine)
+    if gumbel_noise is not None:
+        gate_grad = gate.max(dim=1, keepdim=True)[0]
+        h_dual = h_dual * gate_grad.repeat_interleave(2, dim=-1).repeat_interleave(2, dim=-2)
     mask = torch.where(idx_rep == 0, torch.full_like(idx_rep, 0.25, dtype=torch.float32),
                        torch.ones_like(idx_rep, dtype=torch.float32))
     return dict(h_dual=h_dual, indices=indices, codebook_mask=mask, gate=gate,
@@ -458,7 +478,7 @@ def budget_loss_dual(gate, target_ratio=0.5, gamma=10.0, min_grain=16, max_grain
 
 
 def model_forward(sd, cfg, x, search_bf16=False, forced_gate=None, x_entropy=None, entropy_threshold=None,
-                  forced_codes=None):
+                  forced_codes=None, gumbel_noise=None, forced_index=None):
     """models/stage1_dynamic/dqvae_dual_feat.py:59-78: encode -> quant_conv -> VQ -> post_quant_conv
     -> decode.  Returns dict(xrec, qloss, codes, indices, gate, h_dual)."""
     if cfg.get("grains", 2) == 3:
@@ -467,7 +487,7 @@ def model_forward(sd, cfg, x, search_bf16=False, forced_gate=None, x_entropy=Non
         if cfg["router"] == "entropy" and x_entropy is None and forced_gate is None:
             x_entropy = patch_entropy(x, patch=cfg["resolution"] // (cfg["latent_size"] // 2))
         enc = dual_encoder(sd, cfg, x, x_entropy=x_entropy, forced_gate=forced_gate,
-                           entropy_threshold=entropy_threshold)
+                           entropy_threshold=entropy_threshold, gumbel_noise=gumbel_noise, forced_index=forced_index)
     h = conv2d(sd, "quant_conv", enc["h_dual"])
     quant, qloss, codes = vq_forward(sd, cfg, h, enc["codebook_mask"], search_bf16=search_bf16,
                                      forced_codes=forced_codes)

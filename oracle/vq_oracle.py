@@ -47,6 +47,40 @@ def nearest_fp64(x, weight):
     return idx.astype(np.int64), part[:, 0], part[:, 1]
 
 
+def audit_codes(x, weight, got, rel=1e-6, chunk=2048):
+    """SURVEY.md 8d tie policy, as one function.  x [N,C] and weight [K+1,C] are the operands the
+    search really saw (already bf16-rounded, held in fp32); got [N] are the codes under test.
+
+    Every row is re-searched in fp64 (exact products of bf16 values, lowest index wins exact ties,
+    like quantize2_mask.py:50-55 / torch.argmin).  A row whose code differs from the fp64 answer is
+      * a rounding near-tie when the fp64 distance gap between the two codes is below
+        rel * (||x||^2 + ||e||^2) - the fp32 accumulation cannot resolve it -, counted and reported;
+      * a real mismatch otherwise.
+    Returns dict(mismatch, near_tie, real, worst) with worst = max gap / (||x||^2 + ||e||^2)."""
+    cb = weight[:-1, :].astype(np.float64)
+    e_sq = (cb * cb).sum(axis=1)
+    got = np.asarray(got).reshape(-1).astype(np.int64)
+    n = x.shape[0]
+    mismatch = near = real = 0
+    worst = 0.0
+    for r0 in range(0, n, chunk):
+        xs = x[r0:r0 + chunk].astype(np.float64)
+        d = e_sq[None, :] - 2.0 * (xs @ cb.T)
+        best = d.argmin(axis=1)
+        g = got[r0:r0 + chunk]
+        bad = np.nonzero(best != g)[0]
+        if bad.size == 0:
+            continue
+        gap = d[bad, g[bad]] - d[bad, best[bad]]
+        scale = (xs[bad] * xs[bad]).sum(axis=1) + e_sq[best[bad]]
+        ratio = gap / scale
+        mismatch += int(bad.size)
+        near += int((ratio < rel).sum())
+        real += int((ratio >= rel).sum())
+        worst = max(worst, float(ratio.max()))
+    return dict(mismatch=mismatch, near_tie=near, real=real, worst=worst)
+
+
 def update_buffers(x, idx, cluster_size_ema, embed_ema, decay, restart_rows=None):
     """quantize2_mask.py:66-105 (single process: no all_reduce).  Returns new (cs_ema, embed_ema).
 

@@ -138,6 +138,37 @@ def model_goldens(cfg, tag, batch, seed):
          loss=loss, grad_norm_names=np.array(names), grad_norms=np.array([gnorm[n] for n in names]), **gsel)
 
 
+def train_routing_goldens():
+    """Training-mode routing of the reference's DualGrainEncoder (EncoderDual.py:130-149): hard gumbel-softmax
+    sample of the router logits, h_dual multiplied by gate.max(dim=1) (the path that trains the router), dual
+    budget loss on the sampled gate.  The Gumbel noise F.gumbel_softmax draws is the first RNG use of the forward
+    (dropout p = 0 draws nothing), so it is replayed by drawing it here after the same seed."""
+    from modules.dynamic_modules.budget import BudgetConstraint_RatioMSE_DualGrain
+    cfg = orc.TINY_CFG
+    m = build_reference_modules(cfg)
+    m.load_state_dict(orc.make_weights(orc.model_shapes(cfg), seed=9), strict=True)
+    m.train()
+    g = torch.Generator().manual_seed(91)
+    x = torch.rand(2, 3, cfg["resolution"], cfg["resolution"], generator=g) * 2 - 1
+    lat = cfg["latent_size"]
+    probe = torch.randn(2, cfg["z_channels"], lat, lat, generator=g)           # cotangent of h_dual
+    torch.manual_seed(777)
+    noise = -torch.empty(2, lat // 2, lat // 2, 2).exponential_().log()
+    torch.manual_seed(777)
+    hd = m.encoder(x, None)
+    budget = BudgetConstraint_RatioMSE_DualGrain(target_ratio=0.5, gamma=10.0, min_grain_size=lat // 2,
+                                                 max_grain_size=lat, calculate_all=True)(hd["gate"])
+    ((hd["h_dual"] * probe).sum() + budget).backward()
+    grads = {n: p.grad for n, p in m.encoder.named_parameters() if p.grad is not None}
+    pick = ["router.gate.0.weight", "router.gate.2.weight", "router.gate.2.bias", "router.feature_norm_fine.weight",
+            "conv_out_fine.weight", "conv_out_coarse.bias", "down.0.block.0.conv1.weight", "conv_in.weight"]
+    save("model_tiny_train_routing.npz", x=x, probe=probe, noise=noise, gate=hd["gate"], indices=hd["indices"],
+         h_dual=hd["h_dual"], mask=hd["codebook_mask"], budget=budget,
+         grad_norm_names=np.array(sorted(grads)),
+         grad_norms=np.array([float(grads[n].double().pow(2).sum().sqrt()) for n in sorted(grads)]),
+         **{"grad__" + k.replace(".", "__"): grads[k] for k in pick})
+
+
 def triple_entropy_goldens():
     """Tiny triple-grain model (EncoderTriple + RouterTriple + triple budget loss) and the entropy
     branch (Entropy module + fixed-threshold router) of the reference, eval mode."""
@@ -467,7 +498,9 @@ def threshold_goldens():
 
 
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["vq", "family", "permuter", "tiny", "dual", "variants", "loss", "thresholds"]
+    what = sys.argv[1:] or ["vq", "family", "permuter", "tiny", "dual", "variants", "loss", "thresholds", "routing"]
+    if "routing" in what:
+        train_routing_goldens()
     if "thresholds" in what:
         threshold_goldens()
     if "loss" in what:

@@ -27,6 +27,9 @@ def _rand_bf(*shape, scale=1.0, seed=0):
 
 
 # ------------------------------------------------------------------------------------------- VQ
+from parity_util import audit_codes as _audit  # noqa: E402
+
+
 @pytest.mark.parametrize("N,K,C", [(4096, 1024, 256), (1000, 1000, 256), (515, 300, 128), (8192, 2048, 64)])
 def test_vq_search_matches_oracle(N, K, C):
     from dynamicvectorquantization_b200 import kernels as kn
@@ -50,17 +53,8 @@ def test_vq_search_matches_oracle(N, K, C):
     # oracle on the same bf16-rounded operands
     xr = xb.float().numpy()
     wr = np.concatenate([vo.bf16_round(w[:-1].numpy()), np.zeros((1, C), np.float32)], 0)
-    ref = vo.find_nearest_embedding(xr, wr)
     got = codes.cpu().numpy()
-    mism = np.nonzero(ref != got)[0]
-    if len(mism):
-        # near-tie audit in fp64: only rounding-level ties may differ
-        _, best, second = vo.nearest_fp64(xr[mism], wr)
-        d64 = (wr[:-1].astype(np.float64) ** 2).sum(1)[None, :] - 2 * xr[mism].astype(np.float64) @ wr[:-1].T.astype(np.float64)
-        gap = np.abs(d64[np.arange(len(mism)), got[mism]] - d64[np.arange(len(mism)), ref[mism]])
-        scale = (xr[mism].astype(np.float64) ** 2).sum(1) + 1.0
-        assert np.all(gap < 1e-6 * scale * 256), f"{len(mism)} real mismatches, max gap {gap.max()}"
-    assert len(mism) <= max(1, N // 2000), f"{len(mism)} near-tie mismatches of {N}"
+    _audit(xr, wr, got, f"search {N}x{K}x{C}")
     # gathered rows are exactly the fp32 codebook rows
     assert torch.equal(xq_f.cpu(), w[got])
     assert torch.equal(xq_b.cpu(), w[got].to(BF))
@@ -102,16 +96,8 @@ def _vq_check(x, w, mask, K, C, out, x_f32=False):
     N = x.shape[0]
     xr = x.to(BF).float().numpy()
     wr = np.concatenate([vo.bf16_round(w[:-1].numpy()), np.zeros((1, C), np.float32)], 0)
-    ref = vo.find_nearest_embedding(xr, wr)
     got = codes.numpy()
-    mism = np.nonzero(ref != got)[0]
-    if len(mism):
-        d64 = (wr[:-1].astype(np.float64) ** 2).sum(1)[None, :] - 2 * xr[mism].astype(np.float64) @ wr[:-1].T.astype(np.float64)
-        gap = np.abs(d64[np.arange(len(mism)), got[mism]] - d64[np.arange(len(mism)), ref[mism]])
-        scale = (xr[mism].astype(np.float64) ** 2).sum(1) + 1.0
-        assert np.all(gap < 1e-6 * scale * 256), f"{len(mism)} real mismatches, max gap {gap.max()}"
-    # rounding-level near-ties scale with the number of candidates per row
-    assert len(mism) <= max(1, N // 2000) * max(1, K // 1024), f"{len(mism)} near-tie mismatches of {N}"
+    _audit(xr, wr, got, f"search {N}x{K}x{C}")
     assert torch.equal(xq_f, w[got])
     assert torch.equal(xq_b, w[got].to(BF))
     rows = x if x_f32 else x.to(BF).float()           # loss / EMA sums use the fp32 rows when given
@@ -167,6 +153,25 @@ def test_vq_search_stream_k_tail(N, K, C, x_f32):
     _vq_check(x, w, mask, K, C, a, x_f32=x_f32)
     c = _vq_run(kn, x, w, mask, K, C, x_f32=x_f32, split=True, max_ctas=37)     # a different cut of the same work
     assert torch.equal(a[0], c[0])
+
+
+@pytest.mark.parametrize("K", [1024, 8192, 16384])
+def test_vq_search_baseline_microbench_shapes(K):
+    """BASELINE.json config 5 / SURVEY 8d input 5: x ~ N(0,1) [65536,256] -> bf16, codebook = x[randperm(N)[:K]] +
+    0.1 N(0,1) -> bf16, seed 0, K in {1024, 8192, 16384}.  Codes against the fp64 search on the same operands;
+    the mismatch count is printed (expected 0).  Gathered rows / loss / per-code statistics checked as well."""
+    from dynamicvectorquantization_b200 import kernels as kn
+    N, C = 65536, 256
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(N, C, generator=g)
+    w = torch.cat([x[torch.randperm(N, generator=g)[:K]] + 0.1 * torch.randn(K, C, generator=g), torch.zeros(1, C)], 0)
+    w = w.contiguous()
+    mask = torch.ones(N)
+    out = _vq_run(kn, x, w, mask, K, C)
+    _vq_check(x, w, mask, K, C, out)
+    # the training shape of the stage-1 configs (batch 32: N = 32768) on the same data
+    out = _vq_run(kn, x[:32768], w, mask[:32768], K, C)
+    _vq_check(x[:32768], w, mask[:32768], K, C, out)
 
 
 def test_vq_search_exact_ties_lowest_index_wins():

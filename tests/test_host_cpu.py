@@ -539,3 +539,31 @@ def test_bench_reference_arm_json_contract():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
                         "--warmup", "1"], capture_output=True, text=True, env=env, timeout=120)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_launcher_puts_the_overlay_ahead_of_the_script_directory(tmp_path):
+    """`PYTHONPATH=<overlay>:... python train.py` from the reference root does NOT activate the
+    overlay (sys.path[0] = the script's directory wins for namespace packages).  A script placed in a stand-in
+    reference tree (its own modules/dynamic_modules/EncoderDual.py) is run (a) the documented-in-round-1 way and (b)
+    through `python -m dynamicvectorquantization_b200.launch`: only (b) resolves the overlay class."""
+    import subprocess
+    fake = tmp_path / "ref"
+    (fake / "modules" / "dynamic_modules").mkdir(parents=True)
+    (fake / "modules" / "dynamic_modules" / "EncoderDual.py").write_text("class DualGrainEncoder:\n    pass\n")
+    (fake / "modules" / "dynamic_modules" / "only_in_reference.py").write_text("MARK = 'reference'\n")
+    (fake / "probe.py").write_text(
+        "import sys, os\nsys.path.append(os.getcwd())\n"                       # what train.py:5 does
+        "import modules.dynamic_modules.EncoderDual as m\n"
+        "import modules.dynamic_modules.only_in_reference as o\n"
+        "print('RESOLVED', m.__file__, o.MARK, sys.argv[1:])\n")
+    from dynamicvectorquantization_b200 import configs
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([configs.OVERLAY, ROOT, str(fake)]))
+    plain = subprocess.run([sys.executable, "probe.py", "--x"], cwd=fake, env=env, capture_output=True, text=True)
+    assert plain.returncode == 0, plain.stderr
+    assert str(fake) in plain.stdout.split("RESOLVED")[1], "expected the PYTHONPATH-only launch to pick the reference file"
+    launched = subprocess.run([sys.executable, "-m", "dynamicvectorquantization_b200.launch", "probe.py", "--x"], cwd=fake,
+                              env=dict(os.environ, PYTHONPATH=ROOT), capture_output=True, text=True)
+    assert launched.returncode == 0, launched.stderr
+    out = launched.stdout.split("RESOLVED")[1]
+    assert os.path.join("dynamicvectorquantization_b200", "overlay") in out, out
+    assert "reference" in out and "['--x']" in out            # fall-through to the reference tree and argv still work

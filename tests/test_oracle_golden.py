@@ -72,8 +72,6 @@ def test_model_oracle_matches_reference(tag, cfg, seed):
     assert np.array_equal(out["indices"].numpy(), g["indices"].astype(np.int64))
     assert torch.allclose(out["xrec"], torch.from_numpy(g["xrec"]), rtol=1e-4, atol=1e-5)
     assert abs(float(out["qloss"]) - float(g["qloss"])) < 1e-5 * abs(float(g["qloss"])) + 1e-8
-    if tag == "dual":
-        return  # backward of the full-size model is covered on the tiny config (keeps the CPU suite fast)
     loss = (out["xrec"] - x).abs().mean() + out["qloss"]
     loss.backward()
     for key in g:
@@ -85,6 +83,34 @@ def test_model_oracle_matches_reference(tag, cfg, seed):
         if n in params and params[n].grad is not None:
             got = float(params[n].grad.double().pow(2).sum().sqrt())
             assert abs(got - ref) <= 2e-3 * ref + 1e-7, (n, got, ref)
+
+
+def test_train_mode_routing_oracle_matches_reference():
+    """EncoderDual.py:130-149 in training mode (hard gumbel-softmax sample with the reference's noise replayed,
+    gate_grad multiply, budget loss): values and the gradients that train the router."""
+    g = _load("model_tiny_train_routing.npz")
+    cfg = orc.TINY_CFG
+    sd = orc.make_weights(orc.model_shapes(cfg), seed=9)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if k.startswith("encoder.")}
+    full = dict(sd); full.update(params)
+    enc = orc.dual_encoder(full, cfg, torch.from_numpy(g["x"]), gumbel_noise=torch.from_numpy(g["noise"]))
+    assert np.array_equal(enc["indices"].numpy(), g["indices"])
+    assert torch.allclose(enc["gate"], torch.from_numpy(g["gate"]), atol=1e-6)
+    assert torch.allclose(enc["h_dual"], torch.from_numpy(g["h_dual"]), rtol=1e-4, atol=1e-5)
+    assert np.array_equal(enc["codebook_mask"].numpy(), g["mask"])
+    lat = cfg["latent_size"]
+    budget = orc.budget_loss_dual(enc["gate"], min_grain=lat // 2, max_grain=lat)
+    assert abs(float(budget) - float(g["budget"])) < 1e-5 * abs(float(g["budget"])) + 1e-8
+    ((enc["h_dual"] * torch.from_numpy(g["probe"])).sum() + budget).backward()
+    assert 0 < int(enc["indices"].sum()) < enc["indices"].numel()              # both grains sampled
+    for key in g:
+        if key.startswith("grad__"):
+            name = "encoder." + key[len("grad__"):].replace("__", ".")
+            assert torch.allclose(params[name].grad, torch.from_numpy(g[key]), rtol=2e-3, atol=1e-6), name
+    for n, ref in zip(g["grad_norm_names"], g["grad_norms"]):
+        got = float(params["encoder." + str(n)].grad.double().pow(2).sum().sqrt())
+        assert abs(got - ref) <= 2e-3 * ref + 1e-7, (n, got, ref)
+    assert float(params["encoder.router.gate.0.weight"].grad.abs().max()) > 0  # the router does get a gradient
 
 
 def test_triple_oracle_matches_reference():

@@ -4,8 +4,12 @@
 """
 import csv
 import json
+import os
 import subprocess
 import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from dynamicvectorquantization_b200.build import source_sha  # noqa: E402
 
 rep, out_md, out_json = sys.argv[1:4]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -41,8 +45,18 @@ for r in rows[2:]:
         (rd + wr) / t / 1e3, val(r, "lts__t_sector_hit_rate.pct") or 0.0,
         (l2sm or 0.0) / 1e9, val(r, "smsp__issue_active.avg.pct_of_peak_sustained_active") or 0.0,
         int(val(r, "launch__registers_per_thread") or 0)))
-    key = ("pconv" if "pconv" in short else "vq" if "vq_search" in short else "wgrad" if "mmgemm" in short else "tapgemm")
+    key = ("pconv" if "pconv" in short else "vq" if "vq_search" in short else "wgrad" if "mmgemm" in short
+           else "gn" if short.startswith("gn_") else "tapgemm")
+    if key == "gn":                                   # the fused GroupNorm backward is the family's dominant kernel
+        if "bwd_fused" not in short:
+            continue
     summary[key + "_dram_bytes_per_launch"] = int(rd + wr)
+    summary[key + "_time_us"] = t
+    summary[key + "_csrc_sha16"] = source_sha(key)   # run from the tree the capture was built from
+if os.path.exists(out_json):                          # keep the entries of kernels this report does not contain
+    old = json.load(open(out_json))
+    for k, v in old.items():
+        summary.setdefault(k, v)
 open(out_md, "w").write("\n".join(lines) + "\n")
 summary["source"] = rep.split("/")[-1] + " (dram__bytes_read.sum + dram__bytes_write.sum per launch)"
 json.dump(summary, open(out_json, "w"), indent=1)
