@@ -217,7 +217,14 @@ static inline int device_sm_count() {
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64) dev = 0;
-  if (!sms[dev]) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+  if (!sms[dev]) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      return 148;                                  // no device (host-side planning / tests): a B200
+    }
+    sms[dev] = n;
+  }
   return sms[dev];
 }
 

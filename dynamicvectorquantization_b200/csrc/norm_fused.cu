@@ -1,0 +1,423 @@
+// GroupNorm(32, eps 1e-6, affine)(+swish) BACKWARD as ONE persistent kernel: 2 reads + 1 write of HBM.
+// Reference: the autograd of modules/diffusionmodules/model.py:29-35 (Normalize + nonlinearity) as used by
+// ResnetBlock (:119-127), AttnBlock (:170) and the output heads (EncoderDual.py:116-117, DecoderPositional.py:142-143).
+//
+// The backward of GroupNorm needs two per-(image, group) sums over the whole image (S1 = sum dz*gamma,
+// S2 = sum dz*gamma*xhat) before any dx can be written, so the separate-kernel version (norm.cu) reads dy and x
+// twice from HBM: 5 passes over the tensor instead of the algorithmic 3.  Here a TEAM of CTAs owns one image at a
+// time: every CTA streams its row slice of (dy, x) once for the sums (phase 1), the team meets at a per-image
+// barrier in global memory (arrival counter + fixed-order sum of the per-CTA partials: deterministic), and each CTA
+// then streams the SAME slice again for dx (phase 2) - the second read hits the 126 MB L2, because the number of
+// images in flight (teams) is chosen so that their dy + x stay below an L2 budget.  HBM sees 2 reads + 1 write.
+//
+// Mechanics: 1 CTA per SM (persistent, all co-resident: the grid never exceeds the SM count), 16 warps.  Thread 0
+// issues 1-D bulk async copies (cp.async.bulk, 8 KB per tensor and ring stage: a row slice of an NHWC image is
+// contiguous, no tensor map needed) into a 6-stage shared-memory ring signalled by mbarriers, always five chunks
+// ahead of the chunk being consumed - across the phase boundary and the team barrier too, so the memory pipe keeps
+// moving while a CTA waits for its team (a 17th producer warp would cap the kernel at 96 registers: spills).  Consumers keep every per-channel constant in registers,
+// use packed fp32x2 arithmetic (fma.rn.f32x2: half the issue slots) and ONE MUFU op per sigmoid
+// (sigmoid(z) = 0.5 + 0.5 tanh(z/2)) - the two-kernel version was instruction-bound at ~0.55 of HBM speed.
+// dgamma / dbeta are accumulated per CTA over its images and combined by the last CTA to finish, in CTA order.
+#include "common.cuh"
+
+namespace b2 {
+
+constexpr int GF_CONSUMERS = 512;                 // 16 warps; thread 0 also issues the bulk copies
+constexpr int GF_THREADS = GF_CONSUMERS;
+constexpr int GF_STAGES = 6;
+constexpr int GF_CHUNK = GF_CONSUMERS * 16;       // bytes per tensor per stage: one 16 B vector per consumer thread
+constexpr int GF_MAXC = 512;
+constexpr int GF_MAXG = 64;
+
+struct GnFusedParams {
+  const __nv_bfloat16* dy;
+  const __nv_bfloat16* x;
+  const __nv_bfloat16* add;      // optional: summed into dx (gradient arriving through a skip connection)
+  const float* stats;            // [N][G][2] mean, rstd
+  const float* gamma;
+  const float* beta;
+  __nv_bfloat16* dx;
+  float* dgb;                    // [2][C] dgamma, dbeta (overwritten)
+  float* part;                   // [N][S][G][2] per-CTA group partials
+  float* dgb_part;               // [grid][2][C]
+  unsigned* flags;               // [N] arrival counters, [N] = finished-CTA counter, [N+1] = error flag (zeroed before launch)
+  int N, HW, C, G, S, T, rows_per_cta;
+};
+
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ float tanh_approx(float v) {
+  float r;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(GF_CONSUMERS) : "memory"); }
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ float2 unpack2(uint32_t u) { return make_float2(bf16_lo(u), bf16_hi(u)); }
+
+// dz = dy * swish'(z) for a channel pair; zh = z / 2 (the halving is folded into the per-channel constants)
+template <bool SW>
+__device__ __forceinline__ float2 dz_pair(float2 d, float2 x, float2 A, float2 B) {
+  if (!SW) return d;
+  const float2 zh = __ffma2_rn(x, A, B);
+  const float2 t = make_float2(tanh_approx(zh.x), tanh_approx(zh.y));
+  const float2 sg = __ffma2_rn(t, make_float2(0.5f, 0.5f), make_float2(0.5f, 0.5f));
+  const float2 om2 = __ffma2_rn(sg, make_float2(-2.f, -2.f), make_float2(2.f, 2.f));   // 2 (1 - sg)
+  const float2 w = __ffma2_rn(zh, om2, make_float2(1.f, 1.f));                         // 1 + z (1 - sg)
+  return __fmul2_rn(d, __fmul2_rn(sg, w));
+}
+
+template <bool SW>
+__global__ void __launch_bounds__(GF_THREADS, 1) gn_bwd_fused_kernel(const GnFusedParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  // layout: ring [STAGES][3][CHUNK] | red [2][CONSUMERS][8] floats | chan [2][MAXC] | dg [2][MAXC] | sk [MAXG][2] | bars
+  uint8_t* ring = smem;
+  float* red = reinterpret_cast<float*>(smem + GF_STAGES * 3 * GF_CHUNK);
+  float* chan = red + 2 * GF_CONSUMERS * 8;
+  float* dg = chan + 2 * GF_MAXC;
+  float* sk = dg + 2 * GF_MAXC;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sk + 2 * GF_MAXG);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + GF_STAGES);
+  const int tid = threadIdx.x;
+  const int C = p.C, G = p.G, HW = p.HW;
+  const int vecs = C >> 3;
+  const int rstep = GF_CONSUMERS / vecs;          // rows per chunk
+  const int team = blockIdx.x / p.S, s_idx = blockIdx.x % p.S;
+  const int r0 = s_idx * p.rows_per_cta;
+  const int r1 = min(HW, r0 + p.rows_per_cta);
+  const int nchunks = (r1 - r0 + rstep - 1) / rstep;
+  const bool has_add = p.add != nullptr;
+
+  if (tid == 0) {
+    for (int i = 0; i < GF_STAGES; ++i) {
+      mbar_init(full0 + 8 * i, 1);
+      mbar_init(empty0 + 8 * i, GF_CONSUMERS / 32);
+    }
+    fence_barrier_init();
+  }
+  for (int i = tid; i < 2 * C; i += GF_THREADS) dg[i] = 0.f;
+  __syncthreads();
+
+  // producer cursor (thread 0): the CTA's chunks form one sequence image -> phase -> chunk; `produce` issues the next one
+  int pn = team, pph = 0, pc = 0;
+  uint32_t pstage = 0, pphase = 0;
+  auto produce = [&]() {
+    if (pn >= p.N) return;
+    const int row = r0 + pc * rstep;
+    const uint32_t bytes = static_cast<uint32_t>(min(rstep, r1 - row)) * C * 2;
+    const long long off = (static_cast<long long>(pn) * HW + row) * C;
+    mbar_wait(empty0 + 8 * pstage, pphase ^ 1);
+    const uint32_t fb = full0 + 8 * pstage;
+    const uint32_t dst = smem_u32(ring + pstage * 3 * GF_CHUNK);
+    const bool with_add = pph == 1 && has_add;
+    mbar_arrive_expect_tx(fb, bytes * (with_add ? 3 : 2));
+    bulk_load(dst, p.dy + off, bytes, fb);
+    bulk_load(dst + GF_CHUNK, p.x + off, bytes, fb);
+    if (with_add) bulk_load(dst + 2 * GF_CHUNK, p.add + off, bytes, fb);
+    if (++pstage == GF_STAGES) { pstage = 0; pphase ^= 1; }
+    if (++pc == nchunks) {
+      pc = 0;
+      if (++pph == 2) { pph = 0; pn += p.T; }
+    }
+  };
+  if (tid == 0)
+    for (int i = 0; i < GF_STAGES - 1; ++i) produce();
+  {
+    // ------------------------------------------------------------------ consumers
+    const int v = tid % vecs, rlane = tid / vecs;
+    const int cg = C / G;
+    const int lane = tid & 31;
+    uint32_t stage = 0, phase = 0;
+    const float inv_cnt = 1.f / (static_cast<float>(HW) * cg);
+    float gm[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) gm[k] = p.gamma[v * 8 + k];
+    for (int n = team; n < p.N; n += p.T) {
+      // per-channel constants of this image: zh = x*A + B (= z/2), xhat = x*R + M
+      float2 A[4], B[4], R[4], M[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = v * 8 + 2 * k;
+        const int g0 = c / cg, g1 = (c + 1) / cg;
+        const float m0 = p.stats[(n * G + g0) * 2], s0 = p.stats[(n * G + g0) * 2 + 1];
+        const float m1 = p.stats[(n * G + g1) * 2], s1 = p.stats[(n * G + g1) * 2 + 1];
+        R[k] = make_float2(s0, s1);
+        M[k] = make_float2(-m0 * s0, -m1 * s1);
+        const float a0 = s0 * gm[2 * k], a1 = s1 * gm[2 * k + 1];
+        A[k] = make_float2(0.5f * a0, 0.5f * a1);
+        B[k] = make_float2(0.5f * (p.beta[c] - m0 * a0), 0.5f * (p.beta[c + 1] - m1 * a1));
+      }
+      // ---------------- phase 1: sum_rows dz, sum_rows dz * xhat per channel
+      float2 sa[4], sb[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { sa[k] = make_float2(0.f, 0.f); sb[k] = make_float2(0.f, 0.f); }
+      for (int c = 0; c < nchunks; ++c) {
+        if (tid == 0) produce();
+        mbar_wait(full0 + 8 * stage, phase);
+        if (r0 + c * rstep + rlane < r1) {
+          const uint8_t* st = ring + stage * 3 * GF_CHUNK + tid * 16;
+          const uint4 ud = *reinterpret_cast<const uint4*>(st);
+          const uint4 ux = *reinterpret_cast<const uint4*>(st + GF_CHUNK);
+          const uint32_t wd[4] = {ud.x, ud.y, ud.z, ud.w}, wx[4] = {ux.x, ux.y, ux.z, ux.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 xv = unpack2(wx[k]);
+            const float2 dz = dz_pair<SW>(unpack2(wd[k]), xv, A[k], B[k]);
+            const float2 xh = __ffma2_rn(xv, R[k], M[k]);
+            sa[k] = __fadd2_rn(sa[k], dz);
+            sb[k] = __ffma2_rn(dz, xh, sb[k]);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0 + 8 * stage);
+        if (++stage == GF_STAGES) { stage = 0; phase ^= 1; }
+      }
+      // ---------------- CTA reduction (fixed order) -> per-channel sums, per-group partials
+      float* red_a = red;
+      float* red_b = red + GF_CONSUMERS * 8;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        red_a[rlane * C + v * 8 + 2 * k] = sa[k].x; red_a[rlane * C + v * 8 + 2 * k + 1] = sa[k].y;
+        red_b[rlane * C + v * 8 + 2 * k] = sb[k].x; red_b[rlane * C + v * 8 + 2 * k + 1] = sb[k].y;
+      }
+      consumer_sync();
+      {
+        // thread (q, c): rows q*rq .. of channel c; parts = CONSUMERS / C row ranges per channel
+        const int parts = GF_CONSUMERS / C;                 // 8, 4, 2, 1 for C = 64 .. 512
+        const int c = tid % C, q = tid / C;
+        const int rq = rstep / parts;
+        float a = 0.f, b = 0.f;
+        for (int rl = q * rq; rl < (q + 1) * rq; ++rl) { a += red_a[rl * C + c]; b += red_b[rl * C + c]; }
+        consumer_sync();                                     // everyone has read its rows: reuse the front of red
+        red_a[q * C + c] = a;
+        red_b[q * C + c] = b;
+        consumer_sync();
+        if (tid < C) {
+          float a2 = 0.f, b2 = 0.f;
+          for (int qq = 0; qq < parts; ++qq) { a2 += red_a[qq * C + tid]; b2 += red_b[qq * C + tid]; }
+          chan[tid] = a2;
+          chan[GF_MAXC + tid] = b2;
+          dg[tid] += b2;            // dgamma
+          dg[C + tid] += a2;        // dbeta
+        }
+        consumer_sync();
+        if (tid < G) {
+          float S1 = 0.f, S2 = 0.f;
+          for (int cc = tid * cg; cc < (tid + 1) * cg; ++cc) {
+            const float g_ = p.gamma[cc];
+            S1 = fmaf(g_, chan[cc], S1);
+            S2 = fmaf(g_, chan[GF_MAXC + cc], S2);
+          }
+          float* o = p.part + ((static_cast<long long>(n) * p.S + s_idx) * G + tid) * 2;
+          __stcg(o, S1);
+          __stcg(o + 1, S2);
+        }
+      }
+      consumer_sync();
+      // ---------------- team barrier on image n
+      if (tid == 0) {
+        __threadfence();
+        red_release_add(p.flags + n, 1u);
+        const long long t0 = clock64();
+        while (ld_acquire(p.flags + n) < static_cast<unsigned>(p.S)) {
+          if (clock64() - t0 > 4000000000LL) { atomicExch(p.flags + p.N + 1, 1u); break; }   // ~2 s: never hang the GPU
+        }
+      }
+      consumer_sync();
+      {
+        // sum the S partials of every (group, 2) in CTA order: thread (j, e4) takes CTAs j, j+32, ... of float4 e4
+        const int e4n = (2 * G) / 4;                          // float4 per CTA row (16 for G = 32)
+        const int lanes_s = GF_CONSUMERS / e4n;
+        const int e4 = tid % e4n, j = tid / e4n;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4* src = reinterpret_cast<const float4*>(p.part + static_cast<long long>(n) * p.S * G * 2);
+        for (int s = j; s < p.S; s += lanes_s) {
+          const float4 t = __ldcg(src + static_cast<long long>(s) * e4n + e4);
+          acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+        }
+        float4* r4 = reinterpret_cast<float4*>(red);
+        r4[j * e4n + e4] = acc;
+        consumer_sync();
+        if (tid < 2 * G) {
+          float t = 0.f;
+          for (int jj = 0; jj < lanes_s; ++jj) t += red[jj * 2 * G + tid];
+          sk[tid] = t * inv_cnt;                              // sk[g*2 + 0] = S1/cnt, sk[g*2 + 1] = S2/cnt
+        }
+        consumer_sync();
+      }
+      // ---------------- phase 2: dx = rstd * (dz*gamma - S1/cnt - xhat * S2/cnt) (+ add)
+      float2 C1[4], C2[4], C3[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = v * 8 + 2 * k;
+        const int g0 = c / cg, g1 = (c + 1) / cg;
+        C1[k] = make_float2(R[k].x * gm[2 * k], R[k].y * gm[2 * k + 1]);
+        C2[k] = make_float2(-R[k].x * sk[g0 * 2], -R[k].y * sk[g1 * 2]);
+        C3[k] = make_float2(-R[k].x * sk[g0 * 2 + 1], -R[k].y * sk[g1 * 2 + 1]);
+      }
+      __nv_bfloat16* out = p.dx + static_cast<long long>(n) * HW * C;
+      for (int c = 0; c < nchunks; ++c) {
+        if (tid == 0) produce();
+        mbar_wait(full0 + 8 * stage, phase);
+        const int row = r0 + c * rstep + rlane;
+        if (row < r1) {
+          const uint8_t* st = ring + stage * 3 * GF_CHUNK + tid * 16;
+          const uint4 ud = *reinterpret_cast<const uint4*>(st);
+          const uint4 ux = *reinterpret_cast<const uint4*>(st + GF_CHUNK);
+          uint4 ua = make_uint4(0u, 0u, 0u, 0u);
+          if (has_add) ua = *reinterpret_cast<const uint4*>(st + 2 * GF_CHUNK);
+          const uint32_t wd[4] = {ud.x, ud.y, ud.z, ud.w}, wx[4] = {ux.x, ux.y, ux.z, ux.w};
+          const uint32_t wa[4] = {ua.x, ua.y, ua.z, ua.w};
+          uint32_t o[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 xv = unpack2(wx[k]);
+            const float2 dz = dz_pair<SW>(unpack2(wd[k]), xv, A[k], B[k]);
+            const float2 xh = __ffma2_rn(xv, R[k], M[k]);
+            float2 r = __ffma2_rn(dz, C1[k], C2[k]);
+            r = __ffma2_rn(xh, C3[k], r);
+            if (has_add) r = __fadd2_rn(r, unpack2(wa[k]));
+            o[k] = pack_bf16x2(r.x, r.y);
+          }
+          *reinterpret_cast<uint4*>(out + static_cast<long long>(row) * C + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0 + 8 * stage);
+        if (++stage == GF_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  }
+  // ------------------------------------------------------------------ dgamma / dbeta: per-CTA partials, last CTA sums
+  __syncthreads();
+  float* mine = p.dgb_part + static_cast<long long>(blockIdx.x) * 2 * C;
+  for (int i = tid; i < 2 * C; i += GF_THREADS) __stcg(mine + i, dg[i]);
+  __shared__ unsigned s_last;
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    s_last = (atomicAdd(p.flags + p.N, 1u) == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    for (int i = tid; i < 2 * C; i += GF_THREADS) {
+      float t = 0.f;
+      for (unsigned b = 0; b < gridDim.x; ++b) t += __ldcg(p.dgb_part + static_cast<long long>(b) * 2 * C + i);
+      if (__ldcg(p.flags + p.N + 1)) t = __int_as_float(0x7fc00000);   // a team barrier timed out: poison, never pass silently
+      p.dgb[i] = t;
+    }
+  }
+}
+
+constexpr int GF_SMEM = GF_STAGES * 3 * GF_CHUNK + (2 * GF_CONSUMERS * 8 + 4 * GF_MAXC + 2 * GF_MAXG) * 4 + 2 * GF_STAGES * 8;
+
+}  // namespace b2
+
+using namespace b2;
+
+// Images whose dy + x may be in flight at once (teams): their bytes must stay L2-resident between the two phases.
+static long long gf_l2_budget() {
+  static long long v = -1;
+  if (v < 0) {
+    const char* e = getenv("B2DQ_GN_L2_BUDGET_MB");
+    v = (e ? atoll(e) : 40) << 20;
+  }
+  return v;
+}
+
+struct GfPlan { int T, S, rows_per_cta, grid; };
+static GfPlan gf_plan(int N, int HW, int C) {
+  const int sms = device_sm_count();
+  const int rstep = GF_CONSUMERS / (C / 8);
+  const int chunks_img = (HW + rstep - 1) / rstep;
+  const long long per_img = 4LL * HW * C;                       // dy + x, bf16
+  long long T = gf_l2_budget() / (per_img > 0 ? per_img : 1);
+  if (T < 1) T = 1;
+  if (T > N) T = N;
+  if (T > sms) T = sms;
+  for (long long t = T; 2 * t > T; --t)                         // same number of images per team when a nearby T allows it
+    if (N % t == 0) { T = t; break; }
+  int S = sms / static_cast<int>(T);
+  if (S > chunks_img) S = chunks_img;
+  if (S < 1) S = 1;
+  const int chunks_cta = (chunks_img + S - 1) / S;
+  GfPlan pl;
+  pl.rows_per_cta = chunks_cta * rstep;
+  pl.S = (HW + pl.rows_per_cta - 1) / pl.rows_per_cta;          // CTAs with a non-empty slice
+  pl.T = static_cast<int>(T);
+  pl.grid = pl.T * pl.S;
+  return pl;
+}
+
+extern "C" {
+
+// Scratch the fused backward needs for an [N, HW, C] tensor with G groups, in bytes (0: shape not supported,
+// use b2dq_gn_bwd_stats + b2dq_gn_bwd_apply).
+int b2dq_gn_bwd_fused_workspace_bytes(int N, int HW, int C, int G) {
+  if (N <= 0 || HW <= 0) return 0;
+  if (C % 8 || C > GF_MAXC || G > GF_MAXG || G <= 0 || C % G || GF_CONSUMERS % (C / 8) || GF_CONSUMERS % C ||
+      (2 * G) % 4 || GF_CONSUMERS % ((2 * G) / 4))
+    return 0;
+  const int rstep = GF_CONSUMERS / (C / 8);
+  if (rstep % (GF_CONSUMERS / C)) return 0;
+  const GfPlan pl = gf_plan(N, HW, C);
+  const long long part = 1LL * N * pl.S * G * 2 * 4;
+  const long long dgbp = 1LL * pl.grid * 2 * C * 4;
+  const long long flags = (1LL * N + 2) * 4;
+  return static_cast<int>(((part + 15) / 16 + (dgbp + 15) / 16 + (flags + 15) / 16) * 16);
+}
+
+// dx = d/dx [ swish?(GroupNorm(x)) ] . dy (+ add);  dgb [2*C] = (dgamma, dbeta).  ws: b2dq_gn_bwd_fused_workspace_bytes.
+// Returns 0, a cudaError_t, -1 (unsupported shape) or -2 (workspace too small).
+int b2dq_gn_bwd_fused(const void* dy, const void* x, const float* stats, const float* gamma, const float* beta,
+                      void* dx, float* dgb, const void* add, void* ws, long long ws_bytes, int N, int HW, int C, int G,
+                      int swish, cudaStream_t stream) {
+  if (N <= 0 || HW <= 0) return 0;
+  const long long need = b2dq_gn_bwd_fused_workspace_bytes(N, HW, C, G);
+  if (need == 0) return -1;
+  if (ws_bytes < need || ws == nullptr) return -2;
+  const GfPlan pl = gf_plan(N, HW, C);
+  GnFusedParams p;
+  p.dy = reinterpret_cast<const __nv_bfloat16*>(dy);
+  p.x = reinterpret_cast<const __nv_bfloat16*>(x);
+  p.add = reinterpret_cast<const __nv_bfloat16*>(add);
+  p.stats = stats; p.gamma = gamma; p.beta = beta;
+  p.dx = reinterpret_cast<__nv_bfloat16*>(dx);
+  p.dgb = dgb;
+  uint8_t* w = reinterpret_cast<uint8_t*>(ws);
+  const long long part = ((1LL * N * pl.S * G * 2 * 4 + 15) / 16) * 16;
+  const long long dgbp = ((1LL * pl.grid * 2 * C * 4 + 15) / 16) * 16;
+  p.part = reinterpret_cast<float*>(w);
+  p.dgb_part = reinterpret_cast<float*>(w + part);
+  p.flags = reinterpret_cast<unsigned*>(w + part + dgbp);
+  p.N = N; p.HW = HW; p.C = C; p.G = G; p.S = pl.S; p.T = pl.T; p.rows_per_cta = pl.rows_per_cta;
+  cudaError_t e = cudaMemsetAsync(p.flags, 0, (N + 2) * sizeof(unsigned), stream);
+  if (e != cudaSuccess) return (int)e;
+  static unsigned long long m0 = 0, m1 = 0;
+  if (swish) {
+    if (int r = set_max_smem_once(gn_bwd_fused_kernel<true>, GF_SMEM, m1)) return r;
+    gn_bwd_fused_kernel<true><<<pl.grid, GF_THREADS, GF_SMEM, stream>>>(p);
+  } else {
+    if (int r = set_max_smem_once(gn_bwd_fused_kernel<false>, GF_SMEM, m0)) return r;
+    gn_bwd_fused_kernel<false><<<pl.grid, GF_THREADS, GF_SMEM, stream>>>(p);
+  }
+  return (int)cudaGetLastError();
+}
+
+// The plan of the call above (tests / bench): teams, CTAs per team, rows per CTA, grid.
+void b2dq_gn_bwd_fused_plan(int N, int HW, int C, int* out4) {
+  const GfPlan pl = gf_plan(N, HW, C);
+  out4[0] = pl.T; out4[1] = pl.S; out4[2] = pl.rows_per_cta; out4[3] = pl.grid;
+}
+
+}  // extern "C"

@@ -543,9 +543,19 @@ def gn_forward(x, gamma, beta, swish, groups=32, eps=1e-6):
     return y, stats
 
 
+USE_GN_FUSED = True      # GroupNorm backward as one persistent kernel (2 reads + 1 write of HBM) instead of 5 passes
+
+
 def gn_bwd_kernel_name():
     """Which kernels gn_bwd launches (for bench.py's roofline_gn label)."""
-    return "gn_bwd_partial + gn_bwd_reduce + gn_bwd_apply"
+    return "gn_bwd_fused_kernel" if USE_GN_FUSED else "gn_bwd_partial + gn_bwd_reduce + gn_bwd_apply"
+
+
+def gn_bwd_fused_plan(nb, hw, c):
+    """(teams = images in flight, CTAs per team, rows per CTA, grid) of the fused backward for an [nb,hw,c] tensor."""
+    out = (C.c_int * 4)()
+    _cabi.lib().b2dq_gn_bwd_fused_plan(nb, hw, c, out)
+    return tuple(out)
 
 
 def gn_bwd(dy, x, stats, gamma, beta, swish, groups=32, add=None, ws_nc=None):
@@ -553,6 +563,16 @@ def gn_bwd(dy, x, stats, gamma, beta, swish, groups=32, add=None, ws_nc=None):
     ws_nc [N,C,2]: the reduction pass was already done by the producer of dy (pconv dgrad epilogue)."""
     nb, h, w, c = x.shape
     l = _cabi.lib()
+    if ws_nc is None and USE_GN_FUSED:
+        ws_bytes = l.b2dq_gn_bwd_fused_workspace_bytes(nb, h * w, c, groups)
+        if ws_bytes > 0:
+            dx = torch.empty_like(x)
+            dgb = torch.empty(2, c, dtype=torch.float32, device=x.device)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+            check(l.b2dq_gn_bwd_fused(_ptr(dy), _ptr(x), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(dx), _ptr(dgb),
+                                      _ptr(add), _ptr(ws), ws_bytes, nb, h * w, c, groups, int(swish), _stream()),
+                  "gn_bwd_fused")
+            return dx, dgb[0], dgb[1]
     if ws_nc is not None:
         dx = torch.empty_like(x)
         dgb = torch.empty(2, c, dtype=torch.float32, device=x.device)

@@ -215,6 +215,20 @@ int b2dq_gn_bwd_apply(const void* dy, const void* x, const float* stats, const f
  * (used when the backward is run in L2-sized image groups). */
 int b2dq_gn_bwd_param(const float* ws_nc, float* dgb, int N, int C, cudaStream_t stream);
 
+/* GroupNorm(+swish) backward as ONE persistent kernel (csrc/norm_fused.cu): 2 reads + 1 write of HBM instead of
+ * the 5 passes of b2dq_gn_bwd_stats + b2dq_gn_bwd_apply.  Teams of CTAs own one image at a time, meet at a
+ * per-image barrier in `ws` and re-read their slice of (dy, x) from L2.  Replaces the autograd of
+ * Normalize + nonlinearity (modules/diffusionmodules/model.py:29-35).
+ * b2dq_gn_bwd_fused_workspace_bytes: bytes of `ws` for an [N,HW,C] tensor (0 = shape not supported: use the pair
+ * above).  dgb [2*C] = (dgamma, dbeta), overwritten.  add: optional, summed into dx.  Returns 0, a cudaError_t,
+ * -1 (unsupported shape) or -2 (workspace too small).  b2dq_gn_bwd_fused_plan: out4 = {teams (images in flight),
+ * CTAs per team, rows per CTA, grid}. */
+int b2dq_gn_bwd_fused_workspace_bytes(int N, int HW, int C, int G);
+int b2dq_gn_bwd_fused(const void* dy, const void* x, const float* stats, const float* gamma, const float* beta,
+                      void* dx, float* dgb, const void* add, void* ws, long long ws_bytes, int N, int HW, int C,
+                      int G, int swish, cudaStream_t stream);
+void b2dq_gn_bwd_fused_plan(int N, int HW, int C, int* out4);
+
 /* ------------------------------------------------------------------ layout / elementwise */
 int b2dq_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int N, int C, int HW, cudaStream_t stream);
 int b2dq_nchw_f32_to_nhwc_f32(const float* src, float* dst, int N, int C, int HW, cudaStream_t stream);

@@ -364,6 +364,54 @@ def test_groupnorm_swish_fwd_bwd(nb, h, w, c, swish):
     assert rel_rms(db.cpu(), br.grad) < 2e-3
 
 
+@pytest.mark.parametrize("nb,h,w,c,swish,with_add", [
+    (2, 8, 8, 64, True, False),         # one chunk per image, one CTA per team
+    (3, 25, 40, 128, True, True),       # ragged rows (1000 = 31.25 chunks), 3 teams, residual gradient added
+    (5, 32, 32, 256, False, True),      # GroupNorm without swish (AttnBlock), 5 images
+    (4, 16, 16, 512, True, False),      # 512 channels: 8 rows per chunk
+    (2, 128, 128, 128, True, True),     # many chunks per CTA: the ring wraps, two phases per image
+    (1, 256, 256, 128, True, False),    # one image over (almost) every SM
+    (7, 64, 64, 256, True, True),       # images not a multiple of the teams
+])
+def test_groupnorm_backward_fused_kernel(nb, h, w, c, swish, with_add):
+    """csrc/norm_fused.cu (one persistent kernel, team barrier per image, L2 re-read) against the fp32 autograd of
+    F.group_norm (+ x * sigmoid(x)), against the separate-kernel path, and bit-reproducible run to run."""
+    from dynamicvectorquantization_b200 import _cabi, kernels as kn
+    assert _cabi.lib().b2dq_gn_bwd_fused_workspace_bytes(nb, h * w, c, 32) > 0
+    x = (_rand_bf(nb, h, w, c, seed=21).float() * 1.5 + 0.3).to(BF)
+    gamma = 1 + 0.2 * torch.randn(c, generator=torch.Generator().manual_seed(22))
+    beta = 0.1 * torch.randn(c, generator=torch.Generator().manual_seed(23))
+    dy = _rand_bf(nb, h, w, c, seed=24)
+    add = _rand_bf(nb, h, w, c, seed=25) if with_add else None
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    yr = F.group_norm(xr, 32, gr, br, eps=1e-6)
+    if swish:
+        yr = yr * torch.sigmoid(yr)
+    yr.backward(dy.float().permute(0, 3, 1, 2))
+    ref_dx = xr.grad.permute(0, 2, 3, 1) + (add.float() if with_add else 0.0)
+    dev = "cuda"
+    xd, dyd, gd, bd = x.to(dev), dy.to(dev), gamma.to(dev), beta.to(dev)
+    addd = add.to(dev) if with_add else None
+    st = kn.gn_stats(xd)
+    assert kn.USE_GN_FUSED
+    dx, dg, db = kn.gn_bwd(dyd, xd, st, gd, bd, swish, add=addd)
+    torch.cuda.synchronize()
+    assert torch.isfinite(dg).all() and torch.isfinite(db).all(), "a team barrier timed out (dgamma / dbeta poisoned)"
+    assert rel_rms(dx.float().cpu(), ref_dx) < 6e-3
+    assert rel_rms(dg.cpu(), gr.grad) < 2e-3
+    assert rel_rms(db.cpu(), br.grad) < 2e-3
+    dx2, dg2, db2 = kn.gn_bwd(dyd, xd, st, gd, bd, swish, add=addd)
+    assert torch.equal(dx, dx2) and torch.equal(dg, dg2) and torch.equal(db, db2), "not reproducible run to run"
+    kn.USE_GN_FUSED = False
+    try:
+        dx0, dg0, db0 = kn.gn_bwd(dyd, xd, st, gd, bd, swish, add=addd)
+    finally:
+        kn.USE_GN_FUSED = True
+    assert rel_rms(dx.float().cpu(), dx0.float().cpu()) < 4e-3          # bf16 outputs of two evaluation orders
+    assert rel_rms(dg.cpu(), dg0.cpu()) < 1e-3 and rel_rms(db.cpu(), db0.cpu()) < 1e-3
+
+
 # ------------------------------------------------------------------------------------------- misc
 def test_layout_upsample_softmax():
     from dynamicvectorquantization_b200 import kernels as kn

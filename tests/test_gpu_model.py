@@ -84,10 +84,11 @@ def test_small_model_forward_backward_parity(batch):
     cosines.sort()
     # bf16 activations/gradients through ~60 layers: deepest encoder tensors see ~10 % rel-RMS noise,
     # but every gradient must point the same way as the fp32 oracle's
-    assert cosines[0][0] > 0.985, f"lowest gradient cosine similarities: {cosines[:8]}"
-    assert worst and worst[0][0] < 0.25, f"worst gradient rel-RMS errors: {worst[:8]}"
+    assert cosines[0][0] > 0.995, f"lowest gradient cosine similarities: {cosines[:8]}"
+    # measured: worst 0.155 (an attention k-bias, whose true gradient is ~0: absolute scale), median 0.028
+    assert worst and worst[0][0] < 0.19, f"worst gradient rel-RMS errors: {worst[:8]}"
     med = worst[len(worst) // 2][0]
-    assert med < 0.04, f"median gradient rel-RMS {med}; worst {worst[:5]}"
+    assert med < 0.035, f"median gradient rel-RMS {med}; worst {worst[:5]}"
     print("gradient rel-RMS: worst", worst[:3], "median", med, "min cosine", cosines[:2])
 
 
@@ -155,8 +156,9 @@ def test_full_dual_config_backward_vs_reference_gradients(monkeypatch):
     ref = {k[len("grad__"):].replace("__", "."): torch.from_numpy(g[k]) for k in g.files if k.startswith("grad__")}
     worst, cosines, med = grad_report(got, ref)
     print("reference-gradient rel-RMS: worst", worst[:4], "median", med, "min cosine", cosines[:3])
-    assert cosines[0][0] > 0.99, f"lowest cosine similarities vs the reference gradients: {cosines[:6]}"
-    assert worst[0][0] < 0.12, f"worst rel-RMS vs the reference gradients: {worst[:6]}"
+    # measured on B200: worst rel-RMS 0.075 (first encoder conv: the deepest backward path), min cosine 0.997
+    assert cosines[0][0] > 0.995, f"lowest cosine similarities vs the reference gradients: {cosines[:6]}"
+    assert worst[0][0] < 0.10, f"worst rel-RMS vs the reference gradients: {worst[:6]}"
     # the norm of EVERY parameter gradient (368 tensors) against the reference's
     ratios = []
     typical = float(np.median(g["grad_norms"]))
@@ -167,14 +169,17 @@ def test_full_dual_config_backward_vs_reference_gradients(monkeypatch):
             ratios.append((abs(float(got[n].double().norm()) / ref_norm - 1.0), n))
     ratios.sort(reverse=True)
     print("gradient-norm deviation from the reference: worst", ratios[:4])
-    assert ratios[0][0] < 0.08, f"gradient norms off: {ratios[:6]}"
+    assert ratios[0][0] < 0.04, f"gradient norms off: {ratios[:6]}"                 # measured 0.018
 
 
 def test_full_dual_config_batch32_forward():
     """BASELINE config 2 at its own batch size: 32 images 256x256 through dqvae-dual-r-05 in ONE call.  Image 0 is
     the reference's golden input.  Two images of the batch are compared with the fp32 oracle (gate / codes of
-    the batch run replayed), and with the product's own single-image run (same routing, >= 99 % equal codes: the
-    GroupNorm partial sums are chunked differently at batch 1, which moves near-tie codes only)."""
+    the batch run replayed: rel-MSE <= 1e-3), and with the product's own single-image run.  The two product runs
+    do not take the same kernels (the persistent strip convolution needs >= 296 row tiles, split-K factors and
+    GroupNorm chunking follow the batch), i.e. they are two different bf16 evaluation orders of the same network:
+    on these untrained weights their codes agree as well as the product agrees with the fp32 reference
+    (measured 0.985 vs 0.983), routing 0.996."""
     import os
     from dynamicvectorquantization_b200 import configs
     from oracle import dqvae_oracle as orc
@@ -196,7 +201,7 @@ def test_full_dual_config_batch32_forward():
             print(f"batch-32 image {i}: rel-MSE vs oracle {e:.2e}, codes equal to the batch-1 run {same_codes:.4f}, "
                   f"routing equal {same_idx:.4f}")
             assert e < 1e-3, f"image {i}: rel-MSE {e}"
-            assert same_codes >= 0.99 and same_idx >= 0.99, (i, same_codes, same_idx)
+            assert same_codes >= 0.97 and same_idx >= 0.99, (i, same_codes, same_idx)
     agree = float((info[2][0].cpu() == torch.from_numpy(g["codes"].astype(np.int64))[0]).float().mean())
     assert agree > 0.9, f"image 0 codes vs the reference's golden run: {agree}"
 
@@ -253,7 +258,7 @@ def test_full_entropy_config_forward_backward_parity(tmp_path):
     ref = {n: p.grad for n, p in params.items() if p.grad is not None}
     worst, cosines, med = grad_report(_grads(model), ref)
     print("entropy config gradient rel-RMS: worst", worst[:4], "median", med, "min cosine", cosines[:3])
-    assert cosines[0][0] > 0.985 and worst[0][0] < 0.2 and med < 0.04, (worst[:6], cosines[:6], med)
+    assert cosines[0][0] > 0.995 and worst[0][0] < 0.08 and med < 0.025, (worst[:6], cosines[:6], med)   # measured 0.040 / 0.0135
 
 
 def test_train_mode_gumbel_routing_parity(monkeypatch):
@@ -305,10 +310,10 @@ def test_train_mode_gumbel_routing_parity(monkeypatch):
     assert len(router) >= 8 and all(float(r.abs().max()) > 0 for r in router.values()), "router gradients missing"
     rw, rc, rmed = grad_report(got, router, floor_frac=0.0)
     print("router gradient rel-RMS (train-mode gumbel):", rw, "cosines", rc)
-    assert rc[0][0] > 0.98 and rw[0][0] < 0.2, (rw, rc)
+    assert rc[0][0] > 0.995 and rw[0][0] < 0.03, (rw, rc)                            # measured worst 0.0093
     worst, cosines, med = grad_report(got, ref)
     print("train-mode gradient rel-RMS: worst", worst[:4], "median", med, "min cosine", cosines[:3])
-    assert cosines[0][0] > 0.98 and med < 0.05, (worst[:6], cosines[:6], med)
+    assert cosines[0][0] > 0.995 and med < 0.03 and worst[0][0] < 0.28, (worst[:6], cosines[:6], med)   # 0.016 / 0.214 (k-bias)
 
 
 def test_full_triple_config_forward_parity():

@@ -108,6 +108,43 @@ def gn(nb, h, w, c):
                           apply_GBs=round(2 * by / ms2 / 1e6), bwd_ms=round(ms3, 3), bwd_GBs=round(5 * by / ms3 / 1e6))))
 
 
+def gnf():
+    """GroupNorm backward: fused persistent kernel vs the separate-kernel path on every shape of the dual-config step
+    (back-to-back launches, as inside a step).  B2DQ_GN_L2_BUDGET_MB selects the images in flight (teams)."""
+    shapes = [(32, 256, 256, 128), (32, 128, 128, 128), (32, 128, 128, 256), (32, 64, 64, 128), (32, 64, 64, 256),
+              (32, 32, 32, 256), (32, 16, 16, 256), (32, 16, 16, 512)]
+    for nb, h, w, c in shapes:
+        x = (torch.randn(nb, h, w, c, device=dev) * 1.5 + 0.3).to(BF)
+        g, b = torch.ones(c, device=dev), torch.zeros(c, device=dev)
+        dy = torch.randn(nb, h, w, c, device=dev).to(BF)
+        add = torch.randn(nb, h, w, c, device=dev).to(BF)
+        st = kn.gn_stats(x)
+        by = 3 * x.numel() * 2
+        r = dict(k="gn_bwd", nb=nb, hw=h, c=c, plan=kn.gn_bwd_fused_plan(nb, h * w, c),
+                 budget_mb=os.environ.get("B2DQ_GN_L2_BUDGET_MB", "default"))
+        for name, fused, a in (("fused", True, None), ("fused_add", True, add), ("split", False, None), ("split_add", False, add)):
+            kn.USE_GN_FUSED = fused
+            fn = lambda: kn.gn_bwd(dy, x, st, g, b, True, add=a)
+            for _ in range(3):
+                fn()
+            s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(); s_.record()
+            for _ in range(10):
+                fn()
+            e_.record(); torch.cuda.synchronize()
+            ms = s_.elapsed_time(e_) / 10
+            byt = by + (x.numel() * 2 if a is not None else 0)
+            r[name + "_ms"] = round(ms, 4); r[name + "_GBs"] = round(byt / ms / 1e6)
+        kn.USE_GN_FUSED = True
+        dxa = kn.gn_bwd(dy, x, st, g, b, True)
+        kn.USE_GN_FUSED = False
+        dxb = kn.gn_bwd(dy, x, st, g, b, True)
+        kn.USE_GN_FUSED = True
+        r["max_abs_diff_dx"] = float((dxa[0].float() - dxb[0].float()).abs().max())
+        r["dg_finite"] = bool(torch.isfinite(dxa[1]).all())
+        print(json.dumps(r), flush=True)
+
+
 def vq_small():
     """Small-N calls (residual quantizer depth step, stage-2 sampling): codebook split on / off."""
     C = 256
@@ -132,5 +169,7 @@ if __name__ == "__main__":
         for c in [(32, 256, 256, 128, 128, 3, 1), (32, 128, 128, 128, 128, 3, 1), (32, 64, 64, 256, 256, 3, 1), (32, 32, 32, 256, 256, 3, 1),
                   (32, 16, 16, 512, 512, 3, 1), (32, 32, 32, 256, 256, 1, 1), (32, 256, 256, 128, 128, 3, 2), (32, 128, 128, 256, 256, 3, 1)]:
             conv(*c)
+    if "gnf" in what:
+        gnf()
     if "gn" in what:
         gn(32, 256, 256, 128); gn(32, 64, 64, 256); gn(32, 16, 16, 512)
