@@ -10,24 +10,27 @@
 // then streams the SAME slice again for dx (phase 2) - the second read hits the 126 MB L2, because the number of
 // images in flight (teams) is chosen so that their dy + x stay below an L2 budget.  HBM sees 2 reads + 1 write.
 //
-// Mechanics: 1 CTA per SM (persistent, all co-resident: the grid never exceeds the SM count), 16 warps.  Thread 0
-// issues 1-D bulk async copies (cp.async.bulk, 8 KB per tensor and ring stage: a row slice of an NHWC image is
-// contiguous, no tensor map needed) into a 6-stage shared-memory ring signalled by mbarriers, always five chunks
-// ahead of the chunk being consumed - across the phase boundary and the team barrier too, so the memory pipe keeps
-// moving while a CTA waits for its team (a 17th producer warp would cap the kernel at 96 registers: spills).  Consumers keep every per-channel constant in registers,
-// use packed fp32x2 arithmetic (fma.rn.f32x2: half the issue slots) and ONE MUFU op per sigmoid
-// (sigmoid(z) = 0.5 + 0.5 tanh(z/2)) - the two-kernel version was instruction-bound at ~0.55 of HBM speed.
+// Mechanics: 2 CTAs per SM (persistent, all co-resident: grid <= 2 x SM count), each 6 compute warps + 1 producer
+// warp (+1 idle warp: 8 warps keep the register allocation at 128 per thread).  Two CTAs per SM belong to different
+// teams whenever there are at least two teams, so one streams while the other waits at its team barrier.  The
+// producer lane issues 1-D bulk async copies (cp.async.bulk, 6 KB per tensor and ring stage: a row slice of an
+// NHWC image is contiguous, no tensor map needed) into a 5-stage shared-memory ring signalled by mbarriers and runs
+// ahead of the consumers across the phase boundary and the team barrier.  Consumers keep every per-channel
+// constant in registers, use packed fp32x2 arithmetic (fma.rn.f32x2: half the issue slots) and ONE MUFU op per
+// sigmoid (sigmoid(z) = 0.5 + 0.5 tanh(z/2)) - the two-kernel version was instruction-bound at ~0.55 of HBM speed.
 // dgamma / dbeta are accumulated per CTA over its images and combined by the last CTA to finish, in CTA order.
 #include "common.cuh"
 
 namespace b2 {
 
-constexpr int GF_CONSUMERS = 512;                 // 16 warps; thread 0 also issues the bulk copies
-constexpr int GF_THREADS = GF_CONSUMERS;
-constexpr int GF_STAGES = 6;
-constexpr int GF_CHUNK = GF_CONSUMERS * 16;       // bytes per tensor per stage: one 16 B vector per consumer thread
+constexpr int GF_CONSUMERS = 192;                 // 6 compute warps
+constexpr int GF_THREADS = 256;                   // + producer warp (warp 6) + one idle warp
+constexpr int GF_VPT = 2;                         // 16 B vectors per consumer thread and stage
+constexpr int GF_STAGES = 5;
+constexpr int GF_CHUNK = GF_CONSUMERS * 16 * GF_VPT;   // bytes per tensor per stage (6 KB)
 constexpr int GF_MAXC = 512;
 constexpr int GF_MAXG = 64;
+constexpr int GF_MAXS = 148;                      // CTAs per team
 
 struct GnFusedParams {
   const __nv_bfloat16* dy;
@@ -77,10 +80,12 @@ __device__ __forceinline__ float2 dz_pair(float2 d, float2 x, float2 A, float2 B
   return __fmul2_rn(d, __fmul2_rn(sg, w));
 }
 
+// shared memory: ring [STAGES][3][CHUNK] | red [2][CONSUMERS][8] | chan [2][MAXC] | dg [2][MAXC] | sk [2][MAXG] | bars
+constexpr int GF_SMEM = GF_STAGES * 3 * GF_CHUNK + (2 * GF_CONSUMERS * 8 + 4 * GF_MAXC + 2 * GF_MAXG) * 4 + 2 * GF_STAGES * 8;
+
 template <bool SW>
-__global__ void __launch_bounds__(GF_THREADS, 1) gn_bwd_fused_kernel(const GnFusedParams p) {
+__global__ void __launch_bounds__(GF_THREADS, 2) gn_bwd_fused_kernel(const GnFusedParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  // layout: ring [STAGES][3][CHUNK] | red [2][CONSUMERS][8] floats | chan [2][MAXC] | dg [2][MAXC] | sk [MAXG][2] | bars
   uint8_t* ring = smem;
   float* red = reinterpret_cast<float*>(smem + GF_STAGES * 3 * GF_CHUNK);
   float* chan = red + 2 * GF_CONSUMERS * 8;
@@ -91,11 +96,12 @@ __global__ void __launch_bounds__(GF_THREADS, 1) gn_bwd_fused_kernel(const GnFus
   const int tid = threadIdx.x;
   const int C = p.C, G = p.G, HW = p.HW;
   const int vecs = C >> 3;
-  const int rstep = GF_CONSUMERS / vecs;          // rows per chunk
+  const int rstep = GF_CONSUMERS / vecs;          // rows covered by one vector step of the compute warps
+  const int srows = rstep * GF_VPT;               // rows per ring stage
   const int team = blockIdx.x / p.S, s_idx = blockIdx.x % p.S;
   const int r0 = s_idx * p.rows_per_cta;
   const int r1 = min(HW, r0 + p.rows_per_cta);
-  const int nchunks = (r1 - r0 + rstep - 1) / rstep;
+  const int nstages = (r1 - r0 + srows - 1) / srows;
   const bool has_add = p.add != nullptr;
 
   if (tid == 0) {
@@ -108,32 +114,32 @@ __global__ void __launch_bounds__(GF_THREADS, 1) gn_bwd_fused_kernel(const GnFus
   for (int i = tid; i < 2 * C; i += GF_THREADS) dg[i] = 0.f;
   __syncthreads();
 
-  // producer cursor (thread 0): the CTA's chunks form one sequence image -> phase -> chunk; `produce` issues the next one
-  int pn = team, pph = 0, pc = 0;
-  uint32_t pstage = 0, pphase = 0;
-  auto produce = [&]() {
-    if (pn >= p.N) return;
-    const int row = r0 + pc * rstep;
-    const uint32_t bytes = static_cast<uint32_t>(min(rstep, r1 - row)) * C * 2;
-    const long long off = (static_cast<long long>(pn) * HW + row) * C;
-    mbar_wait(empty0 + 8 * pstage, pphase ^ 1);
-    const uint32_t fb = full0 + 8 * pstage;
-    const uint32_t dst = smem_u32(ring + pstage * 3 * GF_CHUNK);
-    const bool with_add = pph == 1 && has_add;
-    mbar_arrive_expect_tx(fb, bytes * (with_add ? 3 : 2));
-    bulk_load(dst, p.dy + off, bytes, fb);
-    bulk_load(dst + GF_CHUNK, p.x + off, bytes, fb);
-    if (with_add) bulk_load(dst + 2 * GF_CHUNK, p.add + off, bytes, fb);
-    if (++pstage == GF_STAGES) { pstage = 0; pphase ^= 1; }
-    if (++pc == nchunks) {
-      pc = 0;
-      if (++pph == 2) { pph = 0; pn += p.T; }
+  if (tid >= GF_CONSUMERS) {
+    // ------------------------------------------------------------------ producer (one lane of warp 6)
+    if (tid == GF_CONSUMERS) {
+      uint32_t stage = 0, phase = 0;
+      for (int n = team; n < p.N; n += p.T) {
+        const long long img = static_cast<long long>(n) * HW * C;
+        for (int ph = 0; ph < 2; ++ph) {
+          const bool with_add = ph == 1 && has_add;
+          for (int c = 0; c < nstages; ++c) {
+            const int row = r0 + c * srows;
+            const uint32_t bytes = static_cast<uint32_t>(min(srows, r1 - row)) * C * 2;
+            const long long off = img + static_cast<long long>(row) * C;
+            mbar_wait(empty0 + 8 * stage, phase ^ 1);
+            const uint32_t fb = full0 + 8 * stage;
+            const uint32_t dst = smem_u32(ring + stage * 3 * GF_CHUNK);
+            mbar_arrive_expect_tx(fb, bytes * (with_add ? 3 : 2));
+            bulk_load(dst, p.dy + off, bytes, fb);
+            bulk_load(dst + GF_CHUNK, p.x + off, bytes, fb);
+            if (with_add) bulk_load(dst + 2 * GF_CHUNK, p.add + off, bytes, fb);
+            if (++stage == GF_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
     }
-  };
-  if (tid == 0)
-    for (int i = 0; i < GF_STAGES - 1; ++i) produce();
-  {
-    // ------------------------------------------------------------------ consumers
+  } else {
+    // ------------------------------------------------------------------ consumers (6 warps)
     const int v = tid % vecs, rlane = tid / vecs;
     const int cg = C / G;
     const int lane = tid & 31;
@@ -161,21 +167,23 @@ __global__ void __launch_bounds__(GF_THREADS, 1) gn_bwd_fused_kernel(const GnFus
       float2 sa[4], sb[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) { sa[k] = make_float2(0.f, 0.f); sb[k] = make_float2(0.f, 0.f); }
-      for (int c = 0; c < nchunks; ++c) {
-        if (tid == 0) produce();
+      for (int c = 0; c < nstages; ++c) {
         mbar_wait(full0 + 8 * stage, phase);
-        if (r0 + c * rstep + rlane < r1) {
-          const uint8_t* st = ring + stage * 3 * GF_CHUNK + tid * 16;
-          const uint4 ud = *reinterpret_cast<const uint4*>(st);
-          const uint4 ux = *reinterpret_cast<const uint4*>(st + GF_CHUNK);
-          const uint32_t wd[4] = {ud.x, ud.y, ud.z, ud.w}, wx[4] = {ux.x, ux.y, ux.z, ux.w};
+        const uint8_t* st = ring + stage * 3 * GF_CHUNK + tid * 16;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float2 xv = unpack2(wx[k]);
-            const float2 dz = dz_pair<SW>(unpack2(wd[k]), xv, A[k], B[k]);
-            const float2 xh = __ffma2_rn(xv, R[k], M[k]);
-            sa[k] = __fadd2_rn(sa[k], dz);
-            sb[k] = __ffma2_rn(dz, xh, sb[k]);
+        for (int u = 0; u < GF_VPT; ++u) {
+          if (r0 + c * srows + u * rstep + rlane < r1) {
+            const uint4 ud = *reinterpret_cast<const uint4*>(st + u * (GF_CONSUMERS * 16));
+            const uint4 ux = *reinterpret_cast<const uint4*>(st + u * (GF_CONSUMERS * 16) + GF_CHUNK);
+            const uint32_t wd[4] = {ud.x, ud.y, ud.z, ud.w}, wx[4] = {ux.x, ux.y, ux.z, ux.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 xv = unpack2(wx[k]);
+              const float2 dz = dz_pair<SW>(unpack2(wd[k]), xv, A[k], B[k]);
+              const float2 xh = __ffma2_rn(xv, R[k], M[k]);
+              sa[k] = __fadd2_rn(sa[k], dz);
+              sb[k] = __ffma2_rn(dz, xh, sb[k]);
+            }
           }
         }
         __syncwarp();
@@ -187,41 +195,28 @@ __global__ void __launch_bounds__(GF_THREADS, 1) gn_bwd_fused_kernel(const GnFus
       float* red_b = red + GF_CONSUMERS * 8;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        red_a[rlane * C + v * 8 + 2 * k] = sa[k].x; red_a[rlane * C + v * 8 + 2 * k + 1] = sa[k].y;
-        red_b[rlane * C + v * 8 + 2 * k] = sb[k].x; red_b[rlane * C + v * 8 + 2 * k + 1] = sb[k].y;
+        *reinterpret_cast<float2*>(red_a + rlane * C + v * 8 + 2 * k) = sa[k];
+        *reinterpret_cast<float2*>(red_b + rlane * C + v * 8 + 2 * k) = sb[k];
       }
       consumer_sync();
-      {
-        // thread (q, c): rows q*rq .. of channel c; parts = CONSUMERS / C row ranges per channel
-        const int parts = GF_CONSUMERS / C;                 // 8, 4, 2, 1 for C = 64 .. 512
-        const int c = tid % C, q = tid / C;
-        const int rq = rstep / parts;
-        float a = 0.f, b = 0.f;
-        for (int rl = q * rq; rl < (q + 1) * rq; ++rl) { a += red_a[rl * C + c]; b += red_b[rl * C + c]; }
-        consumer_sync();                                     // everyone has read its rows: reuse the front of red
-        red_a[q * C + c] = a;
-        red_b[q * C + c] = b;
-        consumer_sync();
-        if (tid < C) {
-          float a2 = 0.f, b2 = 0.f;
-          for (int qq = 0; qq < parts; ++qq) { a2 += red_a[qq * C + tid]; b2 += red_b[qq * C + tid]; }
-          chan[tid] = a2;
-          chan[GF_MAXC + tid] = b2;
-          dg[tid] += b2;            // dgamma
-          dg[C + tid] += a2;        // dbeta
+      for (int o = tid; o < 2 * C; o += GF_CONSUMERS) {       // o < C: sum dz (-> dbeta), else sum dz*xhat (-> dgamma)
+        const float* src = (o < C) ? red_a + o : red_b + (o - C);
+        float t = 0.f;
+#pragma unroll 4
+        for (int rl = 0; rl < rstep; ++rl) t += src[rl * C];
+        chan[(o < C) ? o : GF_MAXC + (o - C)] = t;
+        dg[(o < C) ? C + o : (o - C)] += t;                    // dg[0..C) = dgamma, dg[C..2C) = dbeta
+      }
+      consumer_sync();
+      if (tid < G) {
+        float S1 = 0.f, S2 = 0.f;
+        for (int cc = tid * cg; cc < (tid + 1) * cg; ++cc) {
+          const float g_ = p.gamma[cc];
+          S1 = fmaf(g_, chan[cc], S1);
+          S2 = fmaf(g_, chan[GF_MAXC + cc], S2);
         }
-        consumer_sync();
-        if (tid < G) {
-          float S1 = 0.f, S2 = 0.f;
-          for (int cc = tid * cg; cc < (tid + 1) * cg; ++cc) {
-            const float g_ = p.gamma[cc];
-            S1 = fmaf(g_, chan[cc], S1);
-            S2 = fmaf(g_, chan[GF_MAXC + cc], S2);
-          }
-          float* o = p.part + ((static_cast<long long>(n) * p.S + s_idx) * G + tid) * 2;
-          __stcg(o, S1);
-          __stcg(o + 1, S2);
-        }
+        float* o = p.part + ((static_cast<long long>(n) * p.S + s_idx) * G + tid) * 2;
+        __stcg(reinterpret_cast<float2*>(o), make_float2(S1, S2));
       }
       consumer_sync();
       // ---------------- team barrier on image n
@@ -235,23 +230,28 @@ __global__ void __launch_bounds__(GF_THREADS, 1) gn_bwd_fused_kernel(const GnFus
       }
       consumer_sync();
       {
-        // sum the S partials of every (group, 2) in CTA order: thread (j, e4) takes CTAs j, j+32, ... of float4 e4
+        // sum the S partials of every (group, 2) in a fixed order: thread (j, e4) takes CTAs j, j+12, ... of float4 e4
         const int e4n = (2 * G) / 4;                          // float4 per CTA row (16 for G = 32)
-        const int lanes_s = GF_CONSUMERS / e4n;
+        const int lanes_s = GF_CONSUMERS / e4n;               // 12
         const int e4 = tid % e4n, j = tid / e4n;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4* src = reinterpret_cast<const float4*>(p.part + static_cast<long long>(n) * p.S * G * 2);
-        for (int s = j; s < p.S; s += lanes_s) {
-          const float4 t = __ldcg(src + static_cast<long long>(s) * e4n + e4);
-          acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+        const float4* src = reinterpret_cast<const float4*>(p.part + static_cast<long long>(n) * p.S * G * 2) + e4;
+        constexpr int MAXL = (GF_MAXS + 11) / 12;             // loads per thread, all issued before the first add
+        float4 t[MAXL];
+#pragma unroll
+        for (int i = 0; i < MAXL; ++i) {
+          const int s = j + i * lanes_s;
+          t[i] = (s < p.S) ? __ldcg(src + static_cast<long long>(s) * e4n) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        float4* r4 = reinterpret_cast<float4*>(red);
-        r4[j * e4n + e4] = acc;
+        float4 acc = t[0];
+#pragma unroll
+        for (int i = 1; i < MAXL; ++i) { acc.x += t[i].x; acc.y += t[i].y; acc.z += t[i].z; acc.w += t[i].w; }
+        reinterpret_cast<float4*>(red)[j * e4n + e4] = acc;
         consumer_sync();
         if (tid < 2 * G) {
-          float t = 0.f;
-          for (int jj = 0; jj < lanes_s; ++jj) t += red[jj * 2 * G + tid];
-          sk[tid] = t * inv_cnt;                              // sk[g*2 + 0] = S1/cnt, sk[g*2 + 1] = S2/cnt
+          float tsum = 0.f;
+#pragma unroll 4
+          for (int jj = 0; jj < lanes_s; ++jj) tsum += red[jj * 2 * G + tid];
+          sk[tid] = tsum * inv_cnt;                           // sk[g*2 + 0] = S1/cnt, sk[g*2 + 1] = S2/cnt
         }
         consumer_sync();
       }
@@ -265,31 +265,33 @@ __global__ void __launch_bounds__(GF_THREADS, 1) gn_bwd_fused_kernel(const GnFus
         C2[k] = make_float2(-R[k].x * sk[g0 * 2], -R[k].y * sk[g1 * 2]);
         C3[k] = make_float2(-R[k].x * sk[g0 * 2 + 1], -R[k].y * sk[g1 * 2 + 1]);
       }
-      __nv_bfloat16* out = p.dx + static_cast<long long>(n) * HW * C;
-      for (int c = 0; c < nchunks; ++c) {
-        if (tid == 0) produce();
+      __nv_bfloat16* out = p.dx + static_cast<long long>(n) * HW * C + v * 8;
+      for (int c = 0; c < nstages; ++c) {
         mbar_wait(full0 + 8 * stage, phase);
-        const int row = r0 + c * rstep + rlane;
-        if (row < r1) {
-          const uint8_t* st = ring + stage * 3 * GF_CHUNK + tid * 16;
-          const uint4 ud = *reinterpret_cast<const uint4*>(st);
-          const uint4 ux = *reinterpret_cast<const uint4*>(st + GF_CHUNK);
-          uint4 ua = make_uint4(0u, 0u, 0u, 0u);
-          if (has_add) ua = *reinterpret_cast<const uint4*>(st + 2 * GF_CHUNK);
-          const uint32_t wd[4] = {ud.x, ud.y, ud.z, ud.w}, wx[4] = {ux.x, ux.y, ux.z, ux.w};
-          const uint32_t wa[4] = {ua.x, ua.y, ua.z, ua.w};
-          uint32_t o[4];
+        const uint8_t* st = ring + stage * 3 * GF_CHUNK + tid * 16;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float2 xv = unpack2(wx[k]);
-            const float2 dz = dz_pair<SW>(unpack2(wd[k]), xv, A[k], B[k]);
-            const float2 xh = __ffma2_rn(xv, R[k], M[k]);
-            float2 r = __ffma2_rn(dz, C1[k], C2[k]);
-            r = __ffma2_rn(xh, C3[k], r);
-            if (has_add) r = __fadd2_rn(r, unpack2(wa[k]));
-            o[k] = pack_bf16x2(r.x, r.y);
+        for (int u = 0; u < GF_VPT; ++u) {
+          const int row = r0 + c * srows + u * rstep + rlane;
+          if (row < r1) {
+            const uint4 ud = *reinterpret_cast<const uint4*>(st + u * (GF_CONSUMERS * 16));
+            const uint4 ux = *reinterpret_cast<const uint4*>(st + u * (GF_CONSUMERS * 16) + GF_CHUNK);
+            uint4 ua = make_uint4(0u, 0u, 0u, 0u);
+            if (has_add) ua = *reinterpret_cast<const uint4*>(st + u * (GF_CONSUMERS * 16) + 2 * GF_CHUNK);
+            const uint32_t wd[4] = {ud.x, ud.y, ud.z, ud.w}, wx[4] = {ux.x, ux.y, ux.z, ux.w};
+            const uint32_t wa[4] = {ua.x, ua.y, ua.z, ua.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 xv = unpack2(wx[k]);
+              const float2 dz = dz_pair<SW>(unpack2(wd[k]), xv, A[k], B[k]);
+              const float2 xh = __ffma2_rn(xv, R[k], M[k]);
+              float2 r = __ffma2_rn(dz, C1[k], C2[k]);
+              r = __ffma2_rn(xh, C3[k], r);
+              if (has_add) r = __fadd2_rn(r, unpack2(wa[k]));
+              o[k] = pack_bf16x2(r.x, r.y);
+            }
+            *reinterpret_cast<uint4*>(out + static_cast<long long>(row) * C) = make_uint4(o[0], o[1], o[2], o[3]);
           }
-          *reinterpret_cast<uint4*>(out + static_cast<long long>(row) * C + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty0 + 8 * stage);
@@ -310,16 +312,22 @@ __global__ void __launch_bounds__(GF_THREADS, 1) gn_bwd_fused_kernel(const GnFus
   __syncthreads();
   if (s_last) {
     __threadfence();
+    const unsigned poisoned = __ldcg(p.flags + p.N + 1);      // a team barrier timed out: never pass silently
     for (int i = tid; i < 2 * C; i += GF_THREADS) {
-      float t = 0.f;
-      for (unsigned b = 0; b < gridDim.x; ++b) t += __ldcg(p.dgb_part + static_cast<long long>(b) * 2 * C + i);
-      if (__ldcg(p.flags + p.N + 1)) t = __int_as_float(0x7fc00000);   // a team barrier timed out: poison, never pass silently
-      p.dgb[i] = t;
+      float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;           // four fixed interleaved chains (more loads in flight)
+      unsigned b = 0;
+      for (; b + 3 < gridDim.x; b += 4) {
+        t0 += __ldcg(p.dgb_part + static_cast<long long>(b) * 2 * C + i);
+        t1 += __ldcg(p.dgb_part + static_cast<long long>(b + 1) * 2 * C + i);
+        t2 += __ldcg(p.dgb_part + static_cast<long long>(b + 2) * 2 * C + i);
+        t3 += __ldcg(p.dgb_part + static_cast<long long>(b + 3) * 2 * C + i);
+      }
+      for (; b < gridDim.x; ++b) t0 += __ldcg(p.dgb_part + static_cast<long long>(b) * 2 * C + i);
+      const float t = (t0 + t1) + (t2 + t3);
+      p.dgb[i] = poisoned ? __int_as_float(0x7fc00000) : t;
     }
   }
 }
-
-constexpr int GF_SMEM = GF_STAGES * 3 * GF_CHUNK + (2 * GF_CONSUMERS * 8 + 4 * GF_MAXC + 2 * GF_MAXG) * 4 + 2 * GF_STAGES * 8;
 
 }  // namespace b2
 
@@ -330,15 +338,15 @@ static long long gf_l2_budget() {
   static long long v = -1;
   if (v < 0) {
     const char* e = getenv("B2DQ_GN_L2_BUDGET_MB");
-    v = (e ? atoll(e) : 40) << 20;
+    v = (e ? atoll(e) : 70) << 20;
   }
   return v;
 }
 
 struct GfPlan { int T, S, rows_per_cta, grid; };
 static GfPlan gf_plan(int N, int HW, int C) {
-  const int sms = device_sm_count();
-  const int rstep = GF_CONSUMERS / (C / 8);
+  const int sms = 2 * device_sm_count();                        // 2 CTAs per SM
+  const int rstep = GF_VPT * (GF_CONSUMERS / (C / 8));          // rows per ring stage
   const int chunks_img = (HW + rstep - 1) / rstep;
   const long long per_img = 4LL * HW * C;                       // dy + x, bf16
   long long T = gf_l2_budget() / (per_img > 0 ? per_img : 1);
@@ -348,6 +356,7 @@ static GfPlan gf_plan(int N, int HW, int C) {
   for (long long t = T; 2 * t > T; --t)                         // same number of images per team when a nearby T allows it
     if (N % t == 0) { T = t; break; }
   int S = sms / static_cast<int>(T);
+  if (S > GF_MAXS) S = GF_MAXS;
   if (S > chunks_img) S = chunks_img;
   if (S < 1) S = 1;
   const int chunks_cta = (chunks_img + S - 1) / S;
@@ -365,11 +374,9 @@ extern "C" {
 // use b2dq_gn_bwd_stats + b2dq_gn_bwd_apply).
 int b2dq_gn_bwd_fused_workspace_bytes(int N, int HW, int C, int G) {
   if (N <= 0 || HW <= 0) return 0;
-  if (C % 8 || C > GF_MAXC || G > GF_MAXG || G <= 0 || C % G || GF_CONSUMERS % (C / 8) || GF_CONSUMERS % C ||
-      (2 * G) % 4 || GF_CONSUMERS % ((2 * G) / 4))
+  if (C % 8 || C > GF_MAXC || G > GF_MAXG || G <= 0 || C % G || GF_CONSUMERS % (C / 8) || (2 * G) % 4 ||
+      GF_CONSUMERS % ((2 * G) / 4) || (GF_CONSUMERS / ((2 * G) / 4)) * ((GF_MAXS + 11) / 12) < GF_MAXS)
     return 0;
-  const int rstep = GF_CONSUMERS / (C / 8);
-  if (rstep % (GF_CONSUMERS / C)) return 0;
   const GfPlan pl = gf_plan(N, HW, C);
   const long long part = 1LL * N * pl.S * G * 2 * 4;
   const long long dgbp = 1LL * pl.grid * 2 * C * 4;
