@@ -10,6 +10,24 @@
 namespace b2 {
 
 __device__ __forceinline__ float sigmoidf_(float z) { return __fdividef(1.f, 1.f + __expf(-z)); }
+// `swish` argument of every entry point below = activation after the affine normalisation:
+//   0 none, 1 swish (x * sigmoid(x), model.py:29-31), 2 LeakyReLU(0.2) (the PatchGAN stages,
+//   modules/discriminator/model.py:41,52,62: BatchNorm over [N,H,W] = these kernels with N = 1, G = C)
+constexpr float LRELU_SLOPE = 0.2f;
+__device__ __forceinline__ float act_fwd(float z, int act) {
+  if (act == 1) return z * sigmoidf_(z);
+  if (act == 2) return z > 0.f ? z : LRELU_SLOPE * z;
+  return z;
+}
+// d act(z) / dz
+__device__ __forceinline__ float act_bwd(float z, int act) {
+  if (act == 1) {
+    const float sg = sigmoidf_(z);
+    return sg * (1.f + z * (1.f - sg));
+  }
+  if (act == 2) return z > 0.f ? 1.f : LRELU_SLOPE;
+  return 1.f;
+}
 // ------------------------------------------------------------------ forward statistics
 // grid (chunks, N); block 256.  Thread t owns channel vector (8 ch) v = t % (C/8) and walks rows.
 // Deterministic: per-thread sums are combined in a fixed order in shared memory, every CTA writes its
@@ -125,9 +143,7 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float
       unpack8(u[j], f);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        float z = fmaf(f[k], a[k], b[k]);
-        if (swish) z *= sigmoidf_(z);
-        f[k] = z;
+        f[k] = act_fwd(fmaf(f[k], a[k], b[k]), swish);
       }
       *reinterpret_cast<uint4*>(y + off + static_cast<long long>(r + j * rstep) * C) = pack8(f);
     }
@@ -138,9 +154,7 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float
     unpack8(u, f);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      float z = fmaf(f[k], a[k], b[k]);
-      if (swish) z *= sigmoidf_(z);
-      f[k] = z;
+      f[k] = act_fwd(fmaf(f[k], a[k], b[k]), swish);
     }
     *reinterpret_cast<uint4*>(y + off + static_cast<long long>(r) * C) = pack8(f);
   }
@@ -181,11 +195,7 @@ __global__ void gn_bwd_partial_kernel(const __nv_bfloat16* __restrict__ dy,
     for (int k = 0; k < 8; ++k) {
       const float xh = (fx[k] - mean[k]) * rstd[k];
       float dz = fd[k];
-      if (swish) {
-        const float z = fmaf(xh, gm[k], bt[k]);
-        const float sg = sigmoidf_(z);
-        dz *= sg * (1.f + z * (1.f - sg));
-      }
+      if (swish) dz *= act_bwd(fmaf(xh, gm[k], bt[k]), swish);
       a[k] += dz;
       b[k] = fmaf(dz, xh, b[k]);
     }
@@ -266,7 +276,7 @@ __global__ void gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy,
   const float inv_cnt = 1.f / (static_cast<float>(HW) * cg);
   // per-group constants once per CTA (thread g sums its group's channels in channel order), not once
   // per thread: for the small late-stage tensors the old per-thread loop cost more than the rows
-  __shared__ float s_k[64][2];
+  __shared__ float s_k[512][2];
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
     float S1 = 0.f, S2 = 0.f;
     for (int cc = g * cg; cc < (g + 1) * cg; ++cc) {
@@ -304,11 +314,7 @@ __global__ void gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy,
       for (int k = 0; k < 8; ++k) {
         const float xh = (fx[k] - mean[k]) * rstd[k];
         float dz = fd[k];
-        if (swish) {
-          const float z = fmaf(xh, gm[k], bt[k]);
-          const float sg = sigmoidf_(z);
-          dz *= sg * (1.f + z * (1.f - sg));
-        }
+        if (swish) dz *= act_bwd(fmaf(xh, gm[k], bt[k]), swish);
         o[k] = rstd[k] * (dz * gm[k] - k1[k] - xh * k2[k]);
       }
       if (add) {
@@ -329,11 +335,7 @@ __global__ void gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy,
     for (int k = 0; k < 8; ++k) {
       const float xh = (fx[k] - mean[k]) * rstd[k];
       float dz = fd[k];
-      if (swish) {
-        const float z = fmaf(xh, gm[k], bt[k]);
-        const float sg = sigmoidf_(z);
-        dz *= sg * (1.f + z * (1.f - sg));
-      }
+      if (swish) dz *= act_bwd(fmaf(xh, gm[k], bt[k]), swish);
       o[k] = rstd[k] * (dz * gm[k] - k1[k] - xh * k2[k]);
     }
     if (add) {
@@ -419,7 +421,7 @@ int b2dq_gn_bwd_apply(const void* dy, const void* x, const float* stats, const f
                       const float* beta, const float* ws_nc, void* dx, float* dgb, const void* add,
                       int N, int HW, int C, int G, int swish, cudaStream_t stream) {
   if (N <= 0 || HW <= 0) return 0;
-  if (G > 64 || C % 8 || C % G || 256 % (C / 8)) return -1;
+  if (G > 512 || C % 8 || C % G || 256 % (C / 8)) return -1;
   if (dgb) gn_bwd_param_kernel<<<(C + 127) / 128, 128, 0, stream>>>(ws_nc, dgb, N, C);
   const int rpb = pick_rows_per_block(HW, N);
   dim3 grid((HW + rpb - 1) / rpb, N);

@@ -23,10 +23,10 @@
 
 namespace b2 {
 
-constexpr int GF_CONSUMERS = 192;                 // 6 compute warps
-constexpr int GF_THREADS = 256;                   // + producer warp (warp 6) + one idle warp
+constexpr int GF_CONSUMERS = 256;                 // 8 compute warps
+constexpr int GF_THREADS = GF_CONSUMERS + 32;     // + producer warp (warp 8)
 constexpr int GF_VPT = 2;                         // 16 B vectors per consumer thread and stage
-constexpr int GF_STAGES = 5;
+constexpr int GF_STAGES = 3;
 constexpr int GF_CHUNK = GF_CONSUMERS * 16 * GF_VPT;   // bytes per tensor per stage (6 KB)
 constexpr int GF_MAXC = 512;
 constexpr int GF_MAXG = 64;
@@ -42,15 +42,30 @@ struct GnFusedParams {
   __nv_bfloat16* dx;
   float* dgb;                    // [2][C] dgamma, dbeta (overwritten)
   float* part;                   // [N][S][G][2] per-CTA group partials
-  float* dgb_part;               // [grid][2][C]
-  unsigned* flags;               // [N] arrival counters, [N] = finished-CTA counter, [N+1] = error flag (zeroed before launch)
+  float* dgb_part;               // [grid][2][C] per-CTA (dgamma, dbeta) over its images
+  float* team_part;              // [T][2][C] per-team sums of the above
+  unsigned* flags;               // [N] arrival counters | [N] finished teams | [N+1] error flag | [N+2 .. N+2+T) finished
+                                 // CTAs per team (all zeroed before launch)
   int N, HW, C, G, S, T, rows_per_cta;
 };
 
-__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
+// L2 eviction priorities: phase-1 reads are marked evict_last (the same bytes are read again after the team
+// barrier), phase-2 reads and the residual-gradient read evict_first (never needed again by this kernel)
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "l"(pol)
+      : "memory");
 }
 __device__ __forceinline__ float tanh_approx(float v) {
   float r;
@@ -68,11 +83,11 @@ __device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
 }
 __device__ __forceinline__ float2 unpack2(uint32_t u) { return make_float2(bf16_lo(u), bf16_hi(u)); }
 
-// dz = dy * swish'(z) for a channel pair; zh = z / 2 (the halving is folded into the per-channel constants)
+// dz = dy * swish'(z) for a channel pair; zh = z / 2 = xhat * (gamma/2) + beta/2
 template <bool SW>
-__device__ __forceinline__ float2 dz_pair(float2 d, float2 x, float2 A, float2 B) {
+__device__ __forceinline__ float2 dz_pair(float2 d, float2 xh, float2 Gh, float2 Bh) {
   if (!SW) return d;
-  const float2 zh = __ffma2_rn(x, A, B);
+  const float2 zh = __ffma2_rn(xh, Gh, Bh);
   const float2 t = make_float2(tanh_approx(zh.x), tanh_approx(zh.y));
   const float2 sg = __ffma2_rn(t, make_float2(0.5f, 0.5f), make_float2(0.5f, 0.5f));
   const float2 om2 = __ffma2_rn(sg, make_float2(-2.f, -2.f), make_float2(2.f, 2.f));   // 2 (1 - sg)
@@ -118,10 +133,12 @@ __global__ void __launch_bounds__(GF_THREADS, 2) gn_bwd_fused_kernel(const GnFus
     // ------------------------------------------------------------------ producer (one lane of warp 6)
     if (tid == GF_CONSUMERS) {
       uint32_t stage = 0, phase = 0;
+      const uint64_t keep = l2_policy_evict_last(), drop = l2_policy_evict_first();
       for (int n = team; n < p.N; n += p.T) {
         const long long img = static_cast<long long>(n) * HW * C;
         for (int ph = 0; ph < 2; ++ph) {
           const bool with_add = ph == 1 && has_add;
+          const uint64_t pol = ph == 0 ? keep : drop;
           for (int c = 0; c < nstages; ++c) {
             const int row = r0 + c * srows;
             const uint32_t bytes = static_cast<uint32_t>(min(srows, r1 - row)) * C * 2;
@@ -130,9 +147,9 @@ __global__ void __launch_bounds__(GF_THREADS, 2) gn_bwd_fused_kernel(const GnFus
             const uint32_t fb = full0 + 8 * stage;
             const uint32_t dst = smem_u32(ring + stage * 3 * GF_CHUNK);
             mbar_arrive_expect_tx(fb, bytes * (with_add ? 3 : 2));
-            bulk_load(dst, p.dy + off, bytes, fb);
-            bulk_load(dst + GF_CHUNK, p.x + off, bytes, fb);
-            if (with_add) bulk_load(dst + 2 * GF_CHUNK, p.add + off, bytes, fb);
+            bulk_load(dst, p.dy + off, bytes, fb, pol);
+            bulk_load(dst + GF_CHUNK, p.x + off, bytes, fb, pol);
+            if (with_add) bulk_load(dst + 2 * GF_CHUNK, p.add + off, bytes, fb, drop);
             if (++stage == GF_STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -145,23 +162,23 @@ __global__ void __launch_bounds__(GF_THREADS, 2) gn_bwd_fused_kernel(const GnFus
     const int lane = tid & 31;
     uint32_t stage = 0, phase = 0;
     const float inv_cnt = 1.f / (static_cast<float>(HW) * cg);
-    float gm[8];
+    // image-independent per-channel constants: z/2 = xhat * (gamma/2) + beta/2
+    float2 Gh[4], Bh[4];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) gm[k] = p.gamma[v * 8 + k];
+    for (int k = 0; k < 4; ++k) {
+      Gh[k] = make_float2(0.5f * p.gamma[v * 8 + 2 * k], 0.5f * p.gamma[v * 8 + 2 * k + 1]);
+      Bh[k] = make_float2(0.5f * p.beta[v * 8 + 2 * k], 0.5f * p.beta[v * 8 + 2 * k + 1]);
+    }
     for (int n = team; n < p.N; n += p.T) {
-      // per-channel constants of this image: zh = x*A + B (= z/2), xhat = x*R + M
-      float2 A[4], B[4], R[4], M[4];
+      // per-(image, group) constants: xhat = x*R + M.  C/G is even, so a channel pair lies in one group and the
+      // constants are scalars (broadcast operands of the packed instructions)
+      float R[4], M[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int c = v * 8 + 2 * k;
-        const int g0 = c / cg, g1 = (c + 1) / cg;
+        const int g0 = (v * 8 + 2 * k) / cg;
         const float m0 = p.stats[(n * G + g0) * 2], s0 = p.stats[(n * G + g0) * 2 + 1];
-        const float m1 = p.stats[(n * G + g1) * 2], s1 = p.stats[(n * G + g1) * 2 + 1];
-        R[k] = make_float2(s0, s1);
-        M[k] = make_float2(-m0 * s0, -m1 * s1);
-        const float a0 = s0 * gm[2 * k], a1 = s1 * gm[2 * k + 1];
-        A[k] = make_float2(0.5f * a0, 0.5f * a1);
-        B[k] = make_float2(0.5f * (p.beta[c] - m0 * a0), 0.5f * (p.beta[c + 1] - m1 * a1));
+        R[k] = s0;
+        M[k] = -m0 * s0;
       }
       // ---------------- phase 1: sum_rows dz, sum_rows dz * xhat per channel
       float2 sa[4], sb[4];
@@ -178,9 +195,8 @@ __global__ void __launch_bounds__(GF_THREADS, 2) gn_bwd_fused_kernel(const GnFus
             const uint32_t wd[4] = {ud.x, ud.y, ud.z, ud.w}, wx[4] = {ux.x, ux.y, ux.z, ux.w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const float2 xv = unpack2(wx[k]);
-              const float2 dz = dz_pair<SW>(unpack2(wd[k]), xv, A[k], B[k]);
-              const float2 xh = __ffma2_rn(xv, R[k], M[k]);
+              const float2 xh = __ffma2_rn(unpack2(wx[k]), make_float2(R[k], R[k]), make_float2(M[k], M[k]));
+              const float2 dz = dz_pair<SW>(unpack2(wd[k]), xh, Gh[k], Bh[k]);
               sa[k] = __fadd2_rn(sa[k], dz);
               sb[k] = __ffma2_rn(dz, xh, sb[k]);
             }
@@ -230,12 +246,12 @@ __global__ void __launch_bounds__(GF_THREADS, 2) gn_bwd_fused_kernel(const GnFus
       }
       consumer_sync();
       {
-        // sum the S partials of every (group, 2) in a fixed order: thread (j, e4) takes CTAs j, j+12, ... of float4 e4
+        // sum the S partials of every (group, 2) in a fixed order: thread (j, e4) takes CTAs j, j+16, ... of float4 e4
         const int e4n = (2 * G) / 4;                          // float4 per CTA row (16 for G = 32)
-        const int lanes_s = GF_CONSUMERS / e4n;               // 12
+        const int lanes_s = GF_CONSUMERS / e4n;               // 16
         const int e4 = tid % e4n, j = tid / e4n;
         const float4* src = reinterpret_cast<const float4*>(p.part + static_cast<long long>(n) * p.S * G * 2) + e4;
-        constexpr int MAXL = (GF_MAXS + 11) / 12;             // loads per thread, all issued before the first add
+        constexpr int MAXL = (GF_MAXS + 15) / 16;             // loads per thread, all issued before the first add
         float4 t[MAXL];
 #pragma unroll
         for (int i = 0; i < MAXL; ++i) {
@@ -256,14 +272,14 @@ __global__ void __launch_bounds__(GF_THREADS, 2) gn_bwd_fused_kernel(const GnFus
         consumer_sync();
       }
       // ---------------- phase 2: dx = rstd * (dz*gamma - S1/cnt - xhat * S2/cnt) (+ add)
-      float2 C1[4], C2[4], C3[4];
+      // dx = R * (dz*gamma - k1 - xhat*k2) = 2R * (dz*(gamma/2) - k1/2 - xhat*k2/2): reuses Gh, three small constants
+      float R2[4], K1[4], K2[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int c = v * 8 + 2 * k;
-        const int g0 = c / cg, g1 = (c + 1) / cg;
-        C1[k] = make_float2(R[k].x * gm[2 * k], R[k].y * gm[2 * k + 1]);
-        C2[k] = make_float2(-R[k].x * sk[g0 * 2], -R[k].y * sk[g1 * 2]);
-        C3[k] = make_float2(-R[k].x * sk[g0 * 2 + 1], -R[k].y * sk[g1 * 2 + 1]);
+        const int g0 = (v * 8 + 2 * k) / cg;
+        R2[k] = 2.f * R[k];
+        K1[k] = -0.5f * sk[g0 * 2];
+        K2[k] = -0.5f * sk[g0 * 2 + 1];
       }
       __nv_bfloat16* out = p.dx + static_cast<long long>(n) * HW * C + v * 8;
       for (int c = 0; c < nstages; ++c) {
@@ -282,15 +298,15 @@ __global__ void __launch_bounds__(GF_THREADS, 2) gn_bwd_fused_kernel(const GnFus
             uint32_t o[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const float2 xv = unpack2(wx[k]);
-              const float2 dz = dz_pair<SW>(unpack2(wd[k]), xv, A[k], B[k]);
-              const float2 xh = __ffma2_rn(xv, R[k], M[k]);
-              float2 r = __ffma2_rn(dz, C1[k], C2[k]);
-              r = __ffma2_rn(xh, C3[k], r);
-              if (has_add) r = __fadd2_rn(r, unpack2(wa[k]));
+              const float2 xh = __ffma2_rn(unpack2(wx[k]), make_float2(R[k], R[k]), make_float2(M[k], M[k]));
+              const float2 dz = dz_pair<SW>(unpack2(wd[k]), xh, Gh[k], Bh[k]);
+              float2 r = __ffma2_rn(dz, Gh[k], make_float2(K1[k], K1[k]));
+              r = __ffma2_rn(xh, make_float2(K2[k], K2[k]), r);
+              const float2 r2 = make_float2(R2[k], R2[k]);
+              r = has_add ? __ffma2_rn(r, r2, unpack2(wa[k])) : __fmul2_rn(r, r2);
               o[k] = pack_bf16x2(r.x, r.y);
             }
-            *reinterpret_cast<uint4*>(out + static_cast<long long>(row) * C) = make_uint4(o[0], o[1], o[2], o[3]);
+            __stcs(reinterpret_cast<uint4*>(out + static_cast<long long>(row) * C), make_uint4(o[0], o[1], o[2], o[3]));
           }
         }
         __syncwarp();
@@ -299,7 +315,8 @@ __global__ void __launch_bounds__(GF_THREADS, 2) gn_bwd_fused_kernel(const GnFus
       }
     }
   }
-  // ------------------------------------------------------------------ dgamma / dbeta: per-CTA partials, last CTA sums
+  // ------------------------------------------------------------------ dgamma / dbeta, two fixed-order levels:
+  // the last CTA of a team to finish sums the team's S per-CTA partials, the last team to finish sums the T team sums
   __syncthreads();
   float* mine = p.dgb_part + static_cast<long long>(blockIdx.x) * 2 * C;
   for (int i = tid; i < 2 * C; i += GF_THREADS) __stcg(mine + i, dg[i]);
@@ -307,25 +324,39 @@ __global__ void __launch_bounds__(GF_THREADS, 2) gn_bwd_fused_kernel(const GnFus
   __syncthreads();
   if (tid == 0) {
     __threadfence();
-    s_last = (atomicAdd(p.flags + p.N, 1u) == gridDim.x - 1) ? 1u : 0u;
+    s_last = (atomicAdd(p.flags + p.N + 2 + team, 1u) == static_cast<unsigned>(p.S) - 1) ? 1u : 0u;
   }
   __syncthreads();
-  if (s_last) {
-    __threadfence();
-    const unsigned poisoned = __ldcg(p.flags + p.N + 1);      // a team barrier timed out: never pass silently
+  if (!s_last) return;
+  __threadfence();
+  {
+    const float* src = p.dgb_part + static_cast<long long>(team) * p.S * 2 * C;
     for (int i = tid; i < 2 * C; i += GF_THREADS) {
       float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;           // four fixed interleaved chains (more loads in flight)
-      unsigned b = 0;
-      for (; b + 3 < gridDim.x; b += 4) {
-        t0 += __ldcg(p.dgb_part + static_cast<long long>(b) * 2 * C + i);
-        t1 += __ldcg(p.dgb_part + static_cast<long long>(b + 1) * 2 * C + i);
-        t2 += __ldcg(p.dgb_part + static_cast<long long>(b + 2) * 2 * C + i);
-        t3 += __ldcg(p.dgb_part + static_cast<long long>(b + 3) * 2 * C + i);
+      int b = 0;
+      for (; b + 3 < p.S; b += 4) {
+        t0 += __ldcg(src + static_cast<long long>(b) * 2 * C + i);
+        t1 += __ldcg(src + static_cast<long long>(b + 1) * 2 * C + i);
+        t2 += __ldcg(src + static_cast<long long>(b + 2) * 2 * C + i);
+        t3 += __ldcg(src + static_cast<long long>(b + 3) * 2 * C + i);
       }
-      for (; b < gridDim.x; ++b) t0 += __ldcg(p.dgb_part + static_cast<long long>(b) * 2 * C + i);
-      const float t = (t0 + t1) + (t2 + t3);
-      p.dgb[i] = poisoned ? __int_as_float(0x7fc00000) : t;
+      for (; b < p.S; ++b) t0 += __ldcg(src + static_cast<long long>(b) * 2 * C + i);
+      __stcg(p.team_part + static_cast<long long>(team) * 2 * C + i, (t0 + t1) + (t2 + t3));
     }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    s_last = (atomicAdd(p.flags + p.N, 1u) == static_cast<unsigned>(p.T) - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const unsigned poisoned = __ldcg(p.flags + p.N + 1);        // a team barrier timed out: never pass silently
+  for (int i = tid; i < 2 * C; i += GF_THREADS) {
+    float t = 0.f;
+    for (int b = 0; b < p.T; ++b) t += __ldcg(p.team_part + static_cast<long long>(b) * 2 * C + i);
+    p.dgb[i] = poisoned ? __int_as_float(0x7fc00000) : t;
   }
 }
 
@@ -374,13 +405,13 @@ extern "C" {
 // use b2dq_gn_bwd_stats + b2dq_gn_bwd_apply).
 int b2dq_gn_bwd_fused_workspace_bytes(int N, int HW, int C, int G) {
   if (N <= 0 || HW <= 0) return 0;
-  if (C % 8 || C > GF_MAXC || G > GF_MAXG || G <= 0 || C % G || GF_CONSUMERS % (C / 8) || (2 * G) % 4 ||
-      GF_CONSUMERS % ((2 * G) / 4) || (GF_CONSUMERS / ((2 * G) / 4)) * ((GF_MAXS + 11) / 12) < GF_MAXS)
+  if (C % 8 || C > GF_MAXC || G > GF_MAXG || G <= 0 || C % G || (C / G) % 2 || GF_CONSUMERS % (C / 8) || (2 * G) % 4 ||
+      GF_CONSUMERS % ((2 * G) / 4) || (GF_CONSUMERS / ((2 * G) / 4)) * ((GF_MAXS + 15) / 16) < GF_MAXS)
     return 0;
   const GfPlan pl = gf_plan(N, HW, C);
   const long long part = 1LL * N * pl.S * G * 2 * 4;
-  const long long dgbp = 1LL * pl.grid * 2 * C * 4;
-  const long long flags = (1LL * N + 2) * 4;
+  const long long dgbp = 1LL * (pl.grid + pl.T) * 2 * C * 4;   // per-CTA partials, then per-team sums
+  const long long flags = (1LL * N + 2 + pl.T) * 4;
   return static_cast<int>(((part + 15) / 16 + (dgbp + 15) / 16 + (flags + 15) / 16) * 16);
 }
 
@@ -391,7 +422,7 @@ int b2dq_gn_bwd_fused(const void* dy, const void* x, const float* stats, const f
                       int swish, cudaStream_t stream) {
   if (N <= 0 || HW <= 0) return 0;
   const long long need = b2dq_gn_bwd_fused_workspace_bytes(N, HW, C, G);
-  if (need == 0) return -1;
+  if (need == 0 || (swish != 0 && swish != 1)) return -1;
   if (ws_bytes < need || ws == nullptr) return -2;
   const GfPlan pl = gf_plan(N, HW, C);
   GnFusedParams p;
@@ -403,12 +434,13 @@ int b2dq_gn_bwd_fused(const void* dy, const void* x, const float* stats, const f
   p.dgb = dgb;
   uint8_t* w = reinterpret_cast<uint8_t*>(ws);
   const long long part = ((1LL * N * pl.S * G * 2 * 4 + 15) / 16) * 16;
-  const long long dgbp = ((1LL * pl.grid * 2 * C * 4 + 15) / 16) * 16;
+  const long long dgbp = ((1LL * (pl.grid + pl.T) * 2 * C * 4 + 15) / 16) * 16;
   p.part = reinterpret_cast<float*>(w);
   p.dgb_part = reinterpret_cast<float*>(w + part);
+  p.team_part = p.dgb_part + 1LL * pl.grid * 2 * C;
   p.flags = reinterpret_cast<unsigned*>(w + part + dgbp);
   p.N = N; p.HW = HW; p.C = C; p.G = G; p.S = pl.S; p.T = pl.T; p.rows_per_cta = pl.rows_per_cta;
-  cudaError_t e = cudaMemsetAsync(p.flags, 0, (N + 2) * sizeof(unsigned), stream);
+  cudaError_t e = cudaMemsetAsync(p.flags, 0, (N + 2 + pl.T) * sizeof(unsigned), stream);
   if (e != cudaSuccess) return (int)e;
   static unsigned long long m0 = 0, m1 = 0;
   if (swish) {

@@ -563,7 +563,7 @@ def gn_bwd(dy, x, stats, gamma, beta, swish, groups=32, add=None, ws_nc=None):
     ws_nc [N,C,2]: the reduction pass was already done by the producer of dy (pconv dgrad epilogue)."""
     nb, h, w, c = x.shape
     l = _cabi.lib()
-    if ws_nc is None and USE_GN_FUSED:
+    if ws_nc is None and USE_GN_FUSED and int(swish) in (0, 1):
         ws_bytes = l.b2dq_gn_bwd_fused_workspace_bytes(nb, h * w, c, groups)
         if ws_bytes > 0:
             dx = torch.empty_like(x)

@@ -5,7 +5,7 @@ rm -f gpurun_out/r2b_gnf.txt
 timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k "groupnorm" > gpurun_out/r2b_gn_tests.txt 2>&1
 echo "pytest rc=$?" >> gpurun_out/r2b_gn_tests.txt
 tail -3 gpurun_out/r2b_gn_tests.txt
-for mb in 40 70 140; do
+for mb in 70 140; do
   B2DQ_GN_L2_BUDGET_MB=$mb timeout 300 python tools/kernel_bench.py gnf >> gpurun_out/r2b_gnf.txt 2>&1
 done
 cat gpurun_out/r2b_gnf.txt | cut -c1-400
