@@ -95,6 +95,8 @@ SIGNATURES = {
     "b2dq_maxpool2x2": [_vp, _vp, _i, _i, _i, _i, _vp],
     "b2dq_maxpool2x2_bwd": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "b2dq_relu_bwd": [_vp, _vp, _vp, _ll, _vp],
+    "b2dq_lrelu_bwd": [_vp, _vp, _vp, _ll, _f, _vp],
+    "b2dq_im2col_window": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "b2dq_bias_grad_blocks": [_ll],
     "b2dq_bias_grad": [_vp, _vp, _vp, _ll, _i, _vp],
     "b2dq_cast_f32_to_bf16": [_vp, _vp, _ll, _vp],

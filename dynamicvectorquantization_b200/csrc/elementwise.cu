@@ -383,6 +383,51 @@ __global__ void relu_bwd_kernel(const uint4* __restrict__ dy, const uint4* __res
   dx[i] = pack8(g);
 }
 
+// dx = dy where the LeakyReLU output y is positive, else slope * dy (slope > 0 keeps the sign of the input).
+__global__ void lrelu_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ y, uint4* __restrict__ dx,
+                                 float slope, long long total) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  float g[8], v[8];
+  unpack8(__ldg(dy + i), g);
+  unpack8(__ldg(y + i), v);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) g[k] = v[k] > 0.f ? g[k] : slope * g[k];
+  dx[i] = pack8(g);
+}
+
+// Window gather ("im2col") for the few-channel edge convolutions of the PatchGAN (4x4 windows,
+// modules/discriminator/model.py:37,66): dst[n, oh, ow, t*Cs + c] = src[n, oh*stride + sgn*r + off, ow*stride +
+// sgn*s + off, c] with t = r*K + s (zero outside the source, zero in the unused columns up to 64).
+//   forward window of a KxK stride-`stride` pad-`pad` convolution: sgn = +1, off = -pad
+//   window of its data gradient (stride 1):                       sgn = -1, off = +pad
+__global__ void im2col_window_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int Hs,
+                                     int Ws, int Ho, int Wo, int Cs, int K, int stride, int sgn, int off,
+                                     long long total_vecs) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total_vecs) return;
+  const int cv = static_cast<int>(i & 7);
+  const long long pix = i >> 3;
+  const int w = static_cast<int>(pix % Wo);
+  const int h = static_cast<int>((pix / Wo) % Ho);
+  const long long n = pix / (static_cast<long long>(Wo) * Ho);
+  const __nv_bfloat16* img = src + n * Hs * Ws * Cs;
+  __align__(16) __nv_bfloat16 vals[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int col = cv * 8 + k;
+    __nv_bfloat16 v = __float2bfloat16_rn(0.f);
+    if (col < K * K * Cs) {
+      const int t = col / Cs, c = col - t * Cs;
+      const int r = t / K, sx = t - K * r;
+      const int hh = h * stride + sgn * r + off, ww = w * stride + sgn * sx + off;
+      if (hh >= 0 && hh < Hs && ww >= 0 && ww < Ws) v = img[(static_cast<long long>(hh) * Ws + ww) * Cs + c];
+    }
+    vals[k] = v;
+  }
+  reinterpret_cast<uint4*>(dst)[i] = *reinterpret_cast<const uint4*>(vals);
+}
+
 }  // namespace b2
 
 using namespace b2;
@@ -517,6 +562,23 @@ int b2dq_relu_bwd(const void* dy, const void* y, void* dx, long long n, cudaStre
   if (n % 8) return -1;
   return launch1d(relu_bwd_kernel, n / 8, st, reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(y),
                   reinterpret_cast<uint4*>(dx), n / 8);
+}
+
+int b2dq_lrelu_bwd(const void* dy, const void* y, void* dx, long long n, float slope, cudaStream_t st) {
+  if (n <= 0) return 0;
+  if (n % 8) return -1;
+  return launch1d(lrelu_bwd_kernel, n / 8, st, reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(y),
+                  reinterpret_cast<uint4*>(dx), slope, n / 8);
+}
+
+// src [N,Hs,Ws,Cs] bf16 -> dst [N,Ho,Wo,64] bf16, K*K*Cs <= 64 (see im2col_window_kernel).
+int b2dq_im2col_window(const void* src, void* dst, int N, int Hs, int Ws, int Ho, int Wo, int Cs, int K, int stride,
+                       int sgn, int off, cudaStream_t st) {
+  if (K <= 0 || Cs <= 0 || K * K * Cs > 64 || (sgn != 1 && sgn != -1) || stride <= 0) return -1;
+  const long long total = (long long)N * Ho * Wo * 8;
+  if (total <= 0) return 0;
+  return launch1d(im2col_window_kernel, total, st, reinterpret_cast<const __nv_bfloat16*>(src),
+                  reinterpret_cast<__nv_bfloat16*>(dst), Hs, Ws, Ho, Wo, Cs, K, stride, sgn, off, total);
 }
 
 // weight [Cout,Cin,R,S] fp32 -> fwd [Cout, R*S*Cin] and/or dgrad [Cin, R*S*Cout] bf16 (null = skip).

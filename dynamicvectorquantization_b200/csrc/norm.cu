@@ -88,17 +88,26 @@ __global__ void gn_partial_stats_kernel(const __nv_bfloat16* __restrict__ x, flo
     o[1] = b;
   }
 }
+// One warp per (image, group): lanes take the chunks round-robin (fp64 partial sums), then a fixed xor tree -
+// deterministic, and O(chunks / 32) deep (BatchNorm = one "image" of 1184 chunks would otherwise be a serial loop).
 __global__ void gn_finalize_kernel(const float* __restrict__ part, float* stats, int N, int G,
                                    int chunks, double inv_count, float eps) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (i >= N * G) return;
   const int n = i / G, g = i % G;
   double a = 0.0, b = 0.0;
-  for (int c = 0; c < chunks; ++c) {
-    const float* p = part + ((static_cast<long long>(n) * chunks + c) * G + g) * 2;
-    a += p[0];
-    b += p[1];
+  for (int c = lane; c < chunks; c += 32) {
+    const float2 v = *reinterpret_cast<const float2*>(part + ((static_cast<long long>(n) * chunks + c) * G + g) * 2);
+    a += v.x;
+    b += v.y;
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  if (lane) return;
   const double mean = a * inv_count;
   double var = b * inv_count - mean * mean;
   if (var < 0) var = 0;
@@ -230,19 +239,28 @@ __global__ void gn_bwd_partial_kernel(const __nv_bfloat16* __restrict__ dy,
     o[1] = sb;
   }
 }
+// one warp per (image, channel): lanes take the chunks round-robin, fixed xor tree (deterministic)
 __global__ void gn_bwd_reduce_kernel(const float* __restrict__ part, float* ws_nc, int N, int C,
                                      int chunks) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (i >= N * C) return;
   const int n = i / C, c = i % C;
   float a = 0.f, b = 0.f;
-  for (int k = 0; k < chunks; ++k) {
-    const float* p = part + ((static_cast<long long>(n) * chunks + k) * C + c) * 2;
-    a += p[0];
-    b += p[1];
+  for (int k = lane; k < chunks; k += 32) {
+    const float2 v = *reinterpret_cast<const float2*>(part + ((static_cast<long long>(n) * chunks + k) * C + c) * 2);
+    a += v.x;
+    b += v.y;
   }
-  ws_nc[2 * i] = a;
-  ws_nc[2 * i + 1] = b;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  if (lane == 0) {
+    ws_nc[2 * i] = a;
+    ws_nc[2 * i + 1] = b;
+  }
 }
 // dgamma[c] = sum_n ws[n][c][1], dbeta[c] = sum_n ws[n][c][0]
 __global__ void gn_bwd_param_kernel(const float* __restrict__ ws_nc, float* dgb, int N, int C) {
@@ -382,7 +400,7 @@ int b2dq_gn_stats(const void* x, float* stats, float* ws, int N, int HW, int C, 
   gn_partial_stats_kernel<<<grid, 256, 2 * 256 * 8 * sizeof(float), stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), ws, HW, C, G, rpb);
   const int NG = N * G;
-  gn_finalize_kernel<<<(NG + 127) / 128, 128, 0, stream>>>(
+  gn_finalize_kernel<<<(NG + 3) / 4, 128, 0, stream>>>(
       ws, stats, N, G, chunks, 1.0 / (static_cast<double>(HW) * (C / G)), eps);
   return (int)cudaGetLastError();
 }
@@ -412,7 +430,7 @@ int b2dq_gn_bwd_stats(const void* dy, const void* x, const float* stats, const f
   gn_bwd_partial_kernel<<<grid, 256, 2 * 256 * 8 * sizeof(float), stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x), stats,
       gamma, beta, part, HW, C, G, swish, rpb);
-  gn_bwd_reduce_kernel<<<(N * C + 255) / 256, 256, 0, stream>>>(part, ws_nc, N, C, chunks);
+  gn_bwd_reduce_kernel<<<(N * C + 7) / 8, 256, 0, stream>>>(part, ws_nc, N, C, chunks);
   return (int)cudaGetLastError();
 }
 

@@ -44,7 +44,8 @@ struct TapGemmParams {
   const __nv_bfloat16* residual; // same indexing as out via rN/rH/rW, or null
   long long rN, rH, rW;
   float alpha;                   // scale applied to the accumulator before bias/residual
-  int relu;                      // clamp the result at zero (VGG feature stack of the perceptual loss)
+  int relu;                      // 1: clamp the result at zero (VGG feature stack of the perceptual loss);
+                                 // 2: LeakyReLU(0.2) (PatchGAN stem, modules/discriminator/model.py:37)
   int out_f32;
 };
 
@@ -218,9 +219,12 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int i = 0; i < CW; ++i) v[i] += __bfloat162float(p.residual[roff[j] + col + i]);
             }
           }
-          if (p.relu) {
+          if (p.relu == 1) {
 #pragma unroll
             for (int i = 0; i < CW; ++i) v[i] = fmaxf(v[i], 0.f);
+          } else if (p.relu == 2) {
+#pragma unroll
+            for (int i = 0; i < CW; ++i) v[i] = v[i] > 0.f ? v[i] : 0.2f * v[i];
           }
           if (p.out_f32) {
             float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + ooff[j] + col);
@@ -247,7 +251,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (c < p.Cout) {
               float o = v[i];
               if (p.residual) o += __bfloat162float(p.residual[roff[j] + c]);
-              if (p.relu) o = fmaxf(o, 0.f);
+              if (p.relu == 1) o = fmaxf(o, 0.f);
+              else if (p.relu == 2) o = o > 0.f ? o : 0.2f * o;
               if (p.out_f32) static_cast<float*>(p.out)[ooff[j] + c] = o;
               else static_cast<__nv_bfloat16*>(p.out)[ooff[j] + c] = __float2bfloat16_rn(o);
             }
@@ -305,7 +310,7 @@ struct b2dq_tapgemm_desc {
   int out_f32;
   int block_n;                   // 0 = auto
   int m_tiles_per_cta;           // 0 = auto, 1 or 2
-  int relu;                      // != 0: out = max(out, 0)
+  int relu;                      // 1: out = max(out, 0); 2: out = LeakyReLU(0.2)(out)
 };
 
 int b2dq_tapgemm(const b2dq_tapgemm_desc* d, cudaStream_t stream) {

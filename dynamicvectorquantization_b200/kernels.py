@@ -139,7 +139,7 @@ def tapgemm(a, a_dims, a_strides, b, b_rows, b_k, taps, kchunks, out, out_off, o
         m_tiles = -(-wout // d.TW) * -(-hout // d.TH) * -(-nb // d.TN)
         block_n = _pick_block_n(m_tiles, cout)
     d.alpha, d.out_f32, d.block_n, d.m_tiles_per_cta = alpha, int(out_f32), block_n, (m_tiles_per_cta or FORCE_MT)
-    d.relu = int(bool(relu))
+    d.relu = int(relu)                       # 0 none, 1 ReLU, 2 LeakyReLU(0.2)
     check(_cabi.lib().b2dq_tapgemm(C.byref(d), _stream()), "tapgemm")
 
 
@@ -703,6 +703,140 @@ def im2col3x3_small(x, flip=False):
     check(_cabi.lib().b2dq_im2col3x3_small(_ptr(x), _ptr(out), nb, h, w, cs, int(flip), _stream()),
           "im2col3x3_small")
     return out
+
+
+def im2col_window(x, k, stride, sgn, off, out_hw):
+    """x [N,Hs,Ws,Cs] bf16 (k*k*Cs <= 64) -> [N,Ho,Wo,64] bf16: column (r*k+s)*Cs + c holds
+    x[n, oh*stride + sgn*r + off, ow*stride + sgn*s + off, c] (zero outside x / in the unused columns)."""
+    nb, hs, ws, cs = x.shape
+    ho, wo = out_hw
+    out = torch.empty(nb, ho, wo, 64, dtype=BF16, device=x.device)
+    check(_cabi.lib().b2dq_im2col_window(_ptr(x), _ptr(out), nb, hs, ws, ho, wo, cs, k, stride, sgn, off, _stream()),
+          "im2col_window")
+    return out
+
+
+def lrelu_bwd(dy, y, slope=0.2):
+    """dy * (y > 0 ? 1 : slope) for a LeakyReLU whose OUTPUT is y (bf16, same shape)."""
+    dx = torch.empty_like(dy)
+    check(_cabi.lib().b2dq_lrelu_bwd(_ptr(dy), _ptr(y), _ptr(dx), dy.numel(), float(slope), _stream()), "lrelu_bwd")
+    return dx
+
+
+# ------------------------------------------------------------------------------------------ 4x4 convolutions (PatchGAN)
+# modules/discriminator/model.py:37-66: Conv2d(k=4, stride 2 | 1, padding 1).  y[oh,ow] = sum_{r,s} W[r,s] x[st*oh-1+r, st*ow-1+s].
+def _taps4(stride, cin):
+    """(channel offset, dw, row parity, dh, weight column) of the 16 filter taps in the view conv4x4_fwd reads."""
+    taps = []
+    for r in range(4):
+        for s in range(4):
+            if stride == 2:                       # parity view [N, H/2, 2, W/2, 2C]: row 2oh-1+r = 2(oh+dh)+p
+                dh, p = divmod(r - 1, 2)
+                dw, q = divmod(s - 1, 2)
+                taps.append((q * cin, dw, p, dh, (r * 4 + s) * cin))
+            else:
+                taps.append((0, s - 1, 0, r - 1, (r * 4 + s) * cin))
+    return taps
+
+
+def conv4x4_out_hw(h, w, stride):
+    return (h // 2, w // 2) if stride == 2 else (h - 1, w - 1)
+
+
+def conv4x4_fwd(x, wpack, bias, stride, cout, out_f32=False, block_n=0, act=0):
+    """x NHWC bf16 [N,H,W,Cin] (Cin % 64 == 0); wpack [Cout(+pad), 16*Cin] from pack_weight_fwd."""
+    nb, h, w, cin = x.shape
+    assert cin % 64 == 0 and (stride == 1 or (h % 2 == 0 and w % 2 == 0))
+    ho, wo = conv4x4_out_hw(h, w, stride)
+    dims, strs = parity_view(x) if stride == 2 else nhwc_view(x)
+    out = torch.empty(nb, ho, wo, cout, dtype=torch.float32 if out_f32 else BF16, device=x.device)
+    ostr = (ho * wo * cout, wo * cout, cout)
+    tapgemm(x, dims, strs, wpack, wpack.shape[0], wpack.shape[1], _taps4(stride, cin), cin // 64, out, 0, ostr, wo, ho,
+            nb, cout, bias=bias, out_f32=out_f32, block_n=block_n, relu=act)
+    return out
+
+
+def conv4x4_dgrad(dy, wdpack, stride, cin, in_hw):
+    """dy NHWC bf16 [N,Ho,Wo,Cout] -> dx NHWC bf16 [N,H,W,Cin]; wdpack [Cin, 16*Cout] from pack_weight_dgrad."""
+    nb, ho, wo, cout = dy.shape
+    assert cout % 64 == 0
+    h, w = in_hw
+    dx = torch.empty(nb, h, w, cin, dtype=BF16, device=dy.device)
+    dims, strs = nhwc_view(dy)
+    kch = cout // 64
+    if stride == 1:                               # dx[ih,iw] = sum W[r,s]^T dy[ih+1-r, iw+1-s]
+        taps = [(0, 1 - s, 0, 1 - r, (r * 4 + s) * cout) for r in range(4) for s in range(4)]
+        tapgemm(dy, dims, strs, wdpack, wdpack.shape[0], wdpack.shape[1], taps, kch, dx, 0, (h * w * cin, w * cin, cin),
+                w, h, nb, cin)
+        return dx
+    # stride 2: input row 2i+ph receives filter rows r with r = ph+1 (mod 2), from output row i + (ph+1-r)/2
+    rsel = {0: [(1, 0), (3, -1)], 1: [(0, 1), (2, 0)]}
+    for ph in (0, 1):
+        for pw in (0, 1):
+            taps = [(0, dw, 0, dh, (r * 4 + s) * cout) for r, dh in rsel[ph] for s, dw in rsel[pw]]
+            tapgemm(dy, dims, strs, wdpack, wdpack.shape[0], wdpack.shape[1], taps, kch, dx, (ph * w + pw) * cin,
+                    (h * w * cin, 2 * w * cin, 2 * cin), wo, ho, nb, cin)
+    return dx
+
+
+def conv4x4_wgrad(x, dy, stride):
+    """dW fp32 OIHW [Cout,Cin,4,4] of y = conv4x4(x): the 16 taps go through the weight-gradient GEMM in two launches
+    of 8 (its tap table holds 12)."""
+    nb, h, w, cin = x.shape
+    _, ho, wo, cout = dy.shape
+    bdims, bstrs = parity_view(x) if stride == 2 else nhwc_view(x)
+    taps = [t[:4] for t in _taps4(stride, cin)]
+    adims, astrs = nhwc_view(dy)
+    kw, kh, kn = tile_shape(wo, ho, nb, pixels=64)
+    ktw, kth = (wo + kw - 1) // kw, (ho + kh - 1) // kh
+    kblocks = ktw * kth * ((nb + kn - 1) // kn)
+    mt, nt = (cout + 127) // 128, (cin + 127) // 128
+    splits = _wgrad_splits(kblocks, mt * nt * 3)
+    partial = torch.empty(splits, 16, cout, cin, dtype=torch.float32, device=x.device)
+    for half in (0, 1):
+        mmgemm(dy, adims, astrs, True, x, bdims, bstrs, True, cout, cin, kblocks, partial,
+               (16 * cout * cin, cout * cin, cin), taps=taps[8 * half:8 * half + 8], kbox=(kw, kh, kn), ktiles=(ktw, kth),
+               splits=splits, out_f32=True, block_n=128, taps_per_cta=3, out_off=8 * half * cout * cin)
+    dw = torch.empty(cout, cin, 4, 4, dtype=torch.float32, device=x.device)
+    check(_cabi.lib().b2dq_wgrad_reduce(_ptr(partial), _ptr(dw), splits, 16, cout, cin, 0, _stream()), "wgrad_reduce")
+    return dw
+
+
+# ------------------------------------------------------------------------------------------ BatchNorm (PatchGAN)
+# nn.BatchNorm2d over [N,H,W] per channel = the GroupNorm kernels on the tensor seen as ONE image with one group per
+# channel (N = 1, G = C); activation code 2 = LeakyReLU(0.2).
+def bn_stats(x, eps=1e-5):
+    """x NHWC bf16 -> stats [1, C, 2] = (batch mean, 1/sqrt(biased batch variance + eps)) per channel."""
+    nb, h, w, c = x.shape
+    return gn_stats(x.view(1, nb * h, w, c), groups=c, eps=eps)
+
+
+def bn_apply(x, stats, gamma, beta, act):
+    nb, h, w, c = x.shape
+    return gn_apply(x.view(1, nb * h, w, c), stats, gamma, beta, act, groups=c).view(nb, h, w, c)
+
+
+def bn_bwd(dy, x, stats, gamma, beta, act, batch_stats=True):
+    """-> (dx, dgamma, dbeta).  batch_stats=False (eval mode: the statistics are constants, not functions of x):
+    dx = dz * gamma * rstd without the two mean-subtraction terms."""
+    nb, h, w, c = x.shape
+    dyv, xv = dy.view(1, nb * h, w, c), x.view(1, nb * h, w, c)
+    if batch_stats:
+        dx, dg, db = gn_bwd(dyv, xv, stats, gamma, beta, act, groups=c)
+        return dx.view(nb, h, w, c), dg, db
+    l = _cabi.lib()
+    hw = nb * h * w
+    ws = torch.empty(1, c, 2, dtype=torch.float32, device=x.device)
+    part = torch.empty(l.b2dq_gn_chunks(1, hw) * c * 2, dtype=torch.float32, device=x.device)
+    check(l.b2dq_gn_bwd_stats(_ptr(dyv), _ptr(xv), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(part), _ptr(ws), 1, hw, c,
+                              c, int(act), _stream()), "gn_bwd_stats")
+    dgb = torch.empty(2, c, dtype=torch.float32, device=x.device)
+    check(l.b2dq_gn_bwd_param(_ptr(ws), _ptr(dgb), 1, c, _stream()), "gn_bwd_param")
+    dx = torch.empty_like(x)
+    zero = torch.zeros_like(ws)
+    check(l.b2dq_gn_bwd_apply(_ptr(dyv), _ptr(xv), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(zero), _ptr(dx), None, None,
+                              1, hw, c, c, int(act), _stream()), "gn_bwd_apply_nodgb")
+    return dx, dgb[0], dgb[1]
 
 
 # ------------------------------------------------------------------------------------------ VGG pieces

@@ -59,6 +59,9 @@ def _packed(weight, kind):
     elif kind == "col_dgrad":                       # Cout*9 <= 64 (conv_out): [Cin, 64], col = t*Cout + co
         p = torch.zeros(ci, 64, dtype=BF16, device=w.device)
         p[:, :r * s * co] = w.permute(1, 2, 3, 0).reshape(ci, -1).to(BF16)
+    elif kind == "col_dgrad_x2":                    # col_dgrad with every tap column doubled (hi/lo halves of dy)
+        p = torch.zeros(ci, 64, dtype=BF16, device=w.device)
+        p[:, :2 * r * s * co] = w.permute(1, 2, 3, 0).reshape(ci, r * s, 1, co).expand(ci, r * s, 2, co).reshape(ci, -1).to(BF16)
     else:
         raise ValueError(kind)
     cache[kind] = (stamp, p)

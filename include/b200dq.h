@@ -103,7 +103,8 @@ typedef struct b2dq_tapgemm_desc {
   int out_f32;            /* 0: bf16 output, 1: fp32 output */
   int block_n;            /* 0 = auto (16/64/128/256) */
   int m_tiles_per_cta;    /* 0 = auto, 1 or 2 (two 128-pixel tiles share each weight tile) */
-  int relu;               /* != 0: clamp the result at zero (conv + ReLU of the VGG16 stack, lpips.py:88-97) */
+  int relu;               /* 1: clamp the result at zero (conv + ReLU of the VGG16 stack, lpips.py:88-97);
+                           * 2: LeakyReLU(0.2) (PatchGAN stem, modules/discriminator/model.py:37) */
 } b2dq_tapgemm_desc;
 
 int b2dq_tapgemm(const b2dq_tapgemm_desc* desc, cudaStream_t stream);
@@ -170,6 +171,9 @@ int b2dq_maxpool2x2(const void* x_bf16, void* y_bf16, int N, int H, int W, int C
 int b2dq_maxpool2x2_bwd(const void* dy_bf16, const void* x_bf16, void* dx_bf16, int N, int H, int W, int C,
                         cudaStream_t stream);
 int b2dq_relu_bwd(const void* dy_bf16, const void* y_bf16, void* dx_bf16, long long n, cudaStream_t stream);
+/* gradient of LeakyReLU(slope) from its OUTPUT y (nn.LeakyReLU(0.2, True) of modules/discriminator/model.py:37-62) */
+int b2dq_lrelu_bwd(const void* dy_bf16, const void* y_bf16, void* dx_bf16, long long n, float slope,
+                   cudaStream_t stream);
 
 /* LPIPS level head (lpips.py:44-55,116-122): f0, f1 = NHWC bf16 features [N,HW,C] (C in {64,128,256,512}),
  * w = lin weights [C].  fwd: part[n*chunks + j] = partial sums over pixel chunks of
@@ -246,6 +250,11 @@ int b2dq_cast_f32_to_bf16(const float* a, void* out, long long n, cudaStream_t s
 /* 3x3 window gather for the 3-channel edge convolutions: dst [N,H,W,64] */
 int b2dq_im2col3x3_small(const void* src, void* dst, int N, int H, int W, int Cs, int flip,
                          cudaStream_t stream);
+/* KxK window gather for the few-channel edge convolutions of the PatchGAN (modules/discriminator/model.py:37,66):
+ * dst[n,oh,ow,(r*K+s)*Cs+c] = src[n, oh*stride + sgn*r + off, ow*stride + sgn*s + off, c], zero outside src and in
+ * the unused columns; K*K*Cs <= 64.  Forward window: sgn=+1, off=-pad; data-gradient window: sgn=-1, off=+pad. */
+int b2dq_im2col_window(const void* src, void* dst, int N, int Hs, int Ws, int Ho, int Wo, int Cs, int K, int stride,
+                       int sgn, int off, cudaStream_t stream);
 
 
 /* ------------------------------------------------------------------ entropy router input

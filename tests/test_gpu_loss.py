@@ -3,8 +3,9 @@ PatchGAN discriminator and the adaptive-weight loss, against oracle/loss_oracle.
 minted from the reference's own classes (tests/golden/loss_small.npz).
 
 Tolerances: the VGG16 stack runs in bf16 (13 convolution layers, fp32 accumulation), so LPIPS values are compared
-at 2e-2 relative and its gradients at 6e-2 relative RMS; everything that does not pass through the bf16 stack
-(discriminator terms) at 2e-3 (TF32 convolutions are torch's cuDNN default)."""
+at 2e-2 relative and its gradients at 6e-2 relative RMS.  The PatchGAN runs on the same bf16 tensor-core kernels
+(5 convolution layers, fp32 accumulation, fp32 BatchNorm statistics): logits / discriminator-loss terms at 1e-2,
+its gradients at 3e-2 relative RMS (written next to each assert)."""
 import os
 
 import numpy as np
@@ -35,6 +36,150 @@ def _loss_module(monkeypatch, seed=21, budget=True):
     sd = lo.make_loss_weights(seed)
     loss.load_state_dict({k[len("loss."):]: v for k, v in sd.items()}, strict=False)
     return loss.cuda(), sd
+
+
+def _cos(a, b):
+    a, b = a.double().flatten().cpu(), b.double().flatten().cpu()
+    return float(torch.dot(a, b) / (a.norm() * b.norm() + 1e-30))
+
+
+def _nchw(t):
+    return t.float().permute(0, 3, 1, 2)
+
+
+@pytest.mark.parametrize("res,nb", [(64, 2), (256, 2)])
+def test_patchgan_layers_match_fp32_ops(res, nb):
+    """Every PatchGAN layer on its own, on IDENTICAL bf16 inputs and bf16-rounded weights, against torch's fp32 ops on
+    the GPU (F.conv2d, nn.BatchNorm2d in training mode, F.leaky_relu): the 3-channel stem (im2col + GEMM + LeakyReLU
+    epilogue; image / weight / bias gradients), the 4x4 stride-2 and stride-1 convolutions (16-tap GEMMs; data and
+    weight gradients), BatchNorm + LeakyReLU (values, running statistics, dx / dgamma / dbeta) and the one-channel
+    head (two-term bf16 cotangent).  Isolated layers see no activation-sign flips, so the bounds are the bf16
+    rounding of the outputs: 4e-3 for bf16 tensors, 1e-3 for fp32 results."""
+    from dynamicvectorquantization_b200.nn import discriminator as D
+    g = torch.Generator(device="cuda").manual_seed(res)
+    rnd = lambda *s: torch.randn(*s, device="cuda", generator=g)
+    x = (torch.rand(nb, res, res, 3, device="cuda", generator=g) * 2 - 1).to(BF)
+    w0, b0 = (rnd(64, 3, 4, 4) * 0.2).requires_grad_(True), (rnd(64) * 0.1).requires_grad_(True)
+    xg = x.clone().requires_grad_(True)
+    y = D._StemFn.apply(xg, w0, b0)
+    xr = _nchw(x).requires_grad_(True)
+    w0r, b0r = w0.detach().to(BF).float().requires_grad_(True), b0.detach().clone().requires_grad_(True)
+    ref = F.leaky_relu(F.conv2d(xr, w0r, b0r, stride=2, padding=1), 0.2)
+    assert rel_rms(_nchw(y.detach()), ref.detach()) < 4e-3
+    cot = rnd(*ref.shape)
+    gy = torch.autograd.grad(y, [xg, w0, b0], cot.permute(0, 2, 3, 1).to(BF).contiguous())
+    gr = torch.autograd.grad(ref, [xr, w0r, b0r], cot.to(BF).float())
+    assert rel_rms(_nchw(gy[0]), gr[0]) < 4e-3 and rel_rms(gy[1], gr[1]) < 1e-3 and rel_rms(gy[2], gr[2]) < 1e-3
+    h = y.detach()
+    for cin, cout, stride in ((64, 128, 2), (128, 256, 2), (256, 512, 1)):
+        w = (rnd(cout, cin, 4, 4) * (cin * 16) ** -0.5).requires_grad_(True)
+        hg = h.clone().requires_grad_(True)
+        z = D._Conv4x4Fn.apply(hg, w, None, stride)
+        hr = _nchw(h).requires_grad_(True)
+        wr = w.detach().to(BF).float().requires_grad_(True)
+        zr = F.conv2d(hr, wr, None, stride=stride, padding=1)
+        assert rel_rms(_nchw(z.detach()), zr.detach()) < 4e-3, (cin, cout, stride)
+        cot = rnd(*zr.shape)
+        gz = torch.autograd.grad(z, [hg, w], cot.permute(0, 2, 3, 1).to(BF).contiguous())
+        gzr = torch.autograd.grad(zr, [hr, wr], cot.to(BF).float())
+        assert rel_rms(_nchw(gz[0]), gzr[0]) < 4e-3 and rel_rms(gz[1], gzr[1]) < 1e-3, (cin, cout, stride)
+        bn = torch.nn.BatchNorm2d(cout).cuda().train()
+        with torch.no_grad():
+            bn.weight.normal_(1, 0.2); bn.bias.normal_(0, 0.2)
+        bn2 = torch.nn.BatchNorm2d(cout).cuda().train()
+        bn2.load_state_dict(bn.state_dict())
+        zd = z.detach().clone().requires_grad_(True)
+        a = D._batchnorm_lrelu(zd, bn)
+        zrr = _nchw(z.detach()).requires_grad_(True)
+        ar = F.leaky_relu(bn2(zrr), 0.2)
+        assert rel_rms(_nchw(a.detach()), ar.detach()) < 4e-3
+        assert rel_rms(bn.running_mean, bn2.running_mean) < 1e-5 and rel_rms(bn.running_var, bn2.running_var) < 1e-5
+        assert int(bn.num_batches_tracked) == 1
+        cot = rnd(*ar.shape)
+        ga = torch.autograd.grad(a, [zd, bn.weight, bn.bias], cot.permute(0, 2, 3, 1).to(BF).contiguous())
+        gar = torch.autograd.grad(ar, [zrr, bn2.weight, bn2.bias], cot.to(BF).float())
+        assert rel_rms(_nchw(ga[0]), gar[0]) < 4e-3 and rel_rms(ga[1], gar[1]) < 1e-4 and rel_rms(ga[2], gar[2]) < 1e-4
+        # evaluation mode: running statistics are constants of the backward
+        bn.eval(); bn2.eval()
+        ze = z.detach().clone().requires_grad_(True)
+        ae = D._batchnorm_lrelu(ze, bn)
+        zer = _nchw(z.detach()).requires_grad_(True)
+        aer = F.leaky_relu(bn2(zer), 0.2)
+        assert rel_rms(_nchw(ae.detach()), aer.detach()) < 4e-3
+        ge = torch.autograd.grad(ae, [ze, bn.weight, bn.bias], cot.permute(0, 2, 3, 1).to(BF).contiguous())
+        ger = torch.autograd.grad(aer, [zer, bn2.weight, bn2.bias], cot.to(BF).float())
+        assert rel_rms(_nchw(ge[0]), ger[0]) < 4e-3 and rel_rms(ge[1], ger[1]) < 1e-4 and rel_rms(ge[2], ger[2]) < 1e-4
+        h = a.detach()
+    wh, bh = (rnd(1, 512, 4, 4) * (512 * 16) ** -0.5).requires_grad_(True), rnd(1).requires_grad_(True)
+    hg = h.clone().requires_grad_(True)
+    o = D._HeadFn.apply(hg, wh, bh)
+    hr = _nchw(h).requires_grad_(True)
+    whr, bhr = wh.detach().to(BF).float().requires_grad_(True), bh.detach().clone().requires_grad_(True)
+    orf = F.conv2d(hr, whr, bhr, stride=1, padding=1)
+    assert rel_rms(_nchw(o.detach()), orf.detach()) < 1e-4
+    for kind in ("random", "mean"):
+        cot = rnd(*orf.shape) if kind == "random" else torch.full_like(orf, -1.0 / orf.numel())
+        go = torch.autograd.grad(o, [hg, wh, bh], cot.permute(0, 2, 3, 1).contiguous(), retain_graph=True)
+        gor = torch.autograd.grad(orf, [hr, whr, bhr], cot, retain_graph=True)
+        assert rel_rms(_nchw(go[0]), gor[0]) < 4e-3 and rel_rms(go[1], gor[1]) < 1e-3 and rel_rms(go[2], gor[2]) < 1e-5
+        assert abs(float(go[1].norm() / gor[1].norm()) - 1.0) < 1e-3          # no 2^-9 bias from a bf16 cotangent
+
+
+@pytest.mark.parametrize("batch,res,train", [(2, 64, True), (2, 64, False), (3, 128, True), (4, 256, True)])
+def test_patchgan_on_the_kernels_matches_oracle(batch, res, train):
+    """NLayerDiscriminator (modules/discriminator/model.py:17-67) through its reference-facing interface (NCHW fp32
+    in, NCHW fp32 logits out) on the hand-written kernels against the fp32 oracle: logits, updated running
+    statistics, and the gradients w.r.t. every parameter and w.r.t. the input image (the generator-loss path), for a
+    random cotangent and for the constant cotangent of a mean (hinge) loss.
+
+    Gradient bounds: the network is piecewise linear (four LeakyReLU layers).  The bf16 activations differ from the
+    fp32 oracle's by ~2e-3 relative, which flips the sign of the few pre-activations that lie that close to zero; a
+    flipped unit changes its local derivative between 1 and 0.2.  With a flip probability of ~2.5e-3 per unit and
+    layer that is ~5 % RMS per LeakyReLU layer, ~10-14 % end to end (measured), as noise that does not turn the
+    gradient (cosine >= 0.99) nor scale it (norms within 5 %); the layers themselves are exact to bf16 rounding
+    (test_patchgan_layers_match_fp32_ops)."""
+    from dynamicvectorquantization_b200 import configs
+    configs.activate_overlay()
+    from modules.discriminator.model import NLayerDiscriminator
+    from oracle import loss_oracle as lo
+    sd = {k: v for k, v in lo.make_loss_weights(seed=31).items() if k.startswith("loss.discriminator.")}
+    disc = NLayerDiscriminator(input_nc=3, ndf=64, n_layers=3, use_actnorm=False)
+    disc.load_state_dict({k[len("loss.discriminator."):]: v for k, v in sd.items()}, strict=False)
+    disc = disc.cuda().train(train)
+    g = torch.Generator().manual_seed(batch * res)
+    x = torch.rand(batch, 3, res, res, generator=g) * 2 - 1
+    xd = x.cuda().requires_grad_(True)
+    logits = disc(xd)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "running" not in k}
+    full = dict(sd); full.update(params)
+    xr = x.clone().requires_grad_(True)
+    new_stats = {}
+    ref = lo.discriminator(full, xr, train=train, new_stats=new_stats)
+    assert logits.shape == ref.shape
+    e = rel_rms(logits.detach(), ref.detach())
+    assert e < 1e-2, f"logits rel-RMS {e}"
+    if train:
+        for k, v in new_stats.items():
+            got = disc.state_dict()[k[len("loss.discriminator."):]].cpu()
+            if k.endswith("running_var"):
+                assert torch.allclose(got, v, rtol=1e-2), k
+            else:       # means of zero-centred activations: judged against the batch standard deviation of the channel
+                std = ((new_stats[k.replace("running_mean", "running_var")] - 0.9) / 0.1).clamp_min(0).sqrt()
+                assert float(((got - v).abs() / (0.1 * std + 1e-12)).max()) < 1e-2, k
+        assert int(disc.main[3].num_batches_tracked) == 1
+    names = [k for k, _ in disc.named_parameters()]
+    for kind in ("random", "mean"):
+        cot = torch.randn(ref.shape, generator=g) if kind == "random" else torch.full(ref.shape, -1.0 / ref.numel())
+        got = torch.autograd.grad(logits, [xd] + list(disc.parameters()), cot.cuda(), retain_graph=True)
+        want = torch.autograd.grad(ref, [xr] + [params["loss.discriminator." + n] for n in names], cot, retain_graph=True)
+        errs = {n: rel_rms(a, b) for n, a, b in zip(["input"] + names, got, want)}
+        coss = {n: _cos(a, b) for n, a, b in zip(["input"] + names, got, want)}
+        worst, wcos = max(errs.items(), key=lambda kv: kv[1]), min(coss.items(), key=lambda kv: kv[1])
+        print(f"patchgan {batch}x{res} train={train} cotangent={kind}: logits {e:.2e}, worst gradient rel-RMS {worst}, "
+              f"lowest cosine {wcos}")
+        assert worst[1] < 0.16 and wcos[1] > 0.99, (errs, coss)      # measured: 0.10-0.14, cosines 0.990-0.995
+        for n, a, b in zip(["input"] + names, got, want):
+            assert abs(float(a.norm()) / float(b.norm()) - 1.0) < 5e-2, (kind, n, float(a.norm()), float(b.norm()))
 
 
 def test_maxpool_and_relu_gradients_match_torch():
@@ -124,26 +269,36 @@ def test_full_loss_matches_oracle_and_reference_golden(monkeypatch, mode):
     rgw, rgf = torch.autograd.grad(r0, [w2, f2])
     p = mode + "_"
     for got, ref, key, tol in ((l0, r0, "loss0", 2e-2), (log0["train_p_loss"], rlog["p_loss"], "log0_p_loss", 2e-2),
-                               (log0["train_g_loss"], rlog["g_loss"], "log0_g_loss", 2e-3),
+                               (log0["train_g_loss"], rlog["g_loss"], "log0_g_loss", 1e-2),
                                (log0["train_d_weight"], rlog["d_weight"], "log0_d_weight", 5e-2),
                                (log0["train_budget_loss"], rlog["budget_loss"], "log0_budget_loss", 1e-5)):
         assert abs(float(got) - float(ref)) <= tol * abs(float(ref)) + 1e-6, (key, float(got), float(ref))
         assert abs(float(got) - float(gold[p + key])) <= tol * abs(float(gold[p + key])) + 1e-6, (key, "golden")
-    assert rel_rms(gw, rgw) < 6e-2 and rel_rms(gw, torch.from_numpy(gold[p + "g_w_last"])) < 6e-2
-    assert rel_rms(gf, rgf) < 6e-2 and rel_rms(gf, torch.from_numpy(gold[p + "g_feat"])) < 6e-2
+    # the GAN half of these gradients passes through the piecewise-linear PatchGAN in bf16 (see the bound discussion in
+    # test_patchgan_on_the_kernels_matches_oracle): direction and size are pinned, the RMS bound is 0.12
+    for got_g, ref_g, key in ((gw, rgw, "g_w_last"), (gf, rgf, "g_feat")):
+        for want in (ref_g, torch.from_numpy(gold[p + key])):
+            assert rel_rms(got_g, want) < 0.12 and _cos(got_g, want) > 0.993, (key, rel_rms(got_g, want), _cos(got_g, want))
+            assert abs(float(got_g.norm()) / float(want.norm()) - 1.0) < 3e-2, key
     # discriminator pass
     l1, log1 = loss(qd, xd, xrec.detach(), 1, 0, last_layer=wl, split="train")
-    assert abs(float(l1) - float(gold[p + "loss1"])) <= 2e-3 * abs(float(gold[p + "loss1"])) + 1e-6
+    assert abs(float(l1) - float(gold[p + "loss1"])) <= 1e-2 * abs(float(gold[p + "loss1"])) + 1e-6
     dparams = dict(loss.discriminator.named_parameters())
     gds = torch.autograd.grad(l1, list(dparams.values()))
     for k, gr in zip(dparams, gds):
         ref = float(gold[p + "gd_norm_" + k])
-        assert abs(float(gr.norm()) - ref) <= 1e-2 * ref + 1e-7, (k, float(gr.norm()), ref)
+        assert abs(float(gr.norm()) - ref) <= 2e-2 * ref + 1e-7, (k, float(gr.norm()), ref)
     if mode == "train":
         for k, v in loss.state_dict().items():
             if "running" in k:
-                # TF32 convolutions (torch's cuDNN default) feed these statistics
-                assert torch.allclose(v.cpu(), torch.from_numpy(gold[p + "bn1_" + k]), rtol=2e-2, atol=3e-4), k
+                # bf16 convolutions feed these statistics; means of zero-centred activations are judged against the
+                # channel's batch standard deviation (recovered from the golden running variance)
+                ref_v = torch.from_numpy(gold[p + "bn1_" + k])
+                if k.endswith("running_var"):
+                    assert torch.allclose(v.cpu(), ref_v, rtol=2e-2), k
+                else:
+                    rv = torch.from_numpy(gold[p + "bn1_" + k.replace("running_mean", "running_var")])
+                    assert float(((v.cpu() - ref_v).abs() / (rv.sqrt() + 1e-12)).max()) < 2e-3, k
 
 
 def test_training_step_under_the_real_loss(monkeypatch):

@@ -567,3 +567,59 @@ def test_launcher_puts_the_overlay_ahead_of_the_script_directory(tmp_path):
     out = launched.stdout.split("RESOLVED")[1]
     assert os.path.join("dynamicvectorquantization_b200", "overlay") in out, out
     assert "reference" in out and "['--x']" in out            # fall-through to the reference tree and argv still work
+
+
+def test_conv4x4_tap_tables_match_torch_conv():
+    """PatchGAN 4x4 convolutions (modules/discriminator/model.py:37-66) on the tap GEMM: the tap tables of
+    kernels.conv4x4_fwd / conv4x4_dgrad / the stem's image gradient are checked on the CPU by emulating the GEMM's
+    addressing (shifted boxes of the NHWC tensor or of its stride-2 parity view, zero fill outside, strided parity
+    classes of the output) in PyTorch against F.conv2d and its autograd."""
+    import torch.nn.functional as F
+    from dynamicvectorquantization_b200 import kernels as kn
+
+    def box(view, n0, h0, p, w0, c0, cin, hh, ww):
+        """view [N, H2, P, W2, C2] -> [N, hh, ww, cin] box starting at (h0, w0) with zero fill outside."""
+        N, H2, P, W2, C2 = view.shape
+        out = torch.zeros(N, hh, ww, cin, dtype=view.dtype)
+        for i in range(hh):
+            for j in range(ww):
+                y, x = h0 + i, w0 + j
+                if 0 <= y < H2 and 0 <= x < W2:
+                    out[:, i, j] = view[:, y, p, x, c0:c0 + cin]
+        return out
+
+    g = torch.Generator().manual_seed(0)
+    for stride, h, w, cin, cout in ((2, 8, 12, 4, 5), (1, 6, 7, 3, 4)):
+        x = torch.randn(2, h, w, cin, generator=g, dtype=torch.float64)
+        wt = torch.randn(cout, cin, 4, 4, generator=g, dtype=torch.float64)
+        ref = F.conv2d(x.permute(0, 3, 1, 2), wt, stride=stride, padding=1).permute(0, 2, 3, 1)
+        ho, wo = kn.conv4x4_out_hw(h, w, stride)
+        assert ref.shape[1:3] == (ho, wo)
+        wf = wt.permute(0, 2, 3, 1).reshape(cout, 16 * cin)                       # pack_weight_fwd layout
+        view = x.view(2, h // 2, 2, w // 2, 2 * cin) if stride == 2 else x.view(2, h, 1, w, cin)
+        y = torch.zeros(2, ho, wo, cout, dtype=torch.float64)
+        for (dc, dw, dp, dh, bk) in kn._taps4(stride, cin):
+            y += box(view, 0, dh, dp, dw, dc, cin, ho, wo) @ wf[:, bk:bk + cin].t()
+        assert torch.allclose(y, ref, atol=1e-10), f"forward taps, stride {stride}"
+        # data gradient: taps of kernels.conv4x4_dgrad over dy, weights in pack_weight_dgrad layout
+        dy = torch.randn(2, ho, wo, cout, generator=g, dtype=torch.float64)
+        xr = x.permute(0, 3, 1, 2).clone().requires_grad_(True)
+        F.conv2d(xr, wt, stride=stride, padding=1).backward(dy.permute(0, 3, 1, 2))
+        ref_dx = xr.grad.permute(0, 2, 3, 1)
+        wd = wt.permute(1, 2, 3, 0).reshape(cin, 16 * cout)
+        dyv = dy.view(2, ho, 1, wo, cout)
+        dx = torch.zeros(2, h, w, cin, dtype=torch.float64)
+        if stride == 1:
+            for r in range(4):
+                for s_ in range(4):
+                    dx += box(dyv, 0, 1 - r, 0, 1 - s_, 0, cout, h, w) @ wd[:, (r * 4 + s_) * cout:(r * 4 + s_ + 1) * cout].t()
+        else:
+            rsel = {0: [(1, 0), (3, -1)], 1: [(0, 1), (2, 0)]}                     # as in kernels.conv4x4_dgrad
+            for ph in (0, 1):
+                for pw in (0, 1):
+                    acc = torch.zeros(2, ho, wo, cin, dtype=torch.float64)
+                    for r, dh in rsel[ph]:
+                        for s_, dw in rsel[pw]:
+                            acc += box(dyv, 0, dh, 0, dw, 0, cout, ho, wo) @ wd[:, (r * 4 + s_) * cout:(r * 4 + s_ + 1) * cout].t()
+                    dx[:, ph::2, pw::2] = acc
+        assert torch.allclose(dx, ref_dx, atol=1e-10), f"data-gradient taps, stride {stride}"
