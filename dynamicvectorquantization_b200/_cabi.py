@@ -64,8 +64,7 @@ SIGNATURES = {
     "b2dq_vq_bwd": [_vp, _vp, _vp, _vp, _vp, _f, _vp, _ll, _i, _vp],
     "b2dq_tapgemm": [C.POINTER(TapGemmDesc), _vp],
     "b2dq_mmgemm": [C.POINTER(MmDesc), _vp],
-    "b2dq_pconv3x3": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
-    "b2dq_gn_bwd_reduce_tiles": [_vp, _vp, _i, _i, _i, _vp],
+    "b2dq_pconv3x3": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "b2dq_gn_finalize_tiles": [_vp, _vp, _i, _i, _i, _f, _vp],
     "b2dq_colsum_reduce": [_vp, _vp, _i, _i, _vp],
     "b2dq_wgrad_reduce": [_vp, _vp, _i, _i, _i, _i, _i, _vp],

@@ -12,7 +12,14 @@
 //     address bits, so the shifted view needs no descriptor base offset);
 //   * two 128-pixel output tiles share every weight tile (6 MMA groups per 3 weight tiles);
 //   * the CTA is persistent (one per SM) with two TMEM accumulator sets, so the epilogue of one
-//     tile pair overlaps the main loop of the next and the TMA ring never drains.
+//     tile pair overlaps the main loop of the next and the TMA ring never drains;
+//   * the epilogue never touches global memory with per-thread accesses: a thread owns one pixel row of
+//     the tile, so its 16 B stores / residual loads would hit 32 different 128 B lines per warp
+//     instruction (8192 LSU wavefronts per tile pair with a residual - more than the 4608 tensor cycles of
+//     the pair: measured 627 us vs 485 us per launch).  Instead the bf16 tile is staged in shared memory in
+//     the 128 B-swizzled layout of a TMA box {64 ch, 128 px} and written by ONE bulk tensor store per
+//     64-channel half; the residual half-tile arrives the same way (TMA load into the same staging buffer
+//     two units ahead, added in place).  Three 16 KB staging buffers rotate.
 // Per pipeline stage: 2 strips (2 x 16.6 KB) + 3 weight tiles (3 x 16 KB) feed 24 MMAs
 // (128x128x16) = 1536 tensor cycles -> 53 B/cycle/SM instead of 128.
 #include "common.cuh"
@@ -28,7 +35,9 @@ constexpr uint32_t PC_STRIP_BYTES = PC_STRIP_ROWS * 128;           // 16,640
 constexpr uint32_t PC_STRIP_SLOT = 17 * 1024;                      // padded, keeps 1024 B alignment
 constexpr uint32_t PC_B_BYTES = PC_BN * 128;                       // 16 KB
 constexpr uint32_t PC_STAGE_BYTES = PC_MT * PC_STRIP_SLOT + 3 * PC_B_BYTES;   // 83,968
-constexpr uint32_t PC_SMEM = PC_STAGES * PC_STAGE_BYTES + 1024 + 256 + 7168;   // + bias / GN scratch
+constexpr uint32_t PC_OUT_BUFS = 3;                                // staging buffers of the epilogue
+constexpr uint32_t PC_OUT_BYTES = 128 * 128;                       // 128 pixels x 64 channels bf16
+constexpr uint32_t PC_SMEM = PC_STAGES * PC_STAGE_BYTES + PC_OUT_BUFS * PC_OUT_BYTES + 1024 + 256 + 2048;
 
 struct PconvParams {
   int kchunks;                 // Cin / 64
@@ -38,36 +47,26 @@ struct PconvParams {
   int tiles_w, H, NB, W;       // tiles per image row, image height, images, width
   int num_tiles;               // NB * H * tiles_w
   int Cout;
-  __nv_bfloat16* out;
-  long long oN, oH, oW;
   const float* bias;
-  const __nv_bfloat16* residual;
-  long long rN, rH, rW;
+  int has_residual;            // the residual tensor (same shape as the output) is read through tmR
   float* gn_part;              // optional [num_tiles][32 groups][2]: per-tile (sum, sum of squares) of the
                                // OUTPUT per GroupNorm group of 4 channels (statistics for the next GroupNorm)
-  // Data-gradient mode, optional: the output d_a is the gradient wrt a = swish(GroupNorm(gnb_x)); emit
-  // the per-tile, per-channel sums the GroupNorm backward needs (sum dz, sum dz*xhat), so that its own
-  // reduction pass over (d_a, x) disappears.  gnb_x: [NB,H,W,128] like the output.
-  const __nv_bfloat16* gnb_x;
-  const float* gnb_stats;      // [NB][32][2] (mean, rstd)
-  const float* gnb_gamma;      // [128]
-  const float* gnb_beta;       // [128]
-  float* gnb_part;             // [num_tiles][128][2]
 };
 
 __global__ void __launch_bounds__(192, 1)
 pconv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
                 const __grid_constant__ PconvParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sBar = base + PC_STAGES * PC_STAGE_BYTES;
+  const uint32_t sOut = base + PC_STAGES * PC_STAGE_BYTES;          // 1024 B aligned (stage size is a multiple)
+  const uint32_t sBar = sOut + PC_OUT_BUFS * PC_OUT_BYTES;
   const uint32_t bar_full = sBar, bar_empty = sBar + 16, bar_tfull = sBar + 32, bar_tempty = sBar + 48;
+  const uint32_t bar_res = sBar + 96;                               // [PC_OUT_BUFS] residual half-tile landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + (sBar + 64 - smem_u32(smem_raw)));
   float* bias_s = reinterpret_cast<float*>(smem_raw + (sBar + 256 - smem_u32(smem_raw)));
   float* gn_red = bias_s + 128;                  // [4 warps][64]
-  float* gsm = gn_red + 256;                     // GroupNorm gamma [128]
-  float* bsm = gsm + 128;                        // GroupNorm beta  [128]
-  float* red2 = bsm + 128;                       // [4 warps][128 ch][2]
+  uint8_t* out_stage = smem_raw + (sOut - smem_u32(smem_raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_items = (p.num_tiles + PC_MT - 1) / PC_MT;
@@ -82,18 +81,17 @@ pconv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_init(bar_tfull + 8 * i, 1);
       mbar_init(bar_tempty + 8 * i, 4);
     }
+    for (int i = 0; i < (int)PC_OUT_BUFS; ++i) mbar_init(bar_res + 8 * i, 1);
     fence_barrier_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmO);
+    if (p.has_residual) tma_prefetch_desc(&tmR);
   }
   if (warp == 1) tmem_alloc<512>(smem_u32(tmem_slot));
   if (threadIdx.x >= 64) {
     const int t = threadIdx.x - 64;
     bias_s[t] = (p.bias && t < p.Cout) ? p.bias[t] : 0.f;
-    if (p.gnb_part) {
-      gsm[t] = p.gnb_gamma[t];
-      bsm[t] = p.gnb_beta[t];
-    }
   }
   tc_fence_before();
   __syncthreads();
@@ -161,203 +159,152 @@ pconv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   } else {
+    // ---------------------------------------------------------------- epilogue (warps 2..5)
+    // A "unit" is one 64-channel half of one 128-pixel tile: 16 KB of bf16 staged in out_stage[unit % 3] and
+    // written by one TMA store.  Units run in the fixed order item -> tile -> half; the leader thread keeps the
+    // residual half-tiles two units ahead of the arithmetic.
     const int q = warp & 3;
-    const int m = q * 32 + lane;
+    const int m = q * 32 + lane;                 // pixel row of the tile == TMEM lane
+    const bool leader = threadIdx.x == 64;
+    const uint32_t swz = static_cast<uint32_t>(m & 7);
+    const int my_items = (num_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                         static_cast<int>(gridDim.x);
+    const int total_units = my_items * (PC_MT * 2);
+    auto unit_coords = [&](int u, int& c0, int& ow0, int& oh, int& n) {
+      const int item = static_cast<int>(blockIdx.x) + (u / (PC_MT * 2)) * static_cast<int>(gridDim.x);
+      tile_coords(item * PC_MT + ((u >> 1) & (PC_MT - 1)), ow0, oh, n);
+      c0 = (u & 1) * 64;
+    };
+    auto load_residual = [&](int u) {            // leader only
+      if (!p.has_residual || u >= total_units) return;
+      int c0, ow0, oh, n;
+      unit_coords(u, c0, ow0, oh, n);
+      if (n >= p.NB) return;
+      const uint32_t rb = bar_res + 8 * (u % PC_OUT_BUFS);
+      mbar_arrive_expect_tx(rb, PC_OUT_BYTES);
+      tma_load_5d(sOut + (u % PC_OUT_BUFS) * PC_OUT_BYTES, &tmR, rb, c0, ow0, 0, oh, n);
+    };
+    if (leader) { load_residual(0); load_residual(1); }
     uint32_t it_item = 0;
+    int u = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it_item) {
       const uint32_t buf = it_item & 1;
-      bool valid[PC_MT];
-      long long ooff[PC_MT], roff[PC_MT];
-      int nimg[PC_MT];
-#pragma unroll
+      mbar_wait(bar_tfull + 8 * buf, (it_item >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
       for (int j = 0; j < PC_MT; ++j) {
         int ow0, oh, n;
         tile_coords(item * PC_MT + j, ow0, oh, n);
-        const int ow = ow0 + m;
-        valid[j] = (ow < p.W) && (n < p.NB);
-        nimg[j] = n < p.NB ? n : 0;
-        ooff[j] = n * p.oN + oh * p.oH + ow * p.oW;
-        roff[j] = n * p.rN + oh * p.rH + ow * p.rW;
-      }
-      // row prefetched while the main loop runs: the residual (forward) or the GroupNorm input (dgrad)
-      const __nv_bfloat16* aux = p.gnb_part ? p.gnb_x : p.residual;
-      uint4 res[PC_BN / 8];
-      if (aux && valid[0]) {
-        const uint4* rp = reinterpret_cast<const uint4*>(aux + roff[0]);
-#pragma unroll
-        for (int i = 0; i < PC_BN / 8; ++i) res[i] = __ldg(rp + i);
-      }
-      mbar_wait(bar_tfull + 8 * buf, (it_item >> 1) & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int j = 0; j < PC_MT; ++j) {
-        if (j > 0 && aux && valid[j]) {
-          const uint4* rp = reinterpret_cast<const uint4*>(aux + roff[j]);
-#pragma unroll
-          for (int i = 0; i < PC_BN / 8; ++i) res[i] = __ldg(rp + i);
-        }
+        const bool valid = n < p.NB;             // W % 128 == 0: a tile is a full row segment or past the end
         const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * (PC_MT * PC_BN) + j * PC_BN;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half, ++u) {
+          const uint32_t ob = u % PC_OUT_BUFS;
+          uint8_t* row = out_stage + ob * PC_OUT_BYTES + m * 128;
+          if (p.has_residual && valid) mbar_wait(bar_res + 8 * ob, (u / PC_OUT_BUFS) & 1);
 #pragma unroll
-        for (int c0 = 0; c0 < PC_BN; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld_32x32(trow + c0, r);
-          tmem_ld_wait();
-          if (!valid[j] && !p.gn_part && !p.gnb_part) continue;
-          float v[32];
+          for (int cc = 0; cc < 2; ++cc) {
+            const int c0 = half * 64 + cc * 32;
+            uint32_t r[32];
+            tmem_ld_32x32(trow + c0, r);
+            tmem_ld_wait();
+            float v[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + bias_s[c0 + i];
-          if (p.residual) {
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + bias_s[c0 + i];
+            if (p.has_residual && valid) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const uint4 u = res[c0 / 8 + i];
-              v[8 * i + 0] += bf16_lo(u.x); v[8 * i + 1] += bf16_hi(u.x);
-              v[8 * i + 2] += bf16_lo(u.y); v[8 * i + 3] += bf16_hi(u.y);
-              v[8 * i + 4] += bf16_lo(u.z); v[8 * i + 5] += bf16_hi(u.z);
-              v[8 * i + 6] += bf16_lo(u.w); v[8 * i + 7] += bf16_hi(u.w);
-            }
-          }
-          if (valid[j]) {
-            uint4* op = reinterpret_cast<uint4*>(p.out + ooff[j] + c0);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint4 u;
-              u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
-              u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-              u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-              u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-              op[i] = u;
-            }
-          }
-          if (p.gnb_part) {
-            // GroupNorm(+swish) backward partial sums for the 32 channels of this chunk:
-            //   A_c = sum_rows dz,  B_c = sum_rows dz * xhat,  dz = d_a * swish'(z), z = xhat*gamma + beta.
-            // First butterfly step (A_c / B_c pairs, lane bit 4) is fused into the production loop; four
-            // more halving steps leave lane l with entries 2l, 2l+1 of [A_0..A_31, B_0..B_31].
-            float w32[32];
-            const float* stp = p.gnb_stats + (static_cast<long long>(nimg[j]) * 32 + (c0 >> 2)) * 2;
-#pragma unroll
-            for (int g8 = 0; g8 < 8; ++g8) {
-              const float mean = __ldg(stp + 2 * g8), rstd = __ldg(stp + 2 * g8 + 1);
-              const uint4 u = res[(c0 >> 3) + (g8 >> 1)];
-              const uint32_t lo = (g8 & 1) ? u.z : u.x, hi = (g8 & 1) ? u.w : u.y;
-              const float xs[4] = {bf16_lo(lo), bf16_hi(lo), bf16_lo(hi), bf16_hi(hi)};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int i = 4 * g8 + e;
-                const float xh = (xs[e] - mean) * rstd;
-                const float z = fmaf(xh, gsm[c0 + i], bsm[c0 + i]);
-                const float sg = __fdividef(1.f, 1.f + __expf(-z));
-                const float dz = valid[j] ? v[i] * sg * (1.f + z * (1.f - sg)) : 0.f;
-                const float bz = valid[j] ? dz * xh : 0.f;
-                const float send = (lane & 16) ? dz : bz;
-                const float keep = (lane & 16) ? bz : dz;
-                w32[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-              }
-            }
-            float w16[16], w8[8], w4[4], w2[2];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float send = (lane & 8) ? w32[i] : w32[i + 16];
-              const float keep = (lane & 8) ? w32[i + 16] : w32[i];
-              w16[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float send = (lane & 4) ? w16[i] : w16[i + 8];
-              const float keep = (lane & 4) ? w16[i + 8] : w16[i];
-              w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float send = (lane & 2) ? w8[i] : w8[i + 4];
-              const float keep = (lane & 2) ? w8[i + 4] : w8[i];
-              w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-            }
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const float send = (lane & 1) ? w4[i] : w4[i + 2];
-              const float keep = (lane & 1) ? w4[i + 2] : w4[i];
-              w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-            }
-            // lane l: entries 2l, 2l+1; entries 0..31 = A of channel c0+e, 32..63 = B of channel c0+e-32
-            const int e0 = 2 * lane;
-            const int kind = e0 >> 5, ch = c0 + (e0 & 31);
-            red2[q * 256 + ch * 2 + kind] = w2[0];
-            red2[q * 256 + (ch + 1) * 2 + kind] = w2[1];
-          }
-          if (p.gn_part) {
-            // per-group (4 channels) sum / sum of squares of this row, then a fixed-order transposed
-            // butterfly over the warp's 32 rows: 16 values -> lane pair (2i, 2i+1) holds total i
-            float a8[8], a4[4], a2[2], a1;
-            {
-              float vals[16];
-#pragma unroll
-              for (int g8 = 0; g8 < 8; ++g8) {
-                const float x0 = valid[j] ? v[4 * g8] : 0.f, x1 = valid[j] ? v[4 * g8 + 1] : 0.f;
-                const float x2 = valid[j] ? v[4 * g8 + 2] : 0.f, x3 = valid[j] ? v[4 * g8 + 3] : 0.f;
-                vals[g8] = (x0 + x1) + (x2 + x3);
-                vals[8 + g8] = fmaf(x0, x0, x1 * x1) + fmaf(x2, x2, x3 * x3);
-              }
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float send = (lane & 16) ? vals[i] : vals[i + 8];
-                const float keep = (lane & 16) ? vals[i + 8] : vals[i];
-                a8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+              for (int i = 0; i < 4; ++i) {
+                const uint4 uu = *reinterpret_cast<const uint4*>(row + (((cc * 4 + i) ^ swz) << 4));
+                v[8 * i + 0] += bf16_lo(uu.x); v[8 * i + 1] += bf16_hi(uu.x);
+                v[8 * i + 2] += bf16_lo(uu.y); v[8 * i + 3] += bf16_hi(uu.y);
+                v[8 * i + 4] += bf16_lo(uu.z); v[8 * i + 5] += bf16_hi(uu.z);
+                v[8 * i + 6] += bf16_lo(uu.w); v[8 * i + 7] += bf16_hi(uu.w);
               }
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float send = (lane & 8) ? a8[i] : a8[i + 4];
-              const float keep = (lane & 8) ? a8[i + 4] : a8[i];
-              a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+              uint4 uu;
+              uu.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+              uu.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+              uu.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+              uu.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+              *reinterpret_cast<uint4*>(row + (((cc * 4 + i) ^ swz) << 4)) = uu;
             }
+            if (p.gn_part) {
+              // per-group (4 channels) sum / sum of squares of this row, then a fixed-order transposed
+              // butterfly over the warp's 32 rows: 16 values -> lane pair (2i, 2i+1) holds total i
+              float a8[8], a4[4], a2[2], a1;
+              {
+                float vals[16];
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const float send = (lane & 4) ? a4[i] : a4[i + 2];
-              const float keep = (lane & 4) ? a4[i + 2] : a4[i];
-              a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-            }
-            {
-              const float send = (lane & 2) ? a2[0] : a2[1];
-              const float keep = (lane & 2) ? a2[1] : a2[0];
-              a1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-            }
-            a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
-            if ((lane & 1) == 0) {
-              const int idx = lane >> 1;                     // 0..7: group sums, 8..15: group sums of squares
-              const int group = (c0 >> 2) + (idx & 7);
-              gn_red[q * 64 + group * 2 + (idx >> 3)] = a1;
+                for (int g8 = 0; g8 < 8; ++g8) {
+                  const float x0 = valid ? v[4 * g8] : 0.f, x1 = valid ? v[4 * g8 + 1] : 0.f;
+                  const float x2 = valid ? v[4 * g8 + 2] : 0.f, x3 = valid ? v[4 * g8 + 3] : 0.f;
+                  vals[g8] = (x0 + x1) + (x2 + x3);
+                  vals[8 + g8] = fmaf(x0, x0, x1 * x1) + fmaf(x2, x2, x3 * x3);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float send = (lane & 16) ? vals[i] : vals[i + 8];
+                  const float keep = (lane & 16) ? vals[i + 8] : vals[i];
+                  a8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                }
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float send = (lane & 8) ? a8[i] : a8[i + 4];
+                const float keep = (lane & 8) ? a8[i + 4] : a8[i];
+                a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+              }
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                const float send = (lane & 4) ? a4[i] : a4[i + 2];
+                const float keep = (lane & 4) ? a4[i + 2] : a4[i];
+                a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+              }
+              {
+                const float send = (lane & 2) ? a2[0] : a2[1];
+                const float keep = (lane & 2) ? a2[1] : a2[0];
+                a1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+              }
+              a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+              if ((lane & 1) == 0) {
+                const int idx = lane >> 1;                     // 0..7: group sums, 8..15: group sums of squares
+                const int group = (c0 >> 2) + (idx & 7);
+                gn_red[q * 64 + group * 2 + (idx >> 3)] = a1;
+              }
             }
           }
-        }
-        if (p.gnb_part) {
+          // staged half-tile -> global: make the generic-proxy writes visible to the async proxy, then one TMA store
+          fence_proxy_async_smem();
           asm volatile("bar.sync 2, 128;" ::: "memory");
-          const int te = threadIdx.x - 64;
-          const int tile = item * PC_MT + j;
-          if (tile < p.num_tiles) {
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int i = 2 * te + e;
-              p.gnb_part[static_cast<long long>(tile) * 256 + i] =
-                  (red2[i] + red2[256 + i]) + (red2[512 + i] + red2[768 + i]);
+          if (leader) {
+            if (valid) {
+              asm volatile(
+                  "cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4, %5}], [%6];" ::"l"(&tmO),
+                  "r"(half * 64), "r"(ow0), "r"(0), "r"(oh), "r"(n), "r"(sOut + ob * PC_OUT_BYTES)
+                  : "memory");
             }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            // the buffer of unit u+2 was last read by the store of unit u-1: wait for it, then refill / release it
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            load_residual(u + 2);
           }
-          asm volatile("bar.sync 2, 128;" ::: "memory");
-        }
-        if (p.gn_part) {
-          asm volatile("bar.sync 2, 128;" ::: "memory");
-          const int te = threadIdx.x - 64;
-          const int tile = item * PC_MT + j;
-          if (te < 64 && tile < p.num_tiles)
-            p.gn_part[static_cast<long long>(tile) * 64 + te] =
-                (gn_red[te] + gn_red[64 + te]) + (gn_red[128 + te] + gn_red[192 + te]);
-          asm volatile("bar.sync 2, 128;" ::: "memory");
+          if (half == 1 && p.gn_part) {
+            const int te = threadIdx.x - 64;
+            const int tile = item * PC_MT + j;
+            if (te < 64 && tile < p.num_tiles)
+              p.gn_part[static_cast<long long>(tile) * 64 + te] =
+                  (gn_red[te] + gn_red[64 + te]) + (gn_red[128 + te] + gn_red[192 + te]);
+            asm volatile("bar.sync 2, 128;" ::: "memory");     // gn_red is rewritten by the next tile
+          }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
     }
+    if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -378,12 +325,11 @@ extern "C" {
 // W % 128 == 0, Cin % 64 == 0.  b_ptr: [128, 9*Cin] bf16, column = (r*3+s)*Cin + ci.
 // dgrad != 0: tap (r,s) reads the pixel at (+1-r, +1-s) instead of (r-1, s-1).
 int b2dq_pconv3x3(const void* a_ptr, const void* b_ptr, void* out, const float* bias,
-                  const void* residual, float* gn_part, const void* gnb_x, const float* gnb_stats,
-                  const float* gnb_gamma, const float* gnb_beta, float* gnb_part, int NB, int H, int W,
-                  int Cin, int dgrad, int max_ctas, cudaStream_t stream) {
+                  const void* residual, float* gn_part, int NB, int H, int W, int Cin, int dgrad, int max_ctas,
+                  cudaStream_t stream) {
   if (NB <= 0 || H <= 0 || W <= 0) return 0;
   if (W % 128 != 0 || Cin % 64 != 0 || Cin <= 0) return -1;
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmO, tmR;
   {
     uint64_t dims[5] = {(uint64_t)Cin, (uint64_t)W, 1, (uint64_t)H, (uint64_t)NB};
     uint64_t str[5] = {1, (uint64_t)Cin, (uint64_t)W * Cin, (uint64_t)W * Cin, (uint64_t)H * W * Cin};
@@ -398,6 +344,16 @@ int b2dq_pconv3x3(const void* a_ptr, const void* b_ptr, void* out, const float* 
     int r = make_tmap_bf16(&tmB, b_ptr, 2, dims, str, box);
     if (r) return r - 1000;
   }
+  {
+    // output (and residual) [NB,H,W,128]: half-tiles of 128 pixels x 64 channels, 128 B-swizzled in shared memory
+    uint64_t dims[5] = {(uint64_t)PC_BN, (uint64_t)W, 1, (uint64_t)H, (uint64_t)NB};
+    uint64_t str[5] = {1, (uint64_t)PC_BN, (uint64_t)W * PC_BN, (uint64_t)W * PC_BN, (uint64_t)H * W * PC_BN};
+    uint32_t box[5] = {64, 128, 1, 1, 1};
+    int r = make_tmap_bf16(&tmO, out, 5, dims, str, box);
+    if (r) return r - 2000;
+    r = make_tmap_bf16(&tmR, residual ? residual : out, 5, dims, str, box);
+    if (r) return r - 3000;
+  }
   static unsigned long long attr_mask = 0;
   if (int e = set_max_smem_once(pconv3x3_kernel, PC_SMEM, attr_mask)) return e;
   PconvParams p;
@@ -409,23 +365,14 @@ int b2dq_pconv3x3(const void* a_ptr, const void* b_ptr, void* out, const float* 
   p.tiles_w = W / 128; p.H = H; p.NB = NB; p.W = W;
   p.num_tiles = NB * H * p.tiles_w;
   p.Cout = PC_BN;
-  p.out = reinterpret_cast<__nv_bfloat16*>(out);
-  p.oN = (long long)H * W * PC_BN; p.oH = (long long)W * PC_BN; p.oW = PC_BN;
   p.bias = bias;
-  p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
-  p.rN = p.oN; p.rH = p.oH; p.rW = p.oW;
+  p.has_residual = residual != nullptr;
   p.gn_part = gn_part;
-  if (gnb_part && (residual || !gnb_x || !gnb_stats || !gnb_gamma || !gnb_beta)) return -2;
-  p.gnb_x = reinterpret_cast<const __nv_bfloat16*>(gnb_x);
-  p.gnb_stats = gnb_stats; p.gnb_gamma = gnb_gamma; p.gnb_beta = gnb_beta; p.gnb_part = gnb_part;
-  int dev = 0, sms = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  int grid = sms;
+  int grid = device_sm_count();
   if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
   const int items = (p.num_tiles + PC_MT - 1) / PC_MT;
   if (items < grid) grid = items;
-  pconv3x3_kernel<<<grid, 192, PC_SMEM, stream>>>(tmA, tmB, p);
+  pconv3x3_kernel<<<grid, 192, PC_SMEM, stream>>>(tmA, tmB, tmO, tmR, p);
   return (int)cudaGetLastError();
 }
 
@@ -463,25 +410,6 @@ __global__ void gn_finalize_tiles_kernel(const float* __restrict__ part, float* 
     stats[2 * i] = static_cast<float>(mean);
     stats[2 * i + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
   }
-}
-
-// ws_nc[n][c] = (sum dz, sum dz*xhat) over the tiles of image n, added in tile order (deterministic).
-__global__ void gn_bwd_reduce_tiles_kernel(const float* __restrict__ part, float* ws_nc, int N,
-                                           int tiles_per_image) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N * 256) return;
-  const int n = i / 256, e = i % 256;
-  float a = 0.f;
-  const float* pp = part + (static_cast<long long>(n) * tiles_per_image) * 256 + e;
-  for (int t = 0; t < tiles_per_image; ++t) a += pp[static_cast<long long>(t) * 256];
-  ws_nc[i] = a;
-}
-
-int b2dq_gn_bwd_reduce_tiles(const float* gnb_part, float* ws_nc, int N, int H, int W, cudaStream_t stream) {
-  if (N <= 0) return 0;
-  if (W % 128) return -1;
-  gn_bwd_reduce_tiles_kernel<<<(N * 256 + 255) / 256, 256, 0, stream>>>(gnb_part, ws_nc, N, H * (W / 128));
-  return (int)cudaGetLastError();
 }
 
 int b2dq_gn_finalize_tiles(const float* gn_part, float* stats, int N, int H, int W, float eps,

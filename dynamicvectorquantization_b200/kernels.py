@@ -209,16 +209,12 @@ def conv_fwd(x, wpack, bias, ksize, stride, cout, residual=None, out_f32=False, 
     return out
 
 
-def conv_dgrad(dy, wdpack, ksize, stride, cin, in_hw, gn_bwd=None):
-    """dy NHWC bf16 [N,Ho,Wo,Cout] -> dx NHWC bf16 [N,H,W,Cin].
-    gn_bwd = (gn_input, stats, gamma, beta): dx is the gradient wrt swish(GroupNorm(gn_input)); when the
-    persistent kernel runs, kernels.last_dgrad_gn_ws holds the GroupNorm-backward reduction afterwards."""
-    global last_dgrad_gn_ws
-    last_dgrad_gn_ws = None
+def conv_dgrad(dy, wdpack, ksize, stride, cin, in_hw):
+    """dy NHWC bf16 [N,Ho,Wo,Cout] -> dx NHWC bf16 [N,H,W,Cin]."""
     nb, ho, wo, cout = dy.shape
     assert cout % 64 == 0
     if _pconv_ok(ksize, stride, wo, cout, cin, nb, ho):
-        return pconv3x3(dy, wdpack, None, None, dgrad=True, gn_bwd=gn_bwd if FUSE_GN_BWD else None)
+        return pconv3x3(dy, wdpack, None, None, dgrad=True)
     kch = cout // 64
     h, w = in_hw
     dx = torch.empty(nb, h, w, cin, dtype=BF16, device=dy.device)
@@ -279,32 +275,15 @@ FUSE_GN_STATS = True     # pconv forward also emits the GroupNorm statistics of 
 last_conv_stats = None   # (mean, rstd) [N,32,2] of the most recent conv_fwd output, or None
 
 
-# pconv data-gradient can also emit the reduction of the GroupNorm backward it feeds (correct, tested), but the
-# 512 MUFU ops + 500 shuffles per thread and tile pair make the 4 epilogue warps slower than the tensor core:
-# measured 86.9 ms/step with it vs 70.8 ms without (the separate gn_bwd_partial pass runs on all warps of
-# all SMs at HBM speed).  OFF by default.
-FUSE_GN_BWD = False
-last_dgrad_gn_ws = None  # ws_nc [N,128,2] produced by the most recent conv_dgrad(gn_bwd=...), or None
-
-
-def pconv3x3(x, wpack, bias, residual, dgrad, want_stats=False, gn_bwd=None):
-    """gn_bwd = (gn_input, stats, gamma, beta): dgrad launches only, see b2dq_pconv3x3."""
-    global last_conv_stats, last_dgrad_gn_ws
+def pconv3x3(x, wpack, bias, residual, dgrad, want_stats=False):
+    """Persistent strip kernel (b2dq_pconv3x3): 3x3 stride-1 convolution (or its data gradient) to 128 channels."""
+    global last_conv_stats
     nb, h, w, cin = x.shape
     lib = _cabi.lib()
     out = torch.empty(nb, h, w, 128, dtype=BF16, device=x.device)
     part = torch.empty(nb * h * (w // 128), 64, dtype=torch.float32, device=x.device) if want_stats else None
-    gx = gst = gg = gb = gpart = None
-    if gn_bwd is not None:
-        gx, gst, gg, gb = gn_bwd
-        gpart = torch.empty(nb * h * (w // 128), 256, dtype=torch.float32, device=x.device)
-    check(lib.b2dq_pconv3x3(_ptr(x), _ptr(wpack), _ptr(out), _ptr(bias), _ptr(residual), _ptr(part),
-                            _ptr(gx), _ptr(gst), _ptr(gg), _ptr(gb), _ptr(gpart), nb, h, w, cin,
+    check(lib.b2dq_pconv3x3(_ptr(x), _ptr(wpack), _ptr(out), _ptr(bias), _ptr(residual), _ptr(part), nb, h, w, cin,
                             int(dgrad), 0, _stream()), "pconv3x3")
-    if gn_bwd is not None:
-        ws = torch.empty(nb, 128, 2, dtype=torch.float32, device=x.device)
-        check(lib.b2dq_gn_bwd_reduce_tiles(_ptr(gpart), _ptr(ws), nb, h, w, _stream()), "gn_bwd_reduce_tiles")
-        last_dgrad_gn_ws = ws
     if want_stats:
         stats = torch.empty(nb, 32, 2, dtype=torch.float32, device=x.device)
         check(lib.b2dq_gn_finalize_tiles(_ptr(part), _ptr(stats), nb, h, w, 1e-6, _stream()), "gn_finalize_tiles")

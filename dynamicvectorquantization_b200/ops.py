@@ -272,12 +272,10 @@ class ResnetBlockFn(torch.autograd.Function):
         cin, cout = c1w.shape[1], c1w.shape[0]
         hw = x.shape[1:3]
         hb1, hb2, hbs = ctx.bias_flags
-        d_a2 = kn.conv_dgrad(dout, _packed(c2w, "dgrad"), 3, 1, cout, hw, gn_bwd=(h1, st2, g2, b2))
-        ws2 = kn.last_dgrad_gn_ws
+        d_a2 = kn.conv_dgrad(dout, _packed(c2w, "dgrad"), 3, 1, cout, hw)
         dw2, db2 = kn.conv_wgrad(a2, dout, 3, 1, want_bias=True)
-        d_h1, dg2, dbt2 = kn.gn_bwd(d_a2, h1, st2, g2, b2, True, ws_nc=ws2)
-        d_a1 = kn.conv_dgrad(d_h1, _packed(c1w, "dgrad"), 3, 1, cin, hw, gn_bwd=(x, st1, g1, b1))
-        ws1 = kn.last_dgrad_gn_ws
+        d_h1, dg2, dbt2 = kn.gn_bwd(d_a2, h1, st2, g2, b2, True)
+        d_a1 = kn.conv_dgrad(d_h1, _packed(c1w, "dgrad"), 3, 1, cin, hw)
         dw1, db1 = kn.conv_wgrad(a1, d_h1, 3, 1, want_bias=True)
         dws = dbs = None
         if ctx.has_sc:
@@ -286,7 +284,7 @@ class ResnetBlockFn(torch.autograd.Function):
             dws, dbs = kn.conv_wgrad(x, dout, k, 1, want_bias=True)
         else:
             res_grad = dout
-        dx, dg1, dbt1 = kn.gn_bwd(d_a1, x, st1, g1, b1, True, add=res_grad, ws_nc=ws1)
+        dx, dg1, dbt1 = kn.gn_bwd(d_a1, x, st1, g1, b1, True, add=res_grad)
         return (dx, dg1, dbt1, dw1, db1 if hb1 else None, dg2, dbt2, dw2, db2 if hb2 else None,
                 dws, dbs if hbs else None, None)
 

@@ -114,14 +114,8 @@ int b2dq_tapgemm(const b2dq_tapgemm_desc* desc, cudaStream_t stream);
  * each weight tile, epilogue overlapped through double-buffered TMEM.  Same maths as b2dq_tapgemm
  * with the 3x3 tap table; dgrad != 0 mirrors the taps (data gradient).  b: [128, 9*Cin] bf16. */
 int b2dq_pconv3x3(const void* a_bf16, const void* b_bf16, void* out_bf16, const float* bias,
-                  const void* residual_bf16, float* gn_part, const void* gnb_x, const float* gnb_stats,
-                  const float* gnb_gamma, const float* gnb_beta, float* gnb_part, int NB, int H, int W,
-                  int Cin, int dgrad, int max_ctas, cudaStream_t stream);
-/* gnb_* (optional, data-gradient launches): the output is the gradient wrt swish(GroupNorm(gnb_x)); the
- * epilogue also writes gnb_part [tiles][128][2] = per-tile (sum dz, sum dz*xhat) per channel, which
- * b2dq_gn_bwd_reduce_tiles folds into the ws_nc [N][128][2] that b2dq_gn_bwd_apply consumes - the GroupNorm
- * backward then needs no reduction pass of its own. */
-int b2dq_gn_bwd_reduce_tiles(const float* gnb_part, float* ws_nc, int N, int H, int W, cudaStream_t stream);
+                  const void* residual_bf16, float* gn_part, int NB, int H, int W, int Cin, int dgrad,
+                  int max_ctas, cudaStream_t stream);
 /* gn_part (optional, [NB*H*W/128][32][2] floats): per-tile GroupNorm(32) partial sums of the OUTPUT, so the
  * next GroupNorm needs no statistics pass; b2dq_gn_finalize_tiles turns them into stats [NB][32][2]. */
 int b2dq_gn_finalize_tiles(const float* gn_part, float* stats, int N, int H, int W, float eps,

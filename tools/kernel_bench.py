@@ -108,6 +108,31 @@ def gn(nb, h, w, c):
                           apply_GBs=round(2 * by / ms2 / 1e6), bwd_ms=round(ms3, 3), bwd_GBs=round(5 * by / ms3 / 1e6))))
 
 
+def pconv():
+    """Persistent strip convolution 128->128 at 256x256, batch 32: plain / +residual / +residual+stats / data gradient."""
+    nb, h, w, c = 32, 256, 256, 128
+    x = torch.randn(nb, h, w, c, device=dev).to(BF)
+    res = torch.randn(nb, h, w, c, device=dev).to(BF)
+    wt = torch.randn(c, c, 3, 3, device=dev) * (c * 9) ** -0.5
+    b = torch.zeros(c, device=dev)
+    wp, wd = kn.pack_weight_fwd(wt), kn.pack_weight_dgrad(wt)
+    fl = 2.0 * nb * h * w * c * c * 9
+    for name, fn in (("fwd", lambda: kn.pconv3x3(x, wp, b, None, False)),
+                     ("fwd+res", lambda: kn.pconv3x3(x, wp, b, res, False)),
+                     ("fwd+res+stats", lambda: kn.pconv3x3(x, wp, b, res, False, want_stats=True)),
+                     ("fwd+stats", lambda: kn.pconv3x3(x, wp, b, None, False, want_stats=True)),
+                     ("dgrad", lambda: kn.pconv3x3(x, wd, None, None, True))):
+        for _ in range(3):
+            fn()
+        s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); s_.record()
+        for _ in range(10):
+            fn()
+        e_.record(); torch.cuda.synchronize()
+        ms = s_.elapsed_time(e_) / 10
+        print(json.dumps(dict(k="pconv3x3 " + name, ms=round(ms, 4), tflops=round(fl / ms / 1e9, 1))), flush=True)
+
+
 def gnf():
     """GroupNorm backward: fused persistent kernel vs the separate-kernel path on every shape of the dual-config step
     (back-to-back launches, as inside a step).  B2DQ_GN_L2_BUDGET_MB selects the images in flight (teams)."""
@@ -169,6 +194,8 @@ if __name__ == "__main__":
         for c in [(32, 256, 256, 128, 128, 3, 1), (32, 128, 128, 128, 128, 3, 1), (32, 64, 64, 256, 256, 3, 1), (32, 32, 32, 256, 256, 3, 1),
                   (32, 16, 16, 512, 512, 3, 1), (32, 32, 32, 256, 256, 1, 1), (32, 256, 256, 128, 128, 3, 2), (32, 128, 128, 256, 256, 3, 1)]:
             conv(*c)
+    if "pconv" in what:
+        pconv()
     if "gnf" in what:
         gnf()
     if "gn" in what:
