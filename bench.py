@@ -46,6 +46,8 @@ def parse():
                     help="headline = dqvae-dual-r-05; the others are parity-test configs that can be timed too")
     ap.add_argument("--no-real-loss", action="store_true",
                     help="N=1: do not append the `real_loss_step` object (a short `--loss real` run in a child process)")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="N > 1: exchange the gradient buckets only after the backward (A/B of the overlap)")
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph (N=1)")
     ap.add_argument("--loss", default="surrogate", choices=["surrogate", "real"],
                     help="real: time the reference's full training_step (both optimizer passes, LPIPS + PatchGAN + "
@@ -300,6 +302,7 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")    # NCCL work is captured in a CUDA graph
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(2021)                      # the reference's default seed (train.py:41)
     global WORKLOAD
@@ -328,19 +331,17 @@ def run_b200(args):
     except (TypeError, RuntimeError, ValueError):
         opt = torch.optim.Adam(ae_params, lr=model.learning_rate, betas=(0.5, 0.9), capturable=use_graph)
     net = model
-    flat_grad = None
+    ex = None                                    # bucketed gradient exchange overlapped with the backward (N > 1, graph)
+    ex_in_graph = False
     if graph_ddp:
+        from dynamicvectorquantization_b200 import ops as b2ops
+        from dynamicvectorquantization_b200.ddp import BucketedGradExchange
         # every rank starts from rank 0's parameters / buffers (what DDP's constructor does)
         for t in list(model.parameters()) + list(model.buffers()):
             dist.broadcast(t.data, 0)
-        from dynamicvectorquantization_b200 import ops as b2ops
         b2ops.invalidate_caches(model)          # writes through .data do not bump the version the caches key on
-        flat_grad = torch.zeros(sum(p.numel() for p in ae_params), device=dev)
-        off = 0
-        for p in ae_params:
-            p.grad = flat_grad[off:off + p.numel()].view_as(p)
-            off += p.numel()
-        model.quantize.codebook.defer_ema = True
+        ex = BucketedGradExchange(ae_params, bucket_mb=float(os.environ.get("B2DQ_BUCKET_MB", "25")),
+                                  overlap=not args.no_overlap)
     elif world > 1:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
     B = args.batch
@@ -350,28 +351,34 @@ def run_b200(args):
     loss_host = torch.zeros(1).pin_memory()
 
     def fwd_bwd(x):
-        if flat_grad is not None:
-            flat_grad.zero_()                    # gradients stay views into one flat buffer
+        if ex is not None:
+            ex.begin_step()                      # gradients stay views into one flat buffer, zeroed here
         else:
             opt.zero_grad(set_to_none=True)
         xrec, qloss, indices, gate = net(x)[:4]
         loss, _ = model.loss(qloss, x, xrec, 0, 0, last_layer=None, split="train", gate=gate)
-        loss.backward()
+        loss.backward()                          # buckets of the flat buffer are all-reduced as they complete
+        if ex is not None and ex_in_graph:
+            ex.finish()
         return loss
 
     exchange_note = None
     if graph_ddp:
-        exchange_note = ("fwd+bwd replayed from one CUDA graph; after it: packed VQ-statistics all-reduce + restart-row "
-                         "broadcast (1 MiB), ONE flat fp32 gradient all-reduce (%d MB, NCCL over NVLink, not overlapped "
-                         "with the backward), Adam" % (sum(p.numel() for p in ae_params) * 4 // 2 ** 20))
+        exchange_note = ("the whole step (fwd, bwd, exchanges, Adam) is ONE CUDA graph: the packed VQ-statistics all-reduce "
+                         "+ restart-row broadcast (1 MiB) sit inside the forward, the gradient is exchanged in %d buckets "
+                         "of <= %s MB (reverse parameter order, NCCL AVG over NVLink) on a side stream as soon as a "
+                         "bucket's last gradient is written, %s" % (
+                             len(ex.buckets), os.environ.get("B2DQ_BUCKET_MB", "25"),
+                             "overlapped with the rest of the backward" if ex.overlap else "NOT overlapped (--no-overlap)"))
     elif world > 1:
         exchange_note = "torch DistributedDataParallel (bucketed all-reduce overlapped with the backward), eager launches"
 
     def finish(loss):
-        if flat_grad is not None:
-            model.quantize.codebook.apply_deferred_ema(keep=True)   # packed all-reduce + rank-0 restart rows
-            dist.all_reduce(flat_grad)                        # 192 MB over NVLink, then average like DDP
-            flat_grad.div_(world)
+        if ex is not None:
+            if not ex_in_graph:
+                ex.finish()
+            if model.quantize.codebook.defer_ema:
+                model.quantize.codebook.apply_deferred_ema(keep=True)   # packed all-reduce + rank-0 restart rows
         opt.step()
         return loss
 
@@ -395,10 +402,32 @@ def run_b200(args):
             static_x = x_dev.clone()
             l0 = kn.launch_count()
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                static_loss = fwd_bwd(static_x) if graph_ddp else step(static_x)
+            whole_step_graph = True
+            if graph_ddp:
+                try:                              # NCCL collectives (VQ statistics, gradient buckets) inside the capture
+                    ex_in_graph = True
+                    with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                        static_loss = step(static_x)
+                except Exception as e:
+                    sys.stderr.write(f"[bench] whole-step capture with the NCCL exchanges failed ({type(e).__name__}: {e}); "
+                                     f"capturing fwd+bwd only, exchanging after the graph\n")
+                    ex_in_graph = False
+                    whole_step_graph = False
+                    exchange_note += " [whole-step capture failed: gradient / statistics exchanged eagerly after the graph]"
+                    model.quantize.codebook.defer_ema = True
+                    torch.cuda.synchronize()
+                    for _ in range(2):
+                        step(static_x)
+                    torch.cuda.synchronize()
+                    l0 = kn.launch_count()
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        static_loss = fwd_bwd(static_x)
+            else:
+                with torch.cuda.graph(graph):
+                    static_loss = step(static_x)
             launches_per_step = kn.launch_count() - l0
-            if graph_ddp:                         # EMA finalize kernels run eagerly after each replay
+            if not whole_step_graph:              # EMA finalize kernels run eagerly after each replay
                 l1 = kn.launch_count()
                 finish(static_loss)
                 launches_per_step += kn.launch_count() - l1
@@ -407,7 +436,7 @@ def run_b200(args):
                 if x is not static_x:
                     static_x.copy_(x, non_blocking=True)
                 graph.replay()
-                return finish(static_loss) if graph_ddp else static_loss
+                return static_loss if whole_step_graph else finish(static_loss)
             for _ in range(2):
                 step(static_x)
             x_dev = static_x
@@ -445,9 +474,20 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
-    if rank != 0:
+
+    def leave():
+        """N > 1: the captured graph holds NCCL work; tearing the communicator down under it can block for minutes.
+        Everything is measured and printed by now: synchronise, meet the other ranks once more, and leave the
+        process without the destructors."""
         if world > 1:
-            dist.destroy_process_group()
+            sys.stdout.flush(); sys.stderr.flush()
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+            os._exit(0)
+
+    if rank != 0:
+        leave()
         return
     peaks = {}
     try:
@@ -476,8 +516,7 @@ def run_b200(args):
     if world == 1 and not args.no_real_loss:
         line["real_loss_step"] = real_loss_line(args)
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    leave()
 
 
 def kernel_rooflines(torch, kn, dev, peaks, with_cpu=False):

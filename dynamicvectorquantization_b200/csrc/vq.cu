@@ -580,6 +580,16 @@ int b2dq_vq_prepare_codebook(const float* weight_f32, void* cb_bf16, float* cb_s
 struct VqPlan {
   int grid, rounds, tail_tiles, q, split;   // split: some row tile is shared between CTAs (needs the workspace)
 };
+// codebook tiles (of 256 entries) a row tile needs before its tail may be shared between CTAs
+static int vq_split_min_tiles() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B2DQ_VQ_SPLIT_MIN_TILES");
+    v = e ? atoi(e) : 8;
+    if (v < 2) v = 2;
+  }
+  return v;
+}
 static VqPlan vq_plan_for(int N, int K, int G, bool allow_split) {
   VqPlan pl;
   const int tiles = (N + VQ_BM - 1) / VQ_BM;
@@ -594,7 +604,7 @@ static VqPlan vq_plan_for(int N, int K, int G, bool allow_split) {
   // ... and when a row tile has enough codebook tiles to amortise what a shared tile costs (second load of its
   // rows, 128 atomics per sharer, the workspace memset): measured on B200, K = 1024 (4 codebook tiles) loses
   // (N = 32768: 38.8 vs 25.7 us), K >= 8192 gains 8-15 % and small-N calls 3.5-6x
-  if (allow_split && nn >= 8 && pl.tail_tiles > 0 && pl.tail_tiles * 20 <= G * 17) {
+  if (allow_split && nn >= vq_split_min_tiles() && pl.tail_tiles > 0 && pl.tail_tiles * 20 <= G * 17) {
     const long long U = (long long)pl.tail_tiles * nn;
     int q = (int)((U + G - 1) / G);
     if (q < 1) q = 1;
@@ -629,7 +639,7 @@ int b2dq_vq_search_plan(int N, int K, int num_ctas, int allow_split, int* out5) 
 
 // Scratch for the shared row tiles: an upper bound that holds for any max_ctas (0: never needed).
 int b2dq_vq_search_workspace_bytes(int N, int K) {
-  if (N <= 0 || K <= 7 * VQ_BN) return 0;
+  if (N <= 0 || K <= (vq_split_min_tiles() - 1) * VQ_BN) return 0;
   const int tiles = (N + VQ_BM - 1) / VQ_BM;
   const int cap = tiles < 1024 ? tiles : 1024;   // the tail is shorter than one wave of the grid
   return cap * VQ_BM * 8 + cap * 4;

@@ -623,3 +623,53 @@ def test_conv4x4_tap_tables_match_torch_conv():
                             acc += box(dyv, 0, dh, 0, dw, 0, cout, ho, wo) @ wd[:, (r * 4 + s_) * cout:(r * 4 + s_ + 1) * cout].t()
                     dx[:, ph::2, pw::2] = acc
         assert torch.allclose(dx, ref_dx, atol=1e-10), f"data-gradient taps, stride {stride}"
+
+
+def _bucket_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from dynamicvectorquantization_b200.ddp import BucketedGradExchange
+    torch.manual_seed(0)                                    # same parameters on every rank
+    net = torch.nn.Sequential(torch.nn.Linear(12, 40), torch.nn.Tanh(), torch.nn.Linear(40, 40), torch.nn.Tanh(),
+                              torch.nn.Linear(40, 3))
+    unused = torch.nn.Parameter(torch.zeros(5))             # a parameter that never receives a gradient
+    params = list(net.parameters()) + [unused]
+    ex = BucketedGradExchange(params, bucket_mb=0.0005)     # ~130 floats per bucket: several buckets
+    ok = len(ex.buckets) >= 3 and sum(b[2] for b in ex.buckets) == len(params)
+    ok = ok and ex.buckets[0][1] == ex.flat.numel() and ex.buckets[-1][0] == 0         # reverse order, whole buffer
+    for step in range(2):
+        x = torch.randn(6, 12, generator=torch.Generator().manual_seed(10 * step + rank))
+        ex.begin_step()
+        net(x).pow(2).mean().backward()
+        ex.finish()
+        got = [p.grad.clone() for p in params]
+        # reference: local gradients of every rank, averaged by hand
+        ref_net = torch.nn.Sequential(*[type(m)(m.in_features, m.out_features) if isinstance(m, torch.nn.Linear) else type(m)()
+                                        for m in net])
+        ref_net.load_state_dict(net.state_dict())
+        ref_net(x).pow(2).mean().backward()
+        for g_, p in zip(got, ref_net.parameters()):
+            mine = [torch.zeros_like(p.grad) for _ in range(world)]
+            dist.all_gather(mine, p.grad)
+            ok = ok and torch.allclose(g_, sum(mine) / world, rtol=1e-6, atol=1e-8)
+        ok = ok and float(got[-1].abs().max()) == 0.0 and all(p.grad.data_ptr() >= ex.flat.data_ptr() for p in params)
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_bucketed_gradient_exchange_world_size_2():
+    """dynamicvectorquantization_b200/ddp.py on gloo: gradients are views into one flat buffer, buckets are cut in
+    reverse parameter order and cover the buffer exactly, every bucket is averaged over the ranks as soon as its
+    last gradient is accumulated (or in finish() for parameters without a gradient) - equal to averaging the ranks'
+    local gradients by hand, over two steps."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + os.getpid() % 2000
+    procs = [ctx.Process(target=_bucket_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    [p.join(30) for p in procs]
+    assert res == [(0, True), (1, True)]

@@ -108,6 +108,26 @@ def gn(nb, h, w, c):
                           apply_GBs=round(2 * by / ms2 / 1e6), bwd_ms=round(ms3, 3), bwd_GBs=round(5 * by / ms3 / 1e6))))
 
 
+def vqk():
+    """VQ search+gather at K=1024 (the codebook size of every stage-1 config): grid sweep and stream-K tail
+    (B2DQ_VQ_SPLIT_MIN_TILES=4 lets the 4-codebook-tile rows be shared)."""
+    C, K = 256, 1024
+    for N in (65536, 32768):
+        g = torch.Generator(device=dev).manual_seed(0)
+        x = torch.randn(N, C, device=dev, generator=g)
+        w = torch.cat([x[torch.randperm(N, device=dev)[:K]] + 0.1 * torch.randn(K, C, device=dev), torch.zeros(1, C, device=dev)])
+        cb = kn.Codebook(K, C, dev); cb.refresh(w)
+        xb = x.to(BF)
+        ref = kn.vq_search_gather(xb, cb, w, split=False)[0]
+        for mc in (0, 128, 74):
+            for split in (False, True):
+                ms = timeit_graph(lambda: kn.vq_search_gather(xb, cb, w, max_ctas=mc, split=split))
+                same = bool(torch.equal(kn.vq_search_gather(xb, cb, w, max_ctas=mc, split=split)[0], ref))
+                print(json.dumps(dict(k="vq K=1024", N=N, max_ctas=mc, split=split, ms=round(ms, 4), same=same,
+                                      tflops=round(2.0 * N * K * C / ms / 1e9, 1),
+                                      env=os.environ.get("B2DQ_VQ_SPLIT_MIN_TILES", "8"))), flush=True)
+
+
 def pconv():
     """Persistent strip convolution 128->128 at 256x256, batch 32: plain / +residual / +residual+stats / data gradient."""
     nb, h, w, c = 32, 256, 256, 128
@@ -194,6 +214,8 @@ if __name__ == "__main__":
         for c in [(32, 256, 256, 128, 128, 3, 1), (32, 128, 128, 128, 128, 3, 1), (32, 64, 64, 256, 256, 3, 1), (32, 32, 32, 256, 256, 3, 1),
                   (32, 16, 16, 512, 512, 3, 1), (32, 32, 32, 256, 256, 1, 1), (32, 256, 256, 128, 128, 3, 2), (32, 128, 128, 256, 256, 3, 1)]:
             conv(*c)
+    if "vqk" in what:
+        vqk()
     if "pconv" in what:
         pconv()
     if "gnf" in what:
