@@ -454,9 +454,11 @@ int b2dq_gn_bwd_fused(const void* dy, const void* x, const float* stats, const f
 }
 
 // The plan of the call above (tests / bench): teams, CTAs per team, rows per CTA, grid.
-void b2dq_gn_bwd_fused_plan(int N, int HW, int C, int* out4) {
+int b2dq_gn_bwd_fused_plan(int N, int HW, int C, int* out4) {
+  if (N <= 0 || HW <= 0 || C < 8 || !out4) return -1;
   const GfPlan pl = gf_plan(N, HW, C);
   out4[0] = pl.T; out4[1] = pl.S; out4[2] = pl.rows_per_cta; out4[3] = pl.grid;
+  return 0;
 }
 
 }  // extern "C"

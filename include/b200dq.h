@@ -225,7 +225,7 @@ int b2dq_gn_bwd_fused_workspace_bytes(int N, int HW, int C, int G);
 int b2dq_gn_bwd_fused(const void* dy, const void* x, const float* stats, const float* gamma, const float* beta,
                       void* dx, float* dgb, const void* add, void* ws, long long ws_bytes, int N, int HW, int C,
                       int G, int swish, cudaStream_t stream);
-void b2dq_gn_bwd_fused_plan(int N, int HW, int C, int* out4);
+int b2dq_gn_bwd_fused_plan(int N, int HW, int C, int* out4);
 
 /* ------------------------------------------------------------------ layout / elementwise */
 int b2dq_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int N, int C, int HW, cudaStream_t stream);

@@ -236,7 +236,16 @@ ref.discriminator.load_state_dict(md)
 from dynamicvectorquantization_b200.nn.discriminator import NLayerDiscriminator
 d2 = NLayerDiscriminator(input_nc=3, ndf=64, n_layers=3); d2.load_state_dict(md)
 img = torch.randn(2, 3, 64, 64)
-assert torch.equal(ref.discriminator.eval()(img), d2.eval()(img))
+# the overlay's forward runs on the CUDA kernels only: on CPU tensors it must fail loudly, never fall back; its
+# parameter containers are the reference's own nn.Sequential (same modules at the same indices, same state)
+assert [type(a).__name__ for a in d2.main] == [type(a).__name__ for a in ref.discriminator.main]
+assert [tuple(v.shape) for v in d2.state_dict().values()] == [tuple(v.shape) for v in ref.discriminator.state_dict().values()]
+assert torch.equal(ref.discriminator.eval()(img), d2.main.eval()(img))
+try:
+    d2.eval()(img)
+    raise AssertionError("NLayerDiscriminator ran on CPU tensors")
+except RuntimeError as e:
+    assert "no CPU fallback" in str(e)
 print("LOSS_CONFORMANCE_OK")
 ''' % (ROOT, ROOT, REF, REF)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900)
@@ -324,8 +333,9 @@ print("CKPT_CONFORMANCE_OK")
 @pytest.mark.parametrize("mode", ["eval", "train"])
 def test_loss_module_host_logic_matches_reference_golden(monkeypatch, mode):
     """The loss module's own logic (adaptive weight, clamps, hinge terms, budget, BatchNorm bookkeeping, log keys)
-    on CPU: the perceptual term - the only part that needs the CUDA kernels - is replaced by the pinned fp32 oracle,
-    everything else runs as shipped and must reproduce the fixture minted from the reference's class."""
+    on CPU: the two parts that need the CUDA kernels are substituted - the perceptual term by the pinned fp32 oracle,
+    the discriminator's forward by its own nn.Sequential of parameter containers run through torch ops - everything
+    else runs as shipped and must reproduce the fixture minted from the reference's class."""
     monkeypatch.setenv("B200DQ_ALLOW_RANDOM_VGG", "1")
     import torch.nn.functional as F
     from dynamicvectorquantization_b200 import configs
@@ -341,6 +351,7 @@ def test_loss_module_host_logic_matches_reference_golden(monkeypatch, mode):
     loss.load_state_dict({k[len("loss."):]: v for k, v in sd.items()}, strict=False)
     loss.train(mode == "train")
     monkeypatch.setattr(loss.perceptual_loss, "forward", lambda a, b: lo.lpips(sd, a, b))
+    monkeypatch.setattr(loss.discriminator, "forward", lambda inp: loss.discriminator.main(inp))
     x, feat, w_last, qloss, gate = lo.toy_inputs()
     w_last.requires_grad_(True)
     feat.requires_grad_(True)
