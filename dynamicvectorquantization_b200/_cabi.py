@@ -77,6 +77,8 @@ SIGNATURES = {
     "b2dq_gn_bwd_fused_workspace_bytes": [_i, _i, _i, _i],   # returns a byte count, not a status
     "b2dq_gn_bwd_fused": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _vp],
     "b2dq_gn_bwd_fused_plan": [_i, _i, _i, C.POINTER(C.c_int)],
+    "b2dq_gn_fwd_fused_workspace_bytes": [_i, _i, _i, _i],   # returns a byte count, not a status
+    "b2dq_gn_fwd_fused": [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _f, _i, _vp],
     "b2dq_nchw_f32_to_nhwc_bf16": [_vp, _vp, _i, _i, _i, _vp],
     "b2dq_nhwc_bf16_to_nchw_f32": [_vp, _vp, _i, _i, _i, _vp],
     "b2dq_nhwc_f32_to_nchw_f32": [_vp, _vp, _i, _i, _i, _vp],

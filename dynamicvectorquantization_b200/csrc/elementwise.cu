@@ -532,8 +532,11 @@ int b2dq_bias_grad(const void* dy, float* out, float* part, long long rows, int 
   long long rpb = (rows + 148 * 8 - 1) / (148 * 8);
   if (rpb < 64) rpb = 64;
   const unsigned blocks = (unsigned)((rows + rpb - 1) / rpb);
-  if (C % 8 == 0 && 256 % (C / 8) == 0) {
-    bias_grad_kernel<<<blocks, 256, 256 * 8 * sizeof(float), st>>>(
+  if (C % 8 == 0 && C / 8 <= 256) {
+    // threads = the largest multiple of the vectors per row that fits 256 (e.g. the 768 / 1536 channels of the
+    // fused q|k|v gradient: 96 / 192 vectors -> 192 threads)
+    const int threads = (256 / (C / 8)) * (C / 8);
+    bias_grad_kernel<<<blocks, threads, threads * 8 * sizeof(float), st>>>(
         reinterpret_cast<const __nv_bfloat16*>(dy), part, rows, C, (int)rpb);
   } else {
     bias_grad_generic_kernel<<<blocks, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dy), part,

@@ -360,6 +360,220 @@ __global__ void __launch_bounds__(GF_THREADS, 2) gn_bwd_fused_kernel(const GnFus
   }
 }
 
+
+// =============================================================================================================
+// GroupNorm(+swish) FORWARD with the same team scheme: phase 1 streams the team's image once for the per-group sums
+// (sum, sum of squares; fp32 per CTA, fp64 across the team's CTAs), team barrier, phase 2 streams it again - from
+// L2 - and writes y = act(x * rstd*gamma + beta - mean*rstd*gamma).  HBM sees 1 read + 1 write instead of the
+// 2 reads + 1 write of gn_partial_stats + gn_finalize + gn_apply.  stats [N][G][2] = (mean, rstd) is written for
+// the backward.  One tensor per ring stage; exact sigmoid (ex2 + rcp) like the separate apply kernel.
+constexpr int GW_STAGES = 5;
+constexpr int GW_SMEM = GW_STAGES * GF_CHUNK + (2 * GF_CONSUMERS * 8 + 2 * GF_MAXC + 2 * GF_MAXG) * 4 + 2 * GW_STAGES * 8;
+
+struct GnFwdParams {
+  const __nv_bfloat16* x;
+  const float* gamma;
+  const float* beta;
+  __nv_bfloat16* y;
+  float* stats;                  // [N][G][2] mean, rstd (output)
+  float* part;                   // [N][S][G][2] per-CTA group partials
+  unsigned* flags;               // [N] arrival counters | [N] error flag (zeroed before launch)
+  int N, HW, C, G, S, T, rows_per_cta;
+  float eps;
+};
+
+template <bool SW>
+__global__ void __launch_bounds__(GF_THREADS, 2) gn_fwd_fused_kernel(const GnFwdParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* ring = smem;
+  float* red = reinterpret_cast<float*>(smem + GW_STAGES * GF_CHUNK);
+  float* chan = red + 2 * GF_CONSUMERS * 8;
+  float* sk = chan + 2 * GF_MAXC;               // [G][2] mean, rstd of the current image
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sk + 2 * GF_MAXG);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + GW_STAGES);
+  const int tid = threadIdx.x;
+  const int C = p.C, G = p.G, HW = p.HW;
+  const int vecs = C >> 3;
+  const int rstep = GF_CONSUMERS / vecs;
+  const int srows = rstep * GF_VPT;
+  const int team = blockIdx.x / p.S, s_idx = blockIdx.x % p.S;
+  const int r0 = s_idx * p.rows_per_cta;
+  const int r1 = min(HW, r0 + p.rows_per_cta);
+  const int nstages = (r1 - r0 + srows - 1) / srows;
+
+  if (tid == 0) {
+    for (int i = 0; i < GW_STAGES; ++i) {
+      mbar_init(full0 + 8 * i, 1);
+      mbar_init(empty0 + 8 * i, GF_CONSUMERS / 32);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  if (tid >= GF_CONSUMERS) {
+    if (tid == GF_CONSUMERS) {                    // producer lane
+      uint32_t stage = 0, phase = 0;
+      const uint64_t keep = l2_policy_evict_last(), drop = l2_policy_evict_first();
+      for (int n = team; n < p.N; n += p.T) {
+        const long long img = static_cast<long long>(n) * HW * C;
+        for (int ph = 0; ph < 2; ++ph) {
+          for (int c = 0; c < nstages; ++c) {
+            const int row = r0 + c * srows;
+            const uint32_t bytes = static_cast<uint32_t>(min(srows, r1 - row)) * C * 2;
+            mbar_wait(empty0 + 8 * stage, phase ^ 1);
+            const uint32_t fb = full0 + 8 * stage;
+            mbar_arrive_expect_tx(fb, bytes);
+            bulk_load(smem_u32(ring + stage * GF_CHUNK), p.x + img + static_cast<long long>(row) * C, bytes, fb,
+                      ph == 0 ? keep : drop);
+            if (++stage == GW_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+    return;
+  }
+  // ------------------------------------------------------------------ consumers
+  const int v = tid % vecs, rlane = tid / vecs;
+  const int cg = C / G;
+  const int lane = tid & 31;
+  uint32_t stage = 0, phase = 0;
+  const double inv_cnt = 1.0 / (static_cast<double>(HW) * cg);
+  float gm[8], bt[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { gm[k] = p.gamma[v * 8 + k]; bt[k] = p.beta[v * 8 + k]; }
+  for (int n = team; n < p.N; n += p.T) {
+    // ---------------- phase 1: per-channel sum and sum of squares over this CTA's rows
+    float2 sa[4], sb[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { sa[k] = make_float2(0.f, 0.f); sb[k] = make_float2(0.f, 0.f); }
+    for (int c = 0; c < nstages; ++c) {
+      mbar_wait(full0 + 8 * stage, phase);
+      const uint8_t* st = ring + stage * GF_CHUNK + tid * 16;
+#pragma unroll
+      for (int u = 0; u < GF_VPT; ++u) {
+        if (r0 + c * srows + u * rstep + rlane < r1) {
+          const uint4 ux = *reinterpret_cast<const uint4*>(st + u * (GF_CONSUMERS * 16));
+          const uint32_t wx[4] = {ux.x, ux.y, ux.z, ux.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 xv = unpack2(wx[k]);
+            sa[k] = __fadd2_rn(sa[k], xv);
+            sb[k] = __ffma2_rn(xv, xv, sb[k]);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty0 + 8 * stage);
+      if (++stage == GW_STAGES) { stage = 0; phase ^= 1; }
+    }
+    float* red_a = red;
+    float* red_b = red + GF_CONSUMERS * 8;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      *reinterpret_cast<float2*>(red_a + rlane * C + v * 8 + 2 * k) = sa[k];
+      *reinterpret_cast<float2*>(red_b + rlane * C + v * 8 + 2 * k) = sb[k];
+    }
+    consumer_sync();
+    for (int o = tid; o < 2 * C; o += GF_CONSUMERS) {
+      const float* src = (o < C) ? red_a + o : red_b + (o - C);
+      float t = 0.f;
+#pragma unroll 4
+      for (int rl = 0; rl < rstep; ++rl) t += src[rl * C];
+      chan[(o < C) ? o : GF_MAXC + (o - C)] = t;
+    }
+    consumer_sync();
+    if (tid < G) {
+      float S1 = 0.f, S2 = 0.f;
+      for (int cc = tid * cg; cc < (tid + 1) * cg; ++cc) { S1 += chan[cc]; S2 += chan[GF_MAXC + cc]; }
+      float* o = p.part + ((static_cast<long long>(n) * p.S + s_idx) * G + tid) * 2;
+      __stcg(reinterpret_cast<float2*>(o), make_float2(S1, S2));
+    }
+    consumer_sync();
+    // ---------------- team barrier on image n
+    if (tid == 0) {
+      __threadfence();
+      red_release_add(p.flags + n, 1u);
+      const long long t0 = clock64();
+      while (ld_acquire(p.flags + n) < static_cast<unsigned>(p.S)) {
+        if (clock64() - t0 > 4000000000LL) { atomicExch(p.flags + p.N, 1u); break; }
+      }
+    }
+    consumer_sync();
+    {
+      // fixed-order sum of the S partials per (group, 2): lanes over CTAs in fp64, then over the 16 lanes in order
+      const int e4n = (2 * G) / 4;
+      const int lanes_s = GF_CONSUMERS / e4n;
+      const int e4 = tid % e4n, j = tid / e4n;
+      const float4* src = reinterpret_cast<const float4*>(p.part + static_cast<long long>(n) * p.S * G * 2) + e4;
+      constexpr int MAXL = (GF_MAXS + 15) / 16;
+      float4 t[MAXL];
+#pragma unroll
+      for (int i = 0; i < MAXL; ++i) {
+        const int s = j + i * lanes_s;
+        t[i] = (s < p.S) ? __ldcg(src + static_cast<long long>(s) * e4n) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll
+      for (int i = 0; i < MAXL; ++i) { a0 += t[i].x; a1 += t[i].y; a2 += t[i].z; a3 += t[i].w; }
+      double* rd = reinterpret_cast<double*>(red);           // [lanes_s][2G] doubles (16 x 64 x 8 B = 8 KB)
+      rd[j * 2 * G + e4 * 4 + 0] = a0; rd[j * 2 * G + e4 * 4 + 1] = a1;
+      rd[j * 2 * G + e4 * 4 + 2] = a2; rd[j * 2 * G + e4 * 4 + 3] = a3;
+      consumer_sync();
+      if (tid < G) {
+        double S1 = 0.0, S2 = 0.0;
+        for (int jj = 0; jj < lanes_s; ++jj) { S1 += rd[jj * 2 * G + 2 * tid]; S2 += rd[jj * 2 * G + 2 * tid + 1]; }
+        const double mean = S1 * inv_cnt;
+        double var = S2 * inv_cnt - mean * mean;
+        if (var < 0) var = 0;
+        const float m = static_cast<float>(mean), r = static_cast<float>(1.0 / sqrt(var + static_cast<double>(p.eps)));
+        sk[2 * tid] = m;
+        sk[2 * tid + 1] = r;
+        if (s_idx == 0) {
+          p.stats[(static_cast<long long>(n) * G + tid) * 2] = m;
+          p.stats[(static_cast<long long>(n) * G + tid) * 2 + 1] = r;
+        }
+      }
+      consumer_sync();
+    }
+    // ---------------- phase 2: y = act(x * a + b)
+    float2 A[4], B[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int g0 = (v * 8 + 2 * k) / cg;                   // C/G even: the pair lies in one group
+      const float m = sk[2 * g0], r = sk[2 * g0 + 1];
+      A[k] = make_float2(r * gm[2 * k], r * gm[2 * k + 1]);
+      B[k] = make_float2(bt[2 * k] - m * A[k].x, bt[2 * k + 1] - m * A[k].y);
+    }
+    __nv_bfloat16* out = p.y + static_cast<long long>(n) * HW * C + v * 8;
+    for (int c = 0; c < nstages; ++c) {
+      mbar_wait(full0 + 8 * stage, phase);
+      const uint8_t* st = ring + stage * GF_CHUNK + tid * 16;
+#pragma unroll
+      for (int u = 0; u < GF_VPT; ++u) {
+        const int row = r0 + c * srows + u * rstep + rlane;
+        if (row < r1) {
+          const uint4 ux = *reinterpret_cast<const uint4*>(st + u * (GF_CONSUMERS * 16));
+          const uint32_t wx[4] = {ux.x, ux.y, ux.z, ux.w};
+          uint32_t o[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float2 z = __ffma2_rn(unpack2(wx[k]), A[k], B[k]);
+            if (SW) {
+              z.x *= __fdividef(1.f, 1.f + __expf(-z.x));
+              z.y *= __fdividef(1.f, 1.f + __expf(-z.y));
+            }
+            o[k] = pack_bf16x2(z.x, z.y);
+          }
+          *reinterpret_cast<uint4*>(out + static_cast<long long>(row) * C) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty0 + 8 * stage);
+      if (++stage == GW_STAGES) { stage = 0; phase ^= 1; }
+    }
+  }
+}
+
 }  // namespace b2
 
 using namespace b2;
@@ -375,11 +589,11 @@ static long long gf_l2_budget() {
 }
 
 struct GfPlan { int T, S, rows_per_cta, grid; };
-static GfPlan gf_plan(int N, int HW, int C) {
+static GfPlan gf_plan(int N, int HW, int C, int tensors = 2) {
   const int sms = 2 * device_sm_count();                        // 2 CTAs per SM
   const int rstep = GF_VPT * (GF_CONSUMERS / (C / 8));          // rows per ring stage
   const int chunks_img = (HW + rstep - 1) / rstep;
-  const long long per_img = 4LL * HW * C;                       // dy + x, bf16
+  const long long per_img = 2LL * tensors * HW * C;              // bf16 tensors re-read from L2 (dy + x | x)
   long long T = gf_l2_budget() / (per_img > 0 ? per_img : 1);
   if (T < 1) T = 1;
   if (T > N) T = N;
@@ -449,6 +663,44 @@ int b2dq_gn_bwd_fused(const void* dy, const void* x, const float* stats, const f
   } else {
     if (int r = set_max_smem_once(gn_bwd_fused_kernel<false>, GF_SMEM, m0)) return r;
     gn_bwd_fused_kernel<false><<<pl.grid, GF_THREADS, GF_SMEM, stream>>>(p);
+  }
+  return (int)cudaGetLastError();
+}
+
+// ---- forward: y = act(GroupNorm(x)), stats [N][G][2] = (mean, rstd) written for the backward
+int b2dq_gn_fwd_fused_workspace_bytes(int N, int HW, int C, int G) {
+  if (b2dq_gn_bwd_fused_workspace_bytes(N, HW, C, G) == 0) return 0;     // same shape constraints
+  const GfPlan pl = gf_plan(N, HW, C, 1);
+  const long long part = ((1LL * N * pl.S * G * 2 * 4 + 15) / 16) * 16;
+  return static_cast<int>(part + ((1LL * N + 1) * 4 + 15) / 16 * 16);
+}
+
+int b2dq_gn_fwd_fused(const void* x, const float* gamma, const float* beta, void* y, float* stats, void* ws,
+                      long long ws_bytes, int N, int HW, int C, int G, float eps, int swish, cudaStream_t stream) {
+  if (N <= 0 || HW <= 0) return 0;
+  const long long need = b2dq_gn_fwd_fused_workspace_bytes(N, HW, C, G);
+  if (need == 0 || (swish != 0 && swish != 1)) return -1;
+  if (ws_bytes < need || ws == nullptr) return -2;
+  const GfPlan pl = gf_plan(N, HW, C, 1);
+  GnFwdParams p;
+  p.x = reinterpret_cast<const __nv_bfloat16*>(x);
+  p.gamma = gamma; p.beta = beta;
+  p.y = reinterpret_cast<__nv_bfloat16*>(y);
+  p.stats = stats;
+  uint8_t* w = reinterpret_cast<uint8_t*>(ws);
+  const long long part = ((1LL * N * pl.S * G * 2 * 4 + 15) / 16) * 16;
+  p.part = reinterpret_cast<float*>(w);
+  p.flags = reinterpret_cast<unsigned*>(w + part);
+  p.N = N; p.HW = HW; p.C = C; p.G = G; p.S = pl.S; p.T = pl.T; p.rows_per_cta = pl.rows_per_cta; p.eps = eps;
+  cudaError_t e = cudaMemsetAsync(p.flags, 0, (N + 1) * sizeof(unsigned), stream);
+  if (e != cudaSuccess) return (int)e;
+  static unsigned long long m0 = 0, m1 = 0;
+  if (swish) {
+    if (int r = set_max_smem_once(gn_fwd_fused_kernel<true>, GW_SMEM, m1)) return r;
+    gn_fwd_fused_kernel<true><<<pl.grid, GF_THREADS, GW_SMEM, stream>>>(p);
+  } else {
+    if (int r = set_max_smem_once(gn_fwd_fused_kernel<false>, GW_SMEM, m0)) return r;
+    gn_fwd_fused_kernel<false><<<pl.grid, GF_THREADS, GW_SMEM, stream>>>(p);
   }
   return (int)cudaGetLastError();
 }

@@ -503,8 +503,19 @@ def gn_apply(x, stats, gamma, beta, swish, groups=32):
 
 
 def gn_forward(x, gamma, beta, swish, groups=32, eps=1e-6):
-    """stats + apply, in L2-sized image groups.  Returns (y, stats)."""
+    """stats + apply.  Returns (y, stats).  One persistent kernel (statistics, team barrier per image, apply from L2)
+    when the shape allows it, else the statistics kernels followed by the apply kernel."""
     nb, h, w, c = x.shape
+    if USE_GN_FUSED and int(swish) in (0, 1):
+        lib = _cabi.lib()
+        ws_bytes = lib.b2dq_gn_fwd_fused_workspace_bytes(nb, h * w, c, groups)
+        if ws_bytes > 0:
+            y = torch.empty_like(x)
+            stats = torch.empty(nb, groups, 2, dtype=torch.float32, device=x.device)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+            check(lib.b2dq_gn_fwd_fused(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(stats), _ptr(ws), ws_bytes, nb,
+                                        h * w, c, groups, float(eps), int(swish), _stream()), "gn_fwd_fused")
+            return y, stats
     g = _gn_groups(nb, h * w * c * 2, 1)
     if g >= nb:
         stats = gn_stats(x, groups, eps)

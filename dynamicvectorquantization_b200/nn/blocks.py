@@ -109,8 +109,6 @@ class AttnBlock(_Nhwc):
     def forward_nhwc(self, x):
         b, h, w, c = x.shape
         hn = ops.gn_swish(x, self.norm, swish=False)
-        q = ops.conv2d(hn, self.q).view(b, h * w, c)
-        k = ops.conv2d(hn, self.k).view(b, h * w, c)
-        v = ops.conv2d(hn, self.v).view(b, h * w, c)
-        o = ops.AttentionFn.apply(q, k, v).view(b, h, w, c)
+        o = ops.AttnQKVFn.apply(hn, self.q.weight, self.q.bias, self.k.weight, self.k.bias, self.v.weight,
+                                self.v.bias).view(b, h, w, c)
         return ops.conv2d(o, self.proj_out, residual=x)

@@ -343,9 +343,10 @@ class AttentionFn(torch.autograd.Function):
 
 
 def _mm(a, a_mn, b, b_mn, M, N, K, out, alpha=1.0, out_f32=False):
-    """Batched out[z] = alpha * A B^T with A:[M,K] (K-major) or stored [K,M] (a_mn), same for B."""
+    """Batched out[z] = alpha * A B^T with A:[M,K] (K-major) or stored [K,M] (a_mn), same for B.
+    out [bsz, M, N] may be a column slice of a wider buffer (unit stride along N)."""
     bsz = a.shape[0]
-    assert a.stride(2) == 1 and b.stride(2) == 1 and out.is_contiguous()
+    assert a.stride(2) == 1 and b.stride(2) == 1 and out.stride(2) == 1
 
     def view(t, mn, rows):
         sb, sr = t.stride(0), t.stride(1)
@@ -356,8 +357,76 @@ def _mm(a, a_mn, b, b_mn, M, N, K, out, alpha=1.0, out_f32=False):
     ad, as_ = view(a, a_mn, M)
     bd, bs = view(b, b_mn, N)
     kb = (K + 63) // 64                       # a ragged last block reads zeros (TMA out-of-bounds fill)
-    kn.mmgemm(a, ad, as_, a_mn, b, bd, bs, b_mn, M, N, kb, out, (M * N, 0, N),
+    kn.mmgemm(a, ad, as_, a_mn, b, bd, bs, b_mn, M, N, kb, out, (out.stride(0), 0, out.stride(1)),
               kbox=(64, 1, 1), ktiles=(kb, 1), batches=bsz, alpha=alpha, out_f32=out_f32)
+
+
+def _packed_cat(weights, kind):
+    """bf16 packing of several 1x1 OIHW weights stacked along the output channels: "fwd" -> [sum Cout, Cin],
+    "dgrad" -> [Cin, sum Cout].  Cached on the first parameter, validated against every member's version."""
+    head = weights[0]
+    cache = head.__dict__.setdefault("_b2_packs", {})
+    stamp = tuple((w.data_ptr(), w._version, w.device) for w in weights)
+    ent = cache.get("cat_" + kind)
+    if ent is not None and ent[0] == stamp:
+        return ent[1]
+    parts = [kn.pack_weight_fwd(w) if kind == "fwd" else kn.pack_weight_dgrad(w) for w in weights]
+    p = torch.cat(parts, dim=0 if kind == "fwd" else 1).contiguous()
+    cache["cat_" + kind] = (stamp, p)
+    return p
+
+
+class AttnQKVFn(torch.autograd.Function):
+    """q, k, v = three 1x1 convolutions of the same normalised input, then softmax(q k^T / sqrt(C)) v
+    (model.py:170-188), as ONE autograd node: one [C, 3C] GEMM produces q | k | v side by side, the attention
+    GEMMs read them as column slices, the backward writes dq | dk | dv into one buffer that feeds ONE data-gradient
+    GEMM and ONE weight-gradient GEMM (no three-way gradient accumulation, a third of the launches)."""
+
+    @staticmethod
+    def forward(ctx, hn, qw, qb, kw, kb, vw, vb):
+        bsz, h, w, c = hn.shape
+        t = h * w
+        bias = None if qb is None else torch.cat([_f32(qb), _f32(kb), _f32(vb)])
+        qkv = kn.conv_fwd(hn, _packed_cat((qw, kw, vw), "fwd"), bias, 1, 1, 3 * c).view(bsz, t, 3 * c)
+        q, k, v = qkv[..., :c], qkv[..., c:2 * c], qkv[..., 2 * c:]
+        scale = float(int(c) ** -0.5)
+        s = torch.empty(bsz, t, t, dtype=torch.float32, device=hn.device)
+        _mm(q, False, k, False, t, t, c, s, alpha=scale, out_f32=True)
+        p = kn.softmax_rows(s, t)
+        o = torch.empty(bsz, t, c, dtype=BF16, device=hn.device)
+        _mm(p, False, v, True, t, c, t, o)
+        ctx.save_for_backward(hn, qkv, p, qw, kw, vw)
+        ctx.scale, ctx.has_bias = scale, qb is not None
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        hn, qkv, p, qw, kw, vw = ctx.saved_tensors
+        do = do.contiguous()
+        bsz, h, w, c = hn.shape
+        t = h * w
+        q, k, v = qkv[..., :c], qkv[..., c:2 * c], qkv[..., 2 * c:]
+        dqkv = torch.empty_like(qkv)
+        _mm(p, True, do, True, t, c, t, dqkv[..., 2 * c:])               # dV = P^T dO
+        dp = torch.empty(bsz, t, t, dtype=BF16, device=hn.device)
+        _mm(do, False, v, False, t, t, c, dp)                           # dP = dO V^T
+        ds = kn.softmax_bwd_rows(p, dp, t, ctx.scale)
+        _mm(ds, False, k, True, t, c, t, dqkv[..., :c])                 # dQ = dS K
+        _mm(ds, True, q, True, t, c, t, dqkv[..., c:2 * c])             # dK = dS^T Q
+        g = dqkv.view(bsz, h, w, 3 * c)
+        d_hn = None
+        if ctx.needs_input_grad[0]:
+            d_hn = kn.conv_dgrad(g, _packed_cat((qw, kw, vw), "dgrad"), 1, 1, c, (h, w))
+        dws = [None] * 3
+        dbs = [None] * 3
+        if any(ctx.needs_input_grad[i] for i in (1, 3, 5)):
+            if ctx.has_bias:
+                dw, db = kn.conv_wgrad(hn, g, 1, 1, want_bias=True)
+                dbs = list(db.split(c))
+            else:
+                dw = kn.conv_wgrad(hn, g, 1, 1)
+            dws = list(dw.split(c, dim=0))
+        return d_hn, dws[0], dbs[0], dws[1], dbs[1], dws[2], dbs[2]
 
 
 class Upsample2xFn(torch.autograd.Function):

@@ -226,6 +226,11 @@ int b2dq_gn_bwd_fused(const void* dy, const void* x, const float* stats, const f
                       void* dx, float* dgb, const void* add, void* ws, long long ws_bytes, int N, int HW, int C,
                       int G, int swish, cudaStream_t stream);
 int b2dq_gn_bwd_fused_plan(int N, int HW, int C, int* out4);
+/* Forward with the same scheme: statistics + apply in one kernel (1 read + 1 write of HBM, second read from L2).
+ * y = act(GroupNorm(x)) (swish: 0 none, 1 swish); stats [N][G][2] = (mean, rstd) is written for the backward. */
+int b2dq_gn_fwd_fused_workspace_bytes(int N, int HW, int C, int G);
+int b2dq_gn_fwd_fused(const void* x, const float* gamma, const float* beta, void* y, float* stats, void* ws,
+                      long long ws_bytes, int N, int HW, int C, int G, float eps, int swish, cudaStream_t stream);
 
 /* ------------------------------------------------------------------ layout / elementwise */
 int b2dq_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int N, int C, int HW, cudaStream_t stream);

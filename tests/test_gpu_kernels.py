@@ -407,6 +407,14 @@ def test_groupnorm_backward_fused_kernel(nb, h, w, c, swish, with_add):
     addd = add.to(dev) if with_add else None
     st = kn.gn_stats(xd)
     assert kn.USE_GN_FUSED
+    # forward: statistics + apply in one persistent kernel vs the fp32 reference and vs the separate kernels
+    assert _cabi.lib().b2dq_gn_fwd_fused_workspace_bytes(nb, h * w, c, 32) > 0
+    yf, stf = kn.gn_forward(xd, gd, bd, swish)
+    assert rel_rms(yf.float().cpu(), yr.detach().permute(0, 2, 3, 1)) < 5e-3
+    assert torch.allclose(stf[..., 0], st[..., 0], atol=1e-5, rtol=1e-5) and torch.allclose(stf[..., 1], st[..., 1], rtol=1e-5)
+    yf2, stf2 = kn.gn_forward(xd, gd, bd, swish)
+    assert torch.equal(yf, yf2) and torch.equal(stf, stf2), "fused forward not reproducible run to run"
+    assert rel_rms(yf.float().cpu(), kn.gn_apply(xd, st, gd, bd, swish).float().cpu()) < 2e-3
     dx, dg, db = kn.gn_bwd(dyd, xd, st, gd, bd, swish, add=addd)
     torch.cuda.synchronize()
     assert torch.isfinite(dg).all() and torch.isfinite(db).all(), "a team barrier timed out (dgamma / dbeta poisoned)"
@@ -484,7 +492,8 @@ def test_fused_weight_packing_matches_the_torch_packings():
 
 def test_bias_grad_matches_fp32_sum():
     from dynamicvectorquantization_b200 import kernels as kn
-    for rows, c in ((32 * 32 * 32, 256), (70001, 128), (300, 512), (32 * 256 * 64, 128)):
+    for rows, c in ((32 * 32 * 32, 256), (70001, 128), (300, 512), (32 * 256 * 64, 128), (32 * 1024, 768), (5000, 1536),
+                    (999, 24)):
         dy = _rand_bf(rows, c, seed=rows % 97)
         got = kn.bias_grad(dy.cuda().view(1, rows, 1, c)).cpu()
         ref = dy.double().sum(0)

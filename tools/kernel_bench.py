@@ -180,6 +180,18 @@ def gnf():
             ms = s_.elapsed_time(e_) / 10
             byt = by + (x.numel() * 2 if a is not None else 0)
             r[name + "_ms"] = round(ms, 4); r[name + "_GBs"] = round(byt / ms / 1e6)
+        for name, fused in (("fwd_fused", True), ("fwd_split", False)):
+            kn.USE_GN_FUSED = fused
+            fn = lambda: kn.gn_forward(x, g, b, True)
+            for _ in range(3):
+                fn()
+            s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(); s_.record()
+            for _ in range(10):
+                fn()
+            e_.record(); torch.cuda.synchronize()
+            ms = s_.elapsed_time(e_) / 10
+            r[name + "_ms"] = round(ms, 4); r[name + "_GBs"] = round(2 * x.numel() * 2 / ms / 1e6)
         kn.USE_GN_FUSED = True
         dxa = kn.gn_bwd(dy, x, st, g, b, True)
         kn.USE_GN_FUSED = False

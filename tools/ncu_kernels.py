@@ -15,7 +15,9 @@ xv = torch.randn(N, C, device=dev)
 wv = torch.cat([xv[torch.randperm(N, device=dev)[:K]] + 0.1 * torch.randn(K, C, device=dev), torch.zeros(1, C, device=dev)])
 cb = kn.Codebook(K, C, dev); cb.refresh(wv)
 xb = xv.to(BF)
-which = sys.argv[1:] or ["conv", "wgrad", "vq"]
+which = sys.argv[1:] or ["conv", "wgrad", "vq", "gn"]
+gam, bet = torch.ones(c, device=dev), torch.zeros(c, device=dev)
+res = torch.randn(nb, hw, hw, c, device=dev).to(BF)
 for _ in range(3):
     if "conv" in which:
         kn.conv_fwd(x, wp, bias, 3, 1, c)                       # pconv3x3_kernel
@@ -24,5 +26,8 @@ for _ in range(3):
         kn.conv_wgrad(x, dy, 3, 1)
     if "vq" in which:
         kn.vq_search_gather(xb, cb, wv)
+    if "gn" in which:
+        y, st = kn.gn_forward(x, gam, bet, True)                # gn_fwd_fused_kernel
+        kn.gn_bwd(dy, x, st, gam, bet, True, add=res)           # gn_bwd_fused_kernel
 torch.cuda.synchronize()
 print("done")

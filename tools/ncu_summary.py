@@ -46,7 +46,7 @@ for r in rows[2:]:
         (l2sm or 0.0) / 1e9, val(r, "smsp__issue_active.avg.pct_of_peak_sustained_active") or 0.0,
         int(val(r, "launch__registers_per_thread") or 0)))
     key = ("pconv" if "pconv" in short else "vq" if "vq_search" in short else "wgrad" if "mmgemm" in short
-           else "gn" if short.startswith("gn_") else "tapgemm")
+           else "gn" if "gn_" in short else "tapgemm")
     if key == "gn":                                   # the fused GroupNorm backward is the family's dominant kernel
         if "bwd_fused" not in short:
             continue
