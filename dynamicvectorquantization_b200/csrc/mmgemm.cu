@@ -48,11 +48,17 @@ struct MmCfg {
   static constexpr uint32_t TMEM_COLS = (BN * MAXTAPS <= 128) ? 128 : (BN * MAXTAPS <= 256 ? 256 : 512);
 };
 
-template <int BN, int STAGES, int MAXTAPS, bool STRIP = false>
+// CL > 1 (strip variant, launched as clusters of CL = 3 CTAs along x): the three tap groups (filter rows) of one
+// pixel range share the dY tile.  It is fetched from L2 ONCE per cluster - rank 0 loads channel box 0, rank 1 box 1,
+// both multicast to all three CTAs - instead of once per CTA: 21.8 KB instead of 32.5 KB of L2->SM traffic per CTA
+// and k-block (the unicast version ran at the ~42 B/clk/SM L2 limit, tensor pipe 61 %).  A stage is released to
+// the producers by the tcgen05.commit of all three MMA issuers (multicast arrive on every CTA's empty barrier).
+template <int BN, int STAGES, int MAXTAPS, bool STRIP = false, int CL = 1>
 __global__ void __launch_bounds__(192, 1)
 mmgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
               const __grid_constant__ MmParams p) {
   using Cfg = MmCfg<BN, STAGES, MAXTAPS, STRIP>;
+  constexpr uint16_t CL_MASK = static_cast<uint16_t>((1u << CL) - 1u);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sBar = base + STAGES * Cfg::STAGE_BYTES;
@@ -85,7 +91,7 @@ mmgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(bar_full + 8 * i, 1);
-      mbar_init(bar_empty + 8 * i, 1);
+      mbar_init(bar_empty + 8 * i, CL);
     }
     mbar_init(bar_tfull, 1);
     fence_barrier_init();
@@ -95,6 +101,7 @@ mmgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(smem_u32(tmem_slot));
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();        // every CTA's barriers exist before a peer multicasts into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -110,7 +117,12 @@ mmgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
         const uint32_t fb = bar_full + 8 * stage;
         mbar_arrive_expect_tx(fb, tx);
-        if (!p.a_mn) {
+        if constexpr (CL > 1) {
+          // dY tile of the cluster: channel box `group` (ranks 0 and 1) for everybody
+          if (group < 2)
+            tma_load_5d_mc(sa + group * 8192, &tmA, fb, m0 + 64 * group, kw * p.KW, 0, kh * p.KH, kn * p.KN + batch,
+                           CL_MASK);
+        } else if (!p.a_mn) {
           tma_load_5d(sa, &tmA, fb, kb * 64, m0, 0, 0, batch);
         } else {
 #pragma unroll
@@ -167,7 +179,8 @@ mmgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             umma_bf16(tmem_base + MAXTAPS * BN, make_smem_desc(sa + k * a_step, a_lbo, 1024),
                       make_smem_desc(sOnes + k * 32, 0, 1024), idesc1, (it | k) ? 1u : 0u);
         }
-        umma_commit(bar_empty + 8 * stage);
+        if constexpr (CL > 1) umma_commit_mc(bar_empty + 8 * stage, CL_MASK);
+        else umma_commit(bar_empty + 8 * stage);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
       umma_commit(bar_tfull);
@@ -239,6 +252,7 @@ mmgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();        // no CTA leaves while a peer may still arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
@@ -269,13 +283,22 @@ __global__ void colsum_reduce_kernel(const float* __restrict__ part, float* out,
   out[m] = a;
 }
 
-template <int BN, int STAGES, int MAXTAPS, bool STRIP = false>
+template <int BN, int STAGES, int MAXTAPS, bool STRIP = false, int CL = 1>
 static int launch_mm(const CUtensorMap& tmA, const CUtensorMap& tmB, const MmParams& p, dim3 grid,
                      cudaStream_t stream) {
   using Cfg = MmCfg<BN, STAGES, MAXTAPS, STRIP>;
   static unsigned long long attr_mask = 0;
-  if (int e = set_max_smem_once(mmgemm_kernel<BN, STAGES, MAXTAPS, STRIP>, Cfg::SMEM, attr_mask)) return e;
-  mmgemm_kernel<BN, STAGES, MAXTAPS, STRIP><<<grid, 192, Cfg::SMEM, stream>>>(tmA, tmB, p);
+  if (int e = set_max_smem_once(mmgemm_kernel<BN, STAGES, MAXTAPS, STRIP, CL>, Cfg::SMEM, attr_mask)) return e;
+  if constexpr (CL > 1) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = Cfg::SMEM; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return (int)cudaLaunchKernelEx(&cfg, mmgemm_kernel<BN, STAGES, MAXTAPS, STRIP, CL>, tmA, tmB, p);
+  }
+  mmgemm_kernel<BN, STAGES, MAXTAPS, STRIP, CL><<<grid, 192, Cfg::SMEM, stream>>>(tmA, tmB, p);
   return (int)cudaGetLastError();
 }
 
@@ -351,6 +374,15 @@ int b2dq_mmgemm(const b2dq_mm_desc* d, cudaStream_t stream) {
     if (!(d->a_mn && d->b_mn) || d->KW != 64 || d->KH != 1 || d->KN != 1 || bn != 128 || tpc != 3 ||
         d->ntaps % 3 != 0)
       return -6;
+    // opt-in (B2DQ_WGRAD_CLUSTER=1): clusters of 3 (the three filter rows of a pixel range) share the dY tile by TMA
+    // multicast.  Correct, but SLOWER than three unicast loads: L2 already serves the near-simultaneous identical
+    // requests of the three CTAs once, and the lock-step release of a stage by three MMA issuers adds stalls.
+    static int use_cluster = -1;
+    if (use_cluster < 0) {
+      const char* e = getenv("B2DQ_WGRAD_CLUSTER");
+      use_cluster = e ? atoi(e) : 0;   // measured on B200: 0.845 ms clustered vs 0.609 ms unicast
+    }
+    if (use_cluster && ngroups == 3) return launch_mm<128, 5, 3, true, 3>(tmA, tmB, p, grid, stream);
     return launch_mm<128, 5, 3, true>(tmA, tmB, p, grid, stream);
   }
   if (bn == 128) {

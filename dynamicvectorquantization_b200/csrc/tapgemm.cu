@@ -360,7 +360,12 @@ int b2dq_tapgemm(const b2dq_tapgemm_desc* d, cudaStream_t stream) {
     case 128:
       if (mt2) return launch_tapgemm<128, 2, 2>(tmA, tmB, p, grid, stream);
       return launch_tapgemm<128, 3, 1>(tmA, tmB, p, grid, stream);
-    case 256: return launch_tapgemm<256, 4, 1>(tmA, tmB, p, grid, stream);
+    case 256:
+      // two 128-pixel tiles per CTA share every 32 KB weight tile (64 instead of 96 B of operands per tensor cycle:
+      // the 256-channel layers are bound by the operand stream into the SM) once that still leaves >= 2 waves
+      if (d->m_tiles_per_cta == 2 || (d->m_tiles_per_cta == 0 && grid.x * grid.y >= 4 * 148))
+        return launch_tapgemm<256, 3, 2>(tmA, tmB, p, grid, stream);
+      return launch_tapgemm<256, 4, 1>(tmA, tmB, p, grid, stream);
     default: return -3;
   }
 }

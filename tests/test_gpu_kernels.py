@@ -269,6 +269,32 @@ def test_pconv_emits_groupnorm_statistics():
     assert torch.equal(kn.last_conv_stats, st) and torch.equal(y, y2)      # deterministic
 
 
+def test_tapgemm_256_wide_tiles_one_and_two_pixel_tiles_per_cta():
+    """tap GEMM with 256 output channels per tile (the 256-channel 3x3 layers at 64x64): one 128-pixel tile per CTA and
+    the variant where two pixel tiles share every weight tile must agree bit for bit (same accumulation order) and
+    match the fp32 convolution; odd tile count (the second tile of the last CTA is past the end)."""
+    from dynamicvectorquantization_b200 import kernels as kn
+    nb, h, w, c = 3, 24, 64, 256                          # 36 tiles of 128 pixels... 3*24*64/128 = 36; use h=25 -> ragged
+    h = 25
+    x = _rand_bf(nb, h, w, c, seed=71).cuda()
+    wt = _rand_bf(c, c, 3, 3, scale=(c * 9) ** -0.5, seed=72).float().cuda()
+    bias = (0.1 * torch.randn(c, generator=torch.Generator().manual_seed(73))).cuda()
+    res = _rand_bf(nb, h, w, c, seed=74).cuda()
+    wp = kn.pack_weight_fwd(wt)
+    dims, strs = kn.nhwc_view(x)
+    taps = [(0, s - 1, 0, r - 1, (r * 3 + s) * c) for r, s in kn.TAPS_3x3]
+    outs = []
+    for mt in (1, 2):
+        out = torch.empty(nb, h, w, c, dtype=BF, device="cuda")
+        ostr = (h * w * c, w * c, c)
+        kn.tapgemm(x, dims, strs, wp, c, 9 * c, taps, c // 64, out, 0, ostr, w, h, nb, c, bias=bias, residual=res, rstr=ostr,
+                   block_n=256, m_tiles_per_cta=mt)
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1]), "one and two pixel tiles per CTA disagree"
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt, bias, padding=1).permute(0, 2, 3, 1) + res.float()
+    assert rel_rms(outs[1].float(), ref) < 6e-3
+
+
 def test_pconv_staged_epilogue_residual_and_ragged_tile_count():
     """Epilogue of the persistent strip kernel (bf16 tile staged in shared memory, TMA store, residual half-tiles by
     TMA load two units ahead): agreement with the generic tap GEMM on the same operands to the last bf16 bit up to the
