@@ -291,11 +291,20 @@ def pconv3x3(x, wpack, bias, residual, dgrad, want_stats=False):
     return out
 
 
+import os as _os
+# k-blocks (of 64 pixels) a CTA must keep for the split-K weight gradient to be cut into TWO waves of CTAs: every
+# split writes (and the reduction re-reads) a full fp32 copy of the weight gradient, so short CTAs pay more for their
+# epilogue and partial traffic than the second wave gains in balance
+# (measured on B200, tools/gpu_r2k.sh: ONE wave wins on every layer shape of the model - 0.511 -> 0.486 ms at
+# 128->128 @256^2, 0.085 -> 0.064 ms at 256->256 @32^2, step 58.8 -> 57.3 ms - so the default never cuts two)
+WGRAD_TWO_WAVE_MIN_KB = int(_os.environ.get("B2DQ_WGRAD_TWO_WAVE_MIN_KB", str(1 << 30)))
+
+
 def _wgrad_splits(kblocks, ctas_per_split):
     """Split-K factor so that one launch (ctas_per_split output tiles x splits CTAs, 1 CTA/SM)
     fills the 148 SMs in whole waves, with at least 4 k-blocks per CTA."""
     target = max(1, NUM_SMS // max(1, ctas_per_split))
-    if kblocks >= 16 * target * 2:          # plenty of work: two full waves balance better than one
+    if kblocks >= WGRAD_TWO_WAVE_MIN_KB * target * 2:   # plenty of work: two full waves balance better than one
         target *= 2
     return max(1, min(target, kblocks // 4 if kblocks >= 4 else 1))
 
