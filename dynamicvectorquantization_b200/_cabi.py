@@ -53,8 +53,26 @@ _lib = None
 _vp, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 
 # name -> argtypes (restype is always int status).  Mirrors include/b200dq.h.
+class Conv2dGeom(C.Structure):
+    _fields_ = [("N", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cin", C.c_int), ("Cout", C.c_int),
+                ("ksize", C.c_int), ("stride", C.c_int)]
+
+
 SIGNATURES = {
     "b2dq_version": [],
+    # operator-level entries (csrc/oplevel.cu); the geometry struct is passed by reference
+    "b2dq_conv2d_out_hw": [_vp, _vp],
+    "b2dq_conv2d_fwd_workspace_bytes": [_vp],
+    "b2dq_conv2d_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _ll, _vp],
+    "b2dq_conv2d_dgrad": [_vp, _vp, _vp, _vp, _vp],
+    "b2dq_conv2d_wgrad_workspace_bytes": [_vp, _i],
+    "b2dq_conv2d_wgrad": [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _vp],
+    "b2dq_groupnorm_workspace_bytes": [_i, _i, _i, _i, _i],
+    "b2dq_groupnorm_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _f, _i, _vp],
+    "b2dq_groupnorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _vp],
+    "b2dq_attention_workspace_bytes": [_i, _i, _i, _i],
+    "b2dq_attention_fwd": [_vp, _vp, _vp, _vp, _ll, _i, _i, _i, _f, _vp],
+    "b2dq_attention_bwd": [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _f, _vp],
     "b2dq_vq_prepare_codebook": [_vp, _vp, _vp, _i, _i, _vp],
     "b2dq_vq_search_plan": [_i, _i, _i, _i, C.POINTER(C.c_int)],
     "b2dq_vq_search_workspace_bytes": [_i, _i],      # returns a byte count, not a status

@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["vq.cu", "tapgemm.cu", "pconv.cu", "mmgemm.cu", "norm.cu", "norm_fused.cu", "elementwise.cu", "entropy.cu", "permuter.cu", "lpips.cu"]
+SOURCES = ["vq.cu", "tapgemm.cu", "pconv.cu", "mmgemm.cu", "norm.cu", "norm_fused.cu", "elementwise.cu", "entropy.cu", "permuter.cu", "lpips.cu", "oplevel.cu"]
 OUT = os.path.join(HERE, "libb200dq.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]

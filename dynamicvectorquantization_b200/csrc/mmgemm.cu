@@ -9,6 +9,7 @@
 //     any combination of K-major / MN-major A and B, batched over images.
 // Operand tiles are 128 B-swizzled TMA boxes; MN-major tiles are stacks of {64 mn, 64 k} boxes
 // (8 KB each, LBO = 8 KB between 64-wide mn groups, 2 KB per K=16 step).
+#include <cstdlib>
 #include "common.cuh"
 #include "tmap.h"
 
@@ -31,6 +32,7 @@ struct MmParams {
   float* colsum;                  // optional [splits][M] fp32: sum over the contraction index of A[m,k]
                                   // (bias gradient = column sums of dY), computed by the tensor core as
                                   // A x ones; written by the tap-group-0 CTAs (MAXTAPS == 3 kernels only)
+  int tma_out;                    // 1: output tiles leave through shared memory and bulk tensor stores (tmO)
 };
 
 // STRIP: the (up to 3) taps of a CTA are horizontal 1-pixel shifts of each other (one 3x3 filter row):
@@ -56,7 +58,7 @@ struct MmCfg {
 template <int BN, int STAGES, int MAXTAPS, bool STRIP = false, int CL = 1>
 __global__ void __launch_bounds__(192, 1)
 mmgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-              const __grid_constant__ MmParams p) {
+              const __grid_constant__ CUtensorMap tmO, const __grid_constant__ MmParams p) {
   using Cfg = MmCfg<BN, STAGES, MAXTAPS, STRIP>;
   constexpr uint16_t CL_MASK = static_cast<uint16_t>((1u << CL) - 1u);
   extern __shared__ uint8_t smem_raw[];
@@ -97,6 +99,7 @@ mmgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     fence_barrier_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.tma_out) tma_prefetch_desc(&tmO);
   }
   if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(smem_u32(tmem_slot));
   tc_fence_before();
@@ -204,6 +207,60 @@ mmgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       }
       if (valid) p.colsum[static_cast<long long>(blockIdx.z) * p.M + m] = __uint_as_float(r[0]);
     }
+    if (p.tma_out) {
+      // A thread owns one output row, so its 16 B stores hit 32 different lines per warp instruction (32 LSU
+      // wavefronts each): for the short contractions of the attention block (K = 256: 4 k-blocks) the 2048 store
+      // wavefronts per warp of a 128 x 256 fp32 tile cost twice the main loop.  Instead each tap's tile is staged
+      // in the idle operand ring as 16 KB chunks in the 128 B-swizzled layout of a TMA box {128 B of columns,
+      // 128 rows} and leaves as one bulk tensor store per chunk (rows / columns past M / N are clipped by the map).
+      const int ml = q * 32 + lane;
+      const uint32_t swz = static_cast<uint32_t>(ml & 7);
+      const bool leader = threadIdx.x == 64;
+      uint8_t* stage0 = smem_raw + (base - smem_u32(smem_raw));
+      const int cpc = p.out_f32 ? 32 : 64;                       // columns per 16 KB chunk
+      for (int t = 0; t < ntl; ++t) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          if (kiters > 0) {
+            tmem_ld_32x32(trow + t * BN + c0, r);
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = 0u;
+          }
+          if (p.out_f32) {
+            uint8_t* row = stage0 + (c0 >> 5) * 16384 + ml * 128;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              *reinterpret_cast<float4*>(row + ((static_cast<uint32_t>(i) ^ swz) << 4)) =
+                  make_float4(__uint_as_float(r[4 * i]) * p.alpha, __uint_as_float(r[4 * i + 1]) * p.alpha,
+                              __uint_as_float(r[4 * i + 2]) * p.alpha, __uint_as_float(r[4 * i + 3]) * p.alpha);
+          } else {
+            uint8_t* row = stage0 + (c0 >> 6) * 16384 + ml * 128;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 u;
+              u.x = pack_bf16x2(__uint_as_float(r[8 * i + 0]) * p.alpha, __uint_as_float(r[8 * i + 1]) * p.alpha);
+              u.y = pack_bf16x2(__uint_as_float(r[8 * i + 2]) * p.alpha, __uint_as_float(r[8 * i + 3]) * p.alpha);
+              u.z = pack_bf16x2(__uint_as_float(r[8 * i + 4]) * p.alpha, __uint_as_float(r[8 * i + 5]) * p.alpha);
+              u.w = pack_bf16x2(__uint_as_float(r[8 * i + 6]) * p.alpha, __uint_as_float(r[8 * i + 7]) * p.alpha);
+              *reinterpret_cast<uint4*>(row + (((static_cast<uint32_t>((c0 & 63) >> 3) + i) ^ swz) << 4)) = u;
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (leader) {
+          for (int ch = 0; ch * cpc < BN; ++ch)
+            if (n0 + ch * cpc < p.N)
+              tma_store_4d(&tmO, base + ch * 16384, n0 + ch * cpc, m0, tap0 + t, static_cast<int>(blockIdx.z));
+          tma_store_commit();
+          tma_store_wait_read<0>();                              // the staging chunks are rewritten by the next tap
+        }
+        if (t + 1 < ntl) asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+    } else
     for (int t = 0; t < ntl; ++t) {
       const long long ooff = blockIdx.z * p.oZ + (tap0 + t) * p.oT + static_cast<long long>(m) * p.oM;
 #pragma unroll 1
@@ -284,21 +341,22 @@ __global__ void colsum_reduce_kernel(const float* __restrict__ part, float* out,
 }
 
 template <int BN, int STAGES, int MAXTAPS, bool STRIP = false, int CL = 1>
-static int launch_mm(const CUtensorMap& tmA, const CUtensorMap& tmB, const MmParams& p, dim3 grid,
+static int launch_mm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, MmParams p, dim3 grid,
                      cudaStream_t stream) {
   using Cfg = MmCfg<BN, STAGES, MAXTAPS, STRIP>;
   static unsigned long long attr_mask = 0;
   if (int e = set_max_smem_once(mmgemm_kernel<BN, STAGES, MAXTAPS, STRIP, CL>, Cfg::SMEM, attr_mask)) return e;
   if constexpr (CL > 1) {
+    p.tma_out = 0;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = Cfg::SMEM; cfg.stream = stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    return (int)cudaLaunchKernelEx(&cfg, mmgemm_kernel<BN, STAGES, MAXTAPS, STRIP, CL>, tmA, tmB, p);
+    return (int)cudaLaunchKernelEx(&cfg, mmgemm_kernel<BN, STAGES, MAXTAPS, STRIP, CL>, tmA, tmB, tmO, p);
   }
-  mmgemm_kernel<BN, STAGES, MAXTAPS, STRIP, CL><<<grid, 192, Cfg::SMEM, stream>>>(tmA, tmB, p);
+  mmgemm_kernel<BN, STAGES, MAXTAPS, STRIP, CL><<<grid, 192, Cfg::SMEM, stream>>>(tmA, tmB, tmO, p);
   return (int)cudaGetLastError();
 }
 
@@ -370,6 +428,27 @@ int b2dq_mmgemm(const b2dq_mm_desc* d, cudaStream_t stream) {
   if (d->colsum && !p.colsum) return -7;
   dim3 grid((unsigned)(((d->M + 127) / 128) * ngroups), (unsigned)((d->N + bn - 1) / bn),
             (unsigned)(d->batches * d->splits));
+  // output through shared memory + bulk tensor stores when every stride is 16 B aligned
+  static const bool tma_out_enabled = [] {
+    const char* e = getenv("B2DQ_MMGEMM_TMA_OUT");
+    return !(e && e[0] == '0');
+  }();
+  CUtensorMap tmO = tmA;
+  p.tma_out = 0;
+  {
+    const long long esz = d->out_f32 ? 4 : 2, al = 16 / esz;
+    const long long nz = (long long)d->batches * d->splits;
+    const long long sT = d->ntaps > 1 ? d->oT : d->oM * d->M, sZ = nz > 1 ? d->oZ : d->oM * d->M;
+    if (tma_out_enabled && d->oM % al == 0 && sT % al == 0 && sZ % al == 0 && sT > 0 && sZ > 0 &&
+        (reinterpret_cast<uintptr_t>(d->out) & 15) == 0) {
+      uint64_t dims[4] = {(uint64_t)d->N, (uint64_t)d->M, (uint64_t)d->ntaps, (uint64_t)nz};
+      uint64_t str[4] = {1, (uint64_t)d->oM, (uint64_t)sT, (uint64_t)sZ};
+      uint32_t box[4] = {d->out_f32 ? 32u : 64u, 128, 1, 1};
+      int r = make_tmap_elem(&tmO, d->out, 4, dims, str, box, d->out_f32 != 0);
+      if (r) return r - 2000;
+      p.tma_out = 1;
+    }
+  }
   if (d->b_strip) {
     if (!(d->a_mn && d->b_mn) || d->KW != 64 || d->KH != 1 || d->KN != 1 || bn != 128 || tpc != 3 ||
         d->ntaps % 3 != 0)
@@ -382,15 +461,15 @@ int b2dq_mmgemm(const b2dq_mm_desc* d, cudaStream_t stream) {
       const char* e = getenv("B2DQ_WGRAD_CLUSTER");
       use_cluster = e ? atoi(e) : 0;   // measured on B200: 0.845 ms clustered vs 0.609 ms unicast
     }
-    if (use_cluster && ngroups == 3) return launch_mm<128, 5, 3, true, 3>(tmA, tmB, p, grid, stream);
-    return launch_mm<128, 5, 3, true>(tmA, tmB, p, grid, stream);
+    if (use_cluster && ngroups == 3) return launch_mm<128, 5, 3, true, 3>(tmA, tmB, tmO, p, grid, stream);
+    return launch_mm<128, 5, 3, true>(tmA, tmB, tmO, p, grid, stream);
   }
   if (bn == 128) {
-    if (tpc == 1) return launch_mm<128, 4, 1>(tmA, tmB, p, grid, stream);
-    return launch_mm<128, 3, 3>(tmA, tmB, p, grid, stream) ;
+    if (tpc == 1) return launch_mm<128, 4, 1>(tmA, tmB, tmO, p, grid, stream);
+    return launch_mm<128, 3, 3>(tmA, tmB, tmO, p, grid, stream) ;
   } else if (bn == 256) {
     if (tpc != 1) return -4;
-    return launch_mm<256, 4, 1>(tmA, tmB, p, grid, stream);
+    return launch_mm<256, 4, 1>(tmA, tmB, tmO, p, grid, stream);
   }
   return -5;
 }

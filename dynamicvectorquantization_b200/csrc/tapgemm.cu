@@ -19,6 +19,7 @@
 // CTA = 192 threads: warp 0 TMA producer, warp 1 MMA issuer (+TMEM owner), warps 2..5 epilogue
 // (one TMEM lane quadrant each).  One 128 x BN output tile per CTA; 2 CTAs/SM for BN <= 128
 // so one CTA's epilogue overlaps the other's main loop.
+#include <cstdlib>
 #include "common.cuh"
 #include "tmap.h"
 
@@ -47,6 +48,7 @@ struct TapGemmParams {
   int relu;                      // 1: clamp the result at zero (VGG feature stack of the perceptual loss);
                                  // 2: LeakyReLU(0.2) (PatchGAN stem, modules/discriminator/model.py:37)
   int out_f32;
+  int tma_out;                   // 1: the bf16 tile leaves through shared memory and bulk tensor stores (tmO)
 };
 
 // MT = number of 128-pixel output tiles per CTA that share one weight tile per pipeline stage
@@ -64,7 +66,7 @@ struct TgCfg {
 template <int BN, int STAGES, int MT>
 __global__ void __launch_bounds__(192, (TgCfg<BN, STAGES, MT>::CTAS_PER_SM))
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ TapGemmParams p) {
+               const __grid_constant__ CUtensorMap tmO, const __grid_constant__ TapGemmParams p) {
   using Cfg = TgCfg<BN, STAGES, MT>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -94,6 +96,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     fence_barrier_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.tma_out) tma_prefetch_desc(&tmO);
   }
   if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(smem_u32(tmem_slot));
   tc_fence_before();
@@ -169,6 +172,83 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       roff[j] = n * p.rN + oh * p.rH + ow * p.rW;
     }
     uint4 res[RV > 0 ? RV : 1];
+    if constexpr (BN >= 64) {
+      if (p.tma_out) {
+        // A thread owns one pixel row of the tile, so per-thread 16 B global stores touch 32 different 128 B lines
+        // per warp instruction: 32 LSU wavefronts each, 2048 per warp for a 2 x 256-column tile pair - for short K
+        // loops (1x1 convolutions, the 2x2 parity classes of the folded up-convolution, the few-channel edge
+        // layers) more than the main loop itself.  Instead the bf16 tile is staged in the (now idle) operand ring
+        // in the 128 B-swizzled layout of a TMA box {64 ch, TW, 1, TH, TN} and leaves as one bulk tensor store per
+        // 64-channel slice; ragged tiles are clipped by the tensor map.
+        const int ncols = (p.Cout - nt0) < BN ? (p.Cout - nt0) : BN;        // multiple of 64
+        const bool has_res = p.residual != nullptr;
+        const uint32_t swz = static_cast<uint32_t>(m & 7);
+        const bool leader = threadIdx.x == 64;
+        uint8_t* stage0 = smem_raw + (base - smem_u32(smem_raw));
+        auto load_res = [&](int j) {
+          if (!has_res) return;
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + roff[j] + nt0);
+#pragma unroll
+          for (int i = 0; i < RV; ++i)
+            res[i] = (valid[j] && 8 * i < ncols) ? __ldg(rp + i) : make_uint4(0u, 0u, 0u, 0u);
+        };
+        load_res(0);
+        mbar_wait(bar_tfull, 0);
+        tc_fence_after();
+#pragma unroll
+        for (int j = 0; j < MT; ++j) {
+          if (j > 0) load_res(j);
+          const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + j * BN;
+#pragma unroll
+          for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32(trow + c0, r);
+            tmem_ld_wait();
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaf(__uint_as_float(r[i]), p.alpha, bias_s[c0 + i]);
+            if (has_res) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const uint4 u = res[c0 / 8 + i];
+                v[8 * i + 0] += bf16_lo(u.x); v[8 * i + 1] += bf16_hi(u.x);
+                v[8 * i + 2] += bf16_lo(u.y); v[8 * i + 3] += bf16_hi(u.y);
+                v[8 * i + 4] += bf16_lo(u.z); v[8 * i + 5] += bf16_hi(u.z);
+                v[8 * i + 6] += bf16_lo(u.w); v[8 * i + 7] += bf16_hi(u.w);
+              }
+            }
+            if (p.relu == 1) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+            } else if (p.relu == 2) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : 0.2f * v[i];
+            }
+            uint8_t* row = stage0 + (j * (BN / 64) + (c0 >> 6)) * 16384 + m * 128;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 u;
+              u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+              u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+              u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+              u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+              *reinterpret_cast<uint4*>(row + (((((c0 & 63) >> 3) + i) ^ swz) << 4)) = u;
+            }
+          }
+          fence_proxy_async_smem();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (leader && n0[j] < p.NB) {
+#pragma unroll
+            for (int ch = 0; ch < BN / 64; ++ch)
+              if (ch * 64 < ncols)
+                tma_store_5d(&tmO, base + (j * (BN / 64) + ch) * 16384, nt0 + ch * 64, ow0[j], 0, oh0[j], n0[j]);
+            tma_store_commit();
+          }
+        }
+        if (leader) tma_store_wait_read<0>();
+      }
+    }
+    if (!(BN >= 64 && p.tma_out)) {
     const bool pre_res = (BN >= 64) && p.residual && vec_ok;
     if (pre_res && valid[0]) {
       const uint4* rp = reinterpret_cast<const uint4*>(p.residual + roff[0] + nt0);
@@ -260,6 +340,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
+    }
   }
 
   tc_fence_before();
@@ -271,13 +352,13 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 template <int BN, int STAGES, int MT>
-static int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const TapGemmParams& p,
-                          dim3 grid, cudaStream_t stream) {
+static int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
+                          const TapGemmParams& p, dim3 grid, cudaStream_t stream) {
   using Cfg = TgCfg<BN, STAGES, MT>;
   static unsigned long long attr_mask = 0;
   if (int e = set_max_smem_once(tapgemm_kernel<BN, STAGES, MT>, Cfg::SMEM, attr_mask)) return e;
   grid.x = (grid.x + MT - 1) / MT;
-  tapgemm_kernel<BN, STAGES, MT><<<grid, 192, Cfg::SMEM, stream>>>(tmA, tmB, p);
+  tapgemm_kernel<BN, STAGES, MT><<<grid, 192, Cfg::SMEM, stream>>>(tmA, tmB, tmO, p);
   return (int)cudaGetLastError();
 }
 
@@ -334,7 +415,25 @@ int b2dq_tapgemm(const b2dq_tapgemm_desc* d, cudaStream_t stream) {
     int r = make_tmap_bf16(&tmB, d->b_ptr, 3, dims, str, box);
     if (r) return r - 1000;
   }
+  // bf16 tiles of whole 64-channel slices leave through shared memory + bulk tensor stores (16 B aligned strides)
+  static const bool tma_out_enabled = [] {
+    const char* e = getenv("B2DQ_TAPGEMM_TMA_OUT");
+    return !(e && e[0] == '0');
+  }();
+  const bool tma_out = tma_out_enabled && !d->out_f32 && bn >= 64 && d->Cout % 64 == 0 && d->oW % 8 == 0 &&
+                       d->oH % 8 == 0 && d->oN % 8 == 0 && (reinterpret_cast<uintptr_t>(d->out) & 15) == 0 &&
+                       (!d->residual || ((reinterpret_cast<uintptr_t>(d->residual) & 15) == 0 && d->rW % 8 == 0 &&
+                                         d->rH % 8 == 0 && d->rN % 8 == 0));
+  CUtensorMap tmO = tmA;
+  if (tma_out) {
+    uint64_t dims[5] = {(uint64_t)d->Cout, (uint64_t)d->Wout, 1, (uint64_t)d->Hout, (uint64_t)d->NB};
+    uint64_t str[5] = {1, (uint64_t)d->oW, (uint64_t)d->oH, (uint64_t)d->oH, (uint64_t)d->oN};
+    uint32_t box[5] = {64, (uint32_t)d->TW, 1, (uint32_t)d->TH, (uint32_t)d->TN};
+    int r = make_tmap_bf16(&tmO, d->out, 5, dims, str, box);
+    if (r) return r - 2000;
+  }
   TapGemmParams p;
+  p.tma_out = tma_out ? 1 : 0;
   p.num_taps = d->num_taps; p.kchunks = d->kchunks;
   for (int i = 0; i < TG_MAX_TAPS; ++i) {
     p.tap_c[i] = d->tap_c[i]; p.tap_w[i] = d->tap_w[i]; p.tap_p[i] = d->tap_p[i];
@@ -355,17 +454,17 @@ int b2dq_tapgemm(const b2dq_tapgemm_desc* d, cudaStream_t stream) {
   // two 128-pixel tiles per CTA once there are enough tiles for >= 2 waves of 2 CTAs/SM
   const bool mt2 = d->m_tiles_per_cta == 2 || (d->m_tiles_per_cta == 0 && grid.x * grid.y >= 8 * 148);
   switch (bn) {
-    case 16: return launch_tapgemm<16, 4, 1>(tmA, tmB, p, grid, stream);
-    case 64: return launch_tapgemm<64, 4, 1>(tmA, tmB, p, grid, stream);
+    case 16: return launch_tapgemm<16, 4, 1>(tmA, tmB, tmO, p, grid, stream);
+    case 64: return launch_tapgemm<64, 4, 1>(tmA, tmB, tmO, p, grid, stream);
     case 128:
-      if (mt2) return launch_tapgemm<128, 2, 2>(tmA, tmB, p, grid, stream);
-      return launch_tapgemm<128, 3, 1>(tmA, tmB, p, grid, stream);
+      if (mt2) return launch_tapgemm<128, 2, 2>(tmA, tmB, tmO, p, grid, stream);
+      return launch_tapgemm<128, 3, 1>(tmA, tmB, tmO, p, grid, stream);
     case 256:
       // two 128-pixel tiles per CTA share every 32 KB weight tile (64 instead of 96 B of operands per tensor cycle:
       // the 256-channel layers are bound by the operand stream into the SM) once that still leaves >= 2 waves
       if (d->m_tiles_per_cta == 2 || (d->m_tiles_per_cta == 0 && grid.x * grid.y >= 4 * 148))
-        return launch_tapgemm<256, 3, 2>(tmA, tmB, p, grid, stream);
-      return launch_tapgemm<256, 4, 1>(tmA, tmB, p, grid, stream);
+        return launch_tapgemm<256, 3, 2>(tmA, tmB, tmO, p, grid, stream);
+      return launch_tapgemm<256, 4, 1>(tmA, tmB, tmO, p, grid, stream);
     default: return -3;
   }
 }

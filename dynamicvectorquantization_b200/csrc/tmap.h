@@ -29,8 +29,15 @@ inline PFN_encodeTiled get_encode_tiled() {
 // bf16 tensor, `rank` dims (innermost first), strides in ELEMENTS for dims 1..rank-1
 // (dim 0 is contiguous), box in elements, 128 B swizzle, zero fill out of bounds.
 // Returns 0 on success, a negative code otherwise.
+inline int make_tmap_elem(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
+                          const uint64_t* strides_elems, const uint32_t* box, bool f32);
 inline int make_tmap_bf16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
                           const uint64_t* strides_elems, const uint32_t* box) {
+  return make_tmap_elem(tm, base, rank, dims, strides_elems, box, false);
+}
+// Same for bf16 (f32 = false) or fp32 (f32 = true) elements; the inner box extent must span 128 B.
+inline int make_tmap_elem(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
+                          const uint64_t* strides_elems, const uint32_t* box, bool f32) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return -100;
   // cuTensorMapEncodeTiled is a driver call and needs a current context; a thread that has not made
@@ -48,9 +55,9 @@ inline int make_tmap_bf16(CUtensorMap* tm, const void* base, int rank, const uin
     gdims[i] = dims[i];
     gbox[i] = box[i];
     estr[i] = 1;
-    if (i > 0) gstr[i - 1] = strides_elems[i] * 2;  // bytes
+    if (i > 0) gstr[i - 1] = strides_elems[i] * (f32 ? 4 : 2);  // bytes
   }
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
+  CUresult r = enc(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
                    gdims, gstr, gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

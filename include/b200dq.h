@@ -256,6 +256,57 @@ int b2dq_im2col_window(const void* src, void* dst, int N, int Hs, int Ws, int Ho
                        int sgn, int off, cudaStream_t stream);
 
 
+/* ------------------------------------------------------------------ operator-level entry points
+ * One call per operator (csrc/oplevel.cu): the tile shapes, tap tables, split-K factors and the kernel choice
+ * that dynamicvectorquantization_b200/kernels.py derives in Python are derived here in C from the operator
+ * geometry, and the descriptor-level kernels above are enqueued.  Same inputs, bit-identical outputs on both
+ * routes.  A binding in another host language needs only these.
+ *
+ * nn.Conv2d(Cin, Cout, ksize, stride) as the model uses it (modules/diffusionmodules/model.py:43-47,62-72,
+ * 88-115,146-165): ksize 1 or 3; stride 1 with padding ksize/2, or stride 2 (ksize 3, H and W even) with
+ * Downsample's (0,1,0,1) zero padding.  x [N,H,W,Cin], y [N,H/stride,W/stride,Cout] NHWC bf16.
+ *   wpack        [Cout, ksize*ksize*Cin] bf16 (b2dq_pack_weights fwd), Cin % 64 == 0
+ *   wpack_dgrad  [Cin, ksize*ksize*Cout] bf16 (b2dq_pack_weights dgrad), Cout % 64 == 0
+ *   act          epilogue activation: 0 none, 1 ReLU, 2 LeakyReLU(0.2)
+ *   gn_stats     optional [N,32,2] (mean, rstd) of GroupNorm(32, 1e-6) over y, produced by the convolution's own
+ *                epilogue; only where b2dq_conv2d_fwd_workspace_bytes(g) > 0 (else pass NULL: -3 otherwise)
+ *   dw           [Cout,Cin,ksize,ksize] fp32 (OIHW), overwritten;  db optional [Cout] fp32
+ *   ws           scratch of the matching *_workspace_bytes (256 B aligned); -2 if too small */
+typedef struct b2dq_conv2d_geom {
+  int N, H, W, Cin, Cout, ksize, stride;
+} b2dq_conv2d_geom;
+
+int b2dq_conv2d_out_hw(const b2dq_conv2d_geom* g, int* out2 /* host: Hout, Wout */);
+int b2dq_conv2d_fwd_workspace_bytes(const b2dq_conv2d_geom* g);
+int b2dq_conv2d_fwd(const b2dq_conv2d_geom* g, const void* x, const void* wpack, const float* bias,
+                    const void* residual, void* y, int act, float* gn_stats, void* ws, long long ws_bytes,
+                    cudaStream_t stream);
+int b2dq_conv2d_dgrad(const b2dq_conv2d_geom* g, const void* dy, const void* wpack_dgrad, void* dx,
+                      cudaStream_t stream);
+int b2dq_conv2d_wgrad_workspace_bytes(const b2dq_conv2d_geom* g, int want_bias);
+int b2dq_conv2d_wgrad(const b2dq_conv2d_geom* g, const void* x, const void* dy, float* dw, float* db, void* ws,
+                      long long ws_bytes, cudaStream_t stream);
+
+/* GroupNorm(G, eps) + activation (0 none, 1 swish) of x [N,HW,C] bf16 and its backward (Normalize + nonlinearity,
+ * model.py:29-35): the persistent fused kernels where the shape allows, else the statistics + apply pairs.
+ * stats [N,G,2] is written by the forward and read by the backward; dgb [2,C] = (dgamma, dbeta); add: optional
+ * bf16 tensor summed into dx.  backward = 0 / 1 selects which workspace size is returned. */
+int b2dq_groupnorm_workspace_bytes(int N, int HW, int C, int G, int backward);
+int b2dq_groupnorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* stats, void* ws,
+                       long long ws_bytes, int N, int HW, int C, int G, float eps, int act, cudaStream_t stream);
+int b2dq_groupnorm_bwd(const void* dy, const void* x, const float* stats, const float* gamma, const float* beta,
+                       void* dx, float* dgb, const void* add, void* ws, long long ws_bytes, int N, int HW, int C,
+                       int G, int act, cudaStream_t stream);
+
+/* Attention core of AttnBlock.forward (model.py:176-188): out = softmax(scale * q k^T) v per image.
+ * qkv [N,T,3C] bf16 holds q | k | v side by side (one [C -> 3C] 1x1 convolution); out [N,T,C] bf16; probs [N,T,T]
+ * bf16 is kept for the backward, which writes dq | dk | dv into dqkv [N,T,3C].  scale = C^-0.5 in the model. */
+int b2dq_attention_workspace_bytes(int N, int T, int C, int backward);
+int b2dq_attention_fwd(const void* qkv, void* out, void* probs, void* ws, long long ws_bytes, int N, int T, int C,
+                       float scale, cudaStream_t stream);
+int b2dq_attention_bwd(const void* qkv, const void* probs, const void* dout, void* dqkv, void* ws,
+                       long long ws_bytes, int N, int T, int C, float scale, cudaStream_t stream);
+
 /* ------------------------------------------------------------------ entropy router input
  * Per-patch grey-level entropy (models/stage1_dynamic/dqvae_dual_entropy.py:25-63): x NCHW fp32
  * [B,3,H,W] in [-1,1] -> out [B, H/patch, W/patch] fp32.  Soft histogram over `nbins` (= 32) bin

@@ -462,14 +462,15 @@ def test_groupnorm_backward_fused_kernel(nb, h, w, c, swish, with_add):
 def test_layout_upsample_softmax():
     from dynamicvectorquantization_b200 import kernels as kn
     dev = "cuda"
-    x = torch.randn(2, 3, 40, 24, generator=torch.Generator().manual_seed(1))
-    xn = kn.nchw_f32_to_nhwc_bf16(x.to(dev))
-    assert torch.equal(xn.cpu(), x.permute(0, 2, 3, 1).to(BF))
-    back = kn.nhwc_bf16_to_nchw_f32(xn)
-    assert torch.equal(back.cpu(), x.to(BF).float())
-    x32 = kn.nchw_f32_to_nhwc_f32(x.to(dev))
-    assert torch.equal(x32.cpu(), x.permute(0, 2, 3, 1).contiguous())
-    assert torch.equal(kn.nhwc_f32_to_nchw_f32(x32).cpu(), x)
+    for ch in (3, 1, 40):            # few-channel (one thread per pixel) and tiled transposes
+        x = torch.randn(2, ch, 40, 24, generator=torch.Generator().manual_seed(1))
+        xn = kn.nchw_f32_to_nhwc_bf16(x.to(dev))
+        assert torch.equal(xn.cpu(), x.permute(0, 2, 3, 1).to(BF))
+        back = kn.nhwc_bf16_to_nchw_f32(xn)
+        assert torch.equal(back.cpu(), x.to(BF).float())
+        x32 = kn.nchw_f32_to_nhwc_f32(x.to(dev))
+        assert torch.equal(x32.cpu(), x.permute(0, 2, 3, 1).contiguous())
+        assert torch.equal(kn.nhwc_f32_to_nchw_f32(x32).cpu(), x)
     a = _rand_bf(2, 8, 12, 64, seed=3)
     up = kn.upsample2x(a.to(dev))
     ref = a.float().permute(0, 3, 1, 2).repeat_interleave(2, 2).repeat_interleave(2, 3).permute(0, 2, 3, 1)
@@ -503,6 +504,13 @@ def test_layout_upsample_softmax():
             rr, ss = (2 - r, 2 - s_) if flip else (r, s_)
             assert torch.equal(col[..., t * cs:(t + 1) * cs], pad[:, :, rr:rr + 7, ss:ss + 9].permute(0, 2, 3, 1)), (cs, flip, t)
         assert float(col[..., 9 * cs:].abs().sum()) == 0.0
+    # more pixels than one 256-pixel block, ragged last block
+    img = _rand_bf(2, 20, 17, 3, seed=21)
+    col = kn.im2col3x3_small(img.to(dev)).cpu().float()
+    pad = F.pad(img.float().permute(0, 3, 1, 2), (1, 1, 1, 1))
+    for t, (r, s_) in enumerate([(r, s_) for r in range(3) for s_ in range(3)]):
+        assert torch.equal(col[..., t * 3:(t + 1) * 3], pad[:, :, r:r + 20, s_:s_ + 17].permute(0, 2, 3, 1))
+    assert float(col[..., 27:].abs().sum()) == 0.0
 
 
 def test_fused_weight_packing_matches_the_torch_packings():

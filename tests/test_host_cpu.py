@@ -684,3 +684,30 @@ def test_bucketed_gradient_exchange_world_size_2():
     res = sorted(q.get(timeout=120) for _ in range(2))
     [p.join(30) for p in procs]
     assert res == [(0, True), (1, True)]
+
+
+def test_oplevel_geometry_and_workspace_sizes_match_the_python_heuristics():
+    """The operator-level C entries (csrc/oplevel.cu) derive tiles and split-K factors themselves; their host-only
+    helpers must agree with kernels.py, or the two routes would stop being bit-identical."""
+    import ctypes as C
+    from dynamicvectorquantization_b200 import _cabi, kernels as kn
+    lib = _cabi.lib()
+    for (n, h, w, cin, cout, k, stride) in [(32, 256, 256, 128, 128, 3, 1), (32, 32, 32, 256, 256, 3, 1),
+                                            (2, 32, 32, 256, 768, 1, 1), (32, 128, 128, 128, 128, 3, 2),
+                                            (1, 24, 40, 64, 192, 3, 1)]:
+        g = _cabi.Conv2dGeom(n, h, w, cin, cout, k, stride)
+        out = (C.c_int * 2)()
+        assert lib.b2dq_conv2d_out_hw(C.byref(g), out) == 0
+        ho, wo = h // stride, w // stride
+        assert (out[0], out[1]) == (ho, wo)
+        pconv = kn._pconv_ok(k, stride, w, cin, cout, n, h)
+        assert (lib.b2dq_conv2d_fwd_workspace_bytes(C.byref(g)) > 0) == pconv
+        kw, kh, kn_ = kn.tile_shape(wo, ho, n, pixels=64)
+        kblocks = -(-wo // kw) * -(-ho // kh) * -(-n // kn_)
+        ntaps = k * k
+        splits = kn._wgrad_splits(kblocks, -(-cout // 128) * -(-cin // 128) * ((ntaps + 2) // 3))
+        want = (splits * ntaps * cout * cin * 4 + 255) // 256 * 256
+        assert lib.b2dq_conv2d_wgrad_workspace_bytes(C.byref(g), 0) == want
+    assert lib.b2dq_groupnorm_workspace_bytes(32, 65536, 128, 32, 1) >= lib.b2dq_gn_bwd_fused_workspace_bytes(32, 65536, 128, 32)
+    assert lib.b2dq_groupnorm_workspace_bytes(2, 100, 96, 33, 0) == -1
+    assert lib.b2dq_attention_workspace_bytes(2, 1024, 256, 0) == 2 * 1024 * 1024 * 4

@@ -88,6 +88,21 @@ def conv(nb, h, w, cin, cout, k, stride):
     print(json.dumps(r))
 
 
+def upconv(nb, h, w, cin, cout):
+    """Folded nearest-x2 + 3x3 convolution (four 2x2 parity classes) forward / data gradient, low-res input h x w."""
+    x = torch.randn(nb, h, w, cin, device=dev).to(BF)
+    wt = torch.randn(cout, cin, 3, 3, device=dev) * (cin * 9) ** -0.5
+    b = torch.zeros(cout, device=dev)
+    wf, wd = kn.upconv_pack(wt)
+    dy = torch.randn(nb, 2 * h, 2 * w, cout, device=dev).to(BF)
+    fl = 2.0 * nb * (2 * h) * (2 * w) * cin * cout * 4
+    r = dict(k="upconv", nb=nb, hw=h, cin=cin, cout=cout)
+    for name, fn in (("fwd", lambda: kn.upconv_fwd(x, wf, b, cout)), ("dgrad", lambda: kn.upconv_dgrad(dy, wd, cin))):
+        ms = timeit(fn, iters=5, warm=2)
+        r[name + "_ms"] = round(ms, 3); r[name + "_tflops"] = round(fl / ms / 1e9, 1)
+    print(json.dumps(r))
+
+
 def gn(nb, h, w, c):
     x = torch.randn(nb, h, w, c, device=dev).to(BF)
     g, b = torch.ones(c, device=dev), torch.zeros(c, device=dev)
@@ -226,6 +241,13 @@ if __name__ == "__main__":
         for c in [(32, 256, 256, 128, 128, 3, 1), (32, 128, 128, 128, 128, 3, 1), (32, 64, 64, 256, 256, 3, 1), (32, 32, 32, 256, 256, 3, 1),
                   (32, 16, 16, 512, 512, 3, 1), (32, 32, 32, 256, 256, 1, 1), (32, 256, 256, 128, 128, 3, 2), (32, 128, 128, 256, 256, 3, 1)]:
             conv(*c)
+    if "tap" in what:
+        for c in [(32, 64, 64, 256, 256, 3, 1), (32, 32, 32, 256, 256, 3, 1), (32, 16, 16, 512, 512, 3, 1),
+                  (32, 32, 32, 256, 768, 1, 1), (32, 32, 32, 256, 256, 1, 1), (32, 256, 256, 128, 128, 3, 2),
+                  (32, 128, 128, 128, 256, 3, 1), (32, 256, 256, 64, 128, 1, 1)]:
+            conv(*c)
+        for c in [(32, 128, 128, 128, 128), (32, 64, 64, 256, 256), (32, 32, 32, 256, 256), (32, 16, 16, 512, 512)]:
+            upconv(*c)
     if "vqk" in what:
         vqk()
     if "pconv" in what:
