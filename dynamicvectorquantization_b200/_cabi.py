@@ -86,6 +86,7 @@ SIGNATURES = {
     "b2dq_gn_finalize_tiles": [_vp, _vp, _i, _i, _i, _f, _vp],
     "b2dq_colsum_reduce": [_vp, _vp, _i, _i, _vp],
     "b2dq_wgrad_reduce": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "b2dq_wgrad_reduce_bias": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp],
     "b2dq_gn_chunks": [_i, _i],
     "b2dq_gn_stats": [_vp, _vp, _vp, _i, _i, _i, _i, _f, _vp],
     "b2dq_gn_apply": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
@@ -108,6 +109,7 @@ SIGNATURES = {
     "b2dq_add_bf16": [_vp, _vp, _vp, _ll, _vp],
     "b2dq_im2col3x3_small": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
     "b2dq_pack_weights": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "b2dq_pack_weights_multi": [_vp, _i, _ll, _i, _vp],
     "b2dq_lpips_head_chunks": [_i, _i],              # returns a count, not a status
     "b2dq_lpips_head_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _f, _vp],
     "b2dq_lpips_head_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _f, _vp],

@@ -348,6 +348,57 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
   if (dgr) dgr[(static_cast<long long>(ci) * RS + t) * Cout + co] = v;
 }
 
+// The same for MANY weights in one launch (every convolution weight is repacked after each optimizer step: one
+// launch per layer costs more in launch latency than in bytes).  A block owns a tile of 32 output x 32 input channels
+// (all R*S taps) of one weight: it is read in memory order into shared memory and written out so that both packings
+// get 64 B runs (32 consecutive Cin of a tap for fwd, 32 consecutive Cout for dgrad).
+struct PackItem {
+  const float* w;
+  __nv_bfloat16* fwd;
+  __nv_bfloat16* dgr;
+  int cout, cin, rs, tiles_ci;
+  long long tile_start;          // first block of this weight
+};
+constexpr int PK_T = 32;
+constexpr int PK_MAX_RS = 16;
+__global__ void __launch_bounds__(256)
+pack_weights_multi_kernel(const PackItem* __restrict__ items, int n_items) {
+  extern __shared__ float pk_tile[];             // [32 co][32*RS + 1]
+  int lo = 0, hi = n_items - 1;                  // last item with tile_start <= blockIdx.x
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (items[mid].tile_start <= static_cast<long long>(blockIdx.x)) lo = mid; else hi = mid - 1;
+  }
+  const PackItem it = items[lo];
+  const int local = static_cast<int>(blockIdx.x - it.tile_start);
+  const int co0 = (local / it.tiles_ci) * PK_T, ci0 = (local % it.tiles_ci) * PK_T;
+  const int RS = it.rs, row = PK_T * RS, ld = row + 1;
+  const int nco = min(PK_T, it.cout - co0), nci = min(PK_T, it.cin - ci0);
+  // load: for each co of the tile, the nci*RS floats starting at w[(co*Cin + ci0)*RS] are contiguous
+  for (int co = threadIdx.x >> 5; co < nco; co += 8) {
+    const float* src = it.w + (static_cast<long long>(co0 + co) * it.cin + ci0) * RS;
+    for (int j = threadIdx.x & 31; j < nci * RS; j += 32) pk_tile[co * ld + j] = src[j];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  if (it.fwd) {                                  // fwd[(co*RS + t)*Cin + ci]: lane = ci
+    for (int q = wrp; q < nco * RS; q += 8) {
+      const int co = q / RS, t = q - co * RS;
+      if (lane < nci)
+        it.fwd[(static_cast<long long>(co0 + co) * RS + t) * it.cin + ci0 + lane] =
+            __float2bfloat16_rn(pk_tile[co * ld + lane * RS + t]);
+    }
+  }
+  if (it.dgr) {                                  // dgr[(ci*RS + t)*Cout + co]: lane = co
+    for (int q = wrp; q < nci * RS; q += 8) {
+      const int ci = q / RS, t = q - ci * RS;
+      if (lane < nco)
+        it.dgr[(static_cast<long long>(ci0 + ci) * RS + t) * it.cout + co0 + lane] =
+            __float2bfloat16_rn(pk_tile[lane * ld + ci * RS + t]);
+    }
+  }
+}
+
 // 2x2 / stride 2 max pooling, NHWC bf16, one thread per 8 output channels.
 __device__ __forceinline__ void max8(float (&m)[8], const uint4& u) {
   float f[8];
@@ -636,6 +687,22 @@ int b2dq_pack_weights(const float* weight, void* fwd, void* dgrad, int Cout, int
   const long long total = (long long)Cout * Cin * R * S;
   return launch1d(pack_weights_kernel, total, st, weight, reinterpret_cast<__nv_bfloat16*>(fwd),
                   reinterpret_cast<__nv_bfloat16*>(dgrad), Cout, Cin, R * S, total);
+}
+
+// items_dev: device array of n_items records of 6 x int64 {weight ptr, fwd ptr (or 0), dgrad ptr (or 0),
+// Cout | Cin << 32, R*S | tiles_ci << 32, tile_start} with tiles_ci = ceil(Cin / 32), tile_start = running sum of
+// ceil(Cout/32) * tiles_ci; total_tiles = that sum over all items; max_rs = the largest R*S (<= 16).
+int b2dq_pack_weights_multi(const void* items_dev, int n_items, long long total_tiles, int max_rs, cudaStream_t st) {
+  if (n_items <= 0 || total_tiles <= 0) return 0;
+  if (max_rs < 1 || max_rs > PK_MAX_RS || total_tiles > 0x7fffffffll) return -1;
+  static_assert(sizeof(PackItem) == 48, "PackItem must be 6 x 8 bytes");
+  const size_t smem = static_cast<size_t>(PK_T) * (PK_T * max_rs + 1) * sizeof(float);
+  static unsigned long long attr_mask = 0;
+  if (smem > 48 * 1024)
+    if (int e = set_max_smem_once(pack_weights_multi_kernel, 72 * 1024, attr_mask)) return e;
+  pack_weights_multi_kernel<<<(unsigned)total_tiles, 256, smem, st>>>(reinterpret_cast<const PackItem*>(items_dev),
+                                                                      n_items);
+  return (int)cudaGetLastError();
 }
 
 }  // extern "C"

@@ -317,8 +317,20 @@ mmgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 }
 
 // partial[split][tap][co][ci] (fp32)  ->  dW[co][ci][tap] (fp32, OIHW with tap = r*S+s), +=
+// The splits are added in index order (deterministic); eight loads are in flight per thread before the first add.
+// Blocks past the weight range (colsum != null) reduce the per-split column sums of dY into the bias gradient db, so
+// a convolution's weight and bias gradients are finished by ONE launch.
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw,
-                                    int splits, int taps, int cout, int cin, int accumulate) {
+                                    int splits, int taps, int cout, int cin, int accumulate,
+                                    const float* __restrict__ colsum, float* __restrict__ db, int wblocks) {
+  if (static_cast<int>(blockIdx.x) >= wblocks) {
+    const int m = (blockIdx.x - wblocks) * blockDim.x + threadIdx.x;
+    if (m >= cout) return;
+    float a = 0.f;
+    for (int sp = 0; sp < splits; ++sp) a += colsum[static_cast<long long>(sp) * cout + m];
+    db[m] = a;
+    return;
+  }
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long per = static_cast<long long>(taps) * cout * cin;
   if (i >= per) return;
@@ -326,7 +338,15 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
   const int co = static_cast<int>((i / cin) % cout);
   const int t = static_cast<int>(i / (static_cast<long long>(cin) * cout));
   float s = 0.f;
-  for (int sp = 0; sp < splits; ++sp) s += partial[sp * per + i];
+  int sp = 0;
+  for (; sp + 8 <= splits; sp += 8) {
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = __ldcs(partial + (sp + k) * per + i);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += v[k];
+  }
+  for (; sp < splits; ++sp) s += __ldcs(partial + sp * per + i);
   float* o = dw + (static_cast<long long>(co) * cin + ci) * taps + t;
   *o = accumulate ? (*o + s) : s;
 }
@@ -484,8 +504,21 @@ int b2dq_wgrad_reduce(const float* partial, float* dw, int splits, int taps, int
                       int accumulate, cudaStream_t stream) {
   const long long per = (long long)taps * cout * cin;
   if (per <= 0) return 0;
-  wgrad_reduce_kernel<<<(unsigned)((per + 255) / 256), 256, 0, stream>>>(partial, dw, splits, taps,
-                                                                         cout, cin, accumulate);
+  const int wblocks = (int)((per + 255) / 256);
+  wgrad_reduce_kernel<<<(unsigned)wblocks, 256, 0, stream>>>(partial, dw, splits, taps, cout, cin, accumulate,
+                                                            nullptr, nullptr, wblocks);
+  return (int)cudaGetLastError();
+}
+
+// b2dq_wgrad_reduce + b2dq_colsum_reduce(colsum -> db [cout]) in one launch.
+int b2dq_wgrad_reduce_bias(const float* partial, float* dw, int splits, int taps, int cout, int cin,
+                           const float* colsum, float* db, cudaStream_t stream) {
+  const long long per = (long long)taps * cout * cin;
+  if (per <= 0) return 0;
+  if (!colsum || !db) return -1;
+  const int wblocks = (int)((per + 255) / 256);
+  wgrad_reduce_kernel<<<(unsigned)(wblocks + (cout + 255) / 256), 256, 0, stream>>>(partial, dw, splits, taps, cout,
+                                                                                   cin, 0, colsum, db, wblocks);
   return (int)cudaGetLastError();
 }
 

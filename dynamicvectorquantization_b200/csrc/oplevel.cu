@@ -296,9 +296,9 @@ int b2dq_conv2d_wgrad(const b2dq_conv2d_geom* g, const void* x, const void* dy, 
   d.colsum = p.fuse_bias ? colsum : nullptr;
   int rc = b2dq_mmgemm(&d, stream);
   if (rc) return rc;
+  if (p.fuse_bias) return b2dq_wgrad_reduce_bias(partial, dw, p.splits, p.ntaps, g->Cout, g->Cin, colsum, db, stream);
   rc = b2dq_wgrad_reduce(partial, dw, p.splits, p.ntaps, g->Cout, g->Cin, 0, stream);
   if (rc || !want_bias) return rc;
-  if (p.fuse_bias) return b2dq_colsum_reduce(colsum, db, p.splits, g->Cout, stream);
   return b2dq_bias_grad(dy, db, bias_part, (long long)g->N * ho * wo, g->Cout, stream);
 }
 

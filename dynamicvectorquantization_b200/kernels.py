@@ -180,6 +180,12 @@ def pack_weights(w, want_fwd=True, want_dgrad=True):
     return fwd, dgr
 
 
+def pack_weights_multi(table, n_items, total_tiles, max_rs):
+    """table: device int64 [n_items, 6] records (see b2dq_pack_weights_multi); repacks all of them in one launch."""
+    check(_cabi.lib().b2dq_pack_weights_multi(_ptr(table), int(n_items), int(total_tiles), int(max_rs), _stream()),
+          "pack_weights_multi")
+
+
 def conv_fwd(x, wpack, bias, ksize, stride, cout, residual=None, out_f32=False, relu=False):
     """x NHWC bf16; wpack from pack_weight_fwd; stride-2 uses pad (0,1,0,1) like Downsample.
     relu: clamp the output at zero in the epilogue (tap-GEMM path only)."""
@@ -352,16 +358,16 @@ def conv_wgrad(x, dy, ksize, stride, want_bias=False):
            b_strip=USE_WGRAD_STRIP and ksize == 3 and stride == 1 and (kw, kh, kn) == (64, 1, 1),
            colsum=colsum)
     dw = torch.empty(cout, cin, ksize, ksize, dtype=torch.float32, device=x.device)
+    if fuse_bias:                              # weight and bias gradient finished by one reduction launch
+        db = torch.empty(cout, dtype=torch.float32, device=x.device)
+        check(_cabi.lib().b2dq_wgrad_reduce_bias(_ptr(partial), _ptr(dw), splits, ntaps, cout, cin, _ptr(colsum), _ptr(db),
+                                                 _stream()), "wgrad_reduce_bias")
+        return dw, db
     check(_cabi.lib().b2dq_wgrad_reduce(_ptr(partial), _ptr(dw), splits, ntaps, cout, cin, 0, _stream()),
           "wgrad_reduce")
     if not want_bias:
         return dw
-    if fuse_bias:
-        db = torch.empty(cout, dtype=torch.float32, device=x.device)
-        check(_cabi.lib().b2dq_colsum_reduce(_ptr(colsum), _ptr(db), splits, cout, _stream()), "colsum_reduce")
-    else:
-        db = bias_grad(dy)
-    return dw, db
+    return dw, bias_grad(dy)
 
 
 # ------------------------------------------------------------------------------------------ upsample + conv

@@ -188,6 +188,7 @@ class _GrainVQModelBase(_Base):
         return self._decode_nhwc(ops.to_nhwc(quant))
 
     def forward(self, input):
+        ops.prepack(self)                      # all weight packings an optimizer step made stale, in one launch
         quant, diff, _, grain_indices, gate, x_entropy = self._encode_impl(input)
         dec = self._decode_nhwc(quant)
         out = (dec, diff, grain_indices, gate)

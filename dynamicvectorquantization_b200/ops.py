@@ -68,6 +68,55 @@ def _packed(weight, kind):
     return p
 
 
+def prepack(module):
+    """Refresh every stale "fwd" / "dgrad" packing of `module`'s convolution weights in ONE launch
+    (b2dq_pack_weights_multi).  After an optimizer step all of them are stale and the lazy path of `_packed` would
+    repack them one launch per layer; a forward that starts with `prepack(self)` finds them fresh instead.  Only
+    packings the lazy path has created before are refreshed (the cache is the registry), into the same buffers, so the
+    first step and modules called on their own behave exactly as without this call."""
+    todo = []
+    for p in module.parameters():
+        cache = p.__dict__.get("_b2_packs")
+        if not cache or not p.is_cuda or p.dtype != torch.float32 or p.dim() != 4:
+            continue
+        stamp = (p.data_ptr(), p._version, p.device)
+        f, d = cache.get("fwd"), cache.get("dgrad")
+        sf = f is not None and f[0] != stamp and f[0][2] == p.device
+        sd = d is not None and d[0] != stamp and d[0][2] == p.device
+        if sf or sd:
+            todo.append((p, cache, stamp, f[1] if sf else None, d[1] if sd else None))
+    if len(todo) < 2:
+        return 0
+    key = tuple((p.data_ptr(), 0 if f is None else f.data_ptr(), 0 if d is None else d.data_ptr())
+                for p, _, _, f, d in todo)
+    tabs = module.__dict__.setdefault("_b2_pack_tables", {})
+    ent = tabs.get(key)
+    if ent is None:
+        if torch.cuda.is_current_stream_capturing():
+            return 0                                  # the table upload cannot be captured: lazy path this time
+        rows, start, max_rs = [], 0, 1
+        for p, _, _, f, d in todo:
+            co, ci, r, s_ = p.shape
+            rs, tci = r * s_, (ci + 31) // 32
+            if rs > 16:
+                return 0
+            max_rs = max(max_rs, rs)
+            rows.append([key[len(rows)][0], key[len(rows)][1], key[len(rows)][2], co | (ci << 32), rs | (tci << 32), start])
+            start += ((co + 31) // 32) * tci
+        ent = (torch.tensor(rows, dtype=torch.int64).to(todo[0][0].device), start, max_rs)
+        if len(tabs) >= 4:                            # e.g. autoencoder / discriminator weights in alternation
+            tabs.clear()
+        tabs[key] = ent
+    table, total, max_rs = ent
+    kn.pack_weights_multi(table, len(todo), total, max_rs)
+    for p, cache, stamp, f, d in todo:
+        if f is not None:
+            cache["fwd"] = (stamp, f)
+        if d is not None:
+            cache["dgrad"] = (stamp, d)
+    return len(todo)
+
+
 def invalidate_caches(module):
     """Drop every derived bf16 copy (GEMM weight packings, VQ search codebook + norms) held for `module`'s
     parameters.  The caches are validated by (data_ptr, tensor._version), and a write THROUGH `.data`
@@ -77,6 +126,7 @@ def invalidate_caches(module):
     for p in module.parameters():
         p.__dict__.pop("_b2_packs", None)
     for m in module.modules():
+        m.__dict__.pop("_b2_pack_tables", None)
         if hasattr(m, "_cb_key"):
             m._cb_key = None
 
@@ -370,6 +420,12 @@ def _packed_cat(weights, kind):
     ent = cache.get("cat_" + kind)
     if ent is not None and ent[0] == stamp:
         return ent[1]
+    if head.is_cuda and head.dtype == torch.float32 and all(w.shape[2:] == (1, 1) for w in weights):
+        # one concatenation + ONE packing launch give both layouts of the stacked weight: [sum Cout, Cin] and its
+        # transpose [Cin, sum Cout] (= the per-weight data-gradient packings side by side)
+        fwd, dgr = kn.pack_weights(torch.cat([w.detach() for w in weights], dim=0))
+        cache["cat_fwd"], cache["cat_dgrad"] = (stamp, fwd), (stamp, dgr)
+        return fwd if kind == "fwd" else dgr
     parts = [kn.pack_weight_fwd(w) if kind == "fwd" else kn.pack_weight_dgrad(w) for w in weights]
     p = torch.cat(parts, dim=0 if kind == "fwd" else 1).contiguous()
     cache["cat_" + kind] = (stamp, p)

@@ -157,6 +157,9 @@ int b2dq_colsum_reduce(const float* part, float* out, int splits, int M, cudaStr
 /* partial [splits][taps][cout][cin] fp32 -> dw [cout][cin][taps] fp32 (OIHW); accumulate != 0: += */
 int b2dq_wgrad_reduce(const float* partial, float* dw, int splits, int taps, int cout, int cin,
                       int accumulate, cudaStream_t stream);
+/* the same plus the bias gradient db[cout] = sum_splits colsum[split][cout] (b2dq_colsum_reduce) in one launch */
+int b2dq_wgrad_reduce_bias(const float* partial, float* dw, int splits, int taps, int cout, int cin,
+                           const float* colsum, float* db, cudaStream_t stream);
 
 /* Perceptual-loss feature stack (modules/losses/lpips.py:78-113, torchvision VGG16): 2x2/2 max pooling of
  * NHWC bf16 [N,H,W,C] (H, W even, C % 8 == 0) and its gradient (first maximum in window scan order gets
@@ -186,6 +189,13 @@ int b2dq_lpips_head_bwd(const void* f0_bf16, const void* f1_bf16, const float* w
  * fwd [Cout, R*S*Cin] and/or dgrad [Cin, R*S*Cout] in one pass (null = skip that packing). */
 int b2dq_pack_weights(const float* weight, void* fwd, void* dgrad, int Cout, int Cin, int R, int S,
                       cudaStream_t stream);
+/* The same for many weights in one launch (all convolution weights are repacked after every optimizer step).
+ * items_dev: device array of n_items records of six 64-bit words {weight pointer, fwd pointer or 0, dgrad pointer
+ * or 0, Cout | Cin << 32, R*S | tiles_ci << 32, tile_start} with tiles_ci = ceil(Cin / 32) and tile_start the running
+ * sum of ceil(Cout / 32) * tiles_ci over the preceding records; total_tiles = that sum over all records;
+ * max_rs = the largest R*S among them (<= 16). */
+int b2dq_pack_weights_multi(const void* items_dev, int n_items, long long total_tiles, int max_rs,
+                            cudaStream_t stream);
 
 /* out[c] = sum_rows dy[row][c]; deterministic two-stage sum, part = b2dq_bias_grad_blocks(rows)*C floats */
 int b2dq_bias_grad_blocks(long long rows);

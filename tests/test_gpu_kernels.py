@@ -566,3 +566,40 @@ def test_folded_upsample_conv_matches_upsample_then_conv(nb, h, w, cin, cout):
     y2 = ops.Conv2dFn.apply(ops.Upsample2xFn.apply(x2), w2, b.cuda(), None, 3, 1)
     y2.backward(dy.cuda())
     assert rel_rms(y, y2) < 1e-2 and rel_rms(xd.grad, x2.grad) < 1.5e-2 and rel_rms(wd.grad, w2.grad) < 1e-2
+
+
+def test_prepack_refreshes_all_stale_weight_packings_in_one_launch():
+    """ops.prepack (b2dq_pack_weights_multi) against the per-weight packings, incl. ragged channel counts and 4x4 taps."""
+    from dynamicvectorquantization_b200 import kernels as kn, ops
+    dev = "cuda"
+    g = torch.Generator().manual_seed(11)
+
+    class Holder(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.ws = torch.nn.ParameterList([torch.nn.Parameter(torch.randn(*sh, generator=g)) for sh in
+                                              ((128, 64, 3, 3), (256, 128, 1, 1), (3, 128, 3, 3), (64, 96, 4, 4), (40, 72, 3, 3))])
+
+    m = Holder().to(dev)
+    assert ops.prepack(m) == 0                       # nothing cached yet: the lazy path owns the first step
+    first = [(ops._packed(w, "fwd"), ops._packed(w, "dgrad")) for w in m.ws]
+    assert ops.prepack(m) == 0                       # everything fresh
+    with torch.no_grad():
+        for w in m.ws:
+            w.mul_(0.5).add_(0.25)                   # an optimizer step: bumps the version counters
+    assert ops.prepack(m) == len(m.ws)
+    before = kn.launch_count()
+    for w, (f0, d0) in zip(m.ws, first):
+        f, d = ops._packed(w, "fwd"), ops._packed(w, "dgrad")
+        assert f.data_ptr() == f0.data_ptr() and d.data_ptr() == d0.data_ptr()      # refreshed in place
+        assert torch.equal(f, kn.pack_weight_fwd(w)) and torch.equal(d, kn.pack_weight_dgrad(w))
+    assert kn.launch_count() == before               # all cache hits
+    # only one packing cached for a weight: only that one is refreshed
+    w = m.ws[0]
+    w.__dict__["_b2_packs"].pop("dgrad")
+    with torch.no_grad():
+        for q in m.ws:
+            q.add_(1.0)
+    assert ops.prepack(m) == len(m.ws)
+    assert "dgrad" not in w.__dict__["_b2_packs"]
+    assert torch.equal(ops._packed(w, "fwd"), kn.pack_weight_fwd(w))

@@ -21,9 +21,9 @@ if not REAL:
     for p in model.loss.parameters():
         p.requires_grad_(False)
 else:
-    opt_d = torch.optim.Adam(model.loss.discriminator.parameters(), lr=1e-4, betas=(0.5, 0.9))
+    opt_d = torch.optim.Adam(model.loss.discriminator.parameters(), lr=1e-4, betas=(0.5, 0.9), fused=True)
 params = [p for n, p in model.named_parameters() if not n.startswith("loss.") and p.requires_grad]
-opt = torch.optim.Adam(params, lr=1e-4, betas=(0.5, 0.9))
+opt = torch.optim.Adam(params, lr=1e-4, betas=(0.5, 0.9), fused=True)   # as bench.py
 x = torch.rand(B, 3, 256, 256, device="cuda") * 2 - 1
 
 
