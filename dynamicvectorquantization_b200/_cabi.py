@@ -110,6 +110,8 @@ SIGNATURES = {
     "b2dq_im2col3x3_small": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
     "b2dq_pack_weights": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "b2dq_pack_weights_multi": [_vp, _i, _ll, _i, _vp],
+    "b2dq_upconv_pack": [_vp, _vp, _vp, _i, _i, _vp],
+    "b2dq_upconv_wgrad_reduce": [_vp, _vp, _i, _i, _i, _vp],
     "b2dq_lpips_head_chunks": [_i, _i],              # returns a count, not a status
     "b2dq_lpips_head_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _f, _vp],
     "b2dq_lpips_head_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _f, _vp],

@@ -399,6 +399,66 @@ pack_weights_multi_kernel(const PackItem* __restrict__ items, int n_items) {
   }
 }
 
+// ---------------------------------------------------------------- nearest x2 + 3x3 convolution, folded
+// Upsample.forward (modules/diffusionmodules/model.py:49-53) as four 2x2 convolutions of the low-resolution input,
+// one per output parity class (ph, pw).  Filter row r lands on low-resolution row slot a of parity ph when
+// r is in ROWS(ph, a): (0,0) -> {0}, (0,1) -> {1,2}, (1,0) -> {0,1}, (1,1) -> {2}; the same table serves the columns.
+__device__ __forceinline__ void up_range(int parity, int slot, int& lo, int& hi) {
+  lo = (parity == 0) ? (slot == 0 ? 0 : 1) : (slot == 0 ? 0 : 2);
+  hi = (parity == 0) ? (slot == 0 ? 0 : 2) : (slot == 0 ? 1 : 2);
+}
+// w fp32 [Cout][Cin][3][3] -> fwd bf16 [Cout][16*Cin] and dgr bf16 [Cin][16*Cout], column block ((ph*2+pw)*2+a)*2+b:
+// folded weight = sum of the 3x3 taps that land on slot (a, b) of class (ph, pw), summed in (r, s) order in fp32.
+__global__ void upconv_pack_kernel(const float* __restrict__ w, __nv_bfloat16* fwd, __nv_bfloat16* dgr, int Cout,
+                                   int Cin) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(Cout) * Cin) return;
+  const int ci = static_cast<int>(i % Cin), co = static_cast<int>(i / Cin);
+  float k[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) k[t] = w[i * 9 + t];
+#pragma unroll
+  for (int blk = 0; blk < 16; ++blk) {
+    const int ph = blk >> 3, pw = (blk >> 2) & 1, a = (blk >> 1) & 1, b = blk & 1;
+    int r0, r1, s0, s1;
+    up_range(ph, a, r0, r1);
+    up_range(pw, b, s0, s1);
+    float v = 0.f;
+    for (int r = r0; r <= r1; ++r)
+      for (int s_ = s0; s_ <= s1; ++s_) v += k[r * 3 + s_];
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    if (fwd) fwd[(static_cast<long long>(co) * 16 + blk) * Cin + ci] = h;
+    if (dgr) dgr[(static_cast<long long>(ci) * 16 + blk) * Cout + co] = h;
+  }
+}
+// partial fp32 [4 classes][splits][4 slots (a*2+b)][Cout][Cin] (split-K partial weight gradients of the four class
+// GEMMs) -> dw fp32 [Cout][Cin][3][3]: splits added in index order, then every class/slot sum is scattered onto the
+// 3x3 taps it was folded from (the transpose of the fold above).
+__global__ void upconv_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int splits,
+                                           int Cout, int Cin) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long per = static_cast<long long>(Cout) * Cin;
+  if (i >= per) return;
+  float acc[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) acc[t] = 0.f;
+#pragma unroll
+  for (int blk = 0; blk < 16; ++blk) {
+    const int cls = blk >> 2, slot = blk & 3;
+    const float* src = partial + (static_cast<long long>(cls) * splits * 4 + slot) * per + i;
+    float v = 0.f;
+    for (int sp = 0; sp < splits; ++sp) v += __ldcs(src + static_cast<long long>(sp) * 4 * per);
+    const int ph = cls >> 1, pw = cls & 1, a = slot >> 1, b = slot & 1;
+    int r0, r1, s0, s1;
+    up_range(ph, a, r0, r1);
+    up_range(pw, b, s0, s1);
+    for (int r = r0; r <= r1; ++r)
+      for (int s_ = s0; s_ <= s1; ++s_) acc[r * 3 + s_] += v;
+  }
+#pragma unroll
+  for (int t = 0; t < 9; ++t) dw[i * 9 + t] = acc[t];
+}
+
 // 2x2 / stride 2 max pooling, NHWC bf16, one thread per 8 output channels.
 __device__ __forceinline__ void max8(float (&m)[8], const uint4& u) {
   float f[8];
@@ -687,6 +747,16 @@ int b2dq_pack_weights(const float* weight, void* fwd, void* dgrad, int Cout, int
   const long long total = (long long)Cout * Cin * R * S;
   return launch1d(pack_weights_kernel, total, st, weight, reinterpret_cast<__nv_bfloat16*>(fwd),
                   reinterpret_cast<__nv_bfloat16*>(dgrad), Cout, Cin, R * S, total);
+}
+
+int b2dq_upconv_pack(const float* weight, void* fwd, void* dgrad, int Cout, int Cin, cudaStream_t st) {
+  if (Cout <= 0 || Cin <= 0) return -1;
+  return launch1d(upconv_pack_kernel, (long long)Cout * Cin, st, weight, reinterpret_cast<__nv_bfloat16*>(fwd),
+                  reinterpret_cast<__nv_bfloat16*>(dgrad), Cout, Cin);
+}
+int b2dq_upconv_wgrad_reduce(const float* partial, float* dw, int splits, int Cout, int Cin, cudaStream_t st) {
+  if (Cout <= 0 || Cin <= 0 || splits <= 0) return -1;
+  return launch1d(upconv_wgrad_reduce_kernel, (long long)Cout * Cin, st, partial, dw, splits, Cout, Cin);
 }
 
 // items_dev: device array of n_items records of 6 x int64 {weight ptr, fwd ptr (or 0), dgrad ptr (or 0),

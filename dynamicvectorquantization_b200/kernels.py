@@ -405,8 +405,14 @@ def upconv_unfold_grad(dwf):
 
 def upconv_pack(w):
     """-> (fwd [Cout, 16*Cin], dgrad [Cin, 16*Cout]) bf16; column block ((ph*2+pw)*2+a)*2+b."""
-    wf = upconv_fold(w.detach().float())
     co, ci = w.shape[0], w.shape[1]
+    if w.is_cuda and w.dtype == torch.float32:          # fold + both packings in one launch
+        w = w.detach().contiguous()
+        fwd = torch.empty(co, 16 * ci, dtype=BF16, device=w.device)
+        dgr = torch.empty(ci, 16 * co, dtype=BF16, device=w.device)
+        check(_cabi.lib().b2dq_upconv_pack(_ptr(w), _ptr(fwd), _ptr(dgr), co, ci, _stream()), "upconv_pack")
+        return fwd, dgr
+    wf = upconv_fold(w.detach().float())
     fwd = wf.permute(4, 0, 1, 2, 3, 5).reshape(co, 16 * ci).to(BF16).contiguous()
     dgr = wf.permute(5, 0, 1, 2, 3, 4).reshape(ci, 16 * co).to(BF16).contiguous()
     return fwd, dgr
@@ -449,6 +455,9 @@ def upconv_dgrad(dy, wpack_dgrad, cin):
     return dx
 
 
+UPCONV_WGRAD_TAPS_PER_CTA = int(_os.environ.get("B2DQ_UPCONV_WGRAD_TPC", "1"))   # slots of a class sharing one dY tile per CTA
+
+
 def upconv_wgrad(x, dy, want_bias=False):
     """dW (fp32 OIHW [Cout,Cin,3,3]) [+ db] of conv3x3(upsample2x(x)): per parity class a 4-tap weight-gradient
     GEMM of the strided class view of dy against the low-resolution x, unfolded onto the nine filter taps."""
@@ -459,21 +468,22 @@ def upconv_wgrad(x, dy, want_bias=False):
     ktw, kth = (w + kw - 1) // kw, (h + kh - 1) // kh
     kblocks = ktw * kth * ((nb + kn - 1) // kn)
     mt, nt = (cout + 127) // 128, (cin + 127) // 128
-    splits = _wgrad_splits(kblocks, mt * nt * 4)
+    splits = _wgrad_splits(kblocks, mt * nt * -(-4 // UPCONV_WGRAD_TAPS_PER_CTA))
     dy6 = dy.view(nb, h, 2, w, 2, cout)
-    dwf = torch.empty(2, 2, 2, 2, cout, cin, dtype=torch.float32, device=x.device)
+    partial = torch.empty(4, splits, 4, cout, cin, dtype=torch.float32, device=x.device)
     for ph in (0, 1):
         for pw in (0, 1):
             dyc = dy6[:, :, ph, :, pw, :]                     # [N,H,W,Cout] view, pixel stride 2*Cout
             adims = (cout, w, 1, h, nb)
             astrs = (1, 2 * cout, 2 * w * cout, 4 * w * cout, 4 * h * w * cout)
             taps = [(0, _UP_OFF[pw][b], 0, _UP_OFF[ph][a]) for a in (0, 1) for b in (0, 1)]
-            partial = torch.empty(splits, 4, cout, cin, dtype=torch.float32, device=x.device)
-            mmgemm(dyc, adims, astrs, True, x, bdims, bstrs, True, cout, cin, kblocks, partial,
+            mmgemm(dyc, adims, astrs, True, x, bdims, bstrs, True, cout, cin, kblocks, partial[ph * 2 + pw],
                    (4 * cout * cin, cout * cin, cin), taps=taps, kbox=(kw, kh, kn), ktiles=(ktw, kth), splits=splits,
-                   out_f32=True, block_n=128, taps_per_cta=1)
-            dwf[ph, pw] = partial.sum(0).view(2, 2, cout, cin)
-    dw = upconv_unfold_grad(dwf)
+                   out_f32=True, block_n=128, taps_per_cta=UPCONV_WGRAD_TAPS_PER_CTA)
+    # splits summed and the 16 class/slot gradients scattered back onto the nine filter taps in one launch
+    dw = torch.empty(cout, cin, 3, 3, dtype=torch.float32, device=x.device)
+    check(_cabi.lib().b2dq_upconv_wgrad_reduce(_ptr(partial), _ptr(dw), splits, cout, cin, _stream()),
+          "upconv_wgrad_reduce")
     return (dw, bias_grad(dy)) if want_bias else dw
 
 

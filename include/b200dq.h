@@ -189,6 +189,14 @@ int b2dq_lpips_head_bwd(const void* f0_bf16, const void* f1_bf16, const float* w
  * fwd [Cout, R*S*Cin] and/or dgrad [Cin, R*S*Cout] in one pass (null = skip that packing). */
 int b2dq_pack_weights(const float* weight, void* fwd, void* dgrad, int Cout, int Cin, int R, int S,
                       cudaStream_t stream);
+/* Nearest x2 + 3x3 convolution (Upsample.forward, model.py:49-53) folded into four 2x2 convolutions of the
+ * low-resolution input, one per output parity class (ph, pw): weight [Cout,Cin,3,3] fp32 -> fwd [Cout, 16*Cin] and
+ * dgrad [Cin, 16*Cout] bf16 (null = skip), column block ((ph*2+pw)*2+a)*2+b holds the sum of the taps that land on
+ * low-resolution slot (a, b) of that class.  b2dq_upconv_wgrad_reduce is the transpose for the weight gradient:
+ * partial fp32 [4 classes][splits][4 slots][Cout][Cin] (the split-K partials of the four class GEMMs) ->
+ * dw [Cout,Cin,3,3] fp32, splits added in index order. */
+int b2dq_upconv_pack(const float* weight, void* fwd, void* dgrad, int Cout, int Cin, cudaStream_t stream);
+int b2dq_upconv_wgrad_reduce(const float* partial, float* dw, int splits, int Cout, int Cin, cudaStream_t stream);
 /* The same for many weights in one launch (all convolution weights are repacked after every optimizer step).
  * items_dev: device array of n_items records of six 64-bit words {weight pointer, fwd pointer or 0, dgrad pointer
  * or 0, Cout | Cin << 32, R*S | tiles_ci << 32, tile_start} with tiles_ci = ceil(Cin / 32) and tile_start the running

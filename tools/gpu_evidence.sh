@@ -3,7 +3,7 @@
 # usage: bash tools/gpu_evidence.sh <tag>
 tag=${1:-r02}
 mkdir -p gpurun_out
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"pconv|tapgemm|mmgemm|vq_search|gn_bwd_fused|gn_fwd_fused" -s 6 -c 6 -o gpurun_out/${tag}_kernels -f python tools/ncu_kernels.py > gpurun_out/${tag}_ncu.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"pconv|tapgemm|mmgemm|vq_search|gn_bwd_fused|gn_fwd_fused" -s 11 -c 11 -o gpurun_out/${tag}_kernels -f python tools/ncu_kernels.py > gpurun_out/${tag}_ncu.log 2>&1
 tail -2 gpurun_out/${tag}_ncu.log
 bash tools/gpu_suite.sh ${tag}
 bash tools/launch_list.sh real > gpurun_out/${tag}_launch_real.txt 2>&1
