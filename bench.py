@@ -385,7 +385,7 @@ def run_b200(args):
 
     def fwd_bwd(x):
         if ex is not None:
-            ex.begin_step()                      # gradients stay views into one flat buffer, zeroed here
+            ex.begin_step()                      # gradients dropped: the backward assigns, the exchange gathers them
         else:
             opt.zero_grad(set_to_none=True)
         xrec, qloss, indices, gate = net(x)[:4]
