@@ -53,6 +53,15 @@ _lib = None
 _vp, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 
 # name -> argtypes (restype is always int status).  Mirrors include/b200dq.h.
+class PconvTapsDesc(C.Structure):
+    _fields_ = [
+        ("a_ptr", C.c_void_p), ("a_dims", C.c_longlong * 5), ("a_strides", C.c_longlong * 5),
+        ("b_ptr", C.c_void_p), ("b_k", C.c_longlong), ("kchunks", C.c_int), ("nr", C.c_int), ("ns", C.c_int),
+        ("row_c", C.c_int * 9), ("row_p", C.c_int * 9), ("row_dh", C.c_int * 9), ("col_dw", C.c_int * 3),
+        ("wcol", C.c_int * 27), ("NB", C.c_int), ("H", C.c_int), ("W", C.c_int),
+        ("out", C.c_void_p), ("oN", C.c_longlong), ("oH", C.c_longlong), ("oW", C.c_longlong), ("bias", C.c_void_p)]
+
+
 class Conv2dGeom(C.Structure):
     _fields_ = [("N", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cin", C.c_int), ("Cout", C.c_int),
                 ("ksize", C.c_int), ("stride", C.c_int)]
@@ -110,6 +119,7 @@ SIGNATURES = {
     "b2dq_im2col3x3_small": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
     "b2dq_pack_weights": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "b2dq_pack_weights_multi": [_vp, _i, _ll, _i, _vp],
+    "b2dq_pconv_taps": [_vp, _i, _vp],
     "b2dq_upconv_pack": [_vp, _vp, _vp, _i, _i, _vp],
     "b2dq_upconv_wgrad_reduce": [_vp, _vp, _i, _i, _i, _vp],
     "b2dq_lpips_head_chunks": [_i, _i],              # returns a count, not a status

@@ -234,8 +234,29 @@ int b2dq_conv2d_dgrad(const b2dq_conv2d_geom* g, const void* dy, const void* wpa
   d.Wout = wo; d.Hout = ho;
   d.oN = (long long)g->H * g->W * cin; d.oH = 2ll * g->W * cin; d.oW = 2 * cin;
   d.block_n = pick_block_n((long long)ceil_div(wo, d.TW) * ceil_div(ho, d.TH) * ceil_div(g->N, d.TN), cin);
+  // wide 128-channel outputs: the persistent strip kernel (one strip serves a class's column taps)
+  const bool strips = cin == 128 && wo % 128 == 0 && cout % 64 == 0 && (long long)g->N * ho * (wo / 128) >= 2 * kSMs;
   for (int ph = 0; ph < 2; ++ph)
     for (int pw = 0; pw < 2; ++pw) {
+      if (strips) {
+        b2dq_pconv_taps_desc q;
+        std::memset(&q, 0, sizeof(q));
+        q.a_ptr = dy;
+        nhwc_view(g->N, ho, wo, cout, q.a_dims, q.a_strides);
+        q.b_ptr = wpack_dgrad; q.b_k = 9ll * cout; q.kchunks = cout / 64;
+        q.nr = nsel[ph]; q.ns = nsel[pw];
+        for (int a = 0; a < q.nr; ++a) {
+          q.row_dh[a] = sel[ph][a][1];
+          for (int b = 0; b < q.ns; ++b) q.wcol[a * 3 + b] = (sel[ph][a][0] * 3 + sel[pw][b][0]) * cout;
+        }
+        for (int b = 0; b < q.ns; ++b) q.col_dw[b] = sel[pw][b][1];
+        q.NB = g->N; q.H = ho; q.W = wo;
+        q.out = static_cast<char*>(dx) + 2ll * ((long long)(ph * g->W + pw) * cin);
+        q.oN = d.oN; q.oH = d.oH; q.oW = d.oW;
+        const int rc = b2dq_pconv_taps(&q, 0, stream);
+        if (rc) return rc;
+        continue;
+      }
       int t = 0;
       for (int a = 0; a < nsel[ph]; ++a)
         for (int b = 0; b < nsel[pw]; ++b, ++t) {

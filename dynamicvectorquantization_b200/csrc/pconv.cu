@@ -22,6 +22,7 @@
 //     two units ahead, added in place).  Three 16 KB staging buffers rotate.
 // Per pipeline stage: 2 strips (2 x 16.6 KB) + 3 weight tiles (3 x 16 KB) feed 24 MMAs
 // (128x128x16) = 1536 tensor cycles -> 53 B/cycle/SM instead of 128.
+#include <cstring>
 #include "common.cuh"
 #include "tmap.h"
 
@@ -39,11 +40,16 @@ constexpr uint32_t PC_OUT_BUFS = 3;                                // staging bu
 constexpr uint32_t PC_OUT_BYTES = 128 * 128;                       // 128 pixels x 64 channels bf16
 constexpr uint32_t PC_SMEM = PC_STAGES * PC_STAGE_BYTES + PC_OUT_BUFS * PC_OUT_BYTES + 1024 + 256 + 2048;
 
+constexpr int PC_MAX_ROWS = 9;
 struct PconvParams {
-  int kchunks;                 // Cin / 64
-  int cin;                     // weight column stride between taps
-  int row_dh[3];               // input row offset of filter row r
-  int col_off[3];              // strip row (pixel) offset of filter column s: 0..2
+  int kchunks;                 // channels per tap / 64
+  int nr;                      // row taps: strips loaded per 64-channel chunk (3 filter rows for the 3x3 layers)
+  int row_c[PC_MAX_ROWS];      // A-map coordinates of row tap r: channel base, parity plane, row offset
+  int row_p[PC_MAX_ROWS];
+  int row_dh[PC_MAX_ROWS];
+  int strip_dw;                // the strip of an output tile starts at pixel ow0 + strip_dw
+  int col_off[3];              // strip row (pixel) offset of column tap s: 0..2
+  int wcol[PC_MAX_ROWS * 3];   // weight column base of tap (r, s)
   int tiles_w, H, NB, W;       // tiles per image row, image height, images, width
   int num_tiles;               // NB * H * tiles_w
   int Cout;
@@ -53,6 +59,9 @@ struct PconvParams {
                                // OUTPUT per GroupNorm group of 4 channels (statistics for the next GroupNorm)
 };
 
+// NS = column taps served by one strip (3 for the 3x3 layers; 2 / 1 for the parity classes of the folded
+// up-convolution and of the stride-2 data gradient, b2dq_pconv_taps).
+template <int NS>
 __global__ void __launch_bounds__(192, 1)
 pconv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
@@ -70,7 +79,7 @@ pconv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_items = (p.num_tiles + PC_MT - 1) / PC_MT;
-  const int kiters = 3 * p.kchunks;
+  const int kiters = p.nr * p.kchunks;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < PC_STAGES; ++i) {
@@ -111,19 +120,19 @@ pconv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         int ow0[PC_MT], oh[PC_MT], n[PC_MT];
 #pragma unroll
         for (int j = 0; j < PC_MT; ++j) tile_coords(item * PC_MT + j, ow0[j], oh[j], n[j]);
-        for (int r = 0; r < 3; ++r)
+        for (int r = 0; r < p.nr; ++r)
           for (int kc = 0; kc < p.kchunks; ++kc) {
             mbar_wait(bar_empty + 8 * stage, phase ^ 1);
             const uint32_t sa = base + stage * PC_STAGE_BYTES;
             const uint32_t fb = bar_full + 8 * stage;
-            mbar_arrive_expect_tx(fb, PC_MT * PC_STRIP_BYTES + 3 * PC_B_BYTES);
+            mbar_arrive_expect_tx(fb, PC_MT * PC_STRIP_BYTES + NS * PC_B_BYTES);
 #pragma unroll
             for (int j = 0; j < PC_MT; ++j)
-              tma_load_5d(sa + j * PC_STRIP_SLOT, &tmA, fb, kc * 64, ow0[j] - 1, 0, oh[j] + p.row_dh[r], n[j]);
+              tma_load_5d(sa + j * PC_STRIP_SLOT, &tmA, fb, p.row_c[r] + kc * 64, ow0[j] + p.strip_dw, p.row_p[r],
+                          oh[j] + p.row_dh[r], n[j]);
 #pragma unroll
-            for (int s = 0; s < 3; ++s)
-              tma_load_2d(sa + PC_MT * PC_STRIP_SLOT + s * PC_B_BYTES, &tmB, fb,
-                          (r * 3 + s) * p.cin + kc * 64, 0);
+            for (int s = 0; s < NS; ++s)
+              tma_load_2d(sa + PC_MT * PC_STRIP_SLOT + s * PC_B_BYTES, &tmB, fb, p.wcol[r * 3 + s] + kc * 64, 0);
             if (++stage == PC_STAGES) { stage = 0; phase ^= 1; }
           }
       }
@@ -143,7 +152,7 @@ pconv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
           for (int j = 0; j < PC_MT; ++j) {
 #pragma unroll
-            for (int s = 0; s < 3; ++s) {
+            for (int s = 0; s < NS; ++s) {
               const uint32_t a0 = sa + j * PC_STRIP_SLOT + p.col_off[s] * 128;
               const uint32_t b0 = sa + PC_MT * PC_STRIP_SLOT + s * PC_B_BYTES;
 #pragma unroll
@@ -355,12 +364,14 @@ int b2dq_pconv3x3(const void* a_ptr, const void* b_ptr, void* out, const float* 
     if (r) return r - 3000;
   }
   static unsigned long long attr_mask = 0;
-  if (int e = set_max_smem_once(pconv3x3_kernel, PC_SMEM, attr_mask)) return e;
+  if (int e = set_max_smem_once(pconv3x3_kernel<3>, PC_SMEM, attr_mask)) return e;
   PconvParams p;
-  p.kchunks = Cin / 64; p.cin = Cin;
+  memset(&p, 0, sizeof(p));
+  p.kchunks = Cin / 64; p.nr = 3; p.strip_dw = -1;
   for (int i = 0; i < 3; ++i) {
     p.row_dh[i] = dgrad ? 1 - i : i - 1;
     p.col_off[i] = dgrad ? 2 - i : i;
+    for (int s = 0; s < 3; ++s) p.wcol[i * 3 + s] = (i * 3 + s) * Cin;
   }
   p.tiles_w = W / 128; p.H = H; p.NB = NB; p.W = W;
   p.num_tiles = NB * H * p.tiles_w;
@@ -372,7 +383,93 @@ int b2dq_pconv3x3(const void* a_ptr, const void* b_ptr, void* out, const float* 
   if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
   const int items = (p.num_tiles + PC_MT - 1) / PC_MT;
   if (items < grid) grid = items;
-  pconv3x3_kernel<<<grid, 192, PC_SMEM, stream>>>(tmA, tmB, tmO, tmR, p);
+  pconv3x3_kernel<3><<<grid, 192, PC_SMEM, stream>>>(tmA, tmB, tmO, tmR, p);
+  return (int)cudaGetLastError();
+}
+
+// The same persistent kernel for any group of taps that can be read from row strips: `nr` row taps (A-map channel
+// base / parity plane / row offset each) x `ns` column taps (pixel offsets col_dw[s], at most 2 apart) - the 2x2
+// parity classes of the folded up-convolution and of the stride-2 data gradient, whose four-tap K loop is too short
+// for the one-shot tap GEMM (36 % tensor pipe: prologue and epilogue are not overlapped there).
+struct b2dq_pconv_taps_desc {
+  const void* a_ptr;
+  long long a_dims[5];
+  long long a_strides[5];     // (c, w, p, h, n) view of the input, elements
+  const void* b_ptr;          // [128][b_k] bf16
+  long long b_k;
+  int kchunks;                // channels per tap / 64
+  int nr, ns;                 // row taps (<= 9), column taps (1..3)
+  int row_c[9], row_p[9], row_dh[9];
+  int col_dw[3];              // pixel offset of column tap s (max - min <= 2)
+  int wcol[27];               // weight column base of tap (r, s) at [r*3 + s]
+  int NB, H, W;               // output tile grid: NB images x H rows x W pixels, W % 128 == 0
+  void* out;                  // bf16, pixel (n, h, w) at out + n*oN + h*oH + w*oW, 128 channels
+  long long oN, oH, oW;
+  const float* bias;
+};
+
+int b2dq_pconv_taps(const b2dq_pconv_taps_desc* d, int max_ctas, cudaStream_t stream) {
+  if (!d || d->nr < 1 || d->nr > PC_MAX_ROWS || d->ns < 1 || d->ns > 3 || d->kchunks < 1) return -1;
+  if (d->NB <= 0 || d->H <= 0 || d->W <= 0) return 0;
+  if (d->W % 128 != 0) return -1;
+  int dw_min = d->col_dw[0], dw_max = d->col_dw[0];
+  for (int s = 1; s < d->ns; ++s) {
+    dw_min = d->col_dw[s] < dw_min ? d->col_dw[s] : dw_min;
+    dw_max = d->col_dw[s] > dw_max ? d->col_dw[s] : dw_max;
+  }
+  if (dw_max - dw_min > 2) return -1;
+  if (d->oW % 8 || d->oH % 8 || d->oN % 8 || (reinterpret_cast<uintptr_t>(d->out) & 15)) return -1;
+  CUtensorMap tmA, tmB, tmO;
+  {
+    uint64_t dims[5], str[5];
+    for (int i = 0; i < 5; ++i) { dims[i] = (uint64_t)d->a_dims[i]; str[i] = (uint64_t)d->a_strides[i]; }
+    uint32_t box[5] = {64, PC_STRIP_ROWS, 1, 1, 1};
+    int r = make_tmap_bf16(&tmA, d->a_ptr, 5, dims, str, box);
+    if (r) return r;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)d->b_k, (uint64_t)PC_BN};
+    uint64_t str[2] = {1, (uint64_t)d->b_k};
+    uint32_t box[2] = {64, PC_BN};
+    int r = make_tmap_bf16(&tmB, d->b_ptr, 2, dims, str, box);
+    if (r) return r - 1000;
+  }
+  {
+    uint64_t dims[5] = {(uint64_t)PC_BN, (uint64_t)d->W, 1, (uint64_t)d->H, (uint64_t)d->NB};
+    uint64_t str[5] = {1, (uint64_t)d->oW, (uint64_t)d->oH, (uint64_t)d->oH, (uint64_t)d->oN};
+    uint32_t box[5] = {64, 128, 1, 1, 1};
+    int r = make_tmap_bf16(&tmO, d->out, 5, dims, str, box);
+    if (r) return r - 2000;
+  }
+  PconvParams p;
+  memset(&p, 0, sizeof(p));
+  p.kchunks = d->kchunks; p.nr = d->nr; p.strip_dw = dw_min;
+  for (int r = 0; r < d->nr; ++r) {
+    p.row_c[r] = d->row_c[r]; p.row_p[r] = d->row_p[r]; p.row_dh[r] = d->row_dh[r];
+    for (int s = 0; s < d->ns; ++s) p.wcol[r * 3 + s] = d->wcol[r * 3 + s];
+  }
+  for (int s = 0; s < d->ns; ++s) p.col_off[s] = d->col_dw[s] - dw_min;
+  p.tiles_w = d->W / 128; p.H = d->H; p.NB = d->NB; p.W = d->W;
+  p.num_tiles = d->NB * d->H * p.tiles_w;
+  p.Cout = PC_BN;
+  p.bias = d->bias;
+  p.has_residual = 0;
+  p.gn_part = nullptr;
+  int grid = device_sm_count();
+  if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
+  const int items = (p.num_tiles + PC_MT - 1) / PC_MT;
+  if (items < grid) grid = items;
+  static unsigned long long m1 = 0, m2 = 0, m3 = 0;
+  if (d->ns == 1) {
+    if (int e = set_max_smem_once(pconv3x3_kernel<1>, PC_SMEM, m1)) return e;
+    pconv3x3_kernel<1><<<grid, 192, PC_SMEM, stream>>>(tmA, tmB, tmO, tmO, p);
+  } else if (d->ns == 2) {
+    if (int e = set_max_smem_once(pconv3x3_kernel<2>, PC_SMEM, m2)) return e;
+    pconv3x3_kernel<2><<<grid, 192, PC_SMEM, stream>>>(tmA, tmB, tmO, tmO, p);
+  } else {
+    if (int e = set_max_smem_once(pconv3x3_kernel<3>, PC_SMEM, m3)) return e;
+    pconv3x3_kernel<3><<<grid, 192, PC_SMEM, stream>>>(tmA, tmB, tmO, tmO, p);
+  }
   return (int)cudaGetLastError();
 }
 

@@ -236,8 +236,15 @@ def conv_dgrad(dy, wdpack, ksize, stride, cin, in_hw):
         # y[oh,ow] = sum W[r,s] x[2oh+r, 2ow+s]  =>  dx[2i+ph, 2j+pw] gathers the taps with
         # r = ph (mod 2): (r, dh) in {(0,0),(2,-1)} for ph=0 and {(1,0)} for ph=1 (same for columns).
         rsel = {0: [(0, 0), (2, -1)], 1: [(1, 0)]}
+        strips = _pconv_taps_ok(wo, cout, cin, nb, ho)
         for ph in (0, 1):
             for pw in (0, 1):
+                if strips:                   # persistent strip kernel: one strip serves the class's column taps
+                    pconv_taps(dy, dims, strs, wdpack, kch, [(0, 0, dh) for _, dh in rsel[ph]],
+                               [dw for _, dw in rsel[pw]],
+                               [[(r * 3 + s) * cout for s, _ in rsel[pw]] for r, _ in rsel[ph]], nb, ho, wo, dx,
+                               (ph * w + pw) * cin, (h * w * cin, 2 * w * cin, 2 * cin))
+                    continue
                 taps = [(0, dw, 0, dh, (r * 3 + s) * cout) for r, dh in rsel[ph] for s, dw in rsel[pw]]
                 tapgemm(dy, dims, strs, wdpack, wdpack.shape[0], wdpack.shape[1], taps, kch, dx,
                         (ph * w + pw) * cin, (h * w * cin, 2 * w * cin, 2 * cin), wo, ho, nb, cin)
@@ -295,6 +302,35 @@ def pconv3x3(x, wpack, bias, residual, dgrad, want_stats=False):
         check(lib.b2dq_gn_finalize_tiles(_ptr(part), _ptr(stats), nb, h, w, 1e-6, _stream()), "gn_finalize_tiles")
         last_conv_stats = stats
     return out
+
+
+import os as _os0
+USE_PCONV_TAPS = _os0.environ.get("B2DQ_PCONV_TAPS", "1") != "0"  # parity classes (folded up-convolution, stride-2 data gradient) on the persistent strip kernel
+
+
+def _pconv_taps_ok(w_tiles, cin, cout, nb, h):
+    return (USE_PCONV and USE_PCONV_TAPS and cout == 128 and w_tiles % 128 == 0 and cin % 64 == 0
+            and nb * h * (w_tiles // 128) >= 2 * NUM_SMS)
+
+
+def pconv_taps(a, a_dims, a_strides, b, kchunks, rows, cols, wcol, nb, h, w, out, out_off, ostr, bias=None):
+    """b2dq_pconv_taps: rows = [(c, p, dh)] row taps, cols = [dw] column taps, wcol[r][s] = weight column base."""
+    d = _cabi.PconvTapsDesc()
+    d.a_ptr = a.data_ptr()
+    _fill(d.a_dims, a_dims)
+    _fill(d.a_strides, a_strides)
+    d.b_ptr, d.b_k, d.kchunks = b.data_ptr(), b.shape[1], kchunks
+    d.nr, d.ns = len(rows), len(cols)
+    for i, (rc, rp, rdh) in enumerate(rows):
+        d.row_c[i], d.row_p[i], d.row_dh[i] = rc, rp, rdh
+        for j in range(len(cols)):
+            d.wcol[i * 3 + j] = wcol[i][j]
+    _fill(d.col_dw, cols)
+    d.NB, d.H, d.W = nb, h, w
+    d.out = out.data_ptr() + out_off * 2
+    d.oN, d.oH, d.oW = ostr
+    d.bias = _ptr(bias)
+    check(_cabi.lib().b2dq_pconv_taps(C.byref(d), 0, _stream()), "pconv_taps")
 
 
 import os as _os
@@ -424,9 +460,16 @@ def upconv_fwd(x, wpack_fwd, bias, cout):
     assert cin % 64 == 0
     out = torch.empty(nb, 2 * h, 2 * w, cout, dtype=BF16, device=x.device)
     dims, strs = nhwc_view(x)
+    strips = _pconv_taps_ok(w, cin, cout, nb, h)
     for ph in (0, 1):
         for pw in (0, 1):
             cls = ph * 2 + pw
+            if strips:                       # persistent strip kernel: a 129-pixel strip serves both column slots
+                pconv_taps(x, dims, strs, wpack_fwd, cin // 64, [(0, 0, _UP_OFF[ph][a]) for a in (0, 1)],
+                           [_UP_OFF[pw][b] for b in (0, 1)],
+                           [[((cls * 2 + a) * 2 + b) * cin for b in (0, 1)] for a in (0, 1)], nb, h, w, out,
+                           (ph * 2 * w + pw) * cout, (4 * h * w * cout, 4 * w * cout, 2 * cout), bias=bias)
+                continue
             taps = [(0, _UP_OFF[pw][b], 0, _UP_OFF[ph][a], ((cls * 2 + a) * 2 + b) * cin)
                     for a in (0, 1) for b in (0, 1)]
             tapgemm(x, dims, strs, wpack_fwd, cout, 16 * cin, taps, cin // 64, out, (ph * 2 * w + pw) * cout,

@@ -116,6 +116,28 @@ int b2dq_tapgemm(const b2dq_tapgemm_desc* desc, cudaStream_t stream);
 int b2dq_pconv3x3(const void* a_bf16, const void* b_bf16, void* out_bf16, const float* bias,
                   const void* residual_bf16, float* gn_part, int NB, int H, int W, int Cin, int dgrad,
                   int max_ctas, cudaStream_t stream);
+/* The same persistent kernel for any tap group that can be read from row strips: nr row taps (A-view channel base /
+ * parity plane / row offset each) x ns column taps (pixel offsets col_dw[s], at most 2 apart), e.g. the 2x2 parity
+ * classes of the folded up-convolution (model.py:49-53) and of the stride-2 data gradient (model.py:62-72), whose
+ * four-tap K loop is too short for the one-shot b2dq_tapgemm.  Output tile grid NB x H x W (W % 128 == 0), 128 output
+ * channels, pixel (n, h, w) written at out + n*oN + h*oH + w*oW (strides multiples of 8 elements). */
+typedef struct b2dq_pconv_taps_desc {
+  const void* a_ptr;
+  long long a_dims[5];
+  long long a_strides[5];  /* (c, w, p, h, n) view of the input, elements */
+  const void* b_ptr;       /* [128][b_k] bf16 */
+  long long b_k;
+  int kchunks;             /* channels per tap / 64 */
+  int nr, ns;              /* row taps (1..9), column taps (1..3) */
+  int row_c[9], row_p[9], row_dh[9];
+  int col_dw[3];
+  int wcol[27];            /* weight column base of tap (r, s) at [r*3 + s] */
+  int NB, H, W;
+  void* out;
+  long long oN, oH, oW;
+  const float* bias;       /* [128] or NULL */
+} b2dq_pconv_taps_desc;
+int b2dq_pconv_taps(const b2dq_pconv_taps_desc* desc, int max_ctas, cudaStream_t stream);
 /* gn_part (optional, [NB*H*W/128][32][2] floats): per-tile GroupNorm(32) partial sums of the OUTPUT, so the
  * next GroupNorm needs no statistics pass; b2dq_gn_finalize_tiles turns them into stats [NB][32][2]. */
 int b2dq_gn_finalize_tiles(const float* gn_part, float* stats, int N, int H, int W, float eps,

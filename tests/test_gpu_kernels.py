@@ -535,7 +535,7 @@ def test_bias_grad_matches_fp32_sum():
 
 
 @pytest.mark.parametrize("nb,h,w,cin,cout", [(2, 16, 16, 256, 256), (1, 32, 32, 128, 128), (2, 8, 24, 64, 128),
-                                             (3, 64, 64, 128, 128)])
+                                             (3, 64, 64, 128, 128), (3, 128, 128, 128, 128)])   # last: strip kernel
 def test_folded_upsample_conv_matches_upsample_then_conv(nb, h, w, cin, cout):
     """Upsample(with_conv) as four 2x2 parity-class convolutions of the low-resolution input (kernels.upconv_*)
     against fp32 F.conv2d(F.interpolate(x, 2, 'nearest')) on the same bf16-rounded operands: output, dX, dW, db."""
@@ -603,3 +603,40 @@ def test_prepack_refreshes_all_stale_weight_packings_in_one_launch():
     assert ops.prepack(m) == len(m.ws)
     assert "dgrad" not in w.__dict__["_b2_packs"]
     assert torch.equal(ops._packed(w, "fwd"), kn.pack_weight_fwd(w))
+
+
+def test_parity_classes_on_the_strip_kernel_match_the_tap_gemm():
+    """b2dq_pconv_taps (persistent strip kernel, 2 / 1 column taps per strip) against the one-shot tap GEMM on the same
+    operands: the four parity classes of the folded up-convolution and of the stride-2 data gradient."""
+    from dynamicvectorquantization_b200 import kernels as kn
+    dev = "cuda"
+    nb, h, w = 3, 128, 128
+    for cin in (128, 64):
+        x = _rand_bf(nb, h, w, cin, seed=31).to(dev)
+        wt = torch.randn(128, cin, 3, 3, generator=torch.Generator().manual_seed(cin)) * (cin * 9) ** -0.5
+        b = torch.linspace(-0.5, 0.5, 128, device=dev)
+        wf, _ = kn.upconv_pack(wt.to(dev))
+        assert kn._pconv_taps_ok(w, cin, 128, nb, h)
+        y1 = kn.upconv_fwd(x, wf, b, 128)
+        kn.USE_PCONV_TAPS = False
+        try:
+            y0 = kn.upconv_fwd(x, wf, b, 128)
+        finally:
+            kn.USE_PCONV_TAPS = True
+        assert rel_rms(y1, y0) < 1e-3 and float((y1 != y0).float().mean()) < 0.02
+    # stride-2 data gradient: dy [3,128,128,Cout] -> dx [3,256,256,128]
+    for cout in (128, 256):
+        dy = _rand_bf(nb, h, w, cout, seed=32).to(dev)
+        wt = torch.randn(cout, 128, 3, 3, generator=torch.Generator().manual_seed(7 + cout)) * (cout * 9) ** -0.5
+        wd = kn.pack_weight_dgrad(wt.to(dev))
+        d1 = kn.conv_dgrad(dy, wd, 3, 2, 128, (2 * h, 2 * w))
+        kn.USE_PCONV_TAPS = False
+        try:
+            d0 = kn.conv_dgrad(dy, wd, 3, 2, 128, (2 * h, 2 * w))
+        finally:
+            kn.USE_PCONV_TAPS = True
+        assert rel_rms(d1, d0) < 1e-3 and float((d1 != d0).float().mean()) < 0.02
+        # fp32 reference: gradient of conv(pad(x, (0,1,0,1)), stride 2)
+        xr = torch.zeros(nb, 128, 2 * h, 2 * w, device=dev, requires_grad=True)
+        F.conv2d(F.pad(xr, (0, 1, 0, 1)), wt.to(dev).to(BF).float(), stride=2).backward(dy.float().permute(0, 3, 1, 2))
+        assert rel_rms(d1, xr.grad.permute(0, 2, 3, 1)) < 6e-3

@@ -33,6 +33,7 @@ CONV_CASES = [
     (3, 16, 16, 512, 512, 3, 1),
     (2, 64, 64, 128, 128, 3, 2),        # Downsample: pad (0,1,0,1), stride 2
     (1, 24, 40, 64, 192, 3, 1),         # ragged tiles
+    (3, 256, 256, 128, 128, 3, 2),      # Downsample at full width: data gradient on the strip kernel (b2dq_pconv_taps)
 ]
 
 
