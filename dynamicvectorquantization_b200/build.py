@@ -11,7 +11,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-shared", "-Xcompiler", "-fPIC"]
 
 
-KERNEL_SOURCES = {"pconv": "pconv.cu", "vq": "vq.cu", "wgrad": "mmgemm.cu", "tapgemm": "tapgemm.cu", "gn": "norm_fused.cu"}
+KERNEL_SOURCES = {"pconv": "pconv.cu", "pconv_taps": "pconv.cu", "vq": "vq.cu", "wgrad": "mmgemm.cu", "tapgemm": "tapgemm.cu", "gn": "norm_fused.cu"}
 
 
 def source_sha(kernel):

@@ -39,6 +39,6 @@ for _ in range(3):
         kn.upconv_fwd(xlo, wup, bias, c)
     if "gn" in which:
         y, st = kn.gn_forward(x, gam, bet, True)                # gn_fwd_fused_kernel
-        kn.gn_bwd(dy, x, st, gam, bet, True, add=res)           # gn_bwd_fused_kernel
+        kn.gn_bwd(dy, x, st, gam, bet, True)                    # gn_bwd_fused_kernel (as bench.py's roofline_gn: no residual add)
 torch.cuda.synchronize()
 print("done")

@@ -45,8 +45,8 @@ for r in rows[2:]:
         (rd + wr) / t / 1e3, val(r, "lts__t_sector_hit_rate.pct") or 0.0,
         (l2sm or 0.0) / 1e9, val(r, "smsp__issue_active.avg.pct_of_peak_sustained_active") or 0.0,
         int(val(r, "launch__registers_per_thread") or 0)))
-    key = ("pconv" if "pconv" in short else "vq" if "vq_search" in short else "wgrad" if "mmgemm" in short
-           else "gn" if "gn_" in short else "tapgemm")
+    key = ("pconv" if ("pconv" in short and ("<3>" in short or "<" not in short)) else "pconv_taps" if "pconv" in short
+           else "vq" if "vq_search" in short else "wgrad" if "mmgemm" in short else "gn" if "gn_" in short else "tapgemm")
     if key == "gn":                                   # the fused GroupNorm backward is the family's dominant kernel
         if "bwd_fused" not in short:
             continue
@@ -59,5 +59,7 @@ if os.path.exists(out_json):                          # keep the entries of kern
         summary.setdefault(k, v)
 open(out_md, "w").write("\n".join(lines) + "\n")
 summary["source"] = rep.split("/")[-1] + " (dram__bytes_read.sum + dram__bytes_write.sum per launch)"
+summary["note"] = ("*_csrc_sha16 = sha256[:16] of the kernel's sources (its .cu + common.cuh + tmap.h) at capture time; "
+                   "bench.py reports a traffic figure only when it matches the sources it runs")
 json.dump(summary, open(out_json, "w"), indent=1)
 print("\n".join(lines))
