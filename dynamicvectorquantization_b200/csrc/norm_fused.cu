@@ -19,7 +19,6 @@
 // constant in registers, use packed fp32x2 arithmetic (fma.rn.f32x2: half the issue slots) and ONE MUFU op per
 // sigmoid (sigmoid(z) = 0.5 + 0.5 tanh(z/2)) - the two-kernel version was instruction-bound at ~0.55 of HBM speed.
 // dgamma / dbeta are accumulated per CTA over its images and combined by the last CTA to finish, in CTA order.
-#include <cstdlib>
 #include "common.cuh"
 
 namespace b2 {
@@ -47,8 +46,6 @@ struct GnFusedParams {
   float* team_part;              // [T][2][C] per-team sums of the above
   unsigned* flags;               // [N] arrival counters | [N] finished teams | [N+1] error flag | [N+2 .. N+2+T) finished
                                  // CTAs per team (all zeroed before launch)
-  unsigned* flags2;              // [N] "group sums of image n published" (pipelined phases; zeroed before launch)
-  float* final_sums;             // [N][2G] S1/cnt, S2/cnt per group (pipelined phases)
   int N, HW, C, G, S, T, rows_per_cta;
 };
 
@@ -81,9 +78,6 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 __device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -104,10 +98,9 @@ __device__ __forceinline__ float2 dz_pair(float2 d, float2 xh, float2 Gh, float2
 // shared memory: ring [STAGES][3][CHUNK] | red [2][CONSUMERS][8] | chan [2][MAXC] | dg [2][MAXC] | sk [2][MAXG] | bars
 constexpr int GF_SMEM = GF_STAGES * 3 * GF_CHUNK + (2 * GF_CONSUMERS * 8 + 4 * GF_MAXC + 2 * GF_MAXG) * 4 + 2 * GF_STAGES * 8;
 
-template <bool SW, bool PIPE>
+template <bool SW>
 __global__ void __launch_bounds__(GF_THREADS, 2) gn_bwd_fused_kernel(const GnFusedParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ unsigned s_flag;
   uint8_t* ring = smem;
   float* red = reinterpret_cast<float*>(smem + GF_STAGES * 3 * GF_CHUNK);
   float* chan = red + 2 * GF_CONSUMERS * 8;
@@ -136,49 +129,34 @@ __global__ void __launch_bounds__(GF_THREADS, 2) gn_bwd_fused_kernel(const GnFus
   for (int i = tid; i < 2 * C; i += GF_THREADS) dg[i] = 0.f;
   __syncthreads();
 
-  // Images of this team, in order: n_k = team + k*T.  PIPE: the phases are software-pipelined across images -
-  // P1(n_0), P1(n_1), P2(n_0), P1(n_2), P2(n_1), ... - so nobody waits at the per-image barrier: the last CTA of the
-  // team to finish P1(n) sums the team's partials (fixed order) and publishes the image's two group sums, and by the
-  // time a CTA starts P2(n) - a whole P1 later - they are there.  Two images per team are in flight (the plan halves
-  // the number of teams for the same L2 budget).
-  const int cnt = (p.N - team + p.T - 1) / p.T;
   if (tid >= GF_CONSUMERS) {
-    // ------------------------------------------------------------------ producer (one lane of warp 8)
+    // ------------------------------------------------------------------ producer (one lane of warp 6)
     if (tid == GF_CONSUMERS) {
       uint32_t stage = 0, phase = 0;
       const uint64_t keep = l2_policy_evict_last(), drop = l2_policy_evict_first();
-      auto stream_image = [&](int n, int ph) {
+      for (int n = team; n < p.N; n += p.T) {
         const long long img = static_cast<long long>(n) * HW * C;
-        const bool with_add = ph == 1 && has_add;
-        const uint64_t pol = ph == 0 ? keep : drop;
-        for (int c = 0; c < nstages; ++c) {
-          const int row = r0 + c * srows;
-          const uint32_t bytes = static_cast<uint32_t>(min(srows, r1 - row)) * C * 2;
-          const long long off = img + static_cast<long long>(row) * C;
-          mbar_wait(empty0 + 8 * stage, phase ^ 1);
-          const uint32_t fb = full0 + 8 * stage;
-          const uint32_t dst = smem_u32(ring + stage * 3 * GF_CHUNK);
-          mbar_arrive_expect_tx(fb, bytes * (with_add ? 3 : 2));
-          bulk_load(dst, p.dy + off, bytes, fb, pol);
-          bulk_load(dst + GF_CHUNK, p.x + off, bytes, fb, pol);
-          if (with_add) bulk_load(dst + 2 * GF_CHUNK, p.add + off, bytes, fb, drop);
-          if (++stage == GF_STAGES) { stage = 0; phase ^= 1; }
-        }
-      };
-      if (PIPE) {
-        for (int k = 0; k <= cnt; ++k) {
-          if (k < cnt) stream_image(team + k * p.T, 0);
-          if (k > 0) stream_image(team + (k - 1) * p.T, 1);
-        }
-      } else {
-        for (int k = 0; k < cnt; ++k) {
-          stream_image(team + k * p.T, 0);
-          stream_image(team + k * p.T, 1);
+        for (int ph = 0; ph < 2; ++ph) {
+          const bool with_add = ph == 1 && has_add;
+          const uint64_t pol = ph == 0 ? keep : drop;
+          for (int c = 0; c < nstages; ++c) {
+            const int row = r0 + c * srows;
+            const uint32_t bytes = static_cast<uint32_t>(min(srows, r1 - row)) * C * 2;
+            const long long off = img + static_cast<long long>(row) * C;
+            mbar_wait(empty0 + 8 * stage, phase ^ 1);
+            const uint32_t fb = full0 + 8 * stage;
+            const uint32_t dst = smem_u32(ring + stage * 3 * GF_CHUNK);
+            mbar_arrive_expect_tx(fb, bytes * (with_add ? 3 : 2));
+            bulk_load(dst, p.dy + off, bytes, fb, pol);
+            bulk_load(dst + GF_CHUNK, p.x + off, bytes, fb, pol);
+            if (with_add) bulk_load(dst + 2 * GF_CHUNK, p.add + off, bytes, fb, drop);
+            if (++stage == GF_STAGES) { stage = 0; phase ^= 1; }
+          }
         }
       }
     }
   } else {
-    // ------------------------------------------------------------------ consumers (8 warps)
+    // ------------------------------------------------------------------ consumers (6 warps)
     const int v = tid % vecs, rlane = tid / vecs;
     const int cg = C / G;
     const int lane = tid & 31;
@@ -191,35 +169,7 @@ __global__ void __launch_bounds__(GF_THREADS, 2) gn_bwd_fused_kernel(const GnFus
       Gh[k] = make_float2(0.5f * p.gamma[v * 8 + 2 * k], 0.5f * p.gamma[v * 8 + 2 * k + 1]);
       Bh[k] = make_float2(0.5f * p.beta[v * 8 + 2 * k], 0.5f * p.beta[v * 8 + 2 * k + 1]);
     }
-    // fixed-order sum of the team's S per-CTA partials of image n -> red[j][2G] -> scaled sums in `dst_sk`
-    auto reduce_partials = [&](int n, float* dst_sk) {
-      const int e4n = (2 * G) / 4;                          // float4 per CTA row (16 for G = 32)
-      const int lanes_s = GF_CONSUMERS / e4n;               // 16
-      const int e4 = tid % e4n, j = tid / e4n;
-      const float4* src = reinterpret_cast<const float4*>(p.part + static_cast<long long>(n) * p.S * G * 2) + e4;
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int i0 = 0; i0 * lanes_s < p.S; i0 += 8) {       // eight loads in flight, added in index order
-        float4 t[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int sidx = j + (i0 + i) * lanes_s;
-          t[i] = (sidx < p.S) ? __ldcg(src + static_cast<long long>(sidx) * e4n) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { acc.x += t[i].x; acc.y += t[i].y; acc.z += t[i].z; acc.w += t[i].w; }
-      }
-      reinterpret_cast<float4*>(red)[j * e4n + e4] = acc;
-      consumer_sync();
-      if (tid < 2 * G) {
-        float tsum = 0.f;
-#pragma unroll 4
-        for (int jj = 0; jj < lanes_s; ++jj) tsum += red[jj * 2 * G + tid];
-        dst_sk[tid] = tsum * inv_cnt;                       // [g*2 + 0] = S1/cnt, [g*2 + 1] = S2/cnt
-      }
-      consumer_sync();
-    };
-    // ---------------- phase 1 of image n: sum_rows dz, sum_rows dz * xhat per channel -> per-group partials
-    auto phase1 = [&](int n) {
+    for (int n = team; n < p.N; n += p.T) {
       // per-(image, group) constants: xhat = x*R + M.  C/G is even, so a channel pair lies in one group and the
       // constants are scalars (broadcast operands of the packed instructions)
       float R[4], M[4];
@@ -230,6 +180,7 @@ __global__ void __launch_bounds__(GF_THREADS, 2) gn_bwd_fused_kernel(const GnFus
         R[k] = s0;
         M[k] = -m0 * s0;
       }
+      // ---------------- phase 1: sum_rows dz, sum_rows dz * xhat per channel
       float2 sa[4], sb[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) { sa[k] = make_float2(0.f, 0.f); sb[k] = make_float2(0.f, 0.f); }
@@ -255,7 +206,7 @@ __global__ void __launch_bounds__(GF_THREADS, 2) gn_bwd_fused_kernel(const GnFus
         if (lane == 0) mbar_arrive(empty0 + 8 * stage);
         if (++stage == GF_STAGES) { stage = 0; phase ^= 1; }
       }
-      // CTA reduction (fixed order) -> per-channel sums, per-group partials
+      // ---------------- CTA reduction (fixed order) -> per-channel sums, per-group partials
       float* red_a = red;
       float* red_b = red + GF_CONSUMERS * 8;
 #pragma unroll
@@ -284,57 +235,43 @@ __global__ void __launch_bounds__(GF_THREADS, 2) gn_bwd_fused_kernel(const GnFus
         __stcg(reinterpret_cast<float2*>(o), make_float2(S1, S2));
       }
       consumer_sync();
-      if (PIPE) {
-        // arrive; the LAST CTA of the team to arrive sums the partials and publishes the result - nobody waits here
-        if (tid == 0) {
-          __threadfence();
-          const unsigned prev = atomicAdd(p.flags + n, 1u);
-          __threadfence();
-          s_flag = (prev == static_cast<unsigned>(p.S) - 1u) ? 1u : 0u;
+      // ---------------- team barrier on image n
+      if (tid == 0) {
+        __threadfence();
+        red_release_add(p.flags + n, 1u);
+        const long long t0 = clock64();
+        while (ld_acquire(p.flags + n) < static_cast<unsigned>(p.S)) {
+          if (clock64() - t0 > 4000000000LL) { atomicExch(p.flags + p.N + 1, 1u); break; }   // ~2 s: never hang the GPU
         }
-        consumer_sync();
-        if (s_flag) {                                          // block-uniform
-          reduce_partials(n, sk);
-          if (tid < 2 * G) __stcg(p.final_sums + static_cast<long long>(n) * 2 * G + tid, sk[tid]);
-          __threadfence();
-          consumer_sync();
-          if (tid == 0) st_release(p.flags2 + n, 1u);
-        }
-      } else {
-        // team barrier on image n, then every CTA sums the partials itself
-        if (tid == 0) {
-          __threadfence();
-          red_release_add(p.flags + n, 1u);
-          const long long t0 = clock64();
-          while (ld_acquire(p.flags + n) < static_cast<unsigned>(p.S)) {
-            if (clock64() - t0 > 4000000000LL) { atomicExch(p.flags + p.N + 1, 1u); break; }   // ~2 s: never hang the GPU
-          }
-        }
-        consumer_sync();
-        reduce_partials(n, sk);
       }
-    };
-    // ---------------- phase 2 of image n: dx = rstd * (dz*gamma - S1/cnt - xhat * S2/cnt) (+ add)
-    auto phase2 = [&](int n) {
-      if (PIPE) {
-        if (tid == 0) {
-          const long long t0 = clock64();
-          while (ld_acquire(p.flags2 + n) == 0u) {
-            if (clock64() - t0 > 4000000000LL) { atomicExch(p.flags + p.N + 1, 1u); break; }
-          }
-        }
-        consumer_sync();
-        if (tid < 2 * G) sk[tid] = __ldcg(p.final_sums + static_cast<long long>(n) * 2 * G + tid);
-        consumer_sync();
-      }
-      float R[4], M[4];
+      consumer_sync();
+      {
+        // sum the S partials of every (group, 2) in a fixed order: thread (j, e4) takes CTAs j, j+16, ... of float4 e4
+        const int e4n = (2 * G) / 4;                          // float4 per CTA row (16 for G = 32)
+        const int lanes_s = GF_CONSUMERS / e4n;               // 16
+        const int e4 = tid % e4n, j = tid / e4n;
+        const float4* src = reinterpret_cast<const float4*>(p.part + static_cast<long long>(n) * p.S * G * 2) + e4;
+        constexpr int MAXL = (GF_MAXS + 15) / 16;             // loads per thread, all issued before the first add
+        float4 t[MAXL];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int g0 = (v * 8 + 2 * k) / cg;
-        const float m0 = p.stats[(n * G + g0) * 2], s0 = p.stats[(n * G + g0) * 2 + 1];
-        R[k] = s0;
-        M[k] = -m0 * s0;
+        for (int i = 0; i < MAXL; ++i) {
+          const int s = j + i * lanes_s;
+          t[i] = (s < p.S) ? __ldcg(src + static_cast<long long>(s) * e4n) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float4 acc = t[0];
+#pragma unroll
+        for (int i = 1; i < MAXL; ++i) { acc.x += t[i].x; acc.y += t[i].y; acc.z += t[i].z; acc.w += t[i].w; }
+        reinterpret_cast<float4*>(red)[j * e4n + e4] = acc;
+        consumer_sync();
+        if (tid < 2 * G) {
+          float tsum = 0.f;
+#pragma unroll 4
+          for (int jj = 0; jj < lanes_s; ++jj) tsum += red[jj * 2 * G + tid];
+          sk[tid] = tsum * inv_cnt;                           // sk[g*2 + 0] = S1/cnt, sk[g*2 + 1] = S2/cnt
+        }
+        consumer_sync();
       }
+      // ---------------- phase 2: dx = rstd * (dz*gamma - S1/cnt - xhat * S2/cnt) (+ add)
       // dx = R * (dz*gamma - k1 - xhat*k2) = 2R * (dz*(gamma/2) - k1/2 - xhat*k2/2): reuses Gh, three small constants
       float R2[4], K1[4], K2[4];
 #pragma unroll
@@ -375,17 +312,6 @@ __global__ void __launch_bounds__(GF_THREADS, 2) gn_bwd_fused_kernel(const GnFus
         __syncwarp();
         if (lane == 0) mbar_arrive(empty0 + 8 * stage);
         if (++stage == GF_STAGES) { stage = 0; phase ^= 1; }
-      }
-    };
-    if (PIPE) {
-      for (int k = 0; k <= cnt; ++k) {
-        if (k < cnt) phase1(team + k * p.T);
-        if (k > 0) phase2(team + (k - 1) * p.T);
-      }
-    } else {
-      for (int k = 0; k < cnt; ++k) {
-        phase1(team + k * p.T);
-        phase2(team + k * p.T);
       }
     }
   }
@@ -662,23 +588,8 @@ static long long gf_l2_budget() {
   return v;
 }
 
-// Backward with software-pipelined phases: opt-in (B2DQ_GN_PIPE=1).  Measured on B200 (tools/gpu_r2v.sh): correct, and
-// SLOWER than the per-image team barrier - 0.573 vs 0.441 ms on [32,256,256,128], 0.145 vs 0.120 ms on [32,128,128,128]:
-// two images in flight per team halve the number of teams for the same L2 budget, so every CTA visits twice as many
-// images with half-size slices (the per-image fixed work - statistics loads, CTA reduction, six block barriers -
-// doubles) and the phase-1 bytes have to survive in L2 twice as long.  The barrier wait it removes (17 % of the stall
-// samples) is already hidden by the second CTA on the SM, which belongs to another team.
-static bool gf_pipelined() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("B2DQ_GN_PIPE");
-    v = (e && e[0] == '1') ? 1 : 0;
-  }
-  return v != 0;
-}
-
 struct GfPlan { int T, S, rows_per_cta, grid; };
-static GfPlan gf_plan(int N, int HW, int C, int tensors = 2, int max_s = GF_MAXS) {
+static GfPlan gf_plan(int N, int HW, int C, int tensors = 2) {
   const int sms = 2 * device_sm_count();                        // 2 CTAs per SM
   const int rstep = GF_VPT * (GF_CONSUMERS / (C / 8));          // rows per ring stage
   const int chunks_img = (HW + rstep - 1) / rstep;
@@ -690,7 +601,7 @@ static GfPlan gf_plan(int N, int HW, int C, int tensors = 2, int max_s = GF_MAXS
   for (long long t = T; 2 * t > T; --t)                         // same number of images per team when a nearby T allows it
     if (N % t == 0) { T = t; break; }
   int S = sms / static_cast<int>(T);
-  if (S > max_s) S = max_s;
+  if (S > GF_MAXS) S = GF_MAXS;
   if (S > chunks_img) S = chunks_img;
   if (S < 1) S = 1;
   const int chunks_cta = (chunks_img + S - 1) / S;
@@ -702,11 +613,6 @@ static GfPlan gf_plan(int N, int HW, int C, int tensors = 2, int max_s = GF_MAXS
   return pl;
 }
 
-// plan of the backward: with pipelined phases a team keeps TWO images (dy + x each) in flight and may span every CTA
-static GfPlan gf_plan_bwd(int N, int HW, int C) {
-  return gf_pipelined() ? gf_plan(N, HW, C, 4, 2 * device_sm_count()) : gf_plan(N, HW, C, 2, GF_MAXS);
-}
-
 extern "C" {
 
 // Scratch the fused backward needs for an [N, HW, C] tensor with G groups, in bytes (0: shape not supported,
@@ -716,12 +622,11 @@ int b2dq_gn_bwd_fused_workspace_bytes(int N, int HW, int C, int G) {
   if (C % 8 || C > GF_MAXC || G > GF_MAXG || G <= 0 || C % G || (C / G) % 2 || GF_CONSUMERS % (C / 8) || (2 * G) % 4 ||
       GF_CONSUMERS % ((2 * G) / 4) || (GF_CONSUMERS / ((2 * G) / 4)) * ((GF_MAXS + 15) / 16) < GF_MAXS)
     return 0;
-  const GfPlan pl = gf_plan_bwd(N, HW, C);
+  const GfPlan pl = gf_plan(N, HW, C);
   const long long part = 1LL * N * pl.S * G * 2 * 4;
   const long long dgbp = 1LL * (pl.grid + pl.T) * 2 * C * 4;   // per-CTA partials, then per-team sums
-  const long long flags = (2LL * N + 2 + pl.T) * 4;            // + [N] "sums published" flags of the pipelined phases
-  const long long fin = 1LL * N * 2 * G * 4;                   // published group sums
-  return static_cast<int>(((part + 15) / 16 + (dgbp + 15) / 16 + (flags + 15) / 16 + (fin + 15) / 16) * 16);
+  const long long flags = (1LL * N + 2 + pl.T) * 4;
+  return static_cast<int>(((part + 15) / 16 + (dgbp + 15) / 16 + (flags + 15) / 16) * 16);
 }
 
 // dx = d/dx [ swish?(GroupNorm(x)) ] . dy (+ add);  dgb [2*C] = (dgamma, dbeta).  ws: b2dq_gn_bwd_fused_workspace_bytes.
@@ -733,7 +638,7 @@ int b2dq_gn_bwd_fused(const void* dy, const void* x, const float* stats, const f
   const long long need = b2dq_gn_bwd_fused_workspace_bytes(N, HW, C, G);
   if (need == 0 || (swish != 0 && swish != 1)) return -1;
   if (ws_bytes < need || ws == nullptr) return -2;
-  const GfPlan pl = gf_plan_bwd(N, HW, C);
+  const GfPlan pl = gf_plan(N, HW, C);
   GnFusedParams p;
   p.dy = reinterpret_cast<const __nv_bfloat16*>(dy);
   p.x = reinterpret_cast<const __nv_bfloat16*>(x);
@@ -747,27 +652,17 @@ int b2dq_gn_bwd_fused(const void* dy, const void* x, const float* stats, const f
   p.part = reinterpret_cast<float*>(w);
   p.dgb_part = reinterpret_cast<float*>(w + part);
   p.team_part = p.dgb_part + 1LL * pl.grid * 2 * C;
-  const long long flagb = (((2LL * N + 2 + pl.T) * 4 + 15) / 16) * 16;
   p.flags = reinterpret_cast<unsigned*>(w + part + dgbp);
-  p.flags2 = p.flags + N + 2 + pl.T;
-  p.final_sums = reinterpret_cast<float*>(w + part + dgbp + flagb);
   p.N = N; p.HW = HW; p.C = C; p.G = G; p.S = pl.S; p.T = pl.T; p.rows_per_cta = pl.rows_per_cta;
-  cudaError_t e = cudaMemsetAsync(p.flags, 0, (2 * N + 2 + pl.T) * sizeof(unsigned), stream);
+  cudaError_t e = cudaMemsetAsync(p.flags, 0, (N + 2 + pl.T) * sizeof(unsigned), stream);
   if (e != cudaSuccess) return (int)e;
-  static unsigned long long m00 = 0, m01 = 0, m10 = 0, m11 = 0;
-  const bool pipe = gf_pipelined();
-  if (swish && pipe) {
-    if (int r = set_max_smem_once(gn_bwd_fused_kernel<true, true>, GF_SMEM, m11)) return r;
-    gn_bwd_fused_kernel<true, true><<<pl.grid, GF_THREADS, GF_SMEM, stream>>>(p);
-  } else if (swish) {
-    if (int r = set_max_smem_once(gn_bwd_fused_kernel<true, false>, GF_SMEM, m10)) return r;
-    gn_bwd_fused_kernel<true, false><<<pl.grid, GF_THREADS, GF_SMEM, stream>>>(p);
-  } else if (pipe) {
-    if (int r = set_max_smem_once(gn_bwd_fused_kernel<false, true>, GF_SMEM, m01)) return r;
-    gn_bwd_fused_kernel<false, true><<<pl.grid, GF_THREADS, GF_SMEM, stream>>>(p);
+  static unsigned long long m0 = 0, m1 = 0;
+  if (swish) {
+    if (int r = set_max_smem_once(gn_bwd_fused_kernel<true>, GF_SMEM, m1)) return r;
+    gn_bwd_fused_kernel<true><<<pl.grid, GF_THREADS, GF_SMEM, stream>>>(p);
   } else {
-    if (int r = set_max_smem_once(gn_bwd_fused_kernel<false, false>, GF_SMEM, m00)) return r;
-    gn_bwd_fused_kernel<false, false><<<pl.grid, GF_THREADS, GF_SMEM, stream>>>(p);
+    if (int r = set_max_smem_once(gn_bwd_fused_kernel<false>, GF_SMEM, m0)) return r;
+    gn_bwd_fused_kernel<false><<<pl.grid, GF_THREADS, GF_SMEM, stream>>>(p);
   }
   return (int)cudaGetLastError();
 }
@@ -813,7 +708,7 @@ int b2dq_gn_fwd_fused(const void* x, const float* gamma, const float* beta, void
 // The plan of the call above (tests / bench): teams, CTAs per team, rows per CTA, grid.
 int b2dq_gn_bwd_fused_plan(int N, int HW, int C, int* out4) {
   if (N <= 0 || HW <= 0 || C < 8 || !out4) return -1;
-  const GfPlan pl = gf_plan_bwd(N, HW, C);
+  const GfPlan pl = gf_plan(N, HW, C);
   out4[0] = pl.T; out4[1] = pl.S; out4[2] = pl.rows_per_cta; out4[3] = pl.grid;
   return 0;
 }
