@@ -79,6 +79,8 @@ SIGNATURES = {
     "b2dq_groupnorm_workspace_bytes": [_i, _i, _i, _i, _i],
     "b2dq_groupnorm_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _f, _i, _vp],
     "b2dq_groupnorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _vp],
+    "b2dq_groupnorm_swish_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _vp],
+    "b2dq_groupnorm_swish_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _vp],
     "b2dq_attention_workspace_bytes": [_i, _i, _i, _i],
     "b2dq_attention_fwd": [_vp, _vp, _vp, _vp, _ll, _i, _i, _i, _f, _vp],
     "b2dq_attention_bwd": [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _f, _vp],

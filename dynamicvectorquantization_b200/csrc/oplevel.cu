@@ -358,6 +358,17 @@ int b2dq_groupnorm_bwd(const void* dy, const void* x, const float* stats, const 
   return b2dq_gn_bwd_apply(dy, x, stats, gamma, beta, ws_nc, dx, dgb, add, N, HW, C, G, act, stream);
 }
 
+// Names of SURVEY 8b: GroupNorm(32, 1e-6) + swish, the pair every ResnetBlock / AttnBlock / output head uses.
+int b2dq_groupnorm_swish_fwd(const void* x, const float* gamma, const float* beta, void* y, float* stats, void* ws,
+                             long long ws_bytes, int N, int HW, int C, cudaStream_t stream) {
+  return b2dq_groupnorm_fwd(x, gamma, beta, y, stats, ws, ws_bytes, N, HW, C, 32, 1e-6f, 1, stream);
+}
+int b2dq_groupnorm_swish_bwd(const void* dy, const void* x, const float* stats, const float* gamma, const float* beta,
+                             void* dx, float* dgb, const void* add, void* ws, long long ws_bytes, int N, int HW, int C,
+                             cudaStream_t stream) {
+  return b2dq_groupnorm_bwd(dy, x, stats, gamma, beta, dx, dgb, add, ws, ws_bytes, N, HW, C, 32, 1, stream);
+}
+
 // ------------------------------------------------------------------------------------------ attention core
 // qkv [N][T][3C] bf16: q | k | v side by side (the output of ONE [C -> 3C] 1x1 convolution).
 int b2dq_attention_workspace_bytes(int N, int T, int C, int backward) {

@@ -338,6 +338,13 @@ int b2dq_groupnorm_bwd(const void* dy, const void* x, const float* stats, const 
                        void* dx, float* dgb, const void* add, void* ws, long long ws_bytes, int N, int HW, int C,
                        int G, int act, cudaStream_t stream);
 
+/* The model's own pair - GroupNorm(32, eps 1e-6) + swish (ws sized with G = 32) - under the names of SURVEY 8b */
+int b2dq_groupnorm_swish_fwd(const void* x, const float* gamma, const float* beta, void* y, float* stats, void* ws,
+                             long long ws_bytes, int N, int HW, int C, cudaStream_t stream);
+int b2dq_groupnorm_swish_bwd(const void* dy, const void* x, const float* stats, const float* gamma, const float* beta,
+                             void* dx, float* dgb, const void* add, void* ws, long long ws_bytes, int N, int HW, int C,
+                             cudaStream_t stream);
+
 /* Attention core of AttnBlock.forward (model.py:176-188): out = softmax(scale * q k^T) v per image.
  * qkv [N,T,3C] bf16 holds q | k | v side by side (one [C -> 3C] 1x1 convolution); out [N,T,C] bf16; probs [N,T,T]
  * bf16 is kept for the backward, which writes dq | dk | dv into dqkv [N,T,3C].  scale = C^-0.5 in the model. */
