@@ -225,6 +225,52 @@ def triple_entropy_goldens():
     save("entropy_small.npz", x=xe, entropy=ent, gate=gate_e, threshold=1.5, budget=bud)
 
 
+def triple_backward_goldens():
+    """Gradients of the tiny triple-grain model of the reference (EncoderTriple + RouterTriple, eval-mode routing) under
+    |xrec - x|.mean() + qloss + triple budget loss: norms of every parameter gradient and a few full tensors
+    (SURVEY 8 rows a3 + a18).  Same construction and seeds as triple_entropy_goldens."""
+    from modules.dynamic_modules.budget import BudgetConstraint_NormedSeperateRatioMSE_TripleGrain
+    conf = yaml.safe_load(open(os.path.join(REF, "configs/stage1/dqvae-triple-r-03-03_imagenet.yml")))["model"]["params"]
+    cfg = orc.TINY_TRIPLE_CFG
+    enc_p = dict(conf["encoderconfig"]["params"], ch=cfg["ch"], resolution=cfg["resolution"],
+                 z_channels=cfg["z_channels"], attn_resolutions=list(cfg["attn_resolutions"]))
+    enc_p["router_config"] = dict(enc_p["router_config"], params=dict(enc_p["router_config"]["params"],
+                                                                      num_channels=cfg["z_channels"]))
+    dec_p = dict(conf["decoderconfig"]["params"], ch=cfg["dec_ch"], in_ch=cfg["z_channels"],
+                 resolution=cfg["resolution"], attn_resolutions=list(cfg["dec_attn_resolutions"]),
+                 latent_size=cfg["latent_size"])
+    m = nn.Module()
+    m.encoder = instantiate_from_config(dict(target=conf["encoderconfig"]["target"], params=enc_p))
+    m.decoder = instantiate_from_config(dict(target=conf["decoderconfig"]["target"], params=dec_p))
+    m.quantize = instantiate_from_config(dict(target=conf["vqconfig"]["target"], params=dict(
+        conf["vqconfig"]["params"], codebook_size=cfg["codebook_size"], codebook_dim=cfg["codebook_dim"])))
+    m.quant_conv = nn.Conv2d(cfg["z_channels"], cfg["codebook_dim"], 1)
+    m.post_quant_conv = nn.Conv2d(cfg["codebook_dim"], cfg["z_channels"], 1)
+    m.load_state_dict(orc.make_weights(orc.model_shapes(cfg), seed=5), strict=True)
+    m.eval()
+    g = torch.Generator().manual_seed(55)
+    x = torch.rand(2, 3, cfg["resolution"], cfg["resolution"], generator=g) * 2 - 1
+    hd = m.encoder(x, None)
+    h = m.quant_conv(hd["h_triple"])
+    quant, qloss, (_, _, codes) = m.quantize(x=h, temp=0.0, codebook_mask=hd["codebook_mask"])
+    xrec = m.decoder(m.post_quant_conv(quant), None)
+    budget = BudgetConstraint_NormedSeperateRatioMSE_TripleGrain(
+        target_fine_ratio=0.3, target_median_ratio=0.3, gamma=1.0, min_grain_size=2, median_grain_size=4,
+        max_grain_size=8)(hd["gate"])
+    loss = (xrec - x).abs().mean() + qloss + budget
+    loss.backward()
+    grads = {n: p.grad for n, p in m.named_parameters() if p.grad is not None}
+    pick = [k for k in ("encoder.conv_in.weight", "encoder.conv_out_fine.weight", "encoder.conv_out_median.weight",
+                        "encoder.conv_out_coarse.bias", "encoder.norm_out_median.weight", "quant_conv.weight",
+                        "post_quant_conv.bias", "decoder.conv_in.weight", "decoder.norm_out.weight",
+                        "decoder.conv_out.weight") if k in grads]
+    names = sorted(grads)
+    save("model_tiny_triple_grads.npz", x=x, loss=loss, indices=hd["indices"].to(torch.int8), codes=codes.to(torch.int16),
+         grad_norm_names=np.array(names),
+         grad_norms=np.array([float(grads[n].double().pow(2).sum().sqrt()) for n in names]),
+         **{"grad__" + k.replace(".", "__"): grads[k] for k in pick})
+
+
 # ----------------------------------------------------------------------------------- sibling quantizers
 def vq_family_goldens():
     """quantize2 / quantize2_list / quantize_rqvae / quantize_vqgan of the reference.
@@ -498,7 +544,10 @@ def threshold_goldens():
 
 
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["vq", "family", "permuter", "tiny", "dual", "variants", "loss", "thresholds", "routing"]
+    what = sys.argv[1:] or ["vq", "family", "permuter", "tiny", "dual", "variants", "loss", "thresholds", "routing",
+                            "triple_grads"]
+    if "triple_grads" in what:
+        triple_backward_goldens()
     if "routing" in what:
         train_routing_goldens()
     if "thresholds" in what:

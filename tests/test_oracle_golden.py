@@ -126,6 +126,39 @@ def test_triple_oracle_matches_reference():
     assert abs(float(b) - float(g["budget"])) < 1e-5 * abs(float(g["budget"])) + 1e-8
 
 
+def test_triple_oracle_backward_matches_reference():
+    """Rows a3 + a18 for the triple-grain model: the oracle's autograd of |xrec - x|.mean() + qloss + triple budget loss
+    against the gradients of the reference's own EncoderTriple / Decoder / VectorQuantize2 (eval-mode routing)."""
+    g = _load("model_tiny_triple_grads.npz")
+    cfg = orc.TINY_TRIPLE_CFG
+    sd = orc.make_weights(orc.model_shapes(cfg), seed=5)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if "cluster_size" not in k and "embed_ema" not in k}
+    full = dict(sd); full.update(params)
+    x = torch.from_numpy(g["x"])
+    out = orc.model_forward(full, cfg, x)
+    assert np.array_equal(out["indices"].numpy(), g["indices"].astype(np.int64))
+    assert np.array_equal(out["codes"].numpy(), g["codes"].astype(np.int64))
+    loss = (out["xrec"] - x).abs().mean() + out["qloss"] + orc.budget_loss_triple(out["gate"], min_grain=2, median_grain=4,
+                                                                                  max_grain=8)
+    assert abs(float(loss.detach()) - float(g["loss"])) < 1e-5 * abs(float(g["loss"]))
+    loss.backward()
+    checked = 0
+    for key in g:
+        if key.startswith("grad__"):
+            name = key[len("grad__"):].replace("__", ".")
+            assert torch.allclose(params[name].grad, torch.from_numpy(g[key]), rtol=2e-3, atol=1e-6), name
+            checked += 1
+    assert checked >= 8
+    seen = 0
+    for n, ref in zip(g["grad_norm_names"], g["grad_norms"]):
+        n = str(n)
+        if n in params and params[n].grad is not None:
+            got = float(params[n].grad.double().pow(2).sum().sqrt())
+            assert abs(got - ref) <= 2e-3 * ref + 1e-7, (n, got, ref)
+            seen += 1
+    assert seen >= 400                                          # every trainable tensor of the model
+
+
 def test_entropy_oracle_matches_reference():
     g = _load("entropy_small.npz")
     x = torch.from_numpy(g["x"])
